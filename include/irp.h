@@ -1,0 +1,166 @@
+/*
+ * irp.h — C ABI of libirp_b200.so: the B200-native degradation-analysis +
+ * preprocess hot path of RazonIn4K/image-restoration-platform.
+ *
+ * This is the drop-in boundary.  Every entry point below is
+ * what a Node N-API addon (addon/irp_addon.cc) or the Python ctypes mirror
+ * (image-restoration-platform_b200/_ffi.py) binds; signatures use plain
+ * pointers and sizes only.  Each group cites the reference call it replaces
+ * (paths relative to the reference repo root).
+ *
+ * Pixel layout everywhere: u8, interleaved HWC, `pitch` bytes between rows.
+ * There is NO CPU fallback: without a usable CUDA device irp_create() fails
+ * with IRP_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef IRP_H_
+#define IRP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRP_ABI_VERSION 1
+
+/* status codes (0 = ok, <0 = error; message via irp_last_error) */
+enum {
+  IRP_OK = 0,
+  IRP_ERR_BAD_ARG = -1,     /* null pointer, bad dims, bad channel count        */
+  IRP_ERR_UNSUPPORTED = -2, /* shrink factor >= 4 (needs box pre-shrink), C == 2 */
+  IRP_ERR_CUDA = -3,        /* a CUDA runtime call failed                       */
+  IRP_ERR_NOMEM = -4,       /* host or device allocation failed                 */
+  IRP_ERR_NO_DEVICE = -5,   /* no CUDA device / wrong architecture              */
+  IRP_ERR_CAPACITY = -6     /* caller-provided output buffer too small          */
+};
+
+/* score order == key order of the object ClassifierService.analyze returns
+ * (server-node/src/services/classifier.js:62-70). */
+enum {
+  IRP_SCORE_BLUR = 0,
+  IRP_SCORE_NOISE = 1,
+  IRP_SCORE_LOWLIGHT = 2,
+  IRP_SCORE_COMPRESSION = 3,
+  IRP_SCORE_SCRATCH = 4,
+  IRP_SCORE_FADE = 5,
+  IRP_SCORE_COLORSHIFT = 6,
+  IRP_NUM_SCORES = 7
+};
+
+/* Switches for the libvips details SURVEY.md §8a tags MED/LOW confidence. */
+enum { IRP_LUMA_VIPS_USUAL = 0 /* 0.2/0.7/0.1 */, IRP_LUMA_CIE = 1 /* 0.2126/0.7152/0.0722 */ };
+enum { IRP_COEF_FIXED_POINT_SUM = 0 /* vips_vector_to_fixed_point */, IRP_COEF_TRUNCATE = 1 };
+
+#define IRP_MAX_DIMENSION 2048 /* imagePreprocess.js:4  MAX_DIMENSION */
+#define IRP_FUSION_CANVAS 2048 /* SURVEY.md §8a row P5                */
+#define IRP_FUSION_MAX_IMAGES 3
+
+typedef struct irp_ctx irp_ctx;
+
+typedef struct irp_opts {
+  uint32_t struct_size; /* sizeof(irp_opts), for forward compatibility */
+  int32_t luma_mode;    /* IRP_LUMA_*                                   */
+  int32_t coef_mode;    /* IRP_COEF_*                                   */
+  int32_t reserved0;
+  uint64_t staging_bytes; /* pinned + device staging ring for host inputs; 0 = default */
+} irp_opts;
+
+typedef struct irp_image_desc {
+  const uint8_t *pixels;    /* host or device pointer (see on_device)                 */
+  size_t pitch;             /* bytes per row, >= width*channels                       */
+  int32_t width, height;    /* STORED dims (pre-EXIF), as sharp metadata() reports    */
+  int32_t channels;         /* 1, 3 or 4                                              */
+  int32_t is_jpeg;          /* metadata.format === 'jpeg' (classifier.js:180)         */
+  int32_t exif_orientation; /* 1..8; anything else is treated as 1                    */
+  int32_t on_device;        /* 1: `pixels` already lives in this context's device HBM */
+} irp_image_desc;
+
+/* Everything the classifier derives from pixels.  Integer fields are exact and
+ * order-independent; score[] is computed from them in IEEE double. */
+typedef struct irp_result {
+  double score[IRP_NUM_SCORES];
+  uint64_t sum[4], sumsq[4];     /* per channel Σx, Σx²      (sharp.stats, classifier.js:52)   */
+  uint64_t e_sum[2], e_sumsq[2]; /* clipped Lap8 / Sharp9 responses (classifier.js:107-118,135-145) */
+  uint64_t b_sum, b_sumsq;       /* pooled Σ, Σ² of gaussblur(σ=1) bytes (classifier.js:297)  */
+  uint32_t scratch_v, scratch_h; /* _detectLinearFeatures counts (classifier.js:310-337)      */
+  uint32_t block_edges[2];       /* additive diagnostic: strong grey steps across 8-px column / row boundaries */
+  uint32_t luma_hist[256];       /* additive diagnostic: histogram of the libvips B_W grey    */
+  int32_t status;                /* per-image status (IRP_OK or an error code)                */
+  int32_t reserved;
+} irp_result;
+
+typedef struct irp_out_desc {
+  uint8_t *pixels;  /* caller-owned destination (host or device)                        */
+  size_t pitch;     /* in: bytes per row of the destination; 0 = tight (width*channels) */
+  size_t capacity;  /* in: bytes available at `pixels`                                  */
+  int32_t width, height, channels; /* out: dims of what was written                    */
+  int32_t on_device;
+} irp_out_desc;
+
+/* per-call device timings of the last completed call on this context (ms, CUDA events
+ * on the launch stream). */
+typedef struct irp_timing {
+  float h2d_ms, classify_ms, preprocess_ms, d2h_ms, total_ms;
+  uint32_t kernel_launches; /* kernels of this library launched by the call */
+  uint32_t reserved;
+} irp_timing;
+
+/* ---- library / context ------------------------------------------------- */
+int irp_abi_version(void);
+int irp_device_count(void);
+/* Replaces `new ClassifierService({logger})` + sharp's global libvips init
+ * (server-node/src/context/services.js:48-50).  One context per GPU. */
+irp_ctx *irp_create(int device, const irp_opts *opts);
+void irp_destroy(irp_ctx *ctx);
+/* ctx may be NULL to read the error of a failed irp_create on this thread. */
+const char *irp_last_error(const irp_ctx *ctx);
+/* Launch on a caller-owned CUDA stream (cudaStream_t as void*); NULL = the
+ * context's own stream. */
+int irp_set_stream(irp_ctx *ctx, void *cuda_stream);
+int irp_get_timing(const irp_ctx *ctx, irp_timing *out);
+
+/* ---- pure host helpers (no GPU work) ----------------------------------- */
+/* calculateResizeDimensions + sharp fit:'inside' after .rotate()
+ * (server-node/src/middleware/imagePreprocess.js:7-22,42-53). */
+int irp_preprocess_dims(int width, int height, int exif_orientation, int *out_w, int *out_h);
+/* fusion canvas placement: resized dims + top-left offset. */
+int irp_fusion_dims(int width, int height, int exif_orientation, int *out_w, int *out_h, int *off_x,
+                    int *off_y);
+/* the 7 JS formulas (classifier.js:119-121,146,159-167,180-186,223-228,240-253)
+ * applied to the integer moments already in `r`; fills r->score. */
+int irp_scores_from_moments(irp_result *r, int width, int height, int channels, int is_jpeg);
+/* copies of the baked grey tables (for the exhaustive 2^24 verification test) */
+int irp_grey_tables(int luma_mode, uint32_t lut_r[256], uint32_t lut_g[256], uint32_t lut_b[256],
+                    uint32_t inv[4096]);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* ClassifierService.analyze for n images (classifier.js:40-99): stats,
+ * grey, 3 stencils, blur delta, scratch grid — one pass over each image. */
+int irp_classify_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_result *results);
+/* preprocessImage pixel stages (imagePreprocess.js:42-53): auto-orient,
+ * lanczos3 fit-inside <= 2048, normalise to u8 RGB (grey stays 1 channel). */
+int irp_preprocess_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_out_desc *outs);
+/* classify + preprocess of the same sources in one submission; the second
+ * pass over each source is served from L2 (BASELINE.json configs[1]). */
+int irp_analyze_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_result *results,
+                      irp_out_desc *outs);
+/* up to 3 images -> aligned 2048x2048x3 canvases, centred, black pad
+ * (SURVEY.md §8a row P5).  `canvases` has n_groups*3 entries; unused slots of
+ * a group (pixels == NULL in `imgs`) are skipped. */
+int irp_fusion_prepare_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n_groups,
+                             irp_out_desc *canvases);
+
+/* ---- memory helpers (so non-CUDA hosts can stage device-resident data) -- */
+void *irp_dev_alloc(irp_ctx *ctx, size_t bytes);
+int irp_dev_free(irp_ctx *ctx, void *p);
+void *irp_host_alloc_pinned(irp_ctx *ctx, size_t bytes);
+int irp_host_free_pinned(irp_ctx *ctx, void *p);
+int irp_memcpy_h2d(irp_ctx *ctx, void *dst, const void *src, size_t bytes);
+int irp_memcpy_d2h(irp_ctx *ctx, void *dst, const void *src, size_t bytes);
+int irp_synchronize(irp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRP_H_ */
