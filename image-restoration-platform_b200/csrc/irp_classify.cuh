@@ -1,0 +1,441 @@
+// irp_classify.cuh — fused degradation-statistics kernel (sm_100a).
+//
+// One pass over the source pixels computes everything ClassifierService.analyze
+// (reference: server-node/src/services/classifier.js:40-99) derives from them:
+//   S0  per-channel sum / sum of squares            (classifier.js:52, sharp.stats)
+//   G1  libvips B_W grey, integer restatement       (classifier.js:108,136,200)
+//   A1  sum / sumsq of clip(Lap8 * grey)            (classifier.js:107-118)
+//   A2  sum / sumsq of clip(Sharp9 * grey)          (classifier.js:135-145)
+//   A4  pooled sum / sumsq of gaussblur(1) bytes    (classifier.js:296-300)
+//   A5  stride-4 grid counts on clip(Lap4 * grey)   (classifier.js:310-337)
+//   + luma histogram and 8x8 boundary step counts (additive diagnostics).
+//
+// Layout: a persistent grid walks 256x32-pixel tiles of the whole batch.  Per
+// tile, stage 1 pulls 48-byte RGB segments with 128-bit loads, regroups them to
+// planar R/G/B words (PRMT), accumulates channel moments with IDP.4A, maps the
+// pixels to grey through shared-memory integer LUTs and writes planar + grey
+// tiles (1-pixel replicate halo) to shared memory.  Stage 2 slides a 3-row
+// window down 4-pixel strips of the grey tile in packed 16x2 SIMD; stage 3 does
+// the separable 12/20/12 blur the same way (IDP.4A + IMAD.HI exact /11).
+// Per-thread u32 accumulators live in registers across the tiles of one image
+// and are flushed with one block reduction + 64-bit global atomics per image.
+// HBM-bound byte work: no tensor cores by design (BASELINE.json north_star).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/irp_spec.h"
+
+namespace irp {
+
+constexpr int kTileW = 256;            // owned pixels per tile row
+constexpr int kTileH = 32;             // owned rows per tile
+constexpr int kRows = kTileH + 2;      // + replicate halo rows
+constexpr int kPlanePitch = 16 + kTileW + 16;  // bytes: [..15 = left halo][256 px][0 = right halo ..]
+constexpr int kClassifyThreads = 256;
+constexpr int kSegPx = 16;             // pixels per stage-1 work item
+constexpr int kSegsPerRow = kTileW / kSegPx;
+constexpr int kFlushTiles = 512;       // keeps every u32 accumulator below 2^32
+
+// global accumulator slots (u64) per image
+enum {
+  ACC_SUM = 0,     // 4
+  ACC_SUMSQ = 4,   // 4
+  ACC_E1S = 8, ACC_E1Q = 9, ACC_E2S = 10, ACC_E2Q = 11,
+  ACC_BS = 12, ACC_BQ = 13,
+  ACC_SV = 14, ACC_SH = 15, ACC_BE0 = 16, ACC_BE1 = 17,
+  ACC_COUNT = 18
+};
+
+struct ImgDev {
+  const uint8_t* px;
+  unsigned long long pitch;
+  int w, h, c;
+  int tiles_x, tiles_y;
+  int tile_base;    // first global tile index of this image
+  int aligned16;    // base and pitch are multiples of 16
+  int slot;         // index of this image's accumulators / result
+};
+
+struct ClassifyTables {   // device copies of grey_tables.inc for the chosen luma mode
+  uint32_t lut[3][256];
+  uint32_t inv[4096];
+};
+
+template <int C>
+struct ClassifySmem {
+  uint8_t plane[C][kRows][kPlanePitch];
+  uint8_t grey[kRows][kPlanePitch];
+  uint32_t lut[3][256];
+  uint32_t inv[4096];
+  uint32_t hist[256];
+  unsigned long long red[kClassifyThreads / 32][ACC_COUNT];
+};
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// dp2a with unsigned 16-bit lanes in a and SIGNED bytes in b (low half of b)
+__device__ __forceinline__ int dp2a_lo_u16_s8(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// grey of one pixel from its three LUT byte offsets (already scaled by 4 is not
+// required: plain indices); returns (inv + low bits): grey sits in bits 24..31
+template <int C>
+__device__ __forceinline__ uint32_t grey_top(const ClassifySmem<C>& s, uint32_t r, uint32_t g, uint32_t b) {
+  uint32_t I = s.lut[0][r] + s.lut[1][g] + s.lut[2][b];
+  return s.inv[I >> 20] + (I & 0xFFFFFu);
+}
+
+// exact floor(x / 11) for 0 <= x <= 2810  (x = 3*(l+r) + 5*c + 5)
+__device__ __forceinline__ uint32_t div11(uint32_t x) { return __umulhi(x, 390451573u); }
+
+template <int C>
+struct Acc {
+  uint32_t s[C], q[C];
+  uint32_t e1s, e1q, e2s, e2q, bs, bq, sv, sh, be0, be1;
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < C; i++) s[i] = q[i] = 0;
+    e1s = e1q = e2s = e2q = bs = bq = sv = sh = be0 = be1 = 0;
+  }
+};
+
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int C>
+__device__ void flush_acc(ClassifySmem<C>& sm, Acc<C>& a, unsigned long long* gacc, uint32_t* ghist) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long v[ACC_COUNT];
+#pragma unroll
+  for (int i = 0; i < ACC_COUNT; i++) v[i] = 0;
+#pragma unroll
+  for (int i = 0; i < C; i++) {
+    v[ACC_SUM + i] = a.s[i];
+    v[ACC_SUMSQ + i] = a.q[i];
+  }
+  v[ACC_E1S] = a.e1s; v[ACC_E1Q] = a.e1q; v[ACC_E2S] = a.e2s; v[ACC_E2Q] = a.e2q;
+  v[ACC_BS] = a.bs; v[ACC_BQ] = a.bq; v[ACC_SV] = a.sv; v[ACC_SH] = a.sh;
+  v[ACC_BE0] = a.be0; v[ACC_BE1] = a.be1;
+#pragma unroll
+  for (int i = 0; i < ACC_COUNT; i++) {
+    unsigned long long r = warp_sum64(v[i]);
+    if (lane == 0) sm.red[warp][i] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < ACC_COUNT) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kClassifyThreads / 32; w++) t += sm.red[w][threadIdx.x];
+    if (t) atomicAdd(&gacc[threadIdx.x], t);
+  }
+  {
+    uint32_t hv = sm.hist[threadIdx.x];
+    if (hv) atomicAdd(&ghist[threadIdx.x], hv);
+    sm.hist[threadIdx.x] = 0;
+  }
+  a.clear();
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// stage 1, generic item: any channel count, any alignment, image edges.
+// One item = 16 pixels of one tile row.
+// ---------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void stage1_slow(ClassifySmem<C>& sm, Acc<C>& a, const ImgDev& im, int gy, int xbeg,
+                                            int row, int col0, int npx, bool counted) {
+  const uint8_t* rp = im.px + (size_t)gy * im.pitch;
+  for (int i = 0; i < npx; i++) {
+    int x = xbeg + i;
+    bool inside = x >= 0 && x < im.w;
+    int xc = min(max(x, 0), im.w - 1);
+    uint32_t v[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) v[ch] = rp[(size_t)xc * C + ch];
+    uint32_t g;
+    if constexpr (C >= 3)
+      g = grey_top(sm, v[0], v[1], v[2]) >> 24;
+    else
+      g = v[0];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) sm.plane[ch][row][col0 + i] = (uint8_t)v[ch];
+    sm.grey[row][col0 + i] = (uint8_t)g;
+    if (counted && inside) {
+#pragma unroll
+      for (int ch = 0; ch < C; ch++) {
+        a.s[ch] += v[ch];
+        a.q[ch] += v[ch] * v[ch];
+      }
+      atomicAdd(&sm.hist[g], 1u);
+    }
+  }
+}
+
+// stage 1, fast item: C == 3, 48 aligned bytes fully inside the image.
+__device__ __forceinline__ void stage1_fast(ClassifySmem<3>& sm, Acc<3>& a, const uint8_t* p, int row, int col0,
+                                            bool counted) {
+  uint4 v0 = ldg_nc_v4(p), v1 = ldg_nc_v4(p + 16), v2 = ldg_nc_v4(p + 32);
+  uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+  uint32_t R[4], G[4], B[4], Y[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    // w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3
+    uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+    R[k] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // R0 R1 R2 | R3
+    G[k] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // G0 G1 G2 | G3
+    B[k] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);  // B0 B1 | B2 B3
+  }
+  if (counted) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      a.s[0] = __dp4a(R[k], 0x01010101u, a.s[0]);
+      a.s[1] = __dp4a(G[k], 0x01010101u, a.s[1]);
+      a.s[2] = __dp4a(B[k], 0x01010101u, a.s[2]);
+      a.q[0] = __dp4a(R[k], R[k], a.q[0]);
+      a.q[1] = __dp4a(G[k], G[k], a.q[1]);
+      a.q[2] = __dp4a(B[k], B[k], a.q[2]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint32_t t[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t r = (R[k] >> (8 * j)) & 0xFFu, g = (G[k] >> (8 * j)) & 0xFFu, b = (B[k] >> (8 * j)) & 0xFFu;
+      t[j] = grey_top(sm, r, g, b);
+      if (counted) atomicAdd(&sm.hist[t[j] >> 24], 1u);
+    }
+    Y[k] = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x0073), 0x5410);
+  }
+  *reinterpret_cast<uint4*>(&sm.plane[0][row][col0]) = make_uint4(R[0], R[1], R[2], R[3]);
+  *reinterpret_cast<uint4*>(&sm.plane[1][row][col0]) = make_uint4(G[0], G[1], G[2], G[3]);
+  *reinterpret_cast<uint4*>(&sm.plane[2][row][col0]) = make_uint4(B[0], B[1], B[2], B[3]);
+  *reinterpret_cast<uint4*>(&sm.grey[row][col0]) = make_uint4(Y[0], Y[1], Y[2], Y[3]);
+}
+
+// ---------------------------------------------------------------------------
+// stage 2: 3x3 stencils on the grey tile, packed 16x2.
+// Thread = 4-pixel strip x 8 rows.  Pairs: A = (px0, px1), B = (px2, px3).
+// ---------------------------------------------------------------------------
+struct GreyRow {
+  uint32_t cA, cB;    // centre pairs
+  uint32_t hA, hB;    // horizontal 3-sums
+  uint32_t p34;       // (px3, px4) for the column-boundary diagnostic
+  uint32_t word;      // the 4 centre bytes
+};
+
+// Row layout: bytes 0..15 pad (15 = pixel x0-1), 16..271 = pixels 0..255, 272 = pixel x0+256.
+// Strip s owns word 4+s; word 3+s ends with its left neighbour, word 5+s starts with its right one.
+__device__ __forceinline__ GreyRow load_grey_row(const uint8_t* grey_row, int strip) {
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(grey_row) + 3 + strip;
+  const uint32_t l = rp[0], c = rp[1], r = rp[2];
+  const uint32_t w0 = __funnelshift_r(l, c, 24);  // (l3, c0, c1, c2)
+  const uint32_t w3 = __funnelshift_r(c, r, 16);  // (c2, c3, r0, r1)
+  // 16x2 pairs (low lane = left pixel); selector 4 picks a zero byte from the second operand
+  const uint32_t P_m1_0 = __byte_perm(w0, 0u, 0x4140), P_0_1 = __byte_perm(w0, 0u, 0x4241);
+  const uint32_t P_1_2 = __byte_perm(w0, 0u, 0x4342), P_2_3 = __byte_perm(w3, 0u, 0x4140);
+  const uint32_t P_3_4 = __byte_perm(w3, 0u, 0x4241);
+  GreyRow g;
+  g.word = c;
+  g.cA = P_0_1;
+  g.cB = P_2_3;
+  g.hA = P_m1_0 + P_0_1 + P_1_2;
+  g.hB = P_1_2 + P_2_3 + P_3_4;
+  g.p34 = P_3_4;
+  return g;
+}
+
+// clip(k*c - nb, 0, 255) per 16-bit lane, all operands non-negative lanes
+__device__ __forceinline__ uint32_t clip_diff(uint32_t kc, uint32_t nb) {
+  uint32_t mx = __vmaxu2(kc, nb);
+  return __vminu2(mx - nb, 0x00FF00FFu);
+}
+
+template <int C>
+__device__ __forceinline__ void stage2(const ClassifySmem<C>& sm, Acc<C>& a, int x0, int y0, int W, int H) {
+  const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int x = x0 + strip * 4;
+  if (x >= W) return;
+  const int nvalid = min(4, W - x);
+  // byte masks for partially valid strips (pairs hold values in bytes 0 and 2)
+  const uint32_t mA = nvalid >= 2 ? 0x00FF00FFu : 0x000000FFu;
+  const uint32_t mB = nvalid >= 4 ? 0x00FF00FFu : (nvalid == 3 ? 0x000000FFu : 0u);
+  const int r0 = rg * 8;
+  if (y0 + r0 >= H) return;
+  GreyRow up = load_grey_row(&sm.grey[r0][0], strip), cur = load_grey_row(&sm.grey[r0 + 1][0], strip);
+  uint32_t prev_t0 = 0;  // E3 > 200 at (grid row, px0), consumed by the row below
+  const bool col_boundary = (strip & 1) && x + 4 < W;  // px3 | px4 straddle an 8-px column boundary
+#pragma unroll 2
+  for (int i = 0; i < 8; i++) {
+    const int y = y0 + r0 + i;
+    if (y >= H) break;
+    GreyRow dn = load_grey_row(&sm.grey[r0 + i + 2][0], strip);
+    const uint32_t boxA = up.hA + cur.hA + dn.hA, boxB = up.hB + cur.hB + dn.hB;
+    const uint32_t nineA = cur.cA * 9u, nineB = cur.cB * 9u;
+    const uint32_t e1A = clip_diff(nineA, boxA) & mA, e1B = clip_diff(nineB, boxB) & mB;
+    const uint32_t e2A = clip_diff(nineA + cur.cA, boxA) & mA, e2B = clip_diff(nineB + cur.cB, boxB) & mB;
+    const uint32_t e1 = __byte_perm(e1A, e1B, 0x6240), e2 = __byte_perm(e2A, e2B, 0x6240);  // 4 bytes each
+    a.e1s = __dp4a(e1, 0x01010101u, a.e1s);
+    a.e1q = __dp4a(e1, e1, a.e1q);
+    a.e2s = __dp4a(e2, 0x01010101u, a.e2s);
+    a.e2q = __dp4a(e2, e2, a.e2q);
+    // A5: Lap4 only where _detectLinearFeatures looks.  y0 and r0 are multiples of 4, so
+    // y % 4 == i % 4; grid rows (i = 0, 4) and the rows below them (i = 1, 5) share a thread.
+    const int ym = i & 3;
+    if (ym <= 1) {
+      const uint32_t crossA = up.cA + dn.cA + cur.hA;
+      const uint32_t e3A = clip_diff(cur.cA * 5u, crossA);
+      const uint32_t t0 = (e3A & 0xFFFFu) > IRP_SCRATCH_THRESHOLD, t1 = (e3A >> 16) > IRP_SCRATCH_THRESHOLD;
+      if (ym == 0) {
+        a.sv += t0 & t1 & (uint32_t)(nvalid >= 2);
+        prev_t0 = t0;
+      } else {
+        a.sh += prev_t0 & t0;
+      }
+    }
+    // additive diagnostic: grey steps across 8-px boundaries
+    if (col_boundary) {
+      const int d = dp2a_lo_u16_s8(cur.p34, 0x0000FF01u, IRP_BLOCK_EDGE_THRESHOLD);  // c3 - r0 + T
+      a.be0 += (uint32_t)d > 2u * IRP_BLOCK_EDGE_THRESHOLD;
+    }
+    if ((y & 7) == 7 && y + 1 < H) {
+      const uint32_t ad = __vabsdiffu4(cur.word, dn.word);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        a.be1 += (uint32_t)(j < nvalid) & (uint32_t)(((ad >> (8 * j)) & 0xFFu) > IRP_BLOCK_EDGE_THRESHOLD);
+    }
+    up = cur;
+    cur = dn;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stage 3: separable [12,20,12]/44 blur == floor((3(l+r)+5c+5)/11), H then V,
+// u8 between passes; only pooled sum / sumsq of the result are kept.
+// ---------------------------------------------------------------------------
+struct HRow { uint32_t h[4]; };
+
+__device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
+  const uint32_t* rp = reinterpret_cast<const uint32_t*>(plane_row) + 3 + strip;
+  uint32_t l = rp[0], c = rp[1], r = rp[2];
+  HRow o;
+  uint32_t w0 = __funnelshift_r(l, c, 24);  // (l3, c0, c1, c2)
+  uint32_t w3 = __funnelshift_r(c, r, 16);  // (c2, c3, r0, r1)
+  o.h[0] = div11(__dp4a(w0, 0x00030503u, 5u));
+  o.h[1] = div11(__dp4a(c, 0x00030503u, 5u));
+  o.h[2] = div11(__dp4a(c, 0x03050300u, 5u));
+  o.h[3] = div11(__dp4a(w3, 0x00030503u, 5u));
+  return o;
+}
+
+template <int C>
+__device__ __forceinline__ void stage3(const ClassifySmem<C>& sm, Acc<C>& a, int x0, int y0, int W, int H) {
+  const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int x = x0 + strip * 4;
+  if (x >= W) return;
+  const int nvalid = min(4, W - x);
+  const int r0 = rg * 8;
+  if (y0 + r0 >= H) return;
+#pragma unroll 1
+  for (int ch = 0; ch < C; ch++) {
+    HRow up = hpass_row(&sm.plane[ch][r0][0], strip), cur = hpass_row(&sm.plane[ch][r0 + 1][0], strip);
+#pragma unroll 2
+    for (int i = 0; i < 8; i++) {
+      if (y0 + r0 + i >= H) break;
+      HRow dn = hpass_row(&sm.plane[ch][r0 + i + 2][0], strip);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t b = div11(3u * (up.h[j] + dn.h[j]) + 5u * cur.h[j] + 5u);
+        if (j < nvalid) {
+          a.bs += b;
+          a.bq += b * b;
+        }
+      }
+      up = cur;
+      cur = dn;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kClassifyThreads, 2)
+classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
+                unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ClassifySmem<C>& sm = *reinterpret_cast<ClassifySmem<C>*>(smem_raw);
+  for (int i = threadIdx.x; i < 3 * 256; i += kClassifyThreads) (&sm.lut[0][0])[i] = (&tab->lut[0][0])[i];
+  for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) sm.inv[i] = tab->inv[i];
+  sm.hist[threadIdx.x] = 0;
+  __syncthreads();
+
+  Acc<C> acc;
+  acc.clear();
+  int img = 0, cur_img = -1, since_flush = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    while (img + 1 < n_imgs && tile >= imgs[img + 1].tile_base) img++;
+    if (img != cur_img || since_flush >= kFlushTiles) {
+      if (cur_img >= 0) {
+        const int slot = imgs[cur_img].slot;
+        flush_acc<C>(sm, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+      }
+      cur_img = img;
+      since_flush = 0;
+    }
+    since_flush++;
+    const ImgDev im = imgs[img];
+    const int t = tile - im.tile_base;
+    const int ty = t / im.tiles_x, tx = t - ty * im.tiles_x;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+
+    // ---- stage 1: load, regroup, moments, grey -> shared planar tiles ----
+    for (int item = threadIdx.x; item < kRows * kSegsPerRow; item += kClassifyThreads) {
+      const int row = item / kSegsPerRow, seg = item - row * kSegsPerRow;
+      const int yy = y0 - 1 + row;
+      const int gy = min(max(yy, 0), im.h - 1);
+      const bool counted = row >= 1 && row <= kTileH && yy < im.h;
+      const int xb = x0 + seg * kSegPx;
+      if (xb >= im.w + 4) continue;  // right of the image and of every replicate column a strip reads
+      bool fast = false;
+      if constexpr (C == 3) {
+        if (im.aligned16 && xb + kSegPx <= im.w) {
+          stage1_fast(sm, acc, im.px + (size_t)gy * im.pitch + (size_t)xb * 3, row, 16 + seg * kSegPx, counted);
+          fast = true;
+        }
+      }
+      if (!fast) stage1_slow<C>(sm, acc, im, gy, xb, row, 16 + seg * kSegPx, kSegPx, counted);
+    }
+    // halo columns: pixel x0-1 (byte 15) and x0+256 (byte 16+256) of every row
+    for (int item = threadIdx.x; item < kRows * 2; item += kClassifyThreads) {
+      const int row = item >> 1, right = item & 1;
+      const int gy = min(max(y0 - 1 + row, 0), im.h - 1);
+      stage1_slow<C>(sm, acc, im, gy, right ? x0 + kTileW : x0 - 1, row, right ? 16 + kTileW : 15, 1, false);
+    }
+    __syncthreads();
+    // ---- stage 2 + 3 ----
+    stage2<C>(sm, acc, x0, y0, im.w, im.h);
+    stage3<C>(sm, acc, x0, y0, im.w, im.h);
+    __syncthreads();
+  }
+  if (cur_img >= 0) {
+    const int slot = imgs[cur_img].slot;
+    flush_acc<C>(sm, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+  }
+}
+
+}  // namespace irp

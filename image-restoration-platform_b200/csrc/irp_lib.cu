@@ -1,0 +1,911 @@
+// irp_lib.cu — host side of libirp_b200.so: the C ABI declared in include/irp.h.
+//
+// Replaces, behind the same contracts, the sharp/libvips calls of
+//   server-node/src/services/classifier.js:51-52,107-115,135-143,199-207,296-297
+//   server-node/src/middleware/imagePreprocess.js:40-53
+// One context per GPU; calls on one context are serialised by a mutex (the Node
+// addon / Python mirror give each worker its own context or batch their jobs).
+// No CPU fallback: every entry point that touches pixels needs the device.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/irp.h"
+#include "../../include/irp_spec.h"
+#include "grey_tables.inc"
+#include "irp_classify.cuh"
+#include "irp_resize.cuh"
+
+using namespace irp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// grow-only device / pinned-host scratch
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PlanDev {
+  int32_t* start;
+  int32_t* phase;
+  int16_t* coef;
+  int n;
+};
+
+}  // namespace
+
+struct irp_ctx {
+  int device = 0;
+  int sm_count = 0;
+  irp_opts opts{};
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  ClassifyTables* d_tables = nullptr;
+  DevBuf d_desc, d_acc, d_stage_in, d_stage_out, d_orient, d_jobs;
+  PinBuf h_desc, h_acc, h_jobs;
+  std::vector<void*> plan_chunks;
+  size_t plan_used = 0, plan_cap = 0;
+  std::map<std::tuple<int, int, double>, PlanDev> plans;
+  cudaEvent_t ev[6]{};
+  irp_timing timing{};
+  int occ_classify[5]{};  // CTAs per SM for C = 1, 3, 4
+};
+
+namespace {
+
+int fail(irp_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(ctx, IRP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- P3 geometry: imagePreprocess.js:7-22 + sharp ResolveShrink (fit inside, no enlargement) ----
+void orient_dims(int w, int h, int o, int* ow, int* oh) {
+  if (o >= 5 && o <= 8) {
+    *ow = h;
+    *oh = w;
+  } else {
+    *ow = w;
+    *oh = h;
+  }
+}
+void fit_inside(int wo, int ho, int tw, int th, int* ow, int* oh, double* shrink) {
+  double hs = (double)wo / tw, vs = (double)ho / th;
+  double f = std::max(hs, vs);
+  f = std::max(f, 1.0);
+  f = std::min(f, (double)wo);
+  f = std::min(f, (double)ho);
+  *shrink = f;
+  *ow = std::max(1, (int)std::round((double)wo / f));
+  *oh = std::max(1, (int)std::round((double)ho / f));
+}
+void preprocess_dims(int w, int h, int o, int* ow, int* oh, double* shrink) {
+  int wo, ho;
+  orient_dims(w, h, o, &wo, &ho);
+  if (w > IRP_MAX_DIMENSION || h > IRP_MAX_DIMENSION) {
+    double scale = (double)IRP_MAX_DIMENSION / std::max(w, h);
+    int tw = std::max(1, (int)std::floor(w * scale + 0.5)), th = std::max(1, (int)std::floor(h * scale + 0.5));
+    fit_inside(wo, ho, tw, th, ow, oh, shrink);
+  } else {
+    *ow = wo;
+    *oh = ho;
+    *shrink = 1.0;
+  }
+}
+void fusion_dims(int w, int h, int o, int* ow, int* oh, int* ox, int* oy, double* shrink) {
+  int wo, ho;
+  orient_dims(w, h, o, &wo, &ho);
+  fit_inside(wo, ho, IRP_FUSION_CANVAS, IRP_FUSION_CANVAS, ow, oh, shrink);
+  *ox = (IRP_FUSION_CANVAS - *ow) / 2;
+  *oy = (IRP_FUSION_CANVAS - *oh) / 2;
+}
+
+// ---- P3 coefficients: libvips reduce{v,h} lanczos3 masks, 65 phases, 12-bit fixed point ----
+int reduce_points(double shrink) { return 2 * (int)std::nearbyint(IRP_LANCZOS_A * shrink) + 1; }
+
+void lanczos_mask(double* c, int n, double shrink, double x) {
+  const double a = IRP_LANCZOS_A, pi = 3.14159265358979323846;
+  const double half = x + n / 2 - 1;
+  double sum = 0;
+  for (int i = 0; i < n; i++) {
+    double xp = (i - half) / shrink, l;
+    if (xp == 0.0)
+      l = 1.0;
+    else if (xp < -a || xp > a)
+      l = 0.0;
+    else
+      l = a * std::sin(pi * xp) * std::sin(pi * xp / a) / (pi * pi * xp * xp);
+    c[i] = l;
+    sum += l;
+  }
+  for (int i = 0; i < n; i++) c[i] /= sum;
+}
+void to_fixed_point(const double* in, int16_t* out, int n, int scale) {
+  double fsum = 0;
+  for (int i = 0; i < n; i++) fsum += in[i];
+  int target = (int)std::nearbyint(fsum * scale), sum;
+  double high = scale + (n + 1) / 2, low = scale - (n + 1) / 2, guess;
+  do {
+    guess = (high + low) / 2.0;
+    sum = 0;
+    for (int i = 0; i < n; i++) {
+      out[i] = (int16_t)std::nearbyint(in[i] * guess);
+      sum += out[i];
+    }
+    if (sum == target) break;
+    if (sum < target) low = guess;
+    if (sum > target) high = guess;
+  } while (high - low > 0.01);
+  if (sum != target) {
+    int each = (target - sum) / n, extra = (target - sum) % n;
+    int dir = extra > 0 ? 1 : -1, cnt = std::abs(extra);
+    for (int i = 0; i < n; i++) out[i] += each;
+    for (int i = 0; i < cnt; i++) out[i] += dir;
+  }
+}
+struct HostPlan {
+  int n;
+  std::vector<int32_t> start, phase;
+  std::vector<int16_t> coef;  // [65][kCoefStride]
+};
+bool build_plan(int in_size, int out_size, double shrink, int coef_mode, HostPlan* hp) {
+  int n = reduce_points(shrink);
+  if (n > IRP_MAX_TAPS) return false;
+  hp->n = n;
+  hp->coef.assign((size_t)(IRP_PHASES + 1) * kCoefStride, 0);
+  double mask[IRP_MAX_TAPS];
+  for (int t = 0; t <= IRP_PHASES; t++) {
+    lanczos_mask(mask, n, shrink, (double)t / IRP_PHASES);
+    int16_t* ci = hp->coef.data() + (size_t)t * kCoefStride;
+    if (coef_mode == IRP_COEF_TRUNCATE)
+      for (int i = 0; i < n; i++) ci[i] = (int16_t)(mask[i] * (1 << IRP_INTERP_SHIFT));
+    else
+      to_fixed_point(mask, ci, n, 1 << IRP_INTERP_SHIFT);
+  }
+  hp->start.resize(out_size);
+  hp->phase.resize(out_size);
+  double extra = out_size * shrink - in_size;
+  for (int o = 0; o < out_size; o++) {
+    double c = (o + 0.5) * shrink - 0.5 - extra / 2.0;
+    int p = (int)std::floor(c);
+    int sy = (int)std::floor(c * IRP_PHASES * 2);
+    hp->phase[o] = ((sy & (IRP_PHASES * 2 - 1)) + 1) >> 1;
+    hp->start[o] = p - (n / 2 - 1);
+  }
+  return true;
+}
+
+int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
+  bytes = round_up(bytes, 256);
+  if (ctx->plan_chunks.empty() || ctx->plan_used + bytes > ctx->plan_cap) {
+    size_t cap = std::max<size_t>(bytes, 4u << 20);
+    void* p = nullptr;
+    CK(cudaMalloc(&p, cap));
+    ctx->plan_chunks.push_back(p);
+    ctx->plan_used = 0;
+    ctx->plan_cap = cap;
+  }
+  *out = (char*)ctx->plan_chunks.back() + ctx->plan_used;
+  ctx->plan_used += bytes;
+  return IRP_OK;
+}
+
+int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* ap) {
+  if (in_size == out_size) {
+    *ap = AxisPlan{nullptr, nullptr, nullptr, 0, 0};
+    return IRP_OK;
+  }
+  auto key = std::make_tuple(in_size, out_size, shrink);
+  auto it = ctx->plans.find(key);
+  if (it == ctx->plans.end()) {
+    HostPlan hp;
+    if (!build_plan(in_size, out_size, shrink, ctx->opts.coef_mode, &hp))
+      return fail(ctx, IRP_ERR_UNSUPPORTED, "shrink factor %.4f needs more than %d taps (box pre-shrink not implemented)",
+                  shrink, IRP_MAX_TAPS);
+    PlanDev pd;
+    pd.n = hp.n;
+    void* p;
+    int rc;
+    if ((rc = plan_alloc(ctx, hp.start.size() * 4, &p))) return rc;
+    pd.start = (int32_t*)p;
+    if ((rc = plan_alloc(ctx, hp.phase.size() * 4, &p))) return rc;
+    pd.phase = (int32_t*)p;
+    if ((rc = plan_alloc(ctx, hp.coef.size() * 2, &p))) return rc;
+    pd.coef = (int16_t*)p;
+    // synchronous copies: plans are built once per geometry and cached
+    CK(cudaMemcpy(pd.start, hp.start.data(), hp.start.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd.phase, hp.phase.data(), hp.phase.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd.coef, hp.coef.data(), hp.coef.size() * 2, cudaMemcpyHostToDevice));
+    it = ctx->plans.emplace(key, pd).first;
+  }
+  *ap = AxisPlan{it->second.start, it->second.phase, it->second.coef, it->second.n, 0};
+  return IRP_OK;
+}
+
+// ---- JS formulas on exact integer moments ----
+double pop_variance(uint64_t s, uint64_t q, uint64_t n) {
+  // (n*q - s^2) / n^2, numerator exact in 128 bits
+  unsigned __int128 num = (unsigned __int128)n * q - (unsigned __int128)s * s;
+  return (double)num / ((double)n * (double)n);
+}
+double jsmin(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+double jsmax(double a, double b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+
+int validate_desc(irp_ctx* ctx, const irp_image_desc& d, int i) {
+  if (!d.pixels) return fail(ctx, IRP_ERR_BAD_ARG, "image %d: null pixels", i);
+  if (d.width <= 0 || d.height <= 0) return fail(ctx, IRP_ERR_BAD_ARG, "image %d: bad dims %dx%d", i, d.width, d.height);
+  if (d.channels != 1 && d.channels != 3 && d.channels != 4)
+    return fail(ctx, IRP_ERR_UNSUPPORTED, "image %d: %d channels unsupported (1, 3 or 4)", i, d.channels);
+  if (d.pitch < (size_t)d.width * d.channels) return fail(ctx, IRP_ERR_BAD_ARG, "image %d: pitch < width*channels", i);
+  return IRP_OK;
+}
+
+struct Staged {  // where each input image lives on the device for this call
+  const uint8_t* px;
+  size_t pitch;
+};
+
+// copy host inputs into the device staging buffer (device-resident inputs are used in place)
+int stage_inputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, std::vector<Staged>* st) {
+  st->resize(n);
+  size_t total = 0;
+  std::vector<size_t> off(n, 0);
+  for (int i = 0; i < n; i++) {
+    if (imgs[i].on_device) continue;
+    size_t pitch = round_up((size_t)imgs[i].width * imgs[i].channels, 16);
+    off[i] = total;
+    total += round_up(pitch * imgs[i].height, 256);
+  }
+  if (total) CK(ctx->d_stage_in.reserve(total + 256));
+  for (int i = 0; i < n; i++) {
+    const irp_image_desc& d = imgs[i];
+    if (d.on_device) {
+      (*st)[i] = Staged{d.pixels, d.pitch};
+    } else {
+      size_t pitch = round_up((size_t)d.width * d.channels, 16);
+      uint8_t* dst = (uint8_t*)ctx->d_stage_in.p + off[i];
+      CK(cudaMemcpy2DAsync(dst, pitch, d.pixels, d.pitch, (size_t)d.width * d.channels, d.height,
+                           cudaMemcpyHostToDevice, ctx->stream));
+      (*st)[i] = Staged{dst, pitch};
+    }
+  }
+  return IRP_OK;
+}
+
+template <int C>
+int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, unsigned long long* d_acc,
+                    uint32_t* d_hist) {
+  if (!n) return IRP_OK;
+  size_t smem = sizeof(ClassifySmem<C>);
+  int& occ = ctx->occ_classify[C];
+  if (!occ) {
+    CK(cudaFuncSetAttribute(classify_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, classify_kernel<C>, kClassifyThreads, smem));
+    if (occ < 1) return fail(ctx, IRP_ERR_CUDA, "classify kernel does not fit on an SM");
+  }
+  int grid = std::min(total_tiles, ctx->sm_count * occ);
+  classify_kernel<C><<<grid, kClassifyThreads, smem, ctx->stream>>>(d_imgs, n, total_tiles, ctx->d_tables, d_acc, d_hist);
+  CK(cudaGetLastError());
+  ctx->timing.kernel_launches++;
+  return IRP_OK;
+}
+
+int run_classify(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int n, irp_result* results) {
+  // group by channel count; each group is one launch over all of its tiles
+  const int chans[3] = {1, 3, 4};
+  size_t desc_bytes = round_up(sizeof(ImgDev) * n, 256);
+  size_t acc_bytes = round_up(sizeof(unsigned long long) * ACC_COUNT * n, 256), hist_bytes = sizeof(uint32_t) * 256 * n;
+  CK(ctx->d_desc.reserve(desc_bytes));
+  CK(ctx->h_desc.reserve(desc_bytes));
+  CK(ctx->d_acc.reserve(acc_bytes + hist_bytes));
+  CK(ctx->h_acc.reserve(acc_bytes + hist_bytes));
+  ImgDev* h_imgs = (ImgDev*)ctx->h_desc.p;
+  int pos = 0, group_begin[4], group_tiles[3];
+  for (int g = 0; g < 3; g++) {
+    group_begin[g] = pos;
+    int tiles = 0;
+    for (int i = 0; i < n; i++) {
+      if (imgs[i].channels != chans[g]) continue;
+      ImgDev& d = h_imgs[pos++];
+      d.px = st[i].px;
+      d.pitch = st[i].pitch;
+      d.w = imgs[i].width;
+      d.h = imgs[i].height;
+      d.c = imgs[i].channels;
+      d.tiles_x = (d.w + kTileW - 1) / kTileW;
+      d.tiles_y = (d.h + kTileH - 1) / kTileH;
+      d.tile_base = tiles;
+      d.aligned16 = (((uintptr_t)d.px | d.pitch) & 15) == 0;
+      d.slot = i;
+      tiles += d.tiles_x * d.tiles_y;
+    }
+    group_tiles[g] = tiles;
+  }
+  group_begin[3] = pos;
+  CK(cudaMemcpyAsync(ctx->d_desc.p, h_imgs, sizeof(ImgDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_acc.p, 0, acc_bytes + hist_bytes, ctx->stream));
+  unsigned long long* d_acc = (unsigned long long*)ctx->d_acc.p;
+  uint32_t* d_hist = (uint32_t*)((char*)ctx->d_acc.p + acc_bytes);
+  const ImgDev* d_imgs = (const ImgDev*)ctx->d_desc.p;
+  int rc;
+  if ((rc = launch_classify<1>(ctx, d_imgs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0], d_acc, d_hist))) return rc;
+  if ((rc = launch_classify<3>(ctx, d_imgs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1], d_acc, d_hist))) return rc;
+  if ((rc = launch_classify<4>(ctx, d_imgs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2], d_acc, d_hist))) return rc;
+  CK(cudaMemcpyAsync(ctx->h_acc.p, ctx->d_acc.p, acc_bytes + hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  (void)results;
+  return IRP_OK;
+}
+
+// after the stream has been synchronised: integer moments -> irp_result
+void finish_classify(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results) {
+  size_t acc_bytes = round_up(sizeof(unsigned long long) * ACC_COUNT * n, 256);
+  const unsigned long long* acc = (const unsigned long long*)ctx->h_acc.p;
+  const uint32_t* hist = (const uint32_t*)((const char*)ctx->h_acc.p + acc_bytes);
+  for (int i = 0; i < n; i++) {
+    irp_result& r = results[i];
+    memset(&r, 0, sizeof r);
+    const unsigned long long* a = acc + (size_t)i * ACC_COUNT;
+    for (int ch = 0; ch < 4; ch++) {
+      r.sum[ch] = a[ACC_SUM + ch];
+      r.sumsq[ch] = a[ACC_SUMSQ + ch];
+    }
+    r.e_sum[0] = a[ACC_E1S];
+    r.e_sumsq[0] = a[ACC_E1Q];
+    r.e_sum[1] = a[ACC_E2S];
+    r.e_sumsq[1] = a[ACC_E2Q];
+    r.b_sum = a[ACC_BS];
+    r.b_sumsq = a[ACC_BQ];
+    r.scratch_v = (uint32_t)a[ACC_SV];
+    r.scratch_h = (uint32_t)a[ACC_SH];
+    r.block_edges[0] = (uint32_t)a[ACC_BE0];
+    r.block_edges[1] = (uint32_t)a[ACC_BE1];
+    memcpy(r.luma_hist, hist + (size_t)i * 256, sizeof r.luma_hist);
+    irp_scores_from_moments(&r, imgs[i].width, imgs[i].height, imgs[i].channels, imgs[i].is_jpeg);
+    r.status = IRP_OK;
+  }
+}
+
+struct OutPlan {  // per image: where the kernel writes, and how the result gets to the caller
+  uint8_t* dev;
+  size_t dev_pitch;
+  bool via_stage;
+};
+
+void choose_tile(double fv, int nv, double fh, int nh, int C, int* tow, int* toh, int* rows_max, int* rowbytes_max) {
+  const int cand[5][2] = {{64, 32}, {64, 16}, {32, 16}, {32, 8}, {16, 8}};
+  for (int k = 0; k < 5; k++) {
+    int tw = cand[k][0], th = cand[k][1];
+    int rows = nv ? (int)std::ceil(th * fv) + nv + 2 : th;
+    int rb = (int)round_up((size_t)((nh ? (int)std::ceil(tw * fh) + nh + 2 : tw) * C + 8), 4);
+    *tow = tw;
+    *toh = th;
+    *rows_max = rows;
+    *rowbytes_max = rb;
+    if ((size_t)(rows + th) * rb <= 96 * 1024) return;
+  }
+}
+
+template <int C>
+int launch_resize(irp_ctx* ctx, const ResizeJob* d_jobs, const ResizeJob* h_jobs, int n, int total_tiles) {
+  if (!n) return IRP_OK;
+  size_t smem = 0;
+  for (int i = 0; i < n; i++)
+    smem = std::max(smem, (size_t)(h_jobs[i].src_rows_max + h_jobs[i].toh) * h_jobs[i].src_rowbytes_max);
+  smem = round_up(smem, 16);
+  CK(cudaFuncSetAttribute(resize_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resize_kernel<C>, kResizeThreads, smem));
+  if (occ < 1) return fail(ctx, IRP_ERR_CUDA, "resize kernel does not fit on an SM (%zu bytes smem)", smem);
+  int grid = std::min(total_tiles, ctx->sm_count * occ);
+  resize_kernel<C><<<grid, kResizeThreads, smem, ctx->stream>>>(d_jobs, n, total_tiles);
+  CK(cudaGetLastError());
+  ctx->timing.kernel_launches++;
+  return IRP_OK;
+}
+
+template <int C>
+int launch_orient(irp_ctx* ctx, const uint8_t* src, size_t spitch, int w, int h, int o, uint8_t* dst, size_t dpitch, int ow,
+                  int oh) {
+  dim3 b(32, 8), g((ow + 31) / 32, (oh + 7) / 8);
+  orient_kernel<C><<<g, b, 0, ctx->stream>>>(src, spitch, w, h, o, dst, dpitch, ow, oh);
+  CK(cudaGetLastError());
+  ctx->timing.kernel_launches++;
+  return IRP_OK;
+}
+
+// mode 0: preprocess (imagePreprocess.js), mode 1: fusion canvas
+int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int n, irp_out_desc* outs, int mode,
+               std::vector<OutPlan>* oplans) {
+  oplans->assign(n, OutPlan{nullptr, 0, false});
+  // pass 1: geometry, capacity checks, staging sizes
+  struct Geo { int wo, ho, dw, dh, dc, ox, oy; double f; size_t orient_off, out_off; };
+  std::vector<Geo> geo(n);
+  size_t orient_total = 0, out_total = 0;
+  for (int i = 0; i < n; i++) {
+    if (mode == 1 && !imgs[i].pixels) continue;  // unused fusion slot
+    const irp_image_desc& d = imgs[i];
+    Geo& g = geo[i];
+    int o = (d.exif_orientation >= 1 && d.exif_orientation <= 8) ? d.exif_orientation : 1;
+    orient_dims(d.width, d.height, o, &g.wo, &g.ho);
+    g.ox = g.oy = 0;
+    if (mode == 0) {
+      preprocess_dims(d.width, d.height, o, &g.dw, &g.dh, &g.f);
+      g.dc = d.channels == 1 ? 1 : 3;
+    } else {
+      fusion_dims(d.width, d.height, o, &g.dw, &g.dh, &g.ox, &g.oy, &g.f);
+      g.dc = 3;
+    }
+    if (g.f >= 4.0) return fail(ctx, IRP_ERR_UNSUPPORTED, "image %d: shrink %.3f >= 4 needs libvips' box pre-shrink (not implemented)", i, g.f);
+    int out_w = mode == 0 ? g.dw : IRP_FUSION_CANVAS, out_h = mode == 0 ? g.dh : IRP_FUSION_CANVAS;
+    irp_out_desc& od = outs[i];
+    if (!od.pixels) return fail(ctx, IRP_ERR_BAD_ARG, "output %d: null pixels", i);
+    size_t tight = (size_t)out_w * g.dc;
+    size_t pitch = od.pitch ? od.pitch : tight;
+    if (pitch < tight) return fail(ctx, IRP_ERR_BAD_ARG, "output %d: pitch %zu < %zu", i, pitch, tight);
+    if (od.capacity < pitch * (size_t)(out_h - 1) + tight)
+      return fail(ctx, IRP_ERR_CAPACITY, "output %d: capacity %zu too small for %dx%dx%d", i, od.capacity, out_w, out_h, g.dc);
+    od.width = out_w;
+    od.height = out_h;
+    od.channels = g.dc;
+    if (o != 1) {
+      g.orient_off = orient_total;
+      orient_total += round_up(round_up((size_t)g.wo * d.channels, 16) * g.ho, 256);
+    }
+    if (!od.on_device) {
+      g.out_off = out_total;
+      out_total += round_up(tight * out_h, 256);
+    }
+  }
+  if (orient_total) CK(ctx->d_orient.reserve(orient_total));
+  if (out_total) CK(ctx->d_stage_out.reserve(out_total));
+  size_t job_bytes = sizeof(ResizeJob) * n;
+  CK(ctx->d_jobs.reserve(job_bytes));
+  CK(ctx->h_jobs.reserve(job_bytes));
+  ResizeJob* h_jobs = (ResizeJob*)ctx->h_jobs.p;
+  const int chans[3] = {1, 3, 4};
+  int pos = 0, group_begin[4], group_tiles[3];
+  for (int gi = 0; gi < 3; gi++) {
+    group_begin[gi] = pos;
+    int tiles = 0;
+    for (int i = 0; i < n; i++) {
+      if (mode == 1 && !imgs[i].pixels) continue;
+      const irp_image_desc& d = imgs[i];
+      if (d.channels != chans[gi]) continue;
+      const Geo& g = geo[i];
+      int o = (d.exif_orientation >= 1 && d.exif_orientation <= 8) ? d.exif_orientation : 1;
+      ResizeJob& J = h_jobs[pos++];
+      memset(&J, 0, sizeof J);
+      if (o != 1) {
+        uint8_t* op = (uint8_t*)ctx->d_orient.p + g.orient_off;
+        size_t opitch = round_up((size_t)g.wo * d.channels, 16);
+        int rc;
+        switch (d.channels) {
+          case 1: rc = launch_orient<1>(ctx, st[i].px, st[i].pitch, d.width, d.height, o, op, opitch, g.wo, g.ho); break;
+          case 3: rc = launch_orient<3>(ctx, st[i].px, st[i].pitch, d.width, d.height, o, op, opitch, g.wo, g.ho); break;
+          default: rc = launch_orient<4>(ctx, st[i].px, st[i].pitch, d.width, d.height, o, op, opitch, g.wo, g.ho); break;
+        }
+        if (rc) return rc;
+        J.src = op;
+        J.src_pitch = opitch;
+      } else {
+        J.src = st[i].px;
+        J.src_pitch = st[i].pitch;
+      }
+      irp_out_desc& od = outs[i];
+      int out_w = od.width;
+      OutPlan& op = (*oplans)[i];
+      if (od.on_device) {
+        op.dev = od.pixels;
+        op.dev_pitch = od.pitch ? od.pitch : (size_t)out_w * g.dc;
+        op.via_stage = false;
+      } else {
+        op.dev = (uint8_t*)ctx->d_stage_out.p + g.out_off;
+        op.dev_pitch = (size_t)out_w * g.dc;
+        op.via_stage = true;
+      }
+      if (mode == 1)  // black pad: clear the whole canvas, the tiles then write the image once
+        CK(cudaMemset2DAsync(op.dev, op.dev_pitch, 0, (size_t)out_w * g.dc, od.height, ctx->stream));
+      J.dst = op.dev;
+      J.dst_pitch = op.dev_pitch;
+      J.sw = g.wo;
+      J.sh = g.ho;
+      J.c = d.channels;
+      J.dc = g.dc;
+      J.dw = g.dw;
+      J.dh = g.dh;
+      J.dst_x0 = g.ox;
+      J.dst_y0 = g.oy;
+      J.expand_grey = (d.channels == 1 && g.dc == 3);
+      J.aligned4 = (((uintptr_t)J.src | J.src_pitch) & 3) == 0;
+      int rc;
+      if ((rc = get_plan(ctx, g.ho, g.dh, g.f, &J.v))) return rc;
+      if ((rc = get_plan(ctx, g.wo, g.dw, g.f, &J.h))) return rc;
+      choose_tile(g.f, J.v.n, g.f, J.h.n, d.channels, &J.tow, &J.toh, &J.src_rows_max, &J.src_rowbytes_max);
+      J.tiles_x = (J.dw + J.tow - 1) / J.tow;
+      J.tiles_y = (J.dh + J.toh - 1) / J.toh;
+      J.tile_base = tiles;
+      tiles += J.tiles_x * J.tiles_y;
+    }
+    group_tiles[gi] = tiles;
+  }
+  group_begin[3] = pos;
+  CK(cudaMemcpyAsync(ctx->d_jobs.p, h_jobs, sizeof(ResizeJob) * pos, cudaMemcpyHostToDevice, ctx->stream));
+  const ResizeJob* d_jobs = (const ResizeJob*)ctx->d_jobs.p;
+  int rc;
+  if ((rc = launch_resize<1>(ctx, d_jobs + group_begin[0], h_jobs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0]))) return rc;
+  if ((rc = launch_resize<3>(ctx, d_jobs + group_begin[1], h_jobs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1]))) return rc;
+  if ((rc = launch_resize<4>(ctx, d_jobs + group_begin[2], h_jobs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2]))) return rc;
+  return IRP_OK;
+}
+
+int copy_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* outs, const std::vector<OutPlan>& oplans,
+                 int mode) {
+  for (int i = 0; i < n; i++) {
+    if (mode == 1 && !imgs[i].pixels) continue;
+    if (!oplans[i].via_stage) continue;
+    irp_out_desc& od = outs[i];
+    size_t tight = (size_t)od.width * od.channels;
+    CK(cudaMemcpy2DAsync(od.pixels, od.pitch ? od.pitch : tight, oplans[i].dev, oplans[i].dev_pitch, tight, od.height,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return IRP_OK;
+}
+
+int finish_timing(irp_ctx* ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing.classify_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.preprocess_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.d2h_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->timing.total_ms = ms;
+  return IRP_OK;
+}
+
+// the one driver behind classify / preprocess / analyze / fusion
+int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode) {
+  if (!ctx) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->err.clear();
+  if (n < 0 || (n > 0 && !imgs)) return fail(ctx, IRP_ERR_BAD_ARG, "bad batch arguments");
+  if (n == 0) return IRP_OK;
+  CK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; i++) {
+    if (resize_mode == 1 && !imgs[i].pixels) continue;
+    int rc = validate_desc(ctx, imgs[i], i);
+    if (rc) return rc;
+  }
+  ctx->timing = irp_timing{};
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  std::vector<Staged> st;
+  std::vector<irp_image_desc> tmp;
+  const irp_image_desc* use = imgs;
+  if (resize_mode == 1) {  // staging needs valid descriptors: give unused slots zero size
+    tmp.assign(imgs, imgs + n);
+    for (auto& d : tmp)
+      if (!d.pixels) { d.on_device = 1; d.width = d.height = 0; }
+    use = tmp.data();
+  }
+  int rc = stage_inputs(ctx, use, n, &st);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (results && (rc = run_classify(ctx, imgs, st, n, results))) return rc;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  std::vector<OutPlan> oplans;
+  if (outs && (rc = run_resize(ctx, imgs, st, n, outs, resize_mode, &oplans))) return rc;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (outs && (rc = copy_outputs(ctx, imgs, n, outs, oplans, resize_mode))) return rc;
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  if ((rc = finish_timing(ctx))) return rc;
+  if (results) finish_classify(ctx, imgs, n, results);
+  return IRP_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+extern "C" {
+
+int irp_abi_version(void) { return IRP_ABI_VERSION; }
+
+int irp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+irp_ctx* irp_create(int device, const irp_opts* opts) {
+  irp_ctx* ctx = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    fail(nullptr, IRP_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    fail(nullptr, IRP_ERR_BAD_ARG, "device %d out of range (%d devices)", device, n);
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    fail(nullptr, IRP_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200)", device, prop.major, prop.minor);
+    return nullptr;
+  }
+  ctx = new irp_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (opts) memcpy(&ctx->opts, opts, std::min<size_t>(opts->struct_size, sizeof(irp_opts)));
+  auto bail = [&](const char* what, cudaError_t err) {
+    fail(nullptr, IRP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    irp_destroy(ctx);
+    return (irp_ctx*)nullptr;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  ctx->stream = ctx->own_stream;
+  for (auto& ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  ClassifyTables* ht = new ClassifyTables();
+  const bool cie = ctx->opts.luma_mode == IRP_LUMA_CIE;
+  memcpy(ht->lut[0], cie ? kGreyLut1_r : kGreyLut0_r, sizeof ht->lut[0]);
+  memcpy(ht->lut[1], cie ? kGreyLut1_g : kGreyLut0_g, sizeof ht->lut[1]);
+  memcpy(ht->lut[2], cie ? kGreyLut1_b : kGreyLut0_b, sizeof ht->lut[2]);
+  memcpy(ht->inv, cie ? kGreyInv1 : kGreyInv0, sizeof ht->inv);
+  if ((e = cudaMalloc(&ctx->d_tables, sizeof(ClassifyTables))) != cudaSuccess) { delete ht; return bail("cudaMalloc(tables)", e); }
+  e = cudaMemcpy(ctx->d_tables, ht, sizeof(ClassifyTables), cudaMemcpyHostToDevice);
+  delete ht;
+  if (e != cudaSuccess) return bail("cudaMemcpy(tables)", e);
+  return ctx;
+}
+
+void irp_destroy(irp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs}) b->release();
+  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs}) b->release();
+  for (void* p : ctx->plan_chunks) cudaFree(p);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* irp_last_error(const irp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int irp_set_stream(irp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return IRP_OK;
+}
+
+int irp_get_timing(const irp_ctx* ctx, irp_timing* out) {
+  if (!ctx || !out) return IRP_ERR_BAD_ARG;
+  *out = ctx->timing;
+  return IRP_OK;
+}
+
+int irp_preprocess_dims(int width, int height, int exif_orientation, int* out_w, int* out_h) {
+  if (width <= 0 || height <= 0 || !out_w || !out_h) return IRP_ERR_BAD_ARG;
+  int o = (exif_orientation >= 1 && exif_orientation <= 8) ? exif_orientation : 1;
+  double f;
+  preprocess_dims(width, height, o, out_w, out_h, &f);
+  return f >= 4.0 ? IRP_ERR_UNSUPPORTED : IRP_OK;
+}
+
+int irp_fusion_dims(int width, int height, int exif_orientation, int* out_w, int* out_h, int* off_x, int* off_y) {
+  if (width <= 0 || height <= 0 || !out_w || !out_h || !off_x || !off_y) return IRP_ERR_BAD_ARG;
+  int o = (exif_orientation >= 1 && exif_orientation <= 8) ? exif_orientation : 1;
+  double f;
+  fusion_dims(width, height, o, out_w, out_h, off_x, off_y, &f);
+  return f >= 4.0 ? IRP_ERR_UNSUPPORTED : IRP_OK;
+}
+
+int irp_scores_from_moments(irp_result* r, int width, int height, int channels, int is_jpeg) {
+  if (!r || width <= 0 || height <= 0 || channels < 1 || channels > 4) return IRP_ERR_BAD_ARG;
+  const uint64_t N = (uint64_t)width * height;
+  const int C = channels;
+  double mean[4], stdev[4];
+  uint64_t o_sum = 0, o_sumsq = 0;
+  for (int ch = 0; ch < C; ch++) {
+    double s = (double)r->sum[ch], s2 = (double)r->sumsq[ch], vals = (double)N;
+    mean[ch] = s / vals;                                        // vips_stats mean
+    stdev[ch] = std::sqrt(std::fabs(s2 - (s * s / vals)) / (vals - 1));  // vips_stats deviation
+    o_sum += r->sum[ch];
+    o_sumsq += r->sumsq[ch];
+  }
+  // classifier.js:118-121
+  r->score[IRP_SCORE_BLUR] = jsmax(0, 1.0 - jsmin(pop_variance(r->e_sum[0], r->e_sumsq[0], N) / IRP_BLUR_VAR_DIVISOR, 1.0));
+  // classifier.js:145-146
+  r->score[IRP_SCORE_NOISE] = jsmin(std::sqrt(pop_variance(r->e_sum[1], r->e_sumsq[1], N)) / IRP_NOISE_STD_DIVISOR, 1.0);
+  // classifier.js:159-167
+  {
+    double sum = 0;
+    for (int ch = 0; ch < C; ch++) sum = sum + mean[ch];
+    double nb = (sum / C) / 255;
+    r->score[IRP_SCORE_LOWLIGHT] = nb < IRP_LOWLIGHT_KNEE ? jsmin((IRP_LOWLIGHT_KNEE - nb) * 2, 1.0) : 0.0;
+  }
+  // classifier.js:180-186,296-303
+  if (is_jpeg) {
+    double delta = jsmax(0, pop_variance(o_sum, o_sumsq, N * C) - pop_variance(r->b_sum, r->b_sumsq, N * C));
+    r->score[IRP_SCORE_COMPRESSION] = jsmin(jsmin(delta / IRP_COMPRESSION_DIVISOR, 1.0), 1.0);
+  } else {
+    r->score[IRP_SCORE_COMPRESSION] = 0.0;
+  }
+  // classifier.js:335-336
+  r->score[IRP_SCORE_SCRATCH] = jsmin(jsmin(((double)r->scratch_v + (double)r->scratch_h) / IRP_SCRATCH_DIVISOR, 1.0), 1.0);
+  // classifier.js:223-228,272-286
+  {
+    double colorfulness = C < 3 ? 0.5
+                                : jsmin(std::sqrt(std::pow(stdev[0], 2) + std::pow(stdev[1], 2) + std::pow(stdev[2], 2)) / 255, 1.0);
+    double sum = 0;
+    for (int ch = 0; ch < C; ch++) sum = sum + stdev[ch];
+    double contrast = jsmin((sum / C) / IRP_CONTRAST_DIVISOR, 1.0);
+    r->score[IRP_SCORE_FADE] = jsmin((1.0 - colorfulness) * 0.6 + (1.0 - contrast) * 0.4, 1.0);
+  }
+  // classifier.js:240-253
+  if (C < 3) {
+    r->score[IRP_SCORE_COLORSHIFT] = 0.0;
+  } else {
+    double avg = (mean[0] + mean[1] + mean[2]) / 3;
+    double rd = avg > 0 ? std::fabs(mean[0] - avg) / avg : 0, gd = avg > 0 ? std::fabs(mean[1] - avg) / avg : 0,
+           bd = avg > 0 ? std::fabs(mean[2] - avg) / avg : 0;
+    r->score[IRP_SCORE_COLORSHIFT] = jsmin(jsmax(jsmax(rd, gd), bd) * 2, 1.0);
+  }
+  return IRP_OK;
+}
+
+int irp_grey_tables(int luma_mode, uint32_t lut_r[256], uint32_t lut_g[256], uint32_t lut_b[256], uint32_t inv[4096]) {
+  if (!lut_r || !lut_g || !lut_b || !inv) return IRP_ERR_BAD_ARG;
+  const bool cie = luma_mode == IRP_LUMA_CIE;
+  memcpy(lut_r, cie ? kGreyLut1_r : kGreyLut0_r, 1024);
+  memcpy(lut_g, cie ? kGreyLut1_g : kGreyLut0_g, 1024);
+  memcpy(lut_b, cie ? kGreyLut1_b : kGreyLut0_b, 1024);
+  memcpy(inv, cie ? kGreyInv1 : kGreyInv0, 4096 * 4);
+  return IRP_OK;
+}
+
+int irp_classify_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results) {
+  if (!results) return ctx ? fail(ctx, IRP_ERR_BAD_ARG, "null results") : IRP_ERR_BAD_ARG;
+  return run_batch(ctx, imgs, n, results, nullptr, 0);
+}
+int irp_preprocess_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* outs) {
+  if (!outs) return ctx ? fail(ctx, IRP_ERR_BAD_ARG, "null outputs") : IRP_ERR_BAD_ARG;
+  return run_batch(ctx, imgs, n, nullptr, outs, 0);
+}
+int irp_analyze_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs) {
+  if (!results || !outs) return ctx ? fail(ctx, IRP_ERR_BAD_ARG, "null results/outputs") : IRP_ERR_BAD_ARG;
+  return run_batch(ctx, imgs, n, results, outs, 0);
+}
+int irp_fusion_prepare_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n_groups, irp_out_desc* canvases) {
+  if (!canvases) return ctx ? fail(ctx, IRP_ERR_BAD_ARG, "null canvases") : IRP_ERR_BAD_ARG;
+  return run_batch(ctx, imgs, n_groups * IRP_FUSION_MAX_IMAGES, nullptr, canvases, 1);
+}
+
+void* irp_dev_alloc(irp_ctx* ctx, size_t bytes) {
+  if (!ctx) return nullptr;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  void* p = nullptr;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    fail(ctx, IRP_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+int irp_dev_free(irp_ctx* ctx, void* p) {
+  if (!ctx) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFree(p));
+  return IRP_OK;
+}
+void* irp_host_alloc_pinned(irp_ctx* ctx, size_t bytes) {
+  if (!ctx) return nullptr;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  void* p = nullptr;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) {
+    fail(ctx, IRP_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+int irp_host_free_pinned(irp_ctx* ctx, void* p) {
+  if (!ctx) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CK(cudaFreeHost(p));
+  return IRP_OK;
+}
+int irp_memcpy_h2d(irp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IRP_OK;
+}
+int irp_memcpy_d2h(irp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IRP_OK;
+}
+int irp_synchronize(irp_ctx* ctx) {
+  if (!ctx) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IRP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+"""Engine — one GPU context of libirp_b200.so, numpy in / numpy out.
+
+Thin marshalling over the C ABI (include/irp.h): it builds the descriptor
+arrays, owns nothing but the context handle and optional device buffers, and
+raises IrpError with irp_last_error() when a call returns non-zero — the same
+"whole-call failure = rejected Promise" contract the reference classifier has
+(server-node/src/services/classifier.js:91-95).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _ffi
+
+SCORE_KEYS = ("blur", "noise", "lowLight", "compression", "scratch", "fade", "colorShift")  # classifier.js:62-70
+
+
+class IrpError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"irp error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+@dataclass
+class DeviceImage:
+    """An image (or output buffer) resident in this context's HBM."""
+
+    ptr: int
+    width: int
+    height: int
+    channels: int
+    pitch: int
+    nbytes: int
+    is_jpeg: bool = True
+    orientation: int = 1
+
+
+ImageLike = Union[np.ndarray, DeviceImage]
+
+
+def _as_hwc(a: np.ndarray) -> np.ndarray:
+    if a.dtype != np.uint8:
+        raise TypeError("pixels must be uint8")
+    if a.ndim == 2:
+        a = a[:, :, None]
+    if a.ndim != 3:
+        raise ValueError("pixels must be HxW or HxWxC")
+    if a.strides[2] != 1 or a.strides[1] != a.shape[2]:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def result_to_dict(r: _ffi.Result) -> dict:
+    return {
+        "scores": dict(zip(SCORE_KEYS, [float(x) for x in r.score])),
+        "sum": list(r.sum), "sumsq": list(r.sumsq), "e_sum": list(r.e_sum), "e_sumsq": list(r.e_sumsq),
+        "b_sum": int(r.b_sum), "b_sumsq": int(r.b_sumsq), "scratch_v": int(r.scratch_v), "scratch_h": int(r.scratch_h),
+        "block_edges": list(r.block_edges), "luma_hist": list(r.luma_hist), "status": int(r.status),
+    }
+
+
+class Engine:
+    def __init__(self, device: int = 0, luma_mode: int = 0, coef_mode: int = 0):
+        self._lib = _ffi.load()
+        opts = _ffi.Opts(C.sizeof(_ffi.Opts), luma_mode, coef_mode, 0, 0)
+        self._ctx = self._lib.irp_create(device, C.byref(opts))
+        if not self._ctx:
+            raise IrpError(_ffi.IRP_ERR_NO_DEVICE, (self._lib.irp_last_error(None) or b"irp_create failed").decode())
+        self.device = device
+        self._keep: list = []
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.irp_destroy(self._ctx)
+            self._ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise IrpError(rc, (self._lib.irp_last_error(self._ctx) or b"").decode())
+
+    # -- plumbing -----------------------------------------------------------
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Launch on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._lib.irp_set_stream(self._ctx, cuda_stream or None))
+
+    def timing(self) -> dict:
+        t = _ffi.Timing()
+        self._check(self._lib.irp_get_timing(self._ctx, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in _ffi.Timing._fields_ if k != "reserved"}
+
+    def synchronize(self) -> None:
+        self._check(self._lib.irp_synchronize(self._ctx))
+
+    def upload(self, a: np.ndarray, is_jpeg: bool = True, orientation: int = 1, pitch_align: int = 16) -> DeviceImage:
+        """Stage an image in HBM (rows padded to `pitch_align` bytes) for device-resident calls."""
+        a = _as_hwc(a)
+        h, w, c = a.shape
+        pitch = (w * c + pitch_align - 1) // pitch_align * pitch_align
+        if pitch != w * c:
+            buf = np.zeros((h, pitch), np.uint8)
+            buf[:, : w * c] = a.reshape(h, w * c)
+        else:
+            buf = np.ascontiguousarray(a).reshape(h, pitch)
+        nbytes = pitch * h
+        ptr = self._lib.irp_dev_alloc(self._ctx, nbytes)
+        if not ptr:
+            self._check(_ffi.IRP_ERR_NOMEM)
+        self._check(self._lib.irp_memcpy_h2d(self._ctx, ptr, buf.ctypes.data, nbytes))
+        return DeviceImage(ptr, w, h, c, pitch, nbytes, is_jpeg, orientation)
+
+    def alloc_device(self, width: int, height: int, channels: int) -> DeviceImage:
+        nbytes = width * height * channels
+        ptr = self._lib.irp_dev_alloc(self._ctx, nbytes)
+        if not ptr:
+            self._check(_ffi.IRP_ERR_NOMEM)
+        return DeviceImage(ptr, width, height, channels, width * channels, nbytes)
+
+    def download(self, d: DeviceImage) -> np.ndarray:
+        buf = np.empty((d.height, d.pitch), np.uint8)
+        self._check(self._lib.irp_memcpy_d2h(self._ctx, buf.ctypes.data, d.ptr, d.pitch * d.height))
+        return np.ascontiguousarray(buf[:, : d.width * d.channels]).reshape(d.height, d.width, d.channels)
+
+    def free(self, d: DeviceImage) -> None:
+        self._check(self._lib.irp_dev_free(self._ctx, d.ptr))
+        d.ptr = 0
+
+    def pinned_empty(self, shape: Tuple[int, ...]) -> np.ndarray:
+        """A page-locked uint8 host array (freed with the context)."""
+        n = int(np.prod(shape))
+        ptr = self._lib.irp_host_alloc_pinned(self._ctx, max(n, 1))
+        if not ptr:
+            self._check(_ffi.IRP_ERR_NOMEM)
+        arr = np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr)).reshape(shape)
+        return arr
+
+    # -- descriptor marshalling ----------------------------------------------
+    def _descs(self, images: Sequence[Optional[ImageLike]], is_jpeg, orientations):
+        n = len(images)
+        descs = (_ffi.ImageDesc * n)()
+        keep = []
+        for i, im in enumerate(images):
+            if im is None:
+                descs[i] = _ffi.ImageDesc(None, 0, 0, 0, 0, 0, 1, 0)
+                continue
+            if isinstance(im, DeviceImage):
+                descs[i] = _ffi.ImageDesc(im.ptr, im.pitch, im.width, im.height, im.channels, int(im.is_jpeg), im.orientation, 1)
+            else:
+                a = _as_hwc(im)
+                keep.append(a)
+                h, w, c = a.shape
+                jp = is_jpeg if isinstance(is_jpeg, bool) else bool(is_jpeg[i])
+                o = 1 if orientations is None else int(orientations[i])
+                descs[i] = _ffi.ImageDesc(a.ctypes.data, a.strides[0], w, h, c, int(jp), o, 0)
+        return descs, keep
+
+    @staticmethod
+    def _orient_of(im: ImageLike, orientations, i) -> int:
+        if isinstance(im, DeviceImage):
+            return im.orientation
+        return 1 if orientations is None else int(orientations[i])
+
+    def preprocess_dims(self, width: int, height: int, orientation: int = 1) -> Tuple[int, int]:
+        ow, oh = C.c_int(), C.c_int()
+        self._check_static(self._lib.irp_preprocess_dims(width, height, orientation, C.byref(ow), C.byref(oh)), width, height)
+        return ow.value, oh.value
+
+    def fusion_dims(self, width: int, height: int, orientation: int = 1) -> Tuple[int, int, int, int]:
+        ow, oh, ox, oy = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._check_static(self._lib.irp_fusion_dims(width, height, orientation, C.byref(ow), C.byref(oh), C.byref(ox), C.byref(oy)), width, height)
+        return ow.value, oh.value, ox.value, oy.value
+
+    @staticmethod
+    def _check_static(rc, w, h):
+        if rc:
+            raise IrpError(rc, f"unsupported geometry {w}x{h}")
+
+    def _outs(self, images, orientations, device_outputs: Optional[Sequence[DeviceImage]], fusion: bool):
+        n = len(images)
+        outs = (_ffi.OutDesc * n)()
+        arrays: List[Optional[np.ndarray]] = [None] * n
+        for i, im in enumerate(images):
+            if im is None:
+                continue
+            w, h, c = (im.width, im.height, im.channels) if isinstance(im, DeviceImage) else (im.shape[1], im.shape[0], 1 if im.ndim == 2 else im.shape[2])
+            o = self._orient_of(im, orientations, i)
+            if fusion:
+                ow = oh = _ffi.FUSION_CANVAS
+                oc = 3
+            else:
+                ow, oh = self.preprocess_dims(w, h, o)
+                oc = 1 if c == 1 else 3
+            if device_outputs is not None:
+                d = device_outputs[i]
+                outs[i] = _ffi.OutDesc(d.ptr, d.pitch, d.nbytes, 0, 0, 0, 1)
+            else:
+                arr = np.empty((oh, ow, oc), np.uint8)
+                arrays[i] = arr
+                outs[i] = _ffi.OutDesc(arr.ctypes.data, ow * oc, arr.nbytes, 0, 0, 0, 0)
+        return outs, arrays
+
+    # -- the hot path ---------------------------------------------------------
+    def classify_batch(self, images: Sequence[ImageLike], is_jpeg=True, raw: bool = False):
+        """ClassifierService.analyze for a batch (classifier.js:40-99). Returns list of dicts."""
+        descs, keep = self._descs(images, is_jpeg, None)
+        res = (_ffi.Result * len(images))()
+        self._check(self._lib.irp_classify_batch(self._ctx, descs, len(images), res))
+        return list(res) if raw else [result_to_dict(r) for r in res]
+
+    def preprocess_batch(self, images: Sequence[ImageLike], orientations=None, device_outputs=None):
+        """preprocessImage pixel stages (imagePreprocess.js:42-53). Returns list of HxWxC arrays
+        (or fills `device_outputs`)."""
+        descs, keep = self._descs(images, True, orientations)
+        outs, arrays = self._outs(images, orientations, device_outputs, fusion=False)
+        self._check(self._lib.irp_preprocess_batch(self._ctx, descs, len(images), outs))
+        if device_outputs is not None:
+            for d, o in zip(device_outputs, outs):
+                d.width, d.height, d.channels = o.width, o.height, o.channels
+                d.pitch = o.pitch or o.width * o.channels
+            return device_outputs
+        return arrays
+
+    def analyze_batch(self, images: Sequence[ImageLike], is_jpeg=True, orientations=None, device_outputs=None, raw: bool = False):
+        """classify + preprocess of the same sources in one submission (BASELINE.json configs[1])."""
+        descs, keep = self._descs(images, is_jpeg, orientations)
+        outs, arrays = self._outs(images, orientations, device_outputs, fusion=False)
+        res = (_ffi.Result * len(images))()
+        self._check(self._lib.irp_analyze_batch(self._ctx, descs, len(images), res, outs))
+        results = list(res) if raw else [result_to_dict(r) for r in res]
+        if device_outputs is not None:
+            for d, o in zip(device_outputs, outs):
+                d.width, d.height, d.channels = o.width, o.height, o.channels
+                d.pitch = o.pitch or o.width * o.channels
+            return results, device_outputs
+        return results, arrays
+
+    def fusion_prepare_batch(self, groups: Sequence[Sequence[Optional[ImageLike]]], orientations=None, device_outputs=None):
+        """Each group of <= 3 images -> aligned 2048x2048x3 canvases."""
+        flat: List[Optional[ImageLike]] = []
+        flat_or = []
+        for gi, g in enumerate(groups):
+            g = list(g)
+            if len(g) > _ffi.FUSION_MAX_IMAGES:
+                raise ValueError("a fusion group holds at most 3 images")
+            for k in range(_ffi.FUSION_MAX_IMAGES):
+                flat.append(g[k] if k < len(g) else None)
+                flat_or.append(1 if orientations is None or k >= len(g) else int(orientations[gi][k]))
+        descs, keep = self._descs(flat, True, flat_or)
+        outs, arrays = self._outs(flat, flat_or, device_outputs, fusion=True)
+        self._check(self._lib.irp_fusion_prepare_batch(self._ctx, descs, len(groups), outs))
+        if device_outputs is not None:
+            return device_outputs
+        return [[arrays[gi * 3 + k] for k in range(len(list(g)))] for gi, g in enumerate(groups)]
