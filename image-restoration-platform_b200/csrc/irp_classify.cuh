@@ -35,7 +35,7 @@ constexpr int kPlanePitch = 16 + kTileW + 16;  // bytes: [..15 = left halo][256 
 constexpr int kClassifyThreads = 256;
 constexpr int kSegPx = 16;             // pixels per stage-1 work item
 constexpr int kSegsPerRow = kTileW / kSegPx;
-constexpr int kFlushTiles = 512;       // keeps every u32 accumulator below 2^32
+constexpr int kFlushTiles = 16;        // keeps every per-WARP u32 sum below 2^32 (blur sumsq: 16*6.3e6*32)
 
 // global accumulator slots (u64) per image
 enum {
@@ -63,13 +63,17 @@ struct ClassifyTables {   // device copies of grey_tables.inc for the chosen lum
 };
 
 template <int C>
-struct ClassifySmem {
+struct ClassifySmem {          // dynamic shared memory: the pixel tiles
   uint8_t plane[C][kRows][kPlanePitch];
   uint8_t grey[kRows][kPlanePitch];
+};
+// Static shared memory: the linker knows these offsets, so the random LUT reads compile to
+// LDS [R + UR + imm] with no per-access base add.
+struct ClassifyStatic {
   uint32_t lut[3][256];
   uint32_t inv[4096];
   uint32_t hist[256];
-  unsigned long long red[kClassifyThreads / 32][ACC_COUNT];
+  uint32_t red[kClassifyThreads / 32][ACC_COUNT];
 };
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -89,8 +93,7 @@ __device__ __forceinline__ int dp2a_lo_u16_s8(uint32_t a, uint32_t b, int c) {
 
 // grey of one pixel from its three LUT byte offsets (already scaled by 4 is not
 // required: plain indices); returns (inv + low bits): grey sits in bits 24..31
-template <int C>
-__device__ __forceinline__ uint32_t grey_top(const ClassifySmem<C>& s, uint32_t r, uint32_t g, uint32_t b) {
+__device__ __forceinline__ uint32_t grey_top(const ClassifyStatic& s, uint32_t r, uint32_t g, uint32_t b) {
   uint32_t I = s.lut[0][r] + s.lut[1][g] + s.lut[2][b];
   return s.inv[I >> 20] + (I & 0xFFFFFu);
 }
@@ -109,16 +112,10 @@ struct Acc {
   }
 };
 
-__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 template <int C>
-__device__ void flush_acc(ClassifySmem<C>& sm, Acc<C>& a, unsigned long long* gacc, uint32_t* ghist) {
+__device__ void flush_acc(ClassifyStatic& st, Acc<C>& a, unsigned long long* gacc, uint32_t* ghist) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long v[ACC_COUNT];
+  uint32_t v[ACC_COUNT];
 #pragma unroll
   for (int i = 0; i < ACC_COUNT; i++) v[i] = 0;
 #pragma unroll
@@ -131,20 +128,20 @@ __device__ void flush_acc(ClassifySmem<C>& sm, Acc<C>& a, unsigned long long* ga
   v[ACC_BE0] = a.be0; v[ACC_BE1] = a.be1;
 #pragma unroll
   for (int i = 0; i < ACC_COUNT; i++) {
-    unsigned long long r = warp_sum64(v[i]);
-    if (lane == 0) sm.red[warp][i] = r;
+    const uint32_t r = __reduce_add_sync(0xffffffffu, v[i]);  // REDUX.SUM: one instruction per value
+    if (lane == 0) st.red[warp][i] = r;
   }
   __syncthreads();
   if (threadIdx.x < ACC_COUNT) {
     unsigned long long t = 0;
 #pragma unroll
-    for (int w = 0; w < kClassifyThreads / 32; w++) t += sm.red[w][threadIdx.x];
+    for (int w = 0; w < kClassifyThreads / 32; w++) t += st.red[w][threadIdx.x];
     if (t) atomicAdd(&gacc[threadIdx.x], t);
   }
   {
-    uint32_t hv = sm.hist[threadIdx.x];
+    const uint32_t hv = st.hist[threadIdx.x];
     if (hv) atomicAdd(&ghist[threadIdx.x], hv);
-    sm.hist[threadIdx.x] = 0;
+    st.hist[threadIdx.x] = 0;
   }
   a.clear();
   __syncthreads();
@@ -155,7 +152,7 @@ __device__ void flush_acc(ClassifySmem<C>& sm, Acc<C>& a, unsigned long long* ga
 // One item = 16 pixels of one tile row.
 // ---------------------------------------------------------------------------
 template <int C>
-__device__ __forceinline__ void stage1_slow(ClassifySmem<C>& sm, Acc<C>& a, const ImgDev& im, int gy, int xbeg,
+__device__ __forceinline__ void stage1_slow(ClassifySmem<C>& sm, ClassifyStatic& st, Acc<C>& a, const ImgDev& im, int gy, int xbeg,
                                             int row, int col0, int npx, bool counted) {
   const uint8_t* rp = im.px + (size_t)gy * im.pitch;
   for (int i = 0; i < npx; i++) {
@@ -167,7 +164,7 @@ __device__ __forceinline__ void stage1_slow(ClassifySmem<C>& sm, Acc<C>& a, cons
     for (int ch = 0; ch < C; ch++) v[ch] = rp[(size_t)xc * C + ch];
     uint32_t g;
     if constexpr (C >= 3)
-      g = grey_top(sm, v[0], v[1], v[2]) >> 24;
+      g = grey_top(st, v[0], v[1], v[2]) >> 24;
     else
       g = v[0];
 #pragma unroll
@@ -179,14 +176,14 @@ __device__ __forceinline__ void stage1_slow(ClassifySmem<C>& sm, Acc<C>& a, cons
         a.s[ch] += v[ch];
         a.q[ch] += v[ch] * v[ch];
       }
-      atomicAdd(&sm.hist[g], 1u);
+      atomicAdd(&st.hist[g], 1u);
     }
   }
 }
 
 // stage 1, fast item: C == 3, 48 aligned bytes fully inside the image.
-__device__ __forceinline__ void stage1_fast(ClassifySmem<3>& sm, Acc<3>& a, const uint8_t* p, int row, int col0,
-                                            bool counted) {
+__device__ __forceinline__ void stage1_fast(ClassifySmem<3>& sm, ClassifyStatic& st, Acc<3>& a, const uint8_t* p, int row,
+                                            int col0, bool counted) {
   uint4 v0 = ldg_nc_v4(p), v1 = ldg_nc_v4(p + 16), v2 = ldg_nc_v4(p + 32);
   uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
   uint32_t R[4], G[4], B[4], Y[4];
@@ -215,8 +212,8 @@ __device__ __forceinline__ void stage1_fast(ClassifySmem<3>& sm, Acc<3>& a, cons
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t r = (R[k] >> (8 * j)) & 0xFFu, g = (G[k] >> (8 * j)) & 0xFFu, b = (B[k] >> (8 * j)) & 0xFFu;
-      t[j] = grey_top(sm, r, g, b);
-      if (counted) atomicAdd(&sm.hist[t[j] >> 24], 1u);
+      t[j] = grey_top(st, r, g, b);
+      if (counted) atomicAdd(&st.hist[t[j] >> 24], 1u);
     }
     Y[k] = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x0073), 0x5410);
   }
@@ -264,29 +261,36 @@ __device__ __forceinline__ uint32_t clip_diff(uint32_t kc, uint32_t nb) {
   return __vminu2(mx - nb, 0x00FF00FFu);
 }
 
-template <int C>
+// FULL = the tile lies strictly inside the image (x0 + 256 < W and y0 + 32 < H): no lane masks,
+// no row / column validity tests.  Edge tiles take the masked instantiation.
+template <int C, bool FULL>
 __device__ __forceinline__ void stage2(const ClassifySmem<C>& sm, Acc<C>& a, int x0, int y0, int W, int H) {
   const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int x = x0 + strip * 4;
-  if (x >= W) return;
-  const int nvalid = min(4, W - x);
+  const int r0 = rg * 8;
+  int nvalid = 4, nrows = 8;
+  if (!FULL) {
+    if (x >= W || y0 + r0 >= H) return;
+    nvalid = min(4, W - x);
+    nrows = min(8, H - (y0 + r0));
+  }
   // byte masks for partially valid strips (pairs hold values in bytes 0 and 2)
   const uint32_t mA = nvalid >= 2 ? 0x00FF00FFu : 0x000000FFu;
   const uint32_t mB = nvalid >= 4 ? 0x00FF00FFu : (nvalid == 3 ? 0x000000FFu : 0u);
-  const int r0 = rg * 8;
-  if (y0 + r0 >= H) return;
   GreyRow up = load_grey_row(&sm.grey[r0][0], strip), cur = load_grey_row(&sm.grey[r0 + 1][0], strip);
   uint32_t prev_t0 = 0;  // E3 > 200 at (grid row, px0), consumed by the row below
-  const bool col_boundary = (strip & 1) && x + 4 < W;  // px3 | px4 straddle an 8-px column boundary
-#pragma unroll 2
+  const bool col_boundary = (strip & 1) && (FULL || x + 4 < W);  // px3 | px4 straddle an 8-px column boundary
+#pragma unroll
   for (int i = 0; i < 8; i++) {
-    const int y = y0 + r0 + i;
-    if (y >= H) break;
-    GreyRow dn = load_grey_row(&sm.grey[r0 + i + 2][0], strip);
+    if (!FULL && i >= nrows) break;
+    const GreyRow dn = load_grey_row(&sm.grey[r0 + i + 2][0], strip);
     const uint32_t boxA = up.hA + cur.hA + dn.hA, boxB = up.hB + cur.hB + dn.hB;
     const uint32_t nineA = cur.cA * 9u, nineB = cur.cB * 9u;
-    const uint32_t e1A = clip_diff(nineA, boxA) & mA, e1B = clip_diff(nineB, boxB) & mB;
-    const uint32_t e2A = clip_diff(nineA + cur.cA, boxA) & mA, e2B = clip_diff(nineB + cur.cB, boxB) & mB;
+    uint32_t e1A = clip_diff(nineA, boxA), e1B = clip_diff(nineB, boxB);
+    uint32_t e2A = clip_diff(nineA + cur.cA, boxA), e2B = clip_diff(nineB + cur.cB, boxB);
+    if (!FULL) {
+      e1A &= mA; e1B &= mB; e2A &= mA; e2B &= mB;
+    }
     const uint32_t e1 = __byte_perm(e1A, e1B, 0x6240), e2 = __byte_perm(e2A, e2B, 0x6240);  // 4 bytes each
     a.e1s = __dp4a(e1, 0x01010101u, a.e1s);
     a.e1q = __dp4a(e1, e1, a.e1q);
@@ -294,13 +298,12 @@ __device__ __forceinline__ void stage2(const ClassifySmem<C>& sm, Acc<C>& a, int
     a.e2q = __dp4a(e2, e2, a.e2q);
     // A5: Lap4 only where _detectLinearFeatures looks.  y0 and r0 are multiples of 4, so
     // y % 4 == i % 4; grid rows (i = 0, 4) and the rows below them (i = 1, 5) share a thread.
-    const int ym = i & 3;
-    if (ym <= 1) {
+    if ((i & 3) <= 1) {
       const uint32_t crossA = up.cA + dn.cA + cur.hA;
       const uint32_t e3A = clip_diff(cur.cA * 5u, crossA);
       const uint32_t t0 = (e3A & 0xFFFFu) > IRP_SCRATCH_THRESHOLD, t1 = (e3A >> 16) > IRP_SCRATCH_THRESHOLD;
-      if (ym == 0) {
-        a.sv += t0 & t1 & (uint32_t)(nvalid >= 2);
+      if ((i & 3) == 0) {
+        a.sv += FULL ? (t0 & t1) : (t0 & t1 & (uint32_t)(nvalid >= 2));
         prev_t0 = t0;
       } else {
         a.sh += prev_t0 & t0;
@@ -311,11 +314,12 @@ __device__ __forceinline__ void stage2(const ClassifySmem<C>& sm, Acc<C>& a, int
       const int d = dp2a_lo_u16_s8(cur.p34, 0x0000FF01u, IRP_BLOCK_EDGE_THRESHOLD);  // c3 - r0 + T
       a.be0 += (uint32_t)d > 2u * IRP_BLOCK_EDGE_THRESHOLD;
     }
-    if ((y & 7) == 7 && y + 1 < H) {
+    if ((i & 7) == 7 && (FULL || y0 + r0 + i + 1 < H)) {
+      // |a - b| > T per byte: saturating-free form on 16x2 halves
       const uint32_t ad = __vabsdiffu4(cur.word, dn.word);
 #pragma unroll
       for (int j = 0; j < 4; j++)
-        a.be1 += (uint32_t)(j < nvalid) & (uint32_t)(((ad >> (8 * j)) & 0xFFu) > IRP_BLOCK_EDGE_THRESHOLD);
+        a.be1 += (uint32_t)(FULL || j < nvalid) & (uint32_t)(((ad >> (8 * j)) & 0xFFu) > IRP_BLOCK_EDGE_THRESHOLD);
     }
     up = cur;
     cur = dn;
@@ -330,10 +334,10 @@ struct HRow { uint32_t h[4]; };
 
 __device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
   const uint32_t* rp = reinterpret_cast<const uint32_t*>(plane_row) + 3 + strip;
-  uint32_t l = rp[0], c = rp[1], r = rp[2];
+  const uint32_t l = rp[0], c = rp[1], r = rp[2];
   HRow o;
-  uint32_t w0 = __funnelshift_r(l, c, 24);  // (l3, c0, c1, c2)
-  uint32_t w3 = __funnelshift_r(c, r, 16);  // (c2, c3, r0, r1)
+  const uint32_t w0 = __funnelshift_r(l, c, 24);  // (l3, c0, c1, c2)
+  const uint32_t w3 = __funnelshift_r(c, r, 16);  // (c2, c3, r0, r1)
   o.h[0] = div11(__dp4a(w0, 0x00030503u, 5u));
   o.h[1] = div11(__dp4a(c, 0x00030503u, 5u));
   o.h[2] = div11(__dp4a(c, 0x03050300u, 5u));
@@ -341,25 +345,28 @@ __device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
   return o;
 }
 
-template <int C>
+template <int C, bool FULL>
 __device__ __forceinline__ void stage3(const ClassifySmem<C>& sm, Acc<C>& a, int x0, int y0, int W, int H) {
   const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int x = x0 + strip * 4;
-  if (x >= W) return;
-  const int nvalid = min(4, W - x);
   const int r0 = rg * 8;
-  if (y0 + r0 >= H) return;
+  int nvalid = 4, nrows = 8;
+  if (!FULL) {
+    if (x >= W || y0 + r0 >= H) return;
+    nvalid = min(4, W - x);
+    nrows = min(8, H - (y0 + r0));
+  }
 #pragma unroll 1
   for (int ch = 0; ch < C; ch++) {
     HRow up = hpass_row(&sm.plane[ch][r0][0], strip), cur = hpass_row(&sm.plane[ch][r0 + 1][0], strip);
-#pragma unroll 2
+#pragma unroll
     for (int i = 0; i < 8; i++) {
-      if (y0 + r0 + i >= H) break;
-      HRow dn = hpass_row(&sm.plane[ch][r0 + i + 2][0], strip);
+      if (!FULL && i >= nrows) break;
+      const HRow dn = hpass_row(&sm.plane[ch][r0 + i + 2][0], strip);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        uint32_t b = div11(3u * (up.h[j] + dn.h[j]) + 5u * cur.h[j] + 5u);
-        if (j < nvalid) {
+        const uint32_t b = div11((up.h[j] + dn.h[j]) * 3u + (cur.h[j] * 5u + 5u));
+        if (FULL || j < nvalid) {
           a.bs += b;
           a.bq += b * b;
         }
@@ -374,14 +381,15 @@ __device__ __forceinline__ void stage3(const ClassifySmem<C>& sm, Acc<C>& a, int
 // the kernel
 // ---------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(kClassifyThreads, 2)
+__global__ void __launch_bounds__(kClassifyThreads, 3)
 classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
                 unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ ClassifyStatic st;
   ClassifySmem<C>& sm = *reinterpret_cast<ClassifySmem<C>*>(smem_raw);
-  for (int i = threadIdx.x; i < 3 * 256; i += kClassifyThreads) (&sm.lut[0][0])[i] = (&tab->lut[0][0])[i];
-  for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) sm.inv[i] = tab->inv[i];
-  sm.hist[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < 3 * 256; i += kClassifyThreads) (&st.lut[0][0])[i] = (&tab->lut[0][0])[i];
+  for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) st.inv[i] = tab->inv[i];
+  st.hist[threadIdx.x] = 0;
   __syncthreads();
 
   Acc<C> acc;
@@ -392,7 +400,7 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     if (img != cur_img || since_flush >= kFlushTiles) {
       if (cur_img >= 0) {
         const int slot = imgs[cur_img].slot;
-        flush_acc<C>(sm, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+        flush_acc<C>(st, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
       }
       cur_img = img;
       since_flush = 0;
@@ -414,27 +422,32 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
       bool fast = false;
       if constexpr (C == 3) {
         if (im.aligned16 && xb + kSegPx <= im.w) {
-          stage1_fast(sm, acc, im.px + (size_t)gy * im.pitch + (size_t)xb * 3, row, 16 + seg * kSegPx, counted);
+          stage1_fast(sm, st, acc, im.px + (size_t)gy * im.pitch + (size_t)xb * 3, row, 16 + seg * kSegPx, counted);
           fast = true;
         }
       }
-      if (!fast) stage1_slow<C>(sm, acc, im, gy, xb, row, 16 + seg * kSegPx, kSegPx, counted);
+      if (!fast) stage1_slow<C>(sm, st, acc, im, gy, xb, row, 16 + seg * kSegPx, kSegPx, counted);
     }
     // halo columns: pixel x0-1 (byte 15) and x0+256 (byte 16+256) of every row
     for (int item = threadIdx.x; item < kRows * 2; item += kClassifyThreads) {
       const int row = item >> 1, right = item & 1;
       const int gy = min(max(y0 - 1 + row, 0), im.h - 1);
-      stage1_slow<C>(sm, acc, im, gy, right ? x0 + kTileW : x0 - 1, row, right ? 16 + kTileW : 15, 1, false);
+      stage1_slow<C>(sm, st, acc, im, gy, right ? x0 + kTileW : x0 - 1, row, right ? 16 + kTileW : 15, 1, false);
     }
     __syncthreads();
     // ---- stage 2 + 3 ----
-    stage2<C>(sm, acc, x0, y0, im.w, im.h);
-    stage3<C>(sm, acc, x0, y0, im.w, im.h);
+    if (x0 + kTileW < im.w && y0 + kTileH < im.h) {
+      stage2<C, true>(sm, acc, x0, y0, im.w, im.h);
+      stage3<C, true>(sm, acc, x0, y0, im.w, im.h);
+    } else {
+      stage2<C, false>(sm, acc, x0, y0, im.w, im.h);
+      stage3<C, false>(sm, acc, x0, y0, im.w, im.h);
+    }
     __syncthreads();
   }
   if (cur_img >= 0) {
     const int slot = imgs[cur_img].slot;
-    flush_acc<C>(sm, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+    flush_acc<C>(st, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
   }
 }
 

@@ -252,17 +252,22 @@ int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
 }
 
 int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* ap) {
-  if (in_size == out_size) {
-    *ap = AxisPlan{nullptr, nullptr, nullptr, 0, 0};
-    return IRP_OK;
-  }
-  auto key = std::make_tuple(in_size, out_size, shrink);
+  const bool identity = in_size == out_size;
+  auto key = std::make_tuple(in_size, out_size, identity ? 1.0 : shrink);
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end()) {
     HostPlan hp;
-    if (!build_plan(in_size, out_size, shrink, ctx->opts.coef_mode, &hp))
+    if (identity) {  // one tap of weight 1.0: (4096 * p + 2048) >> 12 == p
+      hp.n = 1;
+      hp.coef.assign((size_t)(IRP_PHASES + 1) * kCoefStride, 0);
+      for (int t = 0; t <= IRP_PHASES; t++) hp.coef[(size_t)t * kCoefStride] = 1 << IRP_INTERP_SHIFT;
+      hp.start.resize(out_size);
+      hp.phase.assign(out_size, 0);
+      for (int o = 0; o < out_size; o++) hp.start[o] = o;
+    } else if (!build_plan(in_size, out_size, shrink, ctx->opts.coef_mode, &hp)) {
       return fail(ctx, IRP_ERR_UNSUPPORTED, "shrink factor %.4f needs more than %d taps (box pre-shrink not implemented)",
                   shrink, IRP_MAX_TAPS);
+    }
     PlanDev pd;
     pd.n = hp.n;
     void* p;
@@ -432,18 +437,16 @@ struct OutPlan {  // per image: where the kernel writes, and how the result gets
   bool via_stage;
 };
 
-void choose_tile(double fv, int nv, double fh, int nh, int C, int* tow, int* toh, int* rows_max, int* rowbytes_max) {
-  const int cand[5][2] = {{64, 32}, {64, 16}, {32, 16}, {32, 8}, {16, 8}};
-  for (int k = 0; k < 5; k++) {
-    int tw = cand[k][0], th = cand[k][1];
-    int rows = nv ? (int)std::ceil(th * fv) + nv + 2 : th;
-    int rb = (int)round_up((size_t)((nh ? (int)std::ceil(tw * fh) + nh + 2 : tw) * C + 8), 4);
-    *tow = tw;
-    *toh = th;
-    *rows_max = rows;
-    *rowbytes_max = rb;
-    if ((size_t)(rows + th) * rb <= 96 * 1024) return;
-  }
+// output tile: toh = 32 rows; tow = the widest of 64/32/16/8 whose source window (plus the 16-pixel
+// alignment slack of the vector-load path) fits the kSrcCols columns a shared tile holds
+void choose_tile(double f, int nv, int nh, int C, int* tow, int* toh, int* pairrows_max) {
+  const int slack = C == 3 ? 15 : 0;
+  int tw = kMaxTow;
+  while (tw > 8 && (int)std::ceil(tw * f) + nh + 2 + slack > kSrcCols) tw >>= 1;
+  *tow = tw;
+  *toh = kMaxToh;
+  int rows = (int)std::ceil(kMaxToh * f) + nv + 3;
+  *pairrows_max = rows / 2 + 2;
 }
 
 template <int C>
@@ -451,7 +454,7 @@ int launch_resize(irp_ctx* ctx, const ResizeJob* d_jobs, const ResizeJob* h_jobs
   if (!n) return IRP_OK;
   size_t smem = 0;
   for (int i = 0; i < n; i++)
-    smem = std::max(smem, (size_t)(h_jobs[i].src_rows_max + h_jobs[i].toh) * h_jobs[i].src_rowbytes_max);
+    smem = std::max(smem, (size_t)C * h_jobs[i].pairrows_max * kPairPitch + (size_t)C * kMaxToh * kMidPitch + 32);
   smem = round_up(smem, 16);
   CK(cudaFuncSetAttribute(resize_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -577,11 +580,11 @@ int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Stage
       J.dst_x0 = g.ox;
       J.dst_y0 = g.oy;
       J.expand_grey = (d.channels == 1 && g.dc == 3);
-      J.aligned4 = (((uintptr_t)J.src | J.src_pitch) & 3) == 0;
+      J.aligned16 = (((uintptr_t)J.src | J.src_pitch) & 15) == 0;
       int rc;
       if ((rc = get_plan(ctx, g.ho, g.dh, g.f, &J.v))) return rc;
       if ((rc = get_plan(ctx, g.wo, g.dw, g.f, &J.h))) return rc;
-      choose_tile(g.f, J.v.n, g.f, J.h.n, d.channels, &J.tow, &J.toh, &J.src_rows_max, &J.src_rowbytes_max);
+      choose_tile(g.f, J.v.n, J.h.n, d.channels, &J.tow, &J.toh, &J.pairrows_max);
       J.tiles_x = (J.dw + J.tow - 1) / J.tow;
       J.tiles_y = (J.dh + J.toh - 1) / J.toh;
       J.tile_base = tiles;

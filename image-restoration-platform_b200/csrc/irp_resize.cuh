@@ -5,12 +5,18 @@
 //   P4 normalise to raw u8 (RGBA flattened on black)       (imagePreprocess.js:57-63, pixel part)
 //   P5 placement on a 2048x2048 fusion canvas              
 //
-// One CTA produces one output tile.  The source footprint of the tile (rows
-// vstart[oy0] .. , byte columns of hstart[ox0] ..; replicate-clamped) is staged in shared
-// memory, the vertical pass runs over it on 4-byte words with IDP.2A (two taps x
-// 16-bit coefficients per instruction, int32 accumulate — exact), its u8 result stays in
-// shared memory, and the horizontal pass reads that and writes the output tile once.
-// The source is read from HBM/L2 once per tile; the intermediate never leaves the SM.
+// One CTA produces one output tile (tow x toh pixels).  Data layout on the SM:
+//   stage A  the tile's source footprint is pulled with 128-bit loads, de-interleaved to planes
+//            (PRMT) and stored ROW-PAIR-INTERLEAVED: for source rows (2q, 2q+1) a shared-memory
+//            word holds (a_k, b_k, a_k+1, b_k+1).  Replicate clamping happens here, once.
+//   stage B  reducev: a thread owns 4 byte-columns of one plane; per tap PAIR it issues one LDS.64
+//            and four IDP.2A (2 taps x s16 coefficient x u8 pixel, int32 accumulate — exact).  Odd
+//            window starts are absorbed by shifting the coefficient pairs, not the data.
+//            The u8 result stays in shared memory (planar).
+//   stage C  reduceh: a thread owns one output column, keeps its (alignment-shifted) coefficient
+//            pairs in registers for the whole tile, and walks rows x planes with LDS.32 + IDP.2A.
+// The source is read from HBM/L2 once per tile and the intermediate never leaves the SM.
+// No tensor cores: the fixed-point semantics are kept bit-exact on the integer pipes.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -20,13 +26,21 @@
 namespace irp {
 
 constexpr int kResizeThreads = 256;
-constexpr int kCoefStride = IRP_MAX_TAPS + 1;  // int16 per phase row (even count, so pairs load as u32)
+constexpr int kCoefStride = IRP_MAX_TAPS + 1;  // int16 per phase row
+constexpr int kSrcCols = 160;                  // source pixel columns a tile may touch
+constexpr int kPairPitch = kSrcCols * 2;       // bytes per pair-row per plane
+constexpr int kMidPitch = kSrcCols;            // bytes per row per plane of the reducev output
+constexpr int kWordCols = kSrcCols / 4;        // 4-pixel word columns per plane
+constexpr int kMaxPairs = (IRP_MAX_TAPS + 1) / 2;      // 13 coefficient pairs (leading zero included)
+constexpr int kVtabStride = 16;                         // words per output row in the vertical table
+constexpr int kMaxHPairs = (IRP_MAX_TAPS + 3 + 1) / 2;  // 14 pairs once shifted to word alignment
+constexpr int kMaxTow = 64, kMaxToh = 32;
 
 struct AxisPlan {            // device pointers into the plan arena
   const int32_t* start;      // [out] first tap (may be < 0 / beyond the edge: clamped)
   const int32_t* phase;      // [out] 0..64
-  const int16_t* coef;       // [65][kCoefStride]
-  int n;                     // taps; 0 = identity on this axis
+  const int16_t* coef;       // [65][kCoefStride], zero padded
+  int n;                     // taps (1 = identity: coef 4096)
   int pad;
 };
 
@@ -41,10 +55,10 @@ struct ResizeJob {
   int dw, dh;                // resized dims
   int dst_x0, dst_y0;        // placement inside dst (fusion canvas), else 0
   int expand_grey;           // 1: C == 1 source replicated to 3 destination channels (fusion canvas)
-  int tow, toh;              // output tile dims chosen by the host
+  int tow, toh;              // output tile dims chosen by the host (<= 64 x 32)
   int tiles_x, tiles_y, tile_base;
-  int src_rows_max, src_rowbytes_max;  // shared-memory tile bounds chosen by the host
-  int aligned4;              // src base and pitch multiples of 4
+  int pairrows_max;          // shared-memory pair-rows reserved per plane
+  int aligned16;             // src base and pitch are multiples of 16
   AxisPlan v, h;
 };
 
@@ -58,12 +72,31 @@ __device__ __forceinline__ int dp2a_hi_s16_u8(uint32_t a, uint32_t b, int c) {
   asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-__device__ __forceinline__ uint32_t fixed_round_u8(int v) {  // unsigned_fixed_round + clip
-  v >>= IRP_INTERP_SHIFT;
-  return (uint32_t)min(max(v, 0), 255);
+// pack sat_u8(a) << 8 | sat_u8(b) into the low half, low half of c into the high half
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
 }
-
+__device__ __forceinline__ uint4 ldg_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// 48 interleaved RGB bytes -> planar words R[4], G[4], B[4]
+__device__ __forceinline__ void deinterleave48(const uint4& v0, const uint4& v1, const uint4& v2, uint32_t* R, uint32_t* G,
+                                               uint32_t* B) {
+  const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+    R[k] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+    G[k] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+    B[k] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+  }
+}
 
 // gather-based orientation (P2); one thread per destination pixel
 template <int C>
@@ -92,9 +125,10 @@ template <int C>
 __global__ void __launch_bounds__(kResizeThreads)
 resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t s_vcoef[IRP_MAX_TAPS / 2 + 1];
+  __shared__ __align__(16) uint32_t s_vtab[kMaxToh * kVtabStride];
+  const int tid = threadIdx.x;
+  int ji = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    int ji = 0;
     while (ji + 1 < n_jobs && tile >= jobs[ji + 1].tile_base) ji++;
     const ResizeJob& J = jobs[ji];
     const int t = tile - J.tile_base;
@@ -102,117 +136,173 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
     const int ox0 = tx * J.tow, oy0 = ty * J.toh;
     const int ow = min(J.tow, J.dw - ox0), oh = min(J.toh, J.dh - oy0);
     const int vn = J.v.n, hn = J.h.n;
-    // source footprint (oriented coordinates, unclamped)
-    const int sy0 = vn ? J.v.start[oy0] : oy0;
-    const int sy1 = vn ? J.v.start[oy0 + oh - 1] + vn : oy0 + oh;  // exclusive
-    const int sx0 = hn ? J.h.start[ox0] : ox0;
-    const int sx1 = hn ? J.h.start[ox0 + ow - 1] + hn : ox0 + ow;  // exclusive
-    const int bx0 = floordiv(sx0 * C, 4) * 4;                       // byte origin, multiple of 4
-    const int rowbytes = ((sx1 * C - bx0) + 3) & ~3;
-    const int nrows = sy1 - sy0;
-    uint8_t* src_t = smem;                                        // [nrows][rowbytes]
-    uint8_t* mid_t = smem + (size_t)J.src_rows_max * J.src_rowbytes_max;  // [oh][rowbytes]
-    const int rowwords = rowbytes >> 2;
-    const int src_rowbytes_total = J.sw * C;
+    const int sy0 = J.v.start[oy0], sy1 = J.v.start[oy0 + oh - 1] + vn;  // [sy0, sy1) source rows, unclamped
+    const int sx0 = J.h.start[ox0], sx1 = J.h.start[ox0 + ow - 1] + hn;  // [sx0, sx1) source columns, unclamped
+    const int sy0e = floordiv(sy0, 2) * 2;                                // pair-row origin (even)
+    const int npairrows = (sy1 - sy0e + 1) >> 1;
+    const bool fast_img = (C == 3) && J.aligned16;
+    const int sx0a = fast_img ? floordiv(sx0, 16) * 16 : sx0;             // column origin
+    const int ncols = sx1 - sx0a;                                         // <= kSrcCols (host guarantees)
+    const int src_plane = J.pairrows_max * kPairPitch;
+    const int mid_plane = kMaxToh * kMidPitch;
+    uint8_t* src_t = smem;                      // [C][pairrows_max][kPairPitch]
+    uint8_t* mid_t = smem + (size_t)C * src_plane;  // [C][kMaxToh][kMidPitch]
 
-    // ---- stage A: source tile -> shared memory (replicate clamp) ----
-    for (int i = threadIdx.x; i < nrows * rowwords; i += kResizeThreads) {
-      const int r = i / rowwords, wj = i - r * rowwords;
-      const int gy = min(max(sy0 + r, 0), J.sh - 1);
-      const uint8_t* rp = J.src + (size_t)gy * J.src_pitch;
-      const int b = bx0 + wj * 4;
-      uint32_t word;
-      if (J.aligned4 && b >= 0 && b + 4 <= src_rowbytes_total) {
-        word = *reinterpret_cast<const uint32_t*>(rp + b);
-      } else {
-        word = 0;
+    // ---- vertical table: per output row, pair-row offset + coefficient pairs aligned to even rows ----
+    if (tid < oh) {
+      const int o = oy0 + tid;
+      const int s = J.v.start[o];
+      const int se = floordiv(s, 2) * 2, lead = s - se;
+      const int16_t* cf = J.v.coef + (size_t)J.v.phase[o] * kCoefStride;
+      uint32_t* vt = s_vtab + tid * kVtabStride;
+      vt[0] = (uint32_t)(((se - sy0e) >> 1) * kPairPitch);
+      const int npv = (vn + lead + 1) >> 1;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          int bb = b + k;
-          int px = floordiv(bb, C), ch = bb - px * C;
-          px = min(max(px, 0), J.sw - 1);
-          word |= (uint32_t)rp[px * C + ch] << (8 * k);
+      for (int p = 0; p < kMaxPairs; p++) {
+        const int i0 = 2 * p - lead, i1 = i0 + 1;
+        const uint32_t c0 = (p < npv && i0 >= 0 && i0 < vn) ? (uint16_t)cf[i0] : 0u;
+        const uint32_t c1 = (p < npv && i1 >= 0 && i1 < vn) ? (uint16_t)cf[i1] : 0u;
+        vt[1 + p] = c0 | (c1 << 16);
+      }
+    }
+
+    // ---- stage A: source footprint -> planar, row-pair-interleaved shared tile ----
+    {
+      const int nchunks = (ncols + 15) >> 4;
+      const int nitems = npairrows * nchunks;
+      for (int item = tid; item < nitems; item += kResizeThreads) {
+        const int q = item / nchunks, k = item - q * nchunks;
+        const int ra = min(max(sy0e + 2 * q, 0), J.sh - 1), rb = min(max(sy0e + 2 * q + 1, 0), J.sh - 1);
+        const uint8_t* pa = J.src + (size_t)ra * J.src_pitch;
+        const uint8_t* pb = J.src + (size_t)rb * J.src_pitch;
+        const int x = sx0a + 16 * k;
+        uint8_t* dst = src_t + q * kPairPitch + 32 * k;
+        bool done = false;
+        if constexpr (C == 3) {
+          if (fast_img && x >= 0 && x + 16 <= J.sw) {
+            uint32_t Ra[4], Ga[4], Ba[4], Rb[4], Gb[4], Bb[4];
+            {
+              const uint4 a0 = ldg_v4(pa + x * 3), a1 = ldg_v4(pa + x * 3 + 16), a2 = ldg_v4(pa + x * 3 + 32);
+              const uint4 b0 = ldg_v4(pb + x * 3), b1 = ldg_v4(pb + x * 3 + 16), b2 = ldg_v4(pb + x * 3 + 32);
+              deinterleave48(a0, a1, a2, Ra, Ga, Ba);
+              deinterleave48(b0, b1, b2, Rb, Gb, Bb);
+            }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+              const int k0 = 2 * h2, k1 = k0 + 1;
+              *reinterpret_cast<uint4*>(dst + 16 * h2) =
+                  make_uint4(__byte_perm(Ra[k0], Rb[k0], 0x5140), __byte_perm(Ra[k0], Rb[k0], 0x7362),
+                             __byte_perm(Ra[k1], Rb[k1], 0x5140), __byte_perm(Ra[k1], Rb[k1], 0x7362));
+              *reinterpret_cast<uint4*>(dst + src_plane + 16 * h2) =
+                  make_uint4(__byte_perm(Ga[k0], Gb[k0], 0x5140), __byte_perm(Ga[k0], Gb[k0], 0x7362),
+                             __byte_perm(Ga[k1], Gb[k1], 0x5140), __byte_perm(Ga[k1], Gb[k1], 0x7362));
+              *reinterpret_cast<uint4*>(dst + 2 * src_plane + 16 * h2) =
+                  make_uint4(__byte_perm(Ba[k0], Bb[k0], 0x5140), __byte_perm(Ba[k0], Bb[k0], 0x7362),
+                             __byte_perm(Ba[k1], Bb[k1], 0x5140), __byte_perm(Ba[k1], Bb[k1], 0x7362));
+            }
+            done = true;
+          }
+        }
+        if (!done) {
+          const int lim = min(16, ncols - 16 * k);
+          for (int i = 0; i < lim; i++) {
+            const int xc = min(max(x + i, 0), J.sw - 1);
+#pragma unroll
+            for (int ch = 0; ch < C; ch++)
+              *reinterpret_cast<uint16_t*>(dst + ch * src_plane + 2 * i) =
+                  (uint16_t)(pa[(size_t)xc * C + ch] | (pb[(size_t)xc * C + ch] << 8));
+          }
         }
       }
-      reinterpret_cast<uint32_t*>(src_t)[(size_t)r * rowwords + wj] = word;
     }
     __syncthreads();
 
-    // ---- stage B: vertical reduce (reducev) on words, IDP.2A ----
-    if (vn) {
-      const int npairs = (vn + 1) >> 1;
-      for (int orow = 0; orow < oh; orow++) {
-        const int o = oy0 + orow;
-        const int s = J.v.start[o] - sy0;
-        const uint32_t* cp = reinterpret_cast<const uint32_t*>(J.v.coef + (size_t)J.v.phase[o] * kCoefStride);
-        if (threadIdx.x < npairs) s_vcoef[threadIdx.x] = cp[threadIdx.x];
-        __syncthreads();
-        for (int wj = threadIdx.x; wj < rowwords; wj += kResizeThreads) {
-          const uint32_t* colp = reinterpret_cast<const uint32_t*>(src_t) + (size_t)s * rowwords + wj;
+    // ---- stage B: reducev (vertical), LDS.64 + 4 x IDP.2A per tap pair ----
+    {
+      const int rg = tid >> 7;                   // two row groups
+      const int rows_per = (oh + 1) >> 1;
+      const int r_begin = rg * rows_per, r_end = min(oh, r_begin + rows_per);
+      const int npv = (vn + 2) >> 1;             // pairs incl. a possible leading zero
+      const int nwc = (ncols + 3) >> 2;          // word columns in use
+      for (int col = tid & 127; col < C * kWordCols; col += 128) {
+        const int plane = col / kWordCols, j = col - plane * kWordCols;
+        if (j >= nwc) continue;
+        const uint8_t* sp = src_t + plane * src_plane + j * 8;
+        uint8_t* mp = mid_t + plane * mid_plane + j * 4;
+        for (int r = r_begin; r < r_end; r++) {
+          const uint32_t* vt = s_vtab + r * kVtabStride;
+          const uint8_t* p = sp + vt[0];
           int a0 = 1 << (IRP_INTERP_SHIFT - 1), a1 = a0, a2 = a0, a3 = a0;
-          for (int p = 0; p < npairs; p++) {
-            uint32_t wa = colp[(size_t)(2 * p) * rowwords];
-            // an odd tap count leaves the last pair's second coefficient 0: reading the row
-            // below is harmless as long as it exists in the tile, so clamp the row index
-            int r2 = min(s + 2 * p + 1, nrows - 1) - s;
-            uint32_t wb = colp[(size_t)r2 * rowwords];
-            uint32_t lo = __byte_perm(wa, wb, 0x5140), hi = __byte_perm(wa, wb, 0x7362);
-            uint32_t c2 = s_vcoef[p];
-            a0 = dp2a_lo_s16_u8(c2, lo, a0);
-            a1 = dp2a_hi_s16_u8(c2, lo, a1);
-            a2 = dp2a_lo_s16_u8(c2, hi, a2);
-            a3 = dp2a_hi_s16_u8(c2, hi, a3);
+#pragma unroll
+          for (int pp = 0; pp < kMaxPairs; pp++) {
+            if (pp < npv) {
+              const uint2 w = *reinterpret_cast<const uint2*>(p + pp * kPairPitch);
+              const uint32_t cp = vt[1 + pp];
+              a0 = dp2a_lo_s16_u8(cp, w.x, a0);
+              a1 = dp2a_hi_s16_u8(cp, w.x, a1);
+              a2 = dp2a_lo_s16_u8(cp, w.y, a2);
+              a3 = dp2a_hi_s16_u8(cp, w.y, a3);
+            }
           }
-          uint32_t out = fixed_round_u8(a0) | (fixed_round_u8(a1) << 8) | (fixed_round_u8(a2) << 16) |
-                         (fixed_round_u8(a3) << 24);
-          reinterpret_cast<uint32_t*>(mid_t)[(size_t)orow * rowwords + wj] = out;
+          const uint32_t hi = pack_sat_u8(a3 >> IRP_INTERP_SHIFT, a2 >> IRP_INTERP_SHIFT, 0u);
+          *reinterpret_cast<uint32_t*>(mp + r * kMidPitch) = pack_sat_u8(a1 >> IRP_INTERP_SHIFT, a0 >> IRP_INTERP_SHIFT, hi);
         }
-        __syncthreads();
       }
-    } else {
-      for (int i = threadIdx.x; i < oh * rowwords; i += kResizeThreads)
-        reinterpret_cast<uint32_t*>(mid_t)[i] = reinterpret_cast<const uint32_t*>(src_t)[i];
-      __syncthreads();
     }
+    __syncthreads();
 
-    // ---- stage C: horizontal reduce (reduceh) + normalise + store ----
-    for (int i = threadIdx.x; i < oh * ow; i += kResizeThreads) {
-      const int orow = i / ow, ocol = i - orow * ow;
-      const int o = ox0 + ocol;
-      const uint8_t* rp = mid_t + (size_t)orow * rowbytes;
-      uint32_t v[C];
-      if (hn) {
+    // ---- stage C: reduceh (horizontal) + normalise + store ----
+    {
+      const int xcol = tid & 63, rgh = tid >> 6;  // four row groups
+      if (xcol < ow) {
+        const int o = ox0 + xcol;
+        const int start = J.h.start[o] - sx0a;    // >= 0
+        const int ob = start & 3;
         const int16_t* cf = J.h.coef + (size_t)J.h.phase[o] * kCoefStride;
-        const int base = J.h.start[o] * C - bx0;
-        int acc[C];
+        const int nph = (hn + 3 + 1) >> 1, nwh = (hn + 3 + 3) >> 2;  // uniform bounds over the tile
+        uint32_t cph[kMaxHPairs];
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) acc[ch] = 1 << (IRP_INTERP_SHIFT - 1);
-        for (int k = 0; k < hn; k++) {
-          const int cv = cf[k];
-#pragma unroll
-          for (int ch = 0; ch < C; ch++) acc[ch] += cv * (int)rp[base + k * C + ch];
+        for (int p = 0; p < kMaxHPairs; p++) {
+          const int i0 = 2 * p - ob, i1 = i0 + 1;
+          const uint32_t c0 = (p < nph && i0 >= 0 && i0 < hn) ? (uint16_t)cf[i0] : 0u;
+          const uint32_t c1 = (p < nph && i1 >= 0 && i1 < hn) ? (uint16_t)cf[i1] : 0u;
+          cph[p] = c0 | (c1 << 16);
         }
+        const int rows_per = (oh + 3) >> 2;
+        const int r_begin = rgh * rows_per, r_end = min(oh, r_begin + rows_per);
+        const uint8_t* mbase = mid_t + (start >> 2) * 4;
+        for (int r = r_begin; r < r_end; r++) {
+          uint32_t v[C];
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) v[ch] = fixed_round_u8(acc[ch]);
-      } else {
-        const int base = o * C - bx0;
+          for (int ch = 0; ch < C; ch++) {
+            const uint32_t* mp = reinterpret_cast<const uint32_t*>(mbase + ch * mid_plane + r * kMidPitch);
+            int acc = 1 << (IRP_INTERP_SHIFT - 1);
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) v[ch] = rp[base + ch];
-      }
-      uint8_t* d = J.dst + (size_t)(J.dst_y0 + oy0 + orow) * J.dst_pitch + (size_t)(J.dst_x0 + o) * J.dc;
-      if (C == 4) {  // libvips flatten on black: p * a / 255, integer
-        d[0] = (uint8_t)((v[0] * v[3]) / 255u);
-        d[1] = (uint8_t)((v[1] * v[3]) / 255u);
-        d[2] = (uint8_t)((v[2] * v[3]) / 255u);
-      } else if (C == 1) {
-        if (J.expand_grey) {
-          d[0] = d[1] = d[2] = (uint8_t)v[0];
-        } else {
-          d[0] = (uint8_t)v[0];
+            for (int wv = 0; wv < kMaxHPairs / 2; wv++) {
+              if (wv < nwh) {
+                const uint32_t w = mp[wv];
+                acc = dp2a_lo_s16_u8(cph[2 * wv], w, acc);
+                acc = dp2a_hi_s16_u8(cph[2 * wv + 1], w, acc);
+              }
+            }
+            v[ch] = (uint32_t)min(max(acc >> IRP_INTERP_SHIFT, 0), 255);
+          }
+          uint8_t* d = J.dst + (size_t)(J.dst_y0 + oy0 + r) * J.dst_pitch + (size_t)(J.dst_x0 + o) * J.dc;
+          if (C == 4) {  // libvips flatten on black: p * a / 255, integer
+            d[0] = (uint8_t)((v[0] * v[3]) / 255u);
+            d[1] = (uint8_t)((v[1] * v[3]) / 255u);
+            d[2] = (uint8_t)((v[2] * v[3]) / 255u);
+          } else if (C == 1) {
+            if (J.expand_grey) {
+              d[0] = d[1] = d[2] = (uint8_t)v[0];
+            } else {
+              d[0] = (uint8_t)v[0];
+            }
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) d[ch] = (uint8_t)v[ch];
+          }
         }
-      } else {
-#pragma unroll
-        for (int ch = 0; ch < C; ch++) d[ch] = (uint8_t)v[ch];
       }
     }
     __syncthreads();
