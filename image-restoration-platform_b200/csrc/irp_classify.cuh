@@ -62,18 +62,39 @@ struct ClassifyTables {   // device copies of grey_tables.inc for the chosen lum
   uint32_t inv[4096];
 };
 
-template <int C>
-struct ClassifySmem {          // dynamic shared memory: the pixel tiles
-  uint8_t plane[C][kRows][kPlanePitch];
-  uint8_t grey[kRows][kPlanePitch];
+// ---------------------------------------------------------------------------
+// Shared-memory layout.  Everything is dynamic shared memory, carved at run time so that the
+// randomly indexed tables sit on power-of-two boundaries of the .shared address space: a lookup is
+// then   SHF (byte -> offset) ; LOP3 ((x & mask) | table_base) ; LDS   — no base add.
+//   grey tile | 1 KB-aligned: lutR, lutG, lutB, hist, red | 16 KB-aligned: inv | C plane tiles
+// ---------------------------------------------------------------------------
+constexpr int kTileBytes = kRows * kPlanePitch;
+constexpr int kRedBytes = (kClassifyThreads / 32) * ACC_COUNT * 4;
+
+struct SmemMap {           // .shared-space byte addresses
+  uint32_t grey, lut_r, lut_g, lut_b, hist, red, inv, planes, end;
 };
-// Static shared memory: the linker knows these offsets, so the random LUT reads compile to
-// LDS [R + UR + imm] with no per-access base add.
-struct ClassifyStatic {
-  uint32_t lut[3][256];
-  uint32_t inv[4096];
-  uint32_t hist[256];
-  uint32_t red[kClassifyThreads / 32][ACC_COUNT];
+__host__ __device__ inline SmemMap make_smem_map(uint32_t base, int C) {
+  SmemMap m;
+  m.grey = base;
+  m.lut_r = (base + kTileBytes + 1023u) & ~1023u;
+  m.lut_g = m.lut_r + 1024u;
+  m.lut_b = m.lut_r + 2048u;
+  m.hist = m.lut_r + 3072u;
+  m.red = m.lut_r + 4096u;
+  m.inv = (m.red + kRedBytes + 16383u) & ~16383u;
+  m.planes = m.inv + 16384u;
+  m.end = m.planes + (uint32_t)C * kTileBytes;
+  return m;
+}
+
+template <int C>
+struct Tiles {             // generic pointers into the same dynamic shared memory
+  uint8_t* grey;           // [kRows][kPlanePitch]
+  uint8_t* plane[C];       // [kRows][kPlanePitch] each
+  uint32_t* hist;          // [256]
+  uint32_t* red;           // [warps][ACC_COUNT]
+  uint32_t a_lut_r, a_lut_g, a_lut_b, a_inv, a_hist;  // aligned .shared addresses of the tables
 };
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -83,6 +104,14 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void red_inc_shared(uint32_t addr) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
 
 // dp2a with unsigned 16-bit lanes in a and SIGNED bytes in b (low half of b)
 __device__ __forceinline__ int dp2a_lo_u16_s8(uint32_t a, uint32_t b, int c) {
@@ -91,11 +120,20 @@ __device__ __forceinline__ int dp2a_lo_u16_s8(uint32_t a, uint32_t b, int c) {
   return d;
 }
 
-// grey of one pixel from its three LUT byte offsets (already scaled by 4 is not
-// required: plain indices); returns (inv + low bits): grey sits in bits 24..31
-__device__ __forceinline__ uint32_t grey_top(const ClassifyStatic& s, uint32_t r, uint32_t g, uint32_t b) {
-  uint32_t I = s.lut[0][r] + s.lut[1][g] + s.lut[2][b];
-  return s.inv[I >> 20] + (I & 0xFFFFFu);
+// byte j of a packed word -> byte offset into a 256 x u32 table
+template <int J>
+__device__ __forceinline__ uint32_t byte_off4(uint32_t w) {
+  return J == 0 ? ((w << 2) & 0x3FCu) : ((w >> (8 * J - 2)) & 0x3FCu);
+}
+// integer restatement of libvips colourspace(B_W): returns inv[I >> 20] + (I & 0xFFFFF); grey = top byte
+template <int C>
+__device__ __forceinline__ uint32_t grey_top_off(const Tiles<C>& T, uint32_t ro, uint32_t go, uint32_t bo) {
+  const uint32_t I = lds_u32(ro | T.a_lut_r) + lds_u32(go | T.a_lut_g) + lds_u32(bo | T.a_lut_b);
+  return lds_u32(((I >> 18) & 0x3FFCu) | T.a_inv) + (I & 0xFFFFFu);
+}
+template <int C>
+__device__ __forceinline__ void hist_add_top(const Tiles<C>& T, uint32_t t) {
+  red_inc_shared(((t >> 22) & 0x3FCu) | T.a_hist);
 }
 
 // exact floor(x / 11) for 0 <= x <= 2810  (x = 3*(l+r) + 5*c + 5)
@@ -113,7 +151,7 @@ struct Acc {
 };
 
 template <int C>
-__device__ void flush_acc(ClassifyStatic& st, Acc<C>& a, unsigned long long* gacc, uint32_t* ghist) {
+__device__ void flush_acc(const Tiles<C>& T, Acc<C>& a, unsigned long long* gacc, uint32_t* ghist) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t v[ACC_COUNT];
 #pragma unroll
@@ -129,19 +167,19 @@ __device__ void flush_acc(ClassifyStatic& st, Acc<C>& a, unsigned long long* gac
 #pragma unroll
   for (int i = 0; i < ACC_COUNT; i++) {
     const uint32_t r = __reduce_add_sync(0xffffffffu, v[i]);  // REDUX.SUM: one instruction per value
-    if (lane == 0) st.red[warp][i] = r;
+    if (lane == 0) T.red[warp * ACC_COUNT + i] = r;
   }
   __syncthreads();
   if (threadIdx.x < ACC_COUNT) {
     unsigned long long t = 0;
 #pragma unroll
-    for (int w = 0; w < kClassifyThreads / 32; w++) t += st.red[w][threadIdx.x];
+    for (int w = 0; w < kClassifyThreads / 32; w++) t += T.red[w * ACC_COUNT + threadIdx.x];
     if (t) atomicAdd(&gacc[threadIdx.x], t);
   }
   {
-    const uint32_t hv = st.hist[threadIdx.x];
+    const uint32_t hv = T.hist[threadIdx.x];
     if (hv) atomicAdd(&ghist[threadIdx.x], hv);
-    st.hist[threadIdx.x] = 0;
+    T.hist[threadIdx.x] = 0;
   }
   a.clear();
   __syncthreads();
@@ -149,53 +187,55 @@ __device__ void flush_acc(ClassifyStatic& st, Acc<C>& a, unsigned long long* gac
 
 // ---------------------------------------------------------------------------
 // stage 1, generic item: any channel count, any alignment, image edges.
-// One item = 16 pixels of one tile row.
+// One item = up to 16 pixels of one tile row.
 // ---------------------------------------------------------------------------
 template <int C>
-__device__ __forceinline__ void stage1_slow(ClassifySmem<C>& sm, ClassifyStatic& st, Acc<C>& a, const ImgDev& im, int gy, int xbeg,
-                                            int row, int col0, int npx, bool counted) {
+__device__ __forceinline__ void stage1_slow(const Tiles<C>& T, Acc<C>& a, const ImgDev& im, int gy, int xbeg, int row, int col0,
+                                            int npx, bool counted) {
   const uint8_t* rp = im.px + (size_t)gy * im.pitch;
+  const int o = row * kPlanePitch + col0;
   for (int i = 0; i < npx; i++) {
-    int x = xbeg + i;
-    bool inside = x >= 0 && x < im.w;
-    int xc = min(max(x, 0), im.w - 1);
+    const int x = xbeg + i;
+    const bool inside = x >= 0 && x < im.w;
+    const int xc = min(max(x, 0), im.w - 1);
     uint32_t v[C];
 #pragma unroll
     for (int ch = 0; ch < C; ch++) v[ch] = rp[(size_t)xc * C + ch];
     uint32_t g;
     if constexpr (C >= 3)
-      g = grey_top(st, v[0], v[1], v[2]) >> 24;
+      g = grey_top_off(T, v[0] << 2, v[1] << 2, v[2] << 2) >> 24;
     else
       g = v[0];
 #pragma unroll
-    for (int ch = 0; ch < C; ch++) sm.plane[ch][row][col0 + i] = (uint8_t)v[ch];
-    sm.grey[row][col0 + i] = (uint8_t)g;
+    for (int ch = 0; ch < C; ch++) T.plane[ch][o + i] = (uint8_t)v[ch];
+    T.grey[o + i] = (uint8_t)g;
     if (counted && inside) {
 #pragma unroll
       for (int ch = 0; ch < C; ch++) {
         a.s[ch] += v[ch];
         a.q[ch] += v[ch] * v[ch];
       }
-      atomicAdd(&st.hist[g], 1u);
+      red_inc_shared((g << 2) | T.a_hist);
     }
   }
 }
 
-// stage 1, fast item: C == 3, 48 aligned bytes fully inside the image.
-__device__ __forceinline__ void stage1_fast(ClassifySmem<3>& sm, ClassifyStatic& st, Acc<3>& a, const uint8_t* p, int row,
-                                            int col0, bool counted) {
-  uint4 v0 = ldg_nc_v4(p), v1 = ldg_nc_v4(p + 16), v2 = ldg_nc_v4(p + 32);
-  uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+// stage 1, fast item: C == 3, 48 aligned bytes fully inside the image.  COUNTED = the row belongs to
+// the tile (moments + histogram); halo rows only feed the stencils.
+template <bool COUNTED>
+__device__ __forceinline__ void stage1_fast(const Tiles<3>& T, Acc<3>& a, const uint8_t* p, int row, int col0) {
+  const uint4 v0 = ldg_nc_v4(p), v1 = ldg_nc_v4(p + 16), v2 = ldg_nc_v4(p + 32);
+  const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
   uint32_t R[4], G[4], B[4], Y[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     // w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3
-    uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+    const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
     R[k] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // R0 R1 R2 | R3
     G[k] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // G0 G1 G2 | G3
     B[k] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);  // B0 B1 | B2 B3
   }
-  if (counted) {
+  if (COUNTED) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       a.s[0] = __dp4a(R[k], 0x01010101u, a.s[0]);
@@ -209,18 +249,21 @@ __device__ __forceinline__ void stage1_fast(ClassifySmem<3>& sm, ClassifyStatic&
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     uint32_t t[4];
+    t[0] = grey_top_off(T, byte_off4<0>(R[k]), byte_off4<0>(G[k]), byte_off4<0>(B[k]));
+    t[1] = grey_top_off(T, byte_off4<1>(R[k]), byte_off4<1>(G[k]), byte_off4<1>(B[k]));
+    t[2] = grey_top_off(T, byte_off4<2>(R[k]), byte_off4<2>(G[k]), byte_off4<2>(B[k]));
+    t[3] = grey_top_off(T, byte_off4<3>(R[k]), byte_off4<3>(G[k]), byte_off4<3>(B[k]));
+    if (COUNTED) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      uint32_t r = (R[k] >> (8 * j)) & 0xFFu, g = (G[k] >> (8 * j)) & 0xFFu, b = (B[k] >> (8 * j)) & 0xFFu;
-      t[j] = grey_top(st, r, g, b);
-      if (counted) atomicAdd(&st.hist[t[j] >> 24], 1u);
+      for (int j = 0; j < 4; j++) hist_add_top(T, t[j]);
     }
     Y[k] = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x0073), 0x5410);
   }
-  *reinterpret_cast<uint4*>(&sm.plane[0][row][col0]) = make_uint4(R[0], R[1], R[2], R[3]);
-  *reinterpret_cast<uint4*>(&sm.plane[1][row][col0]) = make_uint4(G[0], G[1], G[2], G[3]);
-  *reinterpret_cast<uint4*>(&sm.plane[2][row][col0]) = make_uint4(B[0], B[1], B[2], B[3]);
-  *reinterpret_cast<uint4*>(&sm.grey[row][col0]) = make_uint4(Y[0], Y[1], Y[2], Y[3]);
+  const int o = row * kPlanePitch + col0;
+  *reinterpret_cast<uint4*>(T.plane[0] + o) = make_uint4(R[0], R[1], R[2], R[3]);
+  *reinterpret_cast<uint4*>(T.plane[1] + o) = make_uint4(G[0], G[1], G[2], G[3]);
+  *reinterpret_cast<uint4*>(T.plane[2] + o) = make_uint4(B[0], B[1], B[2], B[3]);
+  *reinterpret_cast<uint4*>(T.grey + o) = make_uint4(Y[0], Y[1], Y[2], Y[3]);
 }
 
 // ---------------------------------------------------------------------------
@@ -264,7 +307,7 @@ __device__ __forceinline__ uint32_t clip_diff(uint32_t kc, uint32_t nb) {
 // FULL = the tile lies strictly inside the image (x0 + 256 < W and y0 + 32 < H): no lane masks,
 // no row / column validity tests.  Edge tiles take the masked instantiation.
 template <int C, bool FULL>
-__device__ __forceinline__ void stage2(const ClassifySmem<C>& sm, Acc<C>& a, int x0, int y0, int W, int H) {
+__device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int x0, int y0, int W, int H) {
   const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int x = x0 + strip * 4;
   const int r0 = rg * 8;
@@ -277,13 +320,13 @@ __device__ __forceinline__ void stage2(const ClassifySmem<C>& sm, Acc<C>& a, int
   // byte masks for partially valid strips (pairs hold values in bytes 0 and 2)
   const uint32_t mA = nvalid >= 2 ? 0x00FF00FFu : 0x000000FFu;
   const uint32_t mB = nvalid >= 4 ? 0x00FF00FFu : (nvalid == 3 ? 0x000000FFu : 0u);
-  GreyRow up = load_grey_row(&sm.grey[r0][0], strip), cur = load_grey_row(&sm.grey[r0 + 1][0], strip);
+  GreyRow up = load_grey_row(T.grey + r0 * kPlanePitch, strip), cur = load_grey_row(T.grey + (r0 + 1) * kPlanePitch, strip);
   uint32_t prev_t0 = 0;  // E3 > 200 at (grid row, px0), consumed by the row below
   const bool col_boundary = (strip & 1) && (FULL || x + 4 < W);  // px3 | px4 straddle an 8-px column boundary
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     if (!FULL && i >= nrows) break;
-    const GreyRow dn = load_grey_row(&sm.grey[r0 + i + 2][0], strip);
+    const GreyRow dn = load_grey_row(T.grey + (r0 + i + 2) * kPlanePitch, strip);
     const uint32_t boxA = up.hA + cur.hA + dn.hA, boxB = up.hB + cur.hB + dn.hB;
     const uint32_t nineA = cur.cA * 9u, nineB = cur.cB * 9u;
     uint32_t e1A = clip_diff(nineA, boxA), e1B = clip_diff(nineB, boxB);
@@ -346,7 +389,7 @@ __device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
 }
 
 template <int C, bool FULL>
-__device__ __forceinline__ void stage3(const ClassifySmem<C>& sm, Acc<C>& a, int x0, int y0, int W, int H) {
+__device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int x0, int y0, int W, int H) {
   const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int x = x0 + strip * 4;
   const int r0 = rg * 8;
@@ -356,13 +399,14 @@ __device__ __forceinline__ void stage3(const ClassifySmem<C>& sm, Acc<C>& a, int
     nvalid = min(4, W - x);
     nrows = min(8, H - (y0 + r0));
   }
-#pragma unroll 1
+#pragma unroll
   for (int ch = 0; ch < C; ch++) {
-    HRow up = hpass_row(&sm.plane[ch][r0][0], strip), cur = hpass_row(&sm.plane[ch][r0 + 1][0], strip);
+    const uint8_t* pl = T.plane[ch];
+    HRow up = hpass_row(pl + r0 * kPlanePitch, strip), cur = hpass_row(pl + (r0 + 1) * kPlanePitch, strip);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       if (!FULL && i >= nrows) break;
-      const HRow dn = hpass_row(&sm.plane[ch][r0 + i + 2][0], strip);
+      const HRow dn = hpass_row(pl + (r0 + i + 2) * kPlanePitch, strip);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const uint32_t b = div11((up.h[j] + dn.h[j]) * 3u + (cur.h[j] * 5u + 5u));
@@ -383,13 +427,29 @@ __device__ __forceinline__ void stage3(const ClassifySmem<C>& sm, Acc<C>& a, int
 template <int C>
 __global__ void __launch_bounds__(kClassifyThreads, 3)
 classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
-                unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist) {
+                unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist, uint32_t dyn_smem_bytes,
+                int* __restrict__ error_flag) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ ClassifyStatic st;
-  ClassifySmem<C>& sm = *reinterpret_cast<ClassifySmem<C>*>(smem_raw);
-  for (int i = threadIdx.x; i < 3 * 256; i += kClassifyThreads) (&st.lut[0][0])[i] = (&tab->lut[0][0])[i];
-  for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) st.inv[i] = tab->inv[i];
-  st.hist[threadIdx.x] = 0;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const SmemMap map = make_smem_map(sbase, C);
+  if (map.end - sbase > dyn_smem_bytes) {  // the host sized the allocation from a probed base: must agree
+    if (threadIdx.x == 0) atomicExch(error_flag, 1);
+    return;
+  }
+  Tiles<C> T;
+  T.grey = smem_raw + (map.grey - sbase);
+#pragma unroll
+  for (int ch = 0; ch < C; ch++) T.plane[ch] = smem_raw + (map.planes - sbase) + ch * kTileBytes;
+  T.hist = reinterpret_cast<uint32_t*>(smem_raw + (map.hist - sbase));
+  T.red = reinterpret_cast<uint32_t*>(smem_raw + (map.red - sbase));
+  T.a_lut_r = map.lut_r; T.a_lut_g = map.lut_g; T.a_lut_b = map.lut_b; T.a_inv = map.inv; T.a_hist = map.hist;
+  {
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (map.lut_r - sbase));
+    uint32_t* inv = reinterpret_cast<uint32_t*>(smem_raw + (map.inv - sbase));
+    for (int i = threadIdx.x; i < 3 * 256; i += kClassifyThreads) lut[i] = (&tab->lut[0][0])[i];
+    for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) inv[i] = tab->inv[i];
+    T.hist[threadIdx.x] = 0;
+  }
   __syncthreads();
 
   Acc<C> acc;
@@ -400,7 +460,7 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     if (img != cur_img || since_flush >= kFlushTiles) {
       if (cur_img >= 0) {
         const int slot = imgs[cur_img].slot;
-        flush_acc<C>(st, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+        flush_acc<C>(T, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
       }
       cur_img = img;
       since_flush = 0;
@@ -422,33 +482,43 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
       bool fast = false;
       if constexpr (C == 3) {
         if (im.aligned16 && xb + kSegPx <= im.w) {
-          stage1_fast(sm, st, acc, im.px + (size_t)gy * im.pitch + (size_t)xb * 3, row, 16 + seg * kSegPx, counted);
+          const uint8_t* p = im.px + (size_t)gy * im.pitch + (size_t)xb * 3;
+          if (counted)
+            stage1_fast<true>(T, acc, p, row, 16 + seg * kSegPx);
+          else
+            stage1_fast<false>(T, acc, p, row, 16 + seg * kSegPx);
           fast = true;
         }
       }
-      if (!fast) stage1_slow<C>(sm, st, acc, im, gy, xb, row, 16 + seg * kSegPx, kSegPx, counted);
+      if (!fast) stage1_slow<C>(T, acc, im, gy, xb, row, 16 + seg * kSegPx, kSegPx, counted);
     }
     // halo columns: pixel x0-1 (byte 15) and x0+256 (byte 16+256) of every row
     for (int item = threadIdx.x; item < kRows * 2; item += kClassifyThreads) {
       const int row = item >> 1, right = item & 1;
       const int gy = min(max(y0 - 1 + row, 0), im.h - 1);
-      stage1_slow<C>(sm, st, acc, im, gy, right ? x0 + kTileW : x0 - 1, row, right ? 16 + kTileW : 15, 1, false);
+      stage1_slow<C>(T, acc, im, gy, right ? x0 + kTileW : x0 - 1, row, right ? 16 + kTileW : 15, 1, false);
     }
     __syncthreads();
     // ---- stage 2 + 3 ----
     if (x0 + kTileW < im.w && y0 + kTileH < im.h) {
-      stage2<C, true>(sm, acc, x0, y0, im.w, im.h);
-      stage3<C, true>(sm, acc, x0, y0, im.w, im.h);
+      stage2<C, true>(T, acc, x0, y0, im.w, im.h);
+      stage3<C, true>(T, acc, x0, y0, im.w, im.h);
     } else {
-      stage2<C, false>(sm, acc, x0, y0, im.w, im.h);
-      stage3<C, false>(sm, acc, x0, y0, im.w, im.h);
+      stage2<C, false>(T, acc, x0, y0, im.w, im.h);
+      stage3<C, false>(T, acc, x0, y0, im.w, im.h);
     }
     __syncthreads();
   }
   if (cur_img >= 0) {
     const int slot = imgs[cur_img].slot;
-    flush_acc<C>(st, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+    flush_acc<C>(T, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
   }
+}
+
+// the .shared address dynamic shared memory starts at, for a kernel without static shared memory
+__global__ void probe_smem_base_kernel(uint32_t* out) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  if (threadIdx.x == 0) *out = (uint32_t)__cvta_generic_to_shared(smem_raw);
 }
 
 }  // namespace irp

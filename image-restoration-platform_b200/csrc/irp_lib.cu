@@ -74,6 +74,8 @@ struct PlanDev {
   int32_t* start;
   int32_t* phase;
   int16_t* coef;
+  uint32_t* vpairs;
+  uint32_t* hpairs;
   int n;
 };
 
@@ -95,6 +97,9 @@ struct irp_ctx {
   cudaEvent_t ev[6]{};
   irp_timing timing{};
   int occ_classify[5]{};  // CTAs per SM for C = 1, 3, 4
+  uint32_t smem_base = 0; // .shared address where dynamic shared memory starts (probed once)
+  int* d_error_flag = nullptr;
+  int* h_error_flag = nullptr;
 };
 
 namespace {
@@ -278,13 +283,29 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
     pd.phase = (int32_t*)p;
     if ((rc = plan_alloc(ctx, hp.coef.size() * 2, &p))) return rc;
     pd.coef = (int16_t*)p;
+    // coefficient pairs pre-shifted for the kernels: pair p of shift s = (c[2p - s], c[2p + 1 - s])
+    std::vector<uint32_t> vp((size_t)(IRP_PHASES + 1) * 2 * 16, 0), hq((size_t)(IRP_PHASES + 1) * 4 * 16, 0);
+    for (int t = 0; t <= IRP_PHASES; t++) {
+      const int16_t* ci = hp.coef.data() + (size_t)t * kCoefStride;
+      auto tap = [&](int i) -> uint32_t { return (i >= 0 && i < hp.n) ? (uint16_t)ci[i] : 0u; };
+      for (int sft = 0; sft < 2; sft++)
+        for (int k = 0; k < kMaxPairs; k++) vp[((size_t)t * 2 + sft) * 16 + k] = tap(2 * k - sft) | (tap(2 * k + 1 - sft) << 16);
+      for (int sft = 0; sft < 4; sft++)
+        for (int k = 0; k < kMaxHPairs; k++) hq[((size_t)t * 4 + sft) * 16 + k] = tap(2 * k - sft) | (tap(2 * k + 1 - sft) << 16);
+    }
+    if ((rc = plan_alloc(ctx, vp.size() * 4, &p))) return rc;
+    pd.vpairs = (uint32_t*)p;
+    if ((rc = plan_alloc(ctx, hq.size() * 4, &p))) return rc;
+    pd.hpairs = (uint32_t*)p;
+    CK(cudaMemcpy(pd.vpairs, vp.data(), vp.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd.hpairs, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice));
     // synchronous copies: plans are built once per geometry and cached
     CK(cudaMemcpy(pd.start, hp.start.data(), hp.start.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pd.phase, hp.phase.data(), hp.phase.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pd.coef, hp.coef.data(), hp.coef.size() * 2, cudaMemcpyHostToDevice));
     it = ctx->plans.emplace(key, pd).first;
   }
-  *ap = AxisPlan{it->second.start, it->second.phase, it->second.coef, it->second.n, 0};
+  *ap = AxisPlan{it->second.start, it->second.phase, it->second.coef, it->second.vpairs, it->second.hpairs, it->second.n, 0};
   return IRP_OK;
 }
 
@@ -342,7 +363,8 @@ template <int C>
 int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, unsigned long long* d_acc,
                     uint32_t* d_hist) {
   if (!n) return IRP_OK;
-  size_t smem = sizeof(ClassifySmem<C>);
+  const SmemMap map = make_smem_map(ctx->smem_base, C);
+  const size_t smem = map.end - ctx->smem_base;
   int& occ = ctx->occ_classify[C];
   if (!occ) {
     CK(cudaFuncSetAttribute(classify_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -350,7 +372,8 @@ int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, 
     if (occ < 1) return fail(ctx, IRP_ERR_CUDA, "classify kernel does not fit on an SM");
   }
   int grid = std::min(total_tiles, ctx->sm_count * occ);
-  classify_kernel<C><<<grid, kClassifyThreads, smem, ctx->stream>>>(d_imgs, n, total_tiles, ctx->d_tables, d_acc, d_hist);
+  classify_kernel<C><<<grid, kClassifyThreads, smem, ctx->stream>>>(d_imgs, n, total_tiles, ctx->d_tables, d_acc, d_hist,
+                                                                    (uint32_t)smem, ctx->d_error_flag);
   CK(cudaGetLastError());
   ctx->timing.kernel_launches++;
   return IRP_OK;
@@ -398,6 +421,7 @@ int run_classify(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
   if ((rc = launch_classify<3>(ctx, d_imgs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1], d_acc, d_hist))) return rc;
   if ((rc = launch_classify<4>(ctx, d_imgs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2], d_acc, d_hist))) return rc;
   CK(cudaMemcpyAsync(ctx->h_acc.p, ctx->d_acc.p, acc_bytes + hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_error_flag, ctx->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   (void)results;
   return IRP_OK;
 }
@@ -661,6 +685,8 @@ int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* resul
   if (outs && (rc = copy_outputs(ctx, imgs, n, outs, oplans, resize_mode))) return rc;
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   if ((rc = finish_timing(ctx))) return rc;
+  if (results && *ctx->h_error_flag)
+    return fail(ctx, IRP_ERR_CUDA, "classify kernel: shared-memory layout does not fit the probed allocation");
   if (results) finish_classify(ctx, imgs, n, results);
   return IRP_OK;
 }
@@ -721,6 +747,17 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
   e = cudaMemcpy(ctx->d_tables, ht, sizeof(ClassifyTables), cudaMemcpyHostToDevice);
   delete ht;
   if (e != cudaSuccess) return bail("cudaMemcpy(tables)", e);
+  if ((e = cudaMalloc(&ctx->d_error_flag, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc(flag)", e);
+  if ((e = cudaMemset(ctx->d_error_flag, 0, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMemset(flag)", e);
+  if ((e = cudaMallocHost(&ctx->h_error_flag, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMallocHost(flag)", e);
+  ctx->h_error_flag[0] = ctx->h_error_flag[1] = 0;
+  // where does dynamic shared memory start in the .shared window? (the classify kernel aligns its
+  // lookup tables to that address space and has no static shared memory of its own)
+  probe_smem_base_kernel<<<1, 32, 1024, ctx->own_stream>>>(reinterpret_cast<uint32_t*>(ctx->d_error_flag + 1));
+  if ((e = cudaMemcpyAsync(ctx->h_error_flag + 1, ctx->d_error_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->own_stream)) != cudaSuccess)
+    return bail("probe copy", e);
+  if ((e = cudaStreamSynchronize(ctx->own_stream)) != cudaSuccess) return bail("probe_smem_base_kernel", e);
+  ctx->smem_base = (uint32_t)ctx->h_error_flag[1];
   return ctx;
 }
 
@@ -734,6 +771,8 @@ void irp_destroy(irp_ctx* ctx) {
   for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);
+  if (ctx->h_error_flag) cudaFreeHost(ctx->h_error_flag);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }

@@ -40,6 +40,9 @@ struct AxisPlan {            // device pointers into the plan arena
   const int32_t* start;      // [out] first tap (may be < 0 / beyond the edge: clamped)
   const int32_t* phase;      // [out] 0..64
   const int16_t* coef;       // [65][kCoefStride], zero padded
+  // coefficient PAIRS (lo16 = tap 2p - shift, hi16 = tap 2p + 1 - shift), pre-shifted on the host:
+  const uint32_t* vpairs;    // [65][2][16]  shift = window start parity (row pairs are even-aligned)
+  const uint32_t* hpairs;    // [65][4][16]  shift = window start byte offset within its 32-bit word
   int n;                     // taps (1 = identity: coef 4096)
   int pad;
 };
@@ -98,6 +101,82 @@ __device__ __forceinline__ void deinterleave48(const uint4& v0, const uint4& v1,
   }
 }
 
+// reducev for one 4-byte column of one plane over output rows [r_begin, r_end): straight-line code
+// for NPV tap pairs.  vtab row = 13 coefficient pairs (+ pad) and, in word 15, the pair-row byte offset.
+template <int NPV>
+__device__ __forceinline__ void vpass_column(const uint8_t* sp, uint8_t* mp, const uint32_t* vtab, int r_begin, int r_end) {
+  for (int r = r_begin; r < r_end; r++) {
+    const uint32_t* vt = vtab + r * kVtabStride;
+    uint32_t cp[16];
+#pragma unroll
+    for (int q4 = 0; q4 < (NPV + 3) / 4; q4++) {
+      const uint4 c4 = reinterpret_cast<const uint4*>(vt)[q4];
+      cp[4 * q4] = c4.x; cp[4 * q4 + 1] = c4.y; cp[4 * q4 + 2] = c4.z; cp[4 * q4 + 3] = c4.w;
+    }
+    const uint8_t* p = sp + vt[15];
+    uint2 w[NPV];
+#pragma unroll
+    for (int pp = 0; pp < NPV; pp++) w[pp] = *reinterpret_cast<const uint2*>(p + pp * kPairPitch);
+    int a0 = 1 << (IRP_INTERP_SHIFT - 1), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+    for (int pp = 0; pp < NPV; pp++) {
+      a0 = dp2a_lo_s16_u8(cp[pp], w[pp].x, a0);
+      a1 = dp2a_hi_s16_u8(cp[pp], w[pp].x, a1);
+      a2 = dp2a_lo_s16_u8(cp[pp], w[pp].y, a2);
+      a3 = dp2a_hi_s16_u8(cp[pp], w[pp].y, a3);
+    }
+    const uint32_t hi = pack_sat_u8(a3 >> IRP_INTERP_SHIFT, a2 >> IRP_INTERP_SHIFT, 0u);
+    *reinterpret_cast<uint32_t*>(mp + r * kMidPitch) = pack_sat_u8(a1 >> IRP_INTERP_SHIFT, a0 >> IRP_INTERP_SHIFT, hi);
+  }
+}
+
+// reduceh for one output column over rows [r_begin, r_end) and all planes; NWH aligned words per window.
+template <int C, int NWH>
+__device__ __forceinline__ void hpass_column(const uint8_t* mbase, int mid_plane, const uint32_t* hp, uint8_t* d,
+                                             unsigned long long dst_pitch, int r_begin, int r_end, int expand_grey) {
+  uint32_t cph[2 * NWH + 2];
+#pragma unroll
+  for (int q4 = 0; q4 < (2 * NWH + 3) / 4; q4++) {
+    const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(hp) + q4);
+    if (4 * q4 < 2 * NWH + 2) cph[4 * q4] = c4.x;
+    if (4 * q4 + 1 < 2 * NWH + 2) cph[4 * q4 + 1] = c4.y;
+    if (4 * q4 + 2 < 2 * NWH + 2) cph[4 * q4 + 2] = c4.z;
+    if (4 * q4 + 3 < 2 * NWH + 2) cph[4 * q4 + 3] = c4.w;
+  }
+  for (int r = r_begin; r < r_end; r++) {
+    uint32_t v[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) {
+      const uint32_t* mp = reinterpret_cast<const uint32_t*>(mbase + ch * mid_plane + r * kMidPitch);
+      uint32_t w[NWH];
+#pragma unroll
+      for (int wv = 0; wv < NWH; wv++) w[wv] = mp[wv];
+      int acc = 1 << (IRP_INTERP_SHIFT - 1);
+#pragma unroll
+      for (int wv = 0; wv < NWH; wv++) {
+        acc = dp2a_lo_s16_u8(cph[2 * wv], w[wv], acc);
+        acc = dp2a_hi_s16_u8(cph[2 * wv + 1], w[wv], acc);
+      }
+      v[ch] = pack_sat_u8(0, acc >> IRP_INTERP_SHIFT, 0u);
+    }
+    uint8_t* dp = d + (size_t)r * dst_pitch;
+    if (C == 4) {  // libvips flatten on black: p * a / 255, integer
+      dp[0] = (uint8_t)((v[0] * v[3]) / 255u);
+      dp[1] = (uint8_t)((v[1] * v[3]) / 255u);
+      dp[2] = (uint8_t)((v[2] * v[3]) / 255u);
+    } else if (C == 1) {
+      if (expand_grey) {
+        dp[0] = dp[1] = dp[2] = (uint8_t)v[0];
+      } else {
+        dp[0] = (uint8_t)v[0];
+      }
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < C; ch++) dp[ch] = (uint8_t)v[ch];
+    }
+  }
+}
+
 // gather-based orientation (P2); one thread per destination pixel
 template <int C>
 __global__ void orient_kernel(const uint8_t* __restrict__ src, unsigned long long spitch, int w, int h, int orientation,
@@ -148,22 +227,14 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
     uint8_t* src_t = smem;                      // [C][pairrows_max][kPairPitch]
     uint8_t* mid_t = smem + (size_t)C * src_plane;  // [C][kMaxToh][kMidPitch]
 
-    // ---- vertical table: per output row, pair-row offset + coefficient pairs aligned to even rows ----
-    if (tid < oh) {
-      const int o = oy0 + tid;
-      const int s = J.v.start[o];
-      const int se = floordiv(s, 2) * 2, lead = s - se;
-      const int16_t* cf = J.v.coef + (size_t)J.v.phase[o] * kCoefStride;
-      uint32_t* vt = s_vtab + tid * kVtabStride;
-      vt[0] = (uint32_t)(((se - sy0e) >> 1) * kPairPitch);
-      const int npv = (vn + lead + 1) >> 1;
-#pragma unroll
-      for (int p = 0; p < kMaxPairs; p++) {
-        const int i0 = 2 * p - lead, i1 = i0 + 1;
-        const uint32_t c0 = (p < npv && i0 >= 0 && i0 < vn) ? (uint16_t)cf[i0] : 0u;
-        const uint32_t c1 = (p < npv && i1 >= 0 && i1 < vn) ? (uint16_t)cf[i1] : 0u;
-        vt[1 + p] = c0 | (c1 << 16);
-      }
+    // ---- vertical table: per output row, 13 coefficient pairs (even-row aligned) + pair-row offset ----
+    for (int e = tid; e < oh * kVtabStride; e += kResizeThreads) {
+      const int r = e >> 4, k = e & 15;
+      const int o = oy0 + r;
+      const int s0 = J.v.start[o];
+      const int se = floordiv(s0, 2) * 2, lead = s0 - se;
+      s_vtab[e] = k == 15 ? (uint32_t)(((se - sy0e) >> 1) * kPairPitch)
+                          : J.v.vpairs[((size_t)J.v.phase[o] * 2 + lead) * 16 + k];
     }
 
     // ---- stage A: source footprint -> planar, row-pair-interleaved shared tile ----
@@ -222,30 +293,27 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
       const int rg = tid >> 7;                   // two row groups
       const int rows_per = (oh + 1) >> 1;
       const int r_begin = rg * rows_per, r_end = min(oh, r_begin + rows_per);
-      const int npv = (vn + 2) >> 1;             // pairs incl. a possible leading zero
+      const int npv = (vn + 2) >> 1;             // pairs incl. a possible leading zero (uniform)
       const int nwc = (ncols + 3) >> 2;          // word columns in use
       for (int col = tid & 127; col < C * kWordCols; col += 128) {
         const int plane = col / kWordCols, j = col - plane * kWordCols;
         if (j >= nwc) continue;
         const uint8_t* sp = src_t + plane * src_plane + j * 8;
         uint8_t* mp = mid_t + plane * mid_plane + j * 4;
-        for (int r = r_begin; r < r_end; r++) {
-          const uint32_t* vt = s_vtab + r * kVtabStride;
-          const uint8_t* p = sp + vt[0];
-          int a0 = 1 << (IRP_INTERP_SHIFT - 1), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll
-          for (int pp = 0; pp < kMaxPairs; pp++) {
-            if (pp < npv) {
-              const uint2 w = *reinterpret_cast<const uint2*>(p + pp * kPairPitch);
-              const uint32_t cp = vt[1 + pp];
-              a0 = dp2a_lo_s16_u8(cp, w.x, a0);
-              a1 = dp2a_hi_s16_u8(cp, w.x, a1);
-              a2 = dp2a_lo_s16_u8(cp, w.y, a2);
-              a3 = dp2a_hi_s16_u8(cp, w.y, a3);
-            }
-          }
-          const uint32_t hi = pack_sat_u8(a3 >> IRP_INTERP_SHIFT, a2 >> IRP_INTERP_SHIFT, 0u);
-          *reinterpret_cast<uint32_t*>(mp + r * kMidPitch) = pack_sat_u8(a1 >> IRP_INTERP_SHIFT, a0 >> IRP_INTERP_SHIFT, hi);
+        switch (npv) {
+          case 1: vpass_column<1>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 2: vpass_column<2>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 3: vpass_column<3>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 4: vpass_column<4>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 5: vpass_column<5>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 6: vpass_column<6>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 7: vpass_column<7>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 8: vpass_column<8>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 9: vpass_column<9>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 10: vpass_column<10>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 11: vpass_column<11>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 12: vpass_column<12>(sp, mp, s_vtab, r_begin, r_end); break;
+          default: vpass_column<13>(sp, mp, s_vtab, r_begin, r_end); break;
         }
       }
     }
@@ -257,51 +325,21 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
       if (xcol < ow) {
         const int o = ox0 + xcol;
         const int start = J.h.start[o] - sx0a;    // >= 0
-        const int ob = start & 3;
-        const int16_t* cf = J.h.coef + (size_t)J.h.phase[o] * kCoefStride;
-        const int nph = (hn + 3 + 1) >> 1, nwh = (hn + 3 + 3) >> 2;  // uniform bounds over the tile
-        uint32_t cph[kMaxHPairs];
-#pragma unroll
-        for (int p = 0; p < kMaxHPairs; p++) {
-          const int i0 = 2 * p - ob, i1 = i0 + 1;
-          const uint32_t c0 = (p < nph && i0 >= 0 && i0 < hn) ? (uint16_t)cf[i0] : 0u;
-          const uint32_t c1 = (p < nph && i1 >= 0 && i1 < hn) ? (uint16_t)cf[i1] : 0u;
-          cph[p] = c0 | (c1 << 16);
-        }
+        const uint32_t* hp = J.h.hpairs + ((size_t)J.h.phase[o] * 4 + (start & 3)) * 16;
+        const int nwh = (hn + 3 + 3) >> 2;        // words per window once shifted to word alignment (uniform)
         const int rows_per = (oh + 3) >> 2;
         const int r_begin = rgh * rows_per, r_end = min(oh, r_begin + rows_per);
         const uint8_t* mbase = mid_t + (start >> 2) * 4;
-        for (int r = r_begin; r < r_end; r++) {
-          uint32_t v[C];
-#pragma unroll
-          for (int ch = 0; ch < C; ch++) {
-            const uint32_t* mp = reinterpret_cast<const uint32_t*>(mbase + ch * mid_plane + r * kMidPitch);
-            int acc = 1 << (IRP_INTERP_SHIFT - 1);
-#pragma unroll
-            for (int wv = 0; wv < kMaxHPairs / 2; wv++) {
-              if (wv < nwh) {
-                const uint32_t w = mp[wv];
-                acc = dp2a_lo_s16_u8(cph[2 * wv], w, acc);
-                acc = dp2a_hi_s16_u8(cph[2 * wv + 1], w, acc);
-              }
-            }
-            v[ch] = (uint32_t)min(max(acc >> IRP_INTERP_SHIFT, 0), 255);
-          }
-          uint8_t* d = J.dst + (size_t)(J.dst_y0 + oy0 + r) * J.dst_pitch + (size_t)(J.dst_x0 + o) * J.dc;
-          if (C == 4) {  // libvips flatten on black: p * a / 255, integer
-            d[0] = (uint8_t)((v[0] * v[3]) / 255u);
-            d[1] = (uint8_t)((v[1] * v[3]) / 255u);
-            d[2] = (uint8_t)((v[2] * v[3]) / 255u);
-          } else if (C == 1) {
-            if (J.expand_grey) {
-              d[0] = d[1] = d[2] = (uint8_t)v[0];
-            } else {
-              d[0] = (uint8_t)v[0];
-            }
-          } else {
-#pragma unroll
-            for (int ch = 0; ch < C; ch++) d[ch] = (uint8_t)v[ch];
-          }
+        uint8_t* d = J.dst + (size_t)(J.dst_y0 + oy0) * J.dst_pitch + (size_t)(J.dst_x0 + o) * J.dc;
+        const int eg = J.expand_grey;
+        switch (nwh) {
+          case 1: hpass_column<C, 1>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
+          case 2: hpass_column<C, 2>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
+          case 3: hpass_column<C, 3>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
+          case 4: hpass_column<C, 4>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
+          case 5: hpass_column<C, 5>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
+          case 6: hpass_column<C, 6>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
+          default: hpass_column<C, 7>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
         }
       }
     }
