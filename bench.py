@@ -37,7 +37,7 @@ UNIT = "MPix/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
@@ -79,10 +79,17 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -90,16 +97,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e18) + 0.03]
+        window = "timed region"
+        if len(inside) < 2:  # region shorter than the sampling period: fall back to everything under load
+            inside, window = [r for (_, r) in self.rows], "warm-up + timed region"
+        for r in inside:
             if len(r) < 6:
                 continue
             try:
@@ -112,7 +123,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def run_reference(a, rank: int) -> int:
@@ -195,13 +206,14 @@ def main() -> int:
         return eng.analyze_batch(d_in, device_outputs=d_out, raw=True)
 
     # ---- device-resident timing -------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(a.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local_rank)
     k_ms = {"classify_ms": 0.0, "preprocess_ms": 0.0}
     launches = 0
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
@@ -213,6 +225,7 @@ def main() -> int:
             launches += t["kernel_launches"]
         e1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     if world > 1:

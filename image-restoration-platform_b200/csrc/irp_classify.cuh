@@ -472,11 +472,12 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     const int x0 = tx * kTileW, y0 = ty * kTileH;
 
     // ---- stage 1: load, regroup, moments, grey -> shared planar tiles ----
-    for (int item = threadIdx.x; item < kRows * kSegsPerRow; item += kClassifyThreads) {
-      const int row = item / kSegsPerRow, seg = item - row * kSegsPerRow;
+    // core rows (1..32): 512 sixteen-pixel items, exactly two per thread
+    for (int item = threadIdx.x; item < kTileH * kSegsPerRow; item += kClassifyThreads) {
+      const int row = 1 + item / kSegsPerRow, seg = item & (kSegsPerRow - 1);
       const int yy = y0 - 1 + row;
-      const int gy = min(max(yy, 0), im.h - 1);
-      const bool counted = row >= 1 && row <= kTileH && yy < im.h;
+      const int gy = min(yy, im.h - 1);
+      const bool counted = yy < im.h;
       const int xb = x0 + seg * kSegPx;
       if (xb >= im.w + 4) continue;  // right of the image and of every replicate column a strip reads
       bool fast = false;
@@ -492,11 +493,24 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
       }
       if (!fast) stage1_slow<C>(T, acc, im, gy, xb, row, 16 + seg * kSegPx, kSegPx, counted);
     }
-    // halo columns: pixel x0-1 (byte 15) and x0+256 (byte 16+256) of every row
-    for (int item = threadIdx.x; item < kRows * 2; item += kClassifyThreads) {
-      const int row = item >> 1, right = item & 1;
+    // fringe: the two halo rows (2 x 256 px) and the two halo columns (2 x 34 px) as single-pixel jobs
+    // spread over all threads, so no warp carries a third sixteen-pixel item to the barrier
+    for (int f = threadIdx.x; f < 2 * kTileW + 2 * kRows; f += kClassifyThreads) {
+      int row, xq, col;
+      if (f < 2 * kTileW) {
+        row = f < kTileW ? 0 : kRows - 1;
+        const int px = f & (kTileW - 1);
+        xq = x0 + px;
+        col = 16 + px;
+        if (xq >= im.w + 4) continue;
+      } else {
+        const int h = f - 2 * kTileW;
+        row = h >> 1;
+        xq = (h & 1) ? x0 + kTileW : x0 - 1;
+        col = (h & 1) ? 16 + kTileW : 15;
+      }
       const int gy = min(max(y0 - 1 + row, 0), im.h - 1);
-      stage1_slow<C>(T, acc, im, gy, right ? x0 + kTileW : x0 - 1, row, right ? 16 + kTileW : 15, 1, false);
+      stage1_slow<C>(T, acc, im, gy, xq, row, col, 1, false);
     }
     __syncthreads();
     // ---- stage 2 + 3 ----
