@@ -1,0 +1,70 @@
+// Drop-in for server-node/src/services/classifier.js — SOURCE ONLY / UNVERIFIED (no Node here).
+// Same exports, same analyze() key order, same logging and span calls; the six sharp pipelines
+// and the JS reductions are replaced by ONE native call on the decoded pixels.  Container decode
+// stays with sharp (one decode instead of six) until the nvJPEG stage of SURVEY.md §8f lands.
+import { trace, SpanStatusCode } from '@opentelemetry/api';
+import sharp from 'sharp';
+import { createRequire } from 'node:module';
+
+const native = createRequire(import.meta.url)('./build/Release/irp_addon.node');
+const KEYS = ['blur', 'noise', 'lowLight', 'compression', 'scratch', 'fade', 'colorShift'];
+
+const DEGRADATION_TYPES = {
+  blur: 'Motion blur or out-of-focus areas',
+  noise: 'Grain and digital noise',
+  lowLight: 'Underexposed or shadow detail loss',
+  compression: 'JPEG artifacts and quality loss',
+  scratch: 'Physical damage and blemishes',
+  fade: 'Color loss and contrast reduction',
+  colorShift: 'White balance and color cast issues',
+};
+
+let ctx = null;
+
+export class ClassifierService {
+  constructor({ logger, device = Number(process.env.IRP_DEVICE ?? 0) } = {}) {
+    this.logger = logger ?? console;
+    this.device = device;
+  }
+
+  async analyze(imageBuffer) {
+    const span = trace.getTracer('classifier').startSpan('classifier.analyze', {
+      attributes: { 'image.size_bytes': imageBuffer.length, 'classifier.version': '1.0.0-b200' },
+    });
+    try {
+      ctx ??= native.createContext(this.device);
+      const metadata = await sharp(imageBuffer).metadata();
+      const { data, info } = await sharp(imageBuffer).raw().toBuffer({ resolveWithObject: true });
+      const scores = await native.analyzeRaw(ctx, data, info.width, info.height, info.channels, metadata.format === 'jpeg');
+      const analysis = Object.fromEntries(KEYS.map((k, i) => [k, scores[i]]));
+      const topIssues = Object.entries(analysis).filter(([, s]) => s > 0.3).sort((a, b) => b[1] - a[1]).slice(0, 3);
+      span.setAttributes({
+        'image.width': metadata.width, 'image.height': metadata.height, 'image.format': metadata.format,
+        'image.channels': metadata.channels,
+        'classifier.top_issues': topIssues.map(([t, s]) => `${t}:${s.toFixed(2)}`).join(','),
+        'classifier.issue_count': topIssues.length,
+      });
+      this.logger.debug('[classifier] Analysis complete', {
+        topIssues: topIssues.map(([type, score]) => ({ type, score: score.toFixed(2) })),
+        imageSize: `${metadata.width}x${metadata.height}`,
+      });
+      span.setStatus({ code: SpanStatusCode.OK });
+      return analysis;
+    } catch (error) {
+      span.recordException(error);
+      span.setStatus({ code: SpanStatusCode.ERROR, message: error.message });
+      this.logger.error('[classifier] Analysis failed', { error: error.message });
+      throw error;
+    } finally {
+      span.end();
+    }
+  }
+
+  static getDegradationTypes() {
+    return { ...DEGRADATION_TYPES };
+  }
+}
+
+export function createClassifierService(options = {}) {
+  return new ClassifierService(options);
+}
