@@ -54,7 +54,7 @@ class OutDesc(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("classify_ms", C.c_float), ("preprocess_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("chunks", C.c_uint32)]
 
 
 _lib = None

@@ -97,6 +97,10 @@ struct irp_ctx {
   cudaEvent_t ev[6]{};
   irp_timing timing{};
   int occ_classify[5]{};  // CTAs per SM for C = 1, 3, 4
+  cudaStream_t copy_in_stream = nullptr, copy_out_stream = nullptr;  // H2D / D2H of pipelined host batches
+  std::vector<cudaEvent_t> sync_events, timing_events;
+  size_t chunk_bytes = 256u << 20;   // pixels per pipeline chunk of a host-resident batch
+  size_t smem_optin = 0;             // opt-in dynamic shared memory limit of the device
   uint32_t smem_base = 0; // .shared address where dynamic shared memory starts (probed once)
   int* d_error_flag = nullptr;
   int* h_error_flag = nullptr;
@@ -330,15 +334,40 @@ int validate_desc(irp_ctx* ctx, const irp_image_desc& d, int i) {
 struct Staged {  // where each input image lives on the device for this call
   const uint8_t* px;
   size_t pitch;
+  size_t bytes;   // bytes that cross PCIe for this image (0 if device-resident)
 };
 
-// copy host inputs into the device staging buffer (device-resident inputs are used in place)
-int stage_inputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, std::vector<Staged>* st) {
+struct Geo {      // per-image preprocess geometry
+  int wo, ho, dw, dh, dc, ox, oy, o;
+  double f;
+  size_t orient_off, out_off;
+};
+
+struct OutPlan {  // per image: where the kernel writes, and how the result gets to the caller
+  uint8_t* dev;
+  size_t dev_pitch;
+  bool via_stage;
+};
+
+cudaError_t get_event(irp_ctx* ctx, size_t idx, cudaEvent_t* ev, bool timing) {
+  std::vector<cudaEvent_t>& pool = timing ? ctx->timing_events : ctx->sync_events;
+  while (pool.size() <= idx) {
+    cudaEvent_t e;
+    cudaError_t rc = timing ? cudaEventCreate(&e) : cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (rc != cudaSuccess) return rc;
+    pool.push_back(e);
+  }
+  *ev = pool[idx];
+  return cudaSuccess;
+}
+
+// decide where every input lives on the device; host inputs get a slot in the staging arena
+int plan_inputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, std::vector<Staged>* st) {
   st->resize(n);
   size_t total = 0;
   std::vector<size_t> off(n, 0);
   for (int i = 0; i < n; i++) {
-    if (imgs[i].on_device) continue;
+    if (!imgs[i].pixels || imgs[i].on_device) continue;
     size_t pitch = round_up((size_t)imgs[i].width * imgs[i].channels, 16);
     off[i] = total;
     total += round_up(pitch * imgs[i].height, 256);
@@ -346,15 +375,24 @@ int stage_inputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, std::vector<St
   if (total) CK(ctx->d_stage_in.reserve(total + 256));
   for (int i = 0; i < n; i++) {
     const irp_image_desc& d = imgs[i];
-    if (d.on_device) {
-      (*st)[i] = Staged{d.pixels, d.pitch};
+    if (!d.pixels) {
+      (*st)[i] = Staged{nullptr, 0, 0};
+    } else if (d.on_device) {
+      (*st)[i] = Staged{d.pixels, d.pitch, 0};
     } else {
       size_t pitch = round_up((size_t)d.width * d.channels, 16);
-      uint8_t* dst = (uint8_t*)ctx->d_stage_in.p + off[i];
-      CK(cudaMemcpy2DAsync(dst, pitch, d.pixels, d.pitch, (size_t)d.width * d.channels, d.height,
-                           cudaMemcpyHostToDevice, ctx->stream));
-      (*st)[i] = Staged{dst, pitch};
+      (*st)[i] = Staged{(uint8_t*)ctx->d_stage_in.p + off[i], pitch, (size_t)d.width * d.channels * d.height};
     }
+  }
+  return IRP_OK;
+}
+
+int copy_inputs(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int b, int e, cudaStream_t stream) {
+  for (int i = b; i < e; i++) {
+    const irp_image_desc& d = imgs[i];
+    if (!d.pixels || d.on_device) continue;
+    CK(cudaMemcpy2DAsync((void*)st[i].px, st[i].pitch, d.pixels, d.pitch, (size_t)d.width * d.channels, d.height,
+                         cudaMemcpyHostToDevice, stream));
   }
   return IRP_OK;
 }
@@ -367,7 +405,6 @@ int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, 
   const size_t smem = map.end - ctx->smem_base;
   int& occ = ctx->occ_classify[C];
   if (!occ) {
-    CK(cudaFuncSetAttribute(classify_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, classify_kernel<C>, kClassifyThreads, smem));
     if (occ < 1) return fail(ctx, IRP_ERR_CUDA, "classify kernel does not fit on an SM");
   }
@@ -379,21 +416,18 @@ int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, 
   return IRP_OK;
 }
 
-int run_classify(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int n, irp_result* results) {
-  // group by channel count; each group is one launch over all of its tiles
+inline size_t acc_bytes_for(int n) { return round_up(sizeof(unsigned long long) * ACC_COUNT * n, 256); }
+
+// classify images [b, e): their descriptors occupy slots [b, e) of the batch-wide arrays, grouped by
+// channel count; each group is one launch over all of its tiles
+int classify_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int n, int b, int e) {
   const int chans[3] = {1, 3, 4};
-  size_t desc_bytes = round_up(sizeof(ImgDev) * n, 256);
-  size_t acc_bytes = round_up(sizeof(unsigned long long) * ACC_COUNT * n, 256), hist_bytes = sizeof(uint32_t) * 256 * n;
-  CK(ctx->d_desc.reserve(desc_bytes));
-  CK(ctx->h_desc.reserve(desc_bytes));
-  CK(ctx->d_acc.reserve(acc_bytes + hist_bytes));
-  CK(ctx->h_acc.reserve(acc_bytes + hist_bytes));
   ImgDev* h_imgs = (ImgDev*)ctx->h_desc.p;
-  int pos = 0, group_begin[4], group_tiles[3];
+  int pos = b, group_begin[4], group_tiles[3];
   for (int g = 0; g < 3; g++) {
     group_begin[g] = pos;
     int tiles = 0;
-    for (int i = 0; i < n; i++) {
+    for (int i = b; i < e; i++) {
       if (imgs[i].channels != chans[g]) continue;
       ImgDev& d = h_imgs[pos++];
       d.px = st[i].px;
@@ -411,26 +445,21 @@ int run_classify(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     group_tiles[g] = tiles;
   }
   group_begin[3] = pos;
-  CK(cudaMemcpyAsync(ctx->d_desc.p, h_imgs, sizeof(ImgDev) * n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_acc.p, 0, acc_bytes + hist_bytes, ctx->stream));
+  ImgDev* d_imgs = (ImgDev*)ctx->d_desc.p;
+  CK(cudaMemcpyAsync(d_imgs + b, h_imgs + b, sizeof(ImgDev) * (e - b), cudaMemcpyHostToDevice, ctx->stream));
   unsigned long long* d_acc = (unsigned long long*)ctx->d_acc.p;
-  uint32_t* d_hist = (uint32_t*)((char*)ctx->d_acc.p + acc_bytes);
-  const ImgDev* d_imgs = (const ImgDev*)ctx->d_desc.p;
+  uint32_t* d_hist = (uint32_t*)((char*)ctx->d_acc.p + acc_bytes_for(n));
   int rc;
   if ((rc = launch_classify<1>(ctx, d_imgs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0], d_acc, d_hist))) return rc;
   if ((rc = launch_classify<3>(ctx, d_imgs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1], d_acc, d_hist))) return rc;
   if ((rc = launch_classify<4>(ctx, d_imgs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2], d_acc, d_hist))) return rc;
-  CK(cudaMemcpyAsync(ctx->h_acc.p, ctx->d_acc.p, acc_bytes + hist_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_error_flag, ctx->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  (void)results;
   return IRP_OK;
 }
 
 // after the stream has been synchronised: integer moments -> irp_result
 void finish_classify(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results) {
-  size_t acc_bytes = round_up(sizeof(unsigned long long) * ACC_COUNT * n, 256);
   const unsigned long long* acc = (const unsigned long long*)ctx->h_acc.p;
-  const uint32_t* hist = (const uint32_t*)((const char*)ctx->h_acc.p + acc_bytes);
+  const uint32_t* hist = (const uint32_t*)((const char*)ctx->h_acc.p + acc_bytes_for(n));
   for (int i = 0; i < n; i++) {
     irp_result& r = results[i];
     memset(&r, 0, sizeof r);
@@ -455,12 +484,6 @@ void finish_classify(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result
   }
 }
 
-struct OutPlan {  // per image: where the kernel writes, and how the result gets to the caller
-  uint8_t* dev;
-  size_t dev_pitch;
-  bool via_stage;
-};
-
 // output tile: toh = 32 rows; tow = the widest of 64/32/16/8 whose source window (plus the 16-pixel
 // alignment slack of the vector-load path) fits the kSrcCols columns a shared tile holds
 void choose_tile(double f, int nv, int nh, int C, int* tow, int* toh, int* pairrows_max) {
@@ -480,7 +503,7 @@ int launch_resize(irp_ctx* ctx, const ResizeJob* d_jobs, const ResizeJob* h_jobs
   for (int i = 0; i < n; i++)
     smem = std::max(smem, (size_t)C * h_jobs[i].pairrows_max * kPairPitch + (size_t)C * kMaxToh * kMidPitch + 32);
   smem = round_up(smem, 16);
-  CK(cudaFuncSetAttribute(resize_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > ctx->smem_optin) return fail(ctx, IRP_ERR_CUDA, "resize tile needs %zu bytes of shared memory", smem);
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, resize_kernel<C>, kResizeThreads, smem));
   if (occ < 1) return fail(ctx, IRP_ERR_CUDA, "resize kernel does not fit on an SM (%zu bytes smem)", smem);
@@ -501,26 +524,24 @@ int launch_orient(irp_ctx* ctx, const uint8_t* src, size_t spitch, int w, int h,
   return IRP_OK;
 }
 
-// mode 0: preprocess (imagePreprocess.js), mode 1: fusion canvas
-int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int n, irp_out_desc* outs, int mode,
-               std::vector<OutPlan>* oplans) {
+// geometry, capacity checks and staging slots for every output. mode 0: preprocess, mode 1: fusion canvas
+int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* outs, int mode, std::vector<Geo>* geo,
+                 std::vector<OutPlan>* oplans) {
   oplans->assign(n, OutPlan{nullptr, 0, false});
-  // pass 1: geometry, capacity checks, staging sizes
-  struct Geo { int wo, ho, dw, dh, dc, ox, oy; double f; size_t orient_off, out_off; };
-  std::vector<Geo> geo(n);
+  geo->assign(n, Geo{});
   size_t orient_total = 0, out_total = 0;
   for (int i = 0; i < n; i++) {
-    if (mode == 1 && !imgs[i].pixels) continue;  // unused fusion slot
+    if (!imgs[i].pixels) continue;  // unused fusion slot
     const irp_image_desc& d = imgs[i];
-    Geo& g = geo[i];
-    int o = (d.exif_orientation >= 1 && d.exif_orientation <= 8) ? d.exif_orientation : 1;
-    orient_dims(d.width, d.height, o, &g.wo, &g.ho);
+    Geo& g = (*geo)[i];
+    g.o = (d.exif_orientation >= 1 && d.exif_orientation <= 8) ? d.exif_orientation : 1;
+    orient_dims(d.width, d.height, g.o, &g.wo, &g.ho);
     g.ox = g.oy = 0;
     if (mode == 0) {
-      preprocess_dims(d.width, d.height, o, &g.dw, &g.dh, &g.f);
+      preprocess_dims(d.width, d.height, g.o, &g.dw, &g.dh, &g.f);
       g.dc = d.channels == 1 ? 1 : 3;
     } else {
-      fusion_dims(d.width, d.height, o, &g.dw, &g.dh, &g.ox, &g.oy, &g.f);
+      fusion_dims(d.width, d.height, g.o, &g.dw, &g.dh, &g.ox, &g.oy, &g.f);
       g.dc = 3;
     }
     if (g.f >= 4.0) return fail(ctx, IRP_ERR_UNSUPPORTED, "image %d: shrink %.3f >= 4 needs libvips' box pre-shrink (not implemented)", i, g.f);
@@ -535,7 +556,7 @@ int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Stage
     od.width = out_w;
     od.height = out_h;
     od.channels = g.dc;
-    if (o != 1) {
+    if (g.o != 1) {
       g.orient_off = orient_total;
       orient_total += round_up(round_up((size_t)g.wo * d.channels, 16) * g.ho, 256);
     }
@@ -546,31 +567,44 @@ int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Stage
   }
   if (orient_total) CK(ctx->d_orient.reserve(orient_total));
   if (out_total) CK(ctx->d_stage_out.reserve(out_total));
-  size_t job_bytes = sizeof(ResizeJob) * n;
-  CK(ctx->d_jobs.reserve(job_bytes));
-  CK(ctx->h_jobs.reserve(job_bytes));
+  for (int i = 0; i < n; i++) {
+    if (!imgs[i].pixels) continue;
+    const Geo& g = (*geo)[i];
+    const irp_out_desc& od = outs[i];
+    OutPlan& op = (*oplans)[i];
+    if (od.on_device) {
+      op = OutPlan{od.pixels, od.pitch ? od.pitch : (size_t)od.width * g.dc, false};
+    } else {
+      op = OutPlan{(uint8_t*)ctx->d_stage_out.p + g.out_off, (size_t)od.width * g.dc, true};
+    }
+  }
+  return IRP_OK;
+}
+
+// orient + resize images [b, e); job slots [b, e) of the batch-wide arrays
+int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, const std::vector<Geo>& geo,
+                 const std::vector<OutPlan>& oplans, irp_out_desc* outs, int mode, int b, int e) {
   ResizeJob* h_jobs = (ResizeJob*)ctx->h_jobs.p;
   const int chans[3] = {1, 3, 4};
-  int pos = 0, group_begin[4], group_tiles[3];
+  int pos = b, group_begin[4], group_tiles[3];
   for (int gi = 0; gi < 3; gi++) {
     group_begin[gi] = pos;
     int tiles = 0;
-    for (int i = 0; i < n; i++) {
-      if (mode == 1 && !imgs[i].pixels) continue;
+    for (int i = b; i < e; i++) {
+      if (!imgs[i].pixels) continue;
       const irp_image_desc& d = imgs[i];
       if (d.channels != chans[gi]) continue;
       const Geo& g = geo[i];
-      int o = (d.exif_orientation >= 1 && d.exif_orientation <= 8) ? d.exif_orientation : 1;
       ResizeJob& J = h_jobs[pos++];
       memset(&J, 0, sizeof J);
-      if (o != 1) {
+      if (g.o != 1) {
         uint8_t* op = (uint8_t*)ctx->d_orient.p + g.orient_off;
         size_t opitch = round_up((size_t)g.wo * d.channels, 16);
         int rc;
         switch (d.channels) {
-          case 1: rc = launch_orient<1>(ctx, st[i].px, st[i].pitch, d.width, d.height, o, op, opitch, g.wo, g.ho); break;
-          case 3: rc = launch_orient<3>(ctx, st[i].px, st[i].pitch, d.width, d.height, o, op, opitch, g.wo, g.ho); break;
-          default: rc = launch_orient<4>(ctx, st[i].px, st[i].pitch, d.width, d.height, o, op, opitch, g.wo, g.ho); break;
+          case 1: rc = launch_orient<1>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
+          case 3: rc = launch_orient<3>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
+          default: rc = launch_orient<4>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
         }
         if (rc) return rc;
         J.src = op;
@@ -579,20 +613,10 @@ int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Stage
         J.src = st[i].px;
         J.src_pitch = st[i].pitch;
       }
-      irp_out_desc& od = outs[i];
-      int out_w = od.width;
-      OutPlan& op = (*oplans)[i];
-      if (od.on_device) {
-        op.dev = od.pixels;
-        op.dev_pitch = od.pitch ? od.pitch : (size_t)out_w * g.dc;
-        op.via_stage = false;
-      } else {
-        op.dev = (uint8_t*)ctx->d_stage_out.p + g.out_off;
-        op.dev_pitch = (size_t)out_w * g.dc;
-        op.via_stage = true;
-      }
+      const irp_out_desc& od = outs[i];
+      const OutPlan& op = oplans[i];
       if (mode == 1)  // black pad: clear the whole canvas, the tiles then write the image once
-        CK(cudaMemset2DAsync(op.dev, op.dev_pitch, 0, (size_t)out_w * g.dc, od.height, ctx->stream));
+        CK(cudaMemset2DAsync(op.dev, op.dev_pitch, 0, (size_t)od.width * g.dc, od.height, ctx->stream));
       J.dst = op.dev;
       J.dst_pitch = op.dev_pitch;
       J.sw = g.wo;
@@ -617,8 +641,9 @@ int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Stage
     group_tiles[gi] = tiles;
   }
   group_begin[3] = pos;
-  CK(cudaMemcpyAsync(ctx->d_jobs.p, h_jobs, sizeof(ResizeJob) * pos, cudaMemcpyHostToDevice, ctx->stream));
-  const ResizeJob* d_jobs = (const ResizeJob*)ctx->d_jobs.p;
+  if (pos == b) return IRP_OK;
+  ResizeJob* d_jobs = (ResizeJob*)ctx->d_jobs.p;
+  CK(cudaMemcpyAsync(d_jobs + b, h_jobs + b, sizeof(ResizeJob) * (pos - b), cudaMemcpyHostToDevice, ctx->stream));
   int rc;
   if ((rc = launch_resize<1>(ctx, d_jobs + group_begin[0], h_jobs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0]))) return rc;
   if ((rc = launch_resize<3>(ctx, d_jobs + group_begin[1], h_jobs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1]))) return rc;
@@ -626,31 +651,23 @@ int run_resize(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Stage
   return IRP_OK;
 }
 
-int copy_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* outs, const std::vector<OutPlan>& oplans,
-                 int mode) {
-  for (int i = 0; i < n; i++) {
-    if (mode == 1 && !imgs[i].pixels) continue;
-    if (!oplans[i].via_stage) continue;
+int copy_outputs(irp_ctx* ctx, const irp_image_desc* imgs, irp_out_desc* outs, const std::vector<OutPlan>& oplans, int b, int e,
+                 cudaStream_t stream) {
+  for (int i = b; i < e; i++) {
+    if (!imgs[i].pixels || !oplans[i].via_stage) continue;
     irp_out_desc& od = outs[i];
     size_t tight = (size_t)od.width * od.channels;
     CK(cudaMemcpy2DAsync(od.pixels, od.pitch ? od.pitch : tight, oplans[i].dev, oplans[i].dev_pitch, tight, od.height,
-                         cudaMemcpyDeviceToHost, ctx->stream));
+                         cudaMemcpyDeviceToHost, stream));
   }
   return IRP_OK;
 }
 
-int finish_timing(irp_ctx* ctx) {
-  CK(cudaStreamSynchronize(ctx->stream));
-  float ms;
-  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.h2d_ms = ms;
-  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing.classify_ms = ms;
-  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.preprocess_ms = ms;
-  cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.d2h_ms = ms;
-  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->timing.total_ms = ms;
-  return IRP_OK;
-}
-
-// the one driver behind classify / preprocess / analyze / fusion
+// The one driver behind classify / preprocess / analyze / fusion.
+// Host-resident batches are cut into chunks (~256 MB of pixels) and pipelined over three streams:
+// H2D of chunk c+1, the kernels of chunk c and the D2H of chunk c-1 overlap, so the call is bound by
+// the slower PCIe direction rather than by the sum of copies and kernels.  Device-resident batches
+// are one chunk: one launch per kernel and channel count.
 int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode) {
   if (!ctx) return IRP_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
@@ -658,33 +675,108 @@ int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* resul
   if (n < 0 || (n > 0 && !imgs)) return fail(ctx, IRP_ERR_BAD_ARG, "bad batch arguments");
   if (n == 0) return IRP_OK;
   CK(cudaSetDevice(ctx->device));
+  int rc;
   for (int i = 0; i < n; i++) {
     if (resize_mode == 1 && !imgs[i].pixels) continue;
-    int rc = validate_desc(ctx, imgs[i], i);
-    if (rc) return rc;
+    if ((rc = validate_desc(ctx, imgs[i], i))) return rc;
   }
   ctx->timing = irp_timing{};
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   std::vector<Staged> st;
-  std::vector<irp_image_desc> tmp;
-  const irp_image_desc* use = imgs;
-  if (resize_mode == 1) {  // staging needs valid descriptors: give unused slots zero size
-    tmp.assign(imgs, imgs + n);
-    for (auto& d : tmp)
-      if (!d.pixels) { d.on_device = 1; d.width = d.height = 0; }
-    use = tmp.data();
-  }
-  int rc = stage_inputs(ctx, use, n, &st);
-  if (rc) return rc;
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  if (results && (rc = run_classify(ctx, imgs, st, n, results))) return rc;
-  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  std::vector<Geo> geo;
   std::vector<OutPlan> oplans;
-  if (outs && (rc = run_resize(ctx, imgs, st, n, outs, resize_mode, &oplans))) return rc;
-  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  if (outs && (rc = copy_outputs(ctx, imgs, n, outs, oplans, resize_mode))) return rc;
+  if ((rc = plan_inputs(ctx, imgs, n, &st))) return rc;
+  if (outs && (rc = plan_outputs(ctx, imgs, n, outs, resize_mode, &geo, &oplans))) return rc;
+  if (results) {
+    CK(ctx->d_desc.reserve(sizeof(ImgDev) * n));
+    CK(ctx->h_desc.reserve(sizeof(ImgDev) * n));
+    CK(ctx->d_acc.reserve(acc_bytes_for(n) + sizeof(uint32_t) * 256 * n));
+    CK(ctx->h_acc.reserve(acc_bytes_for(n) + sizeof(uint32_t) * 256 * n));
+  }
+  if (outs) {
+    CK(ctx->d_jobs.reserve(sizeof(ResizeJob) * n));
+    CK(ctx->h_jobs.reserve(sizeof(ResizeJob) * n));
+  }
+  // chunk boundaries
+  std::vector<int> cuts{0};
+  {
+    bool any_host = false;
+    for (int i = 0; i < n; i++) any_host |= st[i].bytes > 0 || (outs && imgs[i].pixels && oplans[i].via_stage);
+    if (any_host) {
+      size_t acc = 0;
+      for (int i = 0; i < n; i++) {
+        acc += st[i].bytes + (outs && imgs[i].pixels && oplans[i].via_stage ? (size_t)outs[i].width * outs[i].height * outs[i].channels : 0);
+        if (acc >= ctx->chunk_bytes && i + 1 < n) {
+          cuts.push_back(i + 1);
+          acc = 0;
+        }
+      }
+    }
+    cuts.push_back(n);
+  }
+  const int nchunks = (int)cuts.size() - 1;
+  const bool piped = nchunks > 1;
+  cudaStream_t s_in = piped ? ctx->copy_in_stream : ctx->stream, s_out = piped ? ctx->copy_out_stream : ctx->stream;
+
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (piped) {  // the copy streams must not start before work already queued on the caller's stream
+    CK(cudaStreamWaitEvent(s_in, ctx->ev[0], 0));
+    CK(cudaStreamWaitEvent(s_out, ctx->ev[0], 0));
+  }
+  if (results) CK(cudaMemsetAsync(ctx->d_acc.p, 0, acc_bytes_for(n) + sizeof(uint32_t) * 256 * n, ctx->stream));
+  for (int c = 0; c < nchunks; c++) {
+    const int b = cuts[c], e = cuts[c + 1];
+    cudaEvent_t ev_in, ev_done, t0, t1, t2;
+    if ((rc = copy_inputs(ctx, imgs, st, b, e, s_in))) return rc;
+    if (piped) {
+      CK(get_event(ctx, 2 * c, &ev_in, false));
+      CK(cudaEventRecord(ev_in, s_in));
+      CK(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+    }
+    CK(get_event(ctx, 3 * c, &t0, true));
+    CK(get_event(ctx, 3 * c + 1, &t1, true));
+    CK(get_event(ctx, 3 * c + 2, &t2, true));
+    CK(cudaEventRecord(t0, ctx->stream));
+    if (results && (rc = classify_range(ctx, imgs, st, n, b, e))) return rc;
+    CK(cudaEventRecord(t1, ctx->stream));
+    if (outs && (rc = resize_range(ctx, imgs, st, geo, oplans, outs, resize_mode, b, e))) return rc;
+    CK(cudaEventRecord(t2, ctx->stream));
+    if (piped) {
+      CK(get_event(ctx, 2 * c + 1, &ev_done, false));
+      CK(cudaEventRecord(ev_done, ctx->stream));
+      CK(cudaStreamWaitEvent(s_out, ev_done, 0));
+    }
+    if (outs && (rc = copy_outputs(ctx, imgs, outs, oplans, b, e, s_out))) return rc;
+  }
+  if (results) {
+    CK(cudaMemcpyAsync(ctx->h_acc.p, ctx->d_acc.p, acc_bytes_for(n) + sizeof(uint32_t) * 256 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_error_flag, ctx->d_error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (piped) {  // join the output stream back into the caller's stream
+    CK(cudaEventRecord(ctx->ev[5], s_out));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[5], 0));
+  }
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-  if ((rc = finish_timing(ctx))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  {
+    float ms = 0, sum_c = 0, sum_p = 0;
+    for (int c = 0; c < nchunks; c++) {
+      cudaEventElapsedTime(&ms, ctx->timing_events[3 * c], ctx->timing_events[3 * c + 1]);
+      sum_c += ms;
+      cudaEventElapsedTime(&ms, ctx->timing_events[3 * c + 1], ctx->timing_events[3 * c + 2]);
+      sum_p += ms;
+    }
+    ctx->timing.classify_ms = sum_c;
+    ctx->timing.preprocess_ms = sum_p;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
+    ctx->timing.total_ms = ms;
+    if (!piped) {
+      cudaEventElapsedTime(&ms, ctx->ev[0], ctx->timing_events[0]);
+      ctx->timing.h2d_ms = ms;
+      cudaEventElapsedTime(&ms, ctx->timing_events[2], ctx->ev[4]);
+      ctx->timing.d2h_ms = ms;
+    }
+    ctx->timing.chunks = (uint32_t)nchunks;
+  }
   if (results && *ctx->h_error_flag)
     return fail(ctx, IRP_ERR_CUDA, "classify kernel: shared-memory layout does not fit the probed allocation");
   if (results) finish_classify(ctx, imgs, n, results);
@@ -735,6 +827,9 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   ctx->stream = ctx->own_stream;
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_in_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_out_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if (ctx->opts.staging_bytes) ctx->chunk_bytes = ctx->opts.staging_bytes;
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   ClassifyTables* ht = new ClassifyTables();
@@ -758,6 +853,14 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
     return bail("probe copy", e);
   if ((e = cudaStreamSynchronize(ctx->own_stream)) != cudaSuccess) return bail("probe_smem_base_kernel", e);
   ctx->smem_base = (uint32_t)ctx->h_error_flag[1];
+  // The dynamic shared-memory attribute is per function and process-wide: raise it once to the
+  // device's opt-in limit instead of tracking per-context maxima.
+  ctx->smem_optin = prop.sharedMemPerBlockOptin - 4096;  // leave room for the kernels' small static arrays
+  const void* kernels[6] = {(const void*)classify_kernel<1>, (const void*)classify_kernel<3>, (const void*)classify_kernel<4>,
+                            (const void*)resize_kernel<1>,   (const void*)resize_kernel<3>,   (const void*)resize_kernel<4>};
+  for (const void* k : kernels)
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(max dynamic shared memory)", e);
   return ctx;
 }
 
@@ -767,6 +870,10 @@ void irp_destroy(irp_ctx* ctx) {
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->sync_events) cudaEventDestroy(ev);
+  for (auto& ev : ctx->timing_events) cudaEventDestroy(ev);
+  if (ctx->copy_in_stream) cudaStreamDestroy(ctx->copy_in_stream);
+  if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
   for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs}) b->release();
   for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);

@@ -104,7 +104,7 @@ class Engine:
     def timing(self) -> dict:
         t = _ffi.Timing()
         self._check(self._lib.irp_get_timing(self._ctx, C.byref(t)))
-        return {k: getattr(t, k) for k, _ in _ffi.Timing._fields_ if k != "reserved"}
+        return {k: getattr(t, k) for k, _ in _ffi.Timing._fields_}
 
     def synchronize(self) -> None:
         self._check(self._lib.irp_synchronize(self._ctx))

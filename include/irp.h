@@ -63,7 +63,7 @@ typedef struct irp_opts {
   int32_t luma_mode;    /* IRP_LUMA_*                                   */
   int32_t coef_mode;    /* IRP_COEF_*                                   */
   int32_t reserved0;
-  uint64_t staging_bytes; /* pinned + device staging ring for host inputs; 0 = default */
+  uint64_t staging_bytes; /* pixels per pipeline chunk of a host-resident batch; 0 = 256 MiB */
 } irp_opts;
 
 typedef struct irp_image_desc {
@@ -99,11 +99,12 @@ typedef struct irp_out_desc {
 } irp_out_desc;
 
 /* per-call device timings of the last completed call on this context (ms, CUDA events
- * on the launch stream). */
+ * on the launch stream).  For a pipelined (chunks > 1) call classify_ms / preprocess_ms are
+ * sums over chunks and h2d_ms / d2h_ms are 0: the copies overlap the kernels. */
 typedef struct irp_timing {
   float h2d_ms, classify_ms, preprocess_ms, d2h_ms, total_ms;
   uint32_t kernel_launches; /* kernels of this library launched by the call */
-  uint32_t reserved;
+  uint32_t chunks;          /* pipeline chunks the batch was cut into (1 = not pipelined) */
 } irp_timing;
 
 /* ---- library / context ------------------------------------------------- */
