@@ -513,6 +513,20 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
       stage1_slow<C>(T, acc, im, gy, xq, row, col, 1, false);
     }
     __syncthreads();
+    // ---- L2 prefetch of this CTA's next tile (same image only): 34 rows x 6 lines of 128 bytes ----
+    {
+      const int tn = t + (int)gridDim.x;
+      if (tn < im.tiles_x * im.tiles_y && threadIdx.x < kRows * 6) {
+        const int tyn = tn / im.tiles_x, txn = tn - tyn * im.tiles_x;
+        const int row = threadIdx.x / 6, l = threadIdx.x - row * 6;
+        const int gy = min(max(tyn * kTileH - 1 + row, 0), im.h - 1);
+        const long long off = (long long)txn * kTileW * C + l * 128;
+        if (off < (long long)im.w * C) {
+          const uint8_t* pp = im.px + (size_t)gy * im.pitch + off;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+        }
+      }
+    }
     // ---- stage 2 + 3 ----
     if (x0 + kTileW < im.w && y0 + kTileH < im.h) {
       stage2<C, true>(T, acc, x0, y0, im.w, im.h);

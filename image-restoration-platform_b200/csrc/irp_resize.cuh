@@ -205,11 +205,19 @@ __global__ void __launch_bounds__(kResizeThreads)
 resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(16) uint32_t s_vtab[kMaxToh * kVtabStride];
+  __shared__ __align__(16) ResizeJob s_job;   // the current job, so its fields are LDS not LDG
   const int tid = threadIdx.x;
-  int ji = 0;
+  int ji = 0, loaded = -1;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     while (ji + 1 < n_jobs && tile >= jobs[ji + 1].tile_base) ji++;
-    const ResizeJob& J = jobs[ji];
+    if (ji != loaded) {  // uniform: every thread sees the same tile sequence
+      __syncthreads();
+      const uint32_t* src32 = reinterpret_cast<const uint32_t*>(jobs + ji);
+      for (int k = tid; k < (int)(sizeof(ResizeJob) / 4); k += kResizeThreads) reinterpret_cast<uint32_t*>(&s_job)[k] = src32[k];
+      loaded = ji;
+      __syncthreads();
+    }
+    const ResizeJob& J = s_job;
     const int t = tile - J.tile_base;
     const int ty = t / J.tiles_x, tx = t - ty * J.tiles_x;
     const int ox0 = tx * J.tow, oy0 = ty * J.toh;
@@ -217,10 +225,10 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
     const int vn = J.v.n, hn = J.h.n;
     const int sy0 = J.v.start[oy0], sy1 = J.v.start[oy0 + oh - 1] + vn;  // [sy0, sy1) source rows, unclamped
     const int sx0 = J.h.start[ox0], sx1 = J.h.start[ox0 + ow - 1] + hn;  // [sx0, sx1) source columns, unclamped
-    const int sy0e = floordiv(sy0, 2) * 2;                                // pair-row origin (even)
+    const int sy0e = sy0 & ~1;                                                                            // pair-row origin (even)
     const int npairrows = (sy1 - sy0e + 1) >> 1;
     const bool fast_img = (C == 3) && J.aligned16;
-    const int sx0a = fast_img ? floordiv(sx0, 16) * 16 : sx0;             // column origin
+    const int sx0a = fast_img ? (sx0 & ~15) : sx0;                         // column origin
     const int ncols = sx1 - sx0a;                                         // <= kSrcCols (host guarantees)
     const int src_plane = J.pairrows_max * kPairPitch;
     const int mid_plane = kMaxToh * kMidPitch;
@@ -232,7 +240,7 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
       const int r = e >> 4, k = e & 15;
       const int o = oy0 + r;
       const int s0 = J.v.start[o];
-      const int se = floordiv(s0, 2) * 2, lead = s0 - se;
+      const int se = s0 & ~1, lead = s0 & 1;
       s_vtab[e] = k == 15 ? (uint32_t)(((se - sy0e) >> 1) * kPairPitch)
                           : J.v.vpairs[((size_t)J.v.phase[o] * 2 + lead) * 16 + k];
     }
@@ -241,8 +249,9 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
     {
       const int nchunks = (ncols + 15) >> 4;
       const int nitems = npairrows * nchunks;
+      const uint32_t inv_chunks = 65536u / (uint32_t)nchunks + 1u;  // exact for item < 65536 / nchunks... (items <= ~1300)
       for (int item = tid; item < nitems; item += kResizeThreads) {
-        const int q = item / nchunks, k = item - q * nchunks;
+        const int q = (int)(((uint32_t)item * inv_chunks) >> 16), k = item - q * nchunks;
         const int ra = min(max(sy0e + 2 * q, 0), J.sh - 1), rb = min(max(sy0e + 2 * q + 1, 0), J.sh - 1);
         const uint8_t* pa = J.src + (size_t)ra * J.src_pitch;
         const uint8_t* pb = J.src + (size_t)rb * J.src_pitch;
@@ -287,6 +296,26 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
       }
     }
     __syncthreads();
+
+    // ---- L2 prefetch of this CTA's next tile (same job only), so its stage A finds the lines in L2 ----
+    {
+      const int tn = t + (int)gridDim.x;
+      if (tn < J.tiles_x * J.tiles_y) {
+        const int tyn = tn / J.tiles_x, txn = tn - tyn * J.tiles_x;
+        const int oxn = txn * J.tow, oyn = tyn * J.toh;
+        const int ohn = min(J.toh, J.dh - oyn), own = min(J.tow, J.dw - oxn);
+        const int ya = J.v.start[oyn], yb = J.v.start[oyn + ohn - 1] + vn;
+        const int xa = max(J.h.start[oxn], 0) * C, xb = min(J.h.start[oxn + own - 1] + hn, J.sw) * C;
+        const int lines = ((xb - (xa & ~127)) + 127) >> 7;   // 128-byte lines per row
+        const int total = (yb - ya) * lines;
+        for (int e = tid; e < total; e += kResizeThreads) {
+          const int r = e / lines, l = e - r * lines;
+          const int gy = min(max(ya + r, 0), J.sh - 1);
+          const uint8_t* pp = J.src + (size_t)gy * J.src_pitch + (xa & ~127) + l * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+        }
+      }
+    }
 
     // ---- stage B: reducev (vertical), LDS.64 + 4 x IDP.2A per tap pair ----
     {
