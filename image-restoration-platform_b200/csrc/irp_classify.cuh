@@ -28,11 +28,14 @@
 
 namespace irp {
 
-constexpr int kTileW = 256;            // owned pixels per tile row
+constexpr int kTileW = 128;            // owned pixels per tile row
 constexpr int kTileH = 32;             // owned rows per tile
 constexpr int kRows = kTileH + 2;      // + replicate halo rows
 constexpr int kPlanePitch = 16 + kTileW + 16;  // bytes: [..15 = left halo][256 px][0 = right halo ..]
-constexpr int kClassifyThreads = 256;
+constexpr int kGroupThreads = 128;       // one tile is worked on by a group of 4 warps ...
+constexpr int kGroups = 2;               // ... and a CTA runs two groups on their own tiles, sharing the lookup tables
+constexpr int kClassifyThreads = kGroupThreads * kGroups;
+constexpr int kStrips = kTileW / 4;      // 4-pixel strips per tile row == threads per row group
 constexpr int kSegPx = 16;             // pixels per stage-1 work item
 constexpr int kSegsPerRow = kTileW / kSegPx;
 constexpr int kFlushTiles = 16;        // keeps every per-WARP u32 sum below 2^32 (blur sumsq: 16*6.3e6*32)
@@ -66,25 +69,30 @@ struct ClassifyTables {   // device copies of grey_tables.inc for the chosen lum
 // Shared-memory layout.  Everything is dynamic shared memory, carved at run time so that the
 // randomly indexed tables sit on power-of-two boundaries of the .shared address space: a lookup is
 // then   SHF (byte -> offset) ; LOP3 ((x & mask) | table_base) ; LDS   — no base add.
-//   grey tile | 1 KB-aligned: lutR, lutG, lutB, hist, red | 16 KB-aligned: inv | C plane tiles
+//   group-0 tiles | group-1 tiles | 16 KB-aligned: inv | 1 KB-aligned: lutR, lutG, lutB, hist x2 | red x2
 // ---------------------------------------------------------------------------
 constexpr int kTileBytes = kRows * kPlanePitch;
-constexpr int kRedBytes = (kClassifyThreads / 32) * ACC_COUNT * 4;
+constexpr int kRedBytes = (kGroupThreads / 32) * ACC_COUNT * 4;
 
 struct SmemMap {           // .shared-space byte addresses
-  uint32_t grey, lut_r, lut_g, lut_b, hist, red, inv, planes, end;
+  uint32_t tiles[kGroups]; // grey + C planes, contiguous, per group
+  uint32_t inv, lut_r, lut_g, lut_b, hist[kGroups], red[kGroups], end;
 };
 __host__ __device__ inline SmemMap make_smem_map(uint32_t base, int C) {
   SmemMap m;
-  m.grey = base;
-  m.lut_r = (base + kTileBytes + 1023u) & ~1023u;
+  const uint32_t tile_set = (uint32_t)(C + 1) * kTileBytes;
+  // both tile sets first (they fit below the first 16 KB boundary for C <= 3 only partly; the map is generic)
+  m.tiles[0] = base;
+  m.tiles[1] = (base + tile_set + 15u) & ~15u;
+  m.inv = (m.tiles[1] + tile_set + 16383u) & ~16383u;
+  m.lut_r = m.inv + 16384u;
   m.lut_g = m.lut_r + 1024u;
   m.lut_b = m.lut_r + 2048u;
-  m.hist = m.lut_r + 3072u;
-  m.red = m.lut_r + 4096u;
-  m.inv = (m.red + kRedBytes + 16383u) & ~16383u;
-  m.planes = m.inv + 16384u;
-  m.end = m.planes + (uint32_t)C * kTileBytes;
+  m.hist[0] = m.lut_r + 3072u;
+  m.hist[1] = m.lut_r + 4096u;
+  m.red[0] = m.lut_r + 5120u;
+  m.red[1] = m.red[0] + kRedBytes;
+  m.end = m.red[1] + kRedBytes;
   return m;
 }
 
@@ -139,6 +147,14 @@ __device__ __forceinline__ void hist_add_top(const Tiles<C>& T, uint32_t t) {
 // exact floor(x / 11) for 0 <= x <= 2810  (x = 3*(l+r) + 5*c + 5)
 __device__ __forceinline__ uint32_t div11(uint32_t x) { return __umulhi(x, 390451573u); }
 
+// barrier over the 128 threads of one group (named barriers 1 / 2; barrier 0 stays __syncthreads)
+__device__ __forceinline__ void group_barrier(int group) {
+  if (group)
+    asm volatile("bar.sync 2, %0;" ::"n"(kGroupThreads) : "memory");
+  else
+    asm volatile("bar.sync 1, %0;" ::"n"(kGroupThreads) : "memory");
+}
+
 template <int C>
 struct Acc {
   uint32_t s[C], q[C];
@@ -151,8 +167,8 @@ struct Acc {
 };
 
 template <int C>
-__device__ void flush_acc(const Tiles<C>& T, Acc<C>& a, unsigned long long* gacc, uint32_t* ghist) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ void flush_acc(const Tiles<C>& T, Acc<C>& a, unsigned long long* gacc, uint32_t* ghist, int tid, int group) {
+  const int lane = tid & 31, warp = tid >> 5;
   uint32_t v[ACC_COUNT];
 #pragma unroll
   for (int i = 0; i < ACC_COUNT; i++) v[i] = 0;
@@ -169,20 +185,20 @@ __device__ void flush_acc(const Tiles<C>& T, Acc<C>& a, unsigned long long* gacc
     const uint32_t r = __reduce_add_sync(0xffffffffu, v[i]);  // REDUX.SUM: one instruction per value
     if (lane == 0) T.red[warp * ACC_COUNT + i] = r;
   }
-  __syncthreads();
-  if (threadIdx.x < ACC_COUNT) {
+  group_barrier(group);
+  if (tid < ACC_COUNT) {
     unsigned long long t = 0;
 #pragma unroll
-    for (int w = 0; w < kClassifyThreads / 32; w++) t += T.red[w * ACC_COUNT + threadIdx.x];
-    if (t) atomicAdd(&gacc[threadIdx.x], t);
+    for (int w = 0; w < kGroupThreads / 32; w++) t += T.red[w * ACC_COUNT + tid];
+    if (t) atomicAdd(&gacc[tid], t);
   }
-  {
-    const uint32_t hv = T.hist[threadIdx.x];
-    if (hv) atomicAdd(&ghist[threadIdx.x], hv);
-    T.hist[threadIdx.x] = 0;
+  for (int b = tid; b < 256; b += kGroupThreads) {
+    const uint32_t hv = T.hist[b];
+    if (hv) atomicAdd(&ghist[b], hv);
+    T.hist[b] = 0;
   }
   a.clear();
-  __syncthreads();
+  group_barrier(group);
 }
 
 // ---------------------------------------------------------------------------
@@ -307,8 +323,8 @@ __device__ __forceinline__ uint32_t clip_diff(uint32_t kc, uint32_t nb) {
 // FULL = the tile lies strictly inside the image (x0 + 256 < W and y0 + 32 < H): no lane masks,
 // no row / column validity tests.  Edge tiles take the masked instantiation.
 template <int C, bool FULL>
-__device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int x0, int y0, int W, int H) {
-  const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
+__device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int tid, int x0, int y0, int W, int H) {
+  const int strip = tid & (kStrips - 1), rg = tid / kStrips;
   const int x = x0 + strip * 4;
   const int r0 = rg * 8;
   int nvalid = 4, nrows = 8;
@@ -389,8 +405,8 @@ __device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
 }
 
 template <int C, bool FULL>
-__device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int x0, int y0, int W, int H) {
-  const int strip = threadIdx.x & 63, rg = threadIdx.x >> 6;
+__device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, int x0, int y0, int W, int H) {
+  const int strip = tid & (kStrips - 1), rg = tid / kStrips;
   const int x = x0 + strip * 4;
   const int r0 = rg * 8;
   int nvalid = 4, nrows = 8;
@@ -436,31 +452,34 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     if (threadIdx.x == 0) atomicExch(error_flag, 1);
     return;
   }
+  const int group = threadIdx.x / kGroupThreads, tid = threadIdx.x & (kGroupThreads - 1);
   Tiles<C> T;
-  T.grey = smem_raw + (map.grey - sbase);
+  T.grey = smem_raw + ((group ? map.tiles[1] : map.tiles[0]) - sbase);
 #pragma unroll
-  for (int ch = 0; ch < C; ch++) T.plane[ch] = smem_raw + (map.planes - sbase) + ch * kTileBytes;
-  T.hist = reinterpret_cast<uint32_t*>(smem_raw + (map.hist - sbase));
-  T.red = reinterpret_cast<uint32_t*>(smem_raw + (map.red - sbase));
-  T.a_lut_r = map.lut_r; T.a_lut_g = map.lut_g; T.a_lut_b = map.lut_b; T.a_inv = map.inv; T.a_hist = map.hist;
+  for (int ch = 0; ch < C; ch++) T.plane[ch] = T.grey + (ch + 1) * kTileBytes;
+  T.hist = reinterpret_cast<uint32_t*>(smem_raw + ((group ? map.hist[1] : map.hist[0]) - sbase));
+  T.red = reinterpret_cast<uint32_t*>(smem_raw + ((group ? map.red[1] : map.red[0]) - sbase));
+  T.a_lut_r = map.lut_r; T.a_lut_g = map.lut_g; T.a_lut_b = map.lut_b; T.a_inv = map.inv;
+  T.a_hist = group ? map.hist[1] : map.hist[0];
   {
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (map.lut_r - sbase));
     uint32_t* inv = reinterpret_cast<uint32_t*>(smem_raw + (map.inv - sbase));
     for (int i = threadIdx.x; i < 3 * 256; i += kClassifyThreads) lut[i] = (&tab->lut[0][0])[i];
     for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) inv[i] = tab->inv[i];
-    T.hist[threadIdx.x] = 0;
+    for (int b = tid; b < 256; b += kGroupThreads) T.hist[b] = 0;
   }
   __syncthreads();
 
+  // from here on the two groups never meet again: each walks its own tile sequence with its own barrier
   Acc<C> acc;
   acc.clear();
   int img = 0, cur_img = -1, since_flush = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x * kGroups + group; tile < total_tiles; tile += gridDim.x * kGroups) {
     while (img + 1 < n_imgs && tile >= imgs[img + 1].tile_base) img++;
     if (img != cur_img || since_flush >= kFlushTiles) {
       if (cur_img >= 0) {
         const int slot = imgs[cur_img].slot;
-        flush_acc<C>(T, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+        flush_acc<C>(T, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256, tid, group);
       }
       cur_img = img;
       since_flush = 0;
@@ -472,8 +491,8 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     const int x0 = tx * kTileW, y0 = ty * kTileH;
 
     // ---- stage 1: load, regroup, moments, grey -> shared planar tiles ----
-    // core rows (1..32): 512 sixteen-pixel items, exactly two per thread
-    for (int item = threadIdx.x; item < kTileH * kSegsPerRow; item += kClassifyThreads) {
+    // core rows (1..32): 256 sixteen-pixel items, exactly two per thread
+    for (int item = tid; item < kTileH * kSegsPerRow; item += kGroupThreads) {
       const int row = 1 + item / kSegsPerRow, seg = item & (kSegsPerRow - 1);
       const int yy = y0 - 1 + row;
       const int gy = min(yy, im.h - 1);
@@ -493,9 +512,9 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
       }
       if (!fast) stage1_slow<C>(T, acc, im, gy, xb, row, 16 + seg * kSegPx, kSegPx, counted);
     }
-    // fringe: the two halo rows (2 x 256 px) and the two halo columns (2 x 34 px) as single-pixel jobs
-    // spread over all threads, so no warp carries a third sixteen-pixel item to the barrier
-    for (int f = threadIdx.x; f < 2 * kTileW + 2 * kRows; f += kClassifyThreads) {
+    // fringe: the two halo rows and the two halo columns as single-pixel jobs spread over the whole
+    // group, so no warp carries a third sixteen-pixel item to the barrier
+    for (int f = tid; f < 2 * kTileW + 2 * kRows; f += kGroupThreads) {
       int row, xq, col;
       if (f < 2 * kTileW) {
         row = f < kTileW ? 0 : kRows - 1;
@@ -512,13 +531,14 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
       const int gy = min(max(y0 - 1 + row, 0), im.h - 1);
       stage1_slow<C>(T, acc, im, gy, xq, row, col, 1, false);
     }
-    __syncthreads();
-    // ---- L2 prefetch of this CTA's next tile (same image only): 34 rows x 6 lines of 128 bytes ----
+    group_barrier(group);
+    // ---- L2 prefetch of this group's next tile (same image only) ----
     {
-      const int tn = t + (int)gridDim.x;
-      if (tn < im.tiles_x * im.tiles_y && threadIdx.x < kRows * 6) {
+      constexpr int kLines = (kTileW * C + 127) / 128;
+      const int tn = t + (int)gridDim.x * kGroups;
+      if (tn < im.tiles_x * im.tiles_y && tid < kRows * kLines) {
         const int tyn = tn / im.tiles_x, txn = tn - tyn * im.tiles_x;
-        const int row = threadIdx.x / 6, l = threadIdx.x - row * 6;
+        const int row = tid / kLines, l = tid - row * kLines;
         const int gy = min(max(tyn * kTileH - 1 + row, 0), im.h - 1);
         const long long off = (long long)txn * kTileW * C + l * 128;
         if (off < (long long)im.w * C) {
@@ -529,17 +549,17 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     }
     // ---- stage 2 + 3 ----
     if (x0 + kTileW < im.w && y0 + kTileH < im.h) {
-      stage2<C, true>(T, acc, x0, y0, im.w, im.h);
-      stage3<C, true>(T, acc, x0, y0, im.w, im.h);
+      stage2<C, true>(T, acc, tid, x0, y0, im.w, im.h);
+      stage3<C, true>(T, acc, tid, x0, y0, im.w, im.h);
     } else {
-      stage2<C, false>(T, acc, x0, y0, im.w, im.h);
-      stage3<C, false>(T, acc, x0, y0, im.w, im.h);
+      stage2<C, false>(T, acc, tid, x0, y0, im.w, im.h);
+      stage3<C, false>(T, acc, tid, x0, y0, im.w, im.h);
     }
-    __syncthreads();
+    group_barrier(group);
   }
   if (cur_img >= 0) {
     const int slot = imgs[cur_img].slot;
-    flush_acc<C>(T, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256);
+    flush_acc<C>(T, acc, gacc + (size_t)slot * ACC_COUNT, ghist + (size_t)slot * 256, tid, group);
   }
 }
 

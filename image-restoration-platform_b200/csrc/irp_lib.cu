@@ -408,7 +408,7 @@ int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, classify_kernel<C>, kClassifyThreads, smem));
     if (occ < 1) return fail(ctx, IRP_ERR_CUDA, "classify kernel does not fit on an SM");
   }
-  int grid = std::min(total_tiles, ctx->sm_count * occ);
+  int grid = std::min((total_tiles + kGroups - 1) / kGroups, ctx->sm_count * occ);
   classify_kernel<C><<<grid, kClassifyThreads, smem, ctx->stream>>>(d_imgs, n, total_tiles, ctx->d_tables, d_acc, d_hist,
                                                                     (uint32_t)smem, ctx->d_error_flag);
   CK(cudaGetLastError());
