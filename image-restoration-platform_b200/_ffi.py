@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libirp_b200.so")
+LIB_PATH = os.environ.get("IRP_LIB_PATH") or os.path.join(_HERE, "libirp_b200.so")  # override: kernel experiments only
 
 IRP_OK = 0
 IRP_ERR_BAD_ARG, IRP_ERR_UNSUPPORTED, IRP_ERR_CUDA, IRP_ERR_NOMEM, IRP_ERR_NO_DEVICE, IRP_ERR_CAPACITY = -1, -2, -3, -4, -5, -6

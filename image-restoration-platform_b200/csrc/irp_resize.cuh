@@ -130,6 +130,60 @@ __device__ __forceinline__ void vpass_column(const uint8_t* sp, uint8_t* mp, con
   }
 }
 
+// Two output rows per window load: rows r and r+1 start D pair-rows apart (D = 0, 1 or 2 for shrink < 4),
+// their windows overlap in NPV - D pairs, so the union (NPV + D LDS.64) serves both: ~43 % fewer
+// shared-memory reads than two single-row passes.
+template <int NPV, int D>
+__device__ __forceinline__ void vpass_two_rows(const uint8_t* sp, uint8_t* mp, const uint32_t* vtab, int r) {
+  const uint32_t* vt0 = vtab + r * kVtabStride;
+  const uint32_t* vt1 = vt0 + kVtabStride;
+  uint32_t c0[16], c1[16];
+#pragma unroll
+  for (int q4 = 0; q4 < (NPV + 3) / 4; q4++) {
+    const uint4 a = reinterpret_cast<const uint4*>(vt0)[q4], b = reinterpret_cast<const uint4*>(vt1)[q4];
+    c0[4 * q4] = a.x; c0[4 * q4 + 1] = a.y; c0[4 * q4 + 2] = a.z; c0[4 * q4 + 3] = a.w;
+    c1[4 * q4] = b.x; c1[4 * q4 + 1] = b.y; c1[4 * q4 + 2] = b.z; c1[4 * q4 + 3] = b.w;
+  }
+  const uint8_t* p = sp + vt0[15];
+  uint2 w[NPV + D];
+#pragma unroll
+  for (int pp = 0; pp < NPV + D; pp++) w[pp] = *reinterpret_cast<const uint2*>(p + pp * kPairPitch);
+  int a0 = 1 << (IRP_INTERP_SHIFT - 1), a1 = a0, a2 = a0, a3 = a0, b0 = a0, b1 = a0, b2 = a0, b3 = a0;
+#pragma unroll
+  for (int pp = 0; pp < NPV; pp++) {
+    a0 = dp2a_lo_s16_u8(c0[pp], w[pp].x, a0);
+    a1 = dp2a_hi_s16_u8(c0[pp], w[pp].x, a1);
+    a2 = dp2a_lo_s16_u8(c0[pp], w[pp].y, a2);
+    a3 = dp2a_hi_s16_u8(c0[pp], w[pp].y, a3);
+    b0 = dp2a_lo_s16_u8(c1[pp], w[pp + D].x, b0);
+    b1 = dp2a_hi_s16_u8(c1[pp], w[pp + D].x, b1);
+    b2 = dp2a_lo_s16_u8(c1[pp], w[pp + D].y, b2);
+    b3 = dp2a_hi_s16_u8(c1[pp], w[pp + D].y, b3);
+  }
+  const uint32_t ha = pack_sat_u8(a3 >> IRP_INTERP_SHIFT, a2 >> IRP_INTERP_SHIFT, 0u);
+  *reinterpret_cast<uint32_t*>(mp + r * kMidPitch) = pack_sat_u8(a1 >> IRP_INTERP_SHIFT, a0 >> IRP_INTERP_SHIFT, ha);
+  const uint32_t hb = pack_sat_u8(b3 >> IRP_INTERP_SHIFT, b2 >> IRP_INTERP_SHIFT, 0u);
+  *reinterpret_cast<uint32_t*>(mp + (r + 1) * kMidPitch) = pack_sat_u8(b1 >> IRP_INTERP_SHIFT, b0 >> IRP_INTERP_SHIFT, hb);
+}
+
+// rows [r_begin, r_end) of one 4-byte column: pairs of rows where their windows are <= 2 pair-rows apart
+template <int NPV>
+__device__ __forceinline__ void vpass_rows(const uint8_t* sp, uint8_t* mp, const uint32_t* vtab, int r_begin, int r_end) {
+  int r = r_begin;
+  for (; r + 1 < r_end; r += 2) {
+    const int d = (int)(vtab[(r + 1) * kVtabStride + 15] - vtab[r * kVtabStride + 15]) / kPairPitch;  // uniform
+    if (d == 1)
+      vpass_two_rows<NPV, 1>(sp, mp, vtab, r);
+    else if (d == 0)
+      vpass_two_rows<NPV, 0>(sp, mp, vtab, r);
+    else if (d == 2)
+      vpass_two_rows<NPV, 2>(sp, mp, vtab, r);
+    else
+      vpass_column<NPV>(sp, mp, vtab, r, r + 2);
+  }
+  if (r < r_end) vpass_column<NPV>(sp, mp, vtab, r, r_end);
+}
+
 // reduceh for one output column over rows [r_begin, r_end) and all planes; NWH aligned words per window.
 template <int C, int NWH>
 __device__ __forceinline__ void hpass_column(const uint8_t* mbase, int mid_plane, const uint32_t* hp, uint8_t* d,
@@ -250,6 +304,7 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
       const int nchunks = (ncols + 15) >> 4;
       const int nitems = npairrows * nchunks;
       const uint32_t inv_chunks = 65536u / (uint32_t)nchunks + 1u;  // exact for item < 65536 / nchunks... (items <= ~1300)
+#ifndef IRP_SKIP_A
       for (int item = tid; item < nitems; item += kResizeThreads) {
         const int q = (int)(((uint32_t)item * inv_chunks) >> 16), k = item - q * nchunks;
         const int ra = min(max(sy0e + 2 * q, 0), J.sh - 1), rb = min(max(sy0e + 2 * q + 1, 0), J.sh - 1);
@@ -294,6 +349,7 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
           }
         }
       }
+#endif
     }
     __syncthreads();
 
@@ -324,6 +380,7 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
       const int r_begin = rg * rows_per, r_end = min(oh, r_begin + rows_per);
       const int npv = (vn + 2) >> 1;             // pairs incl. a possible leading zero (uniform)
       const int nwc = (ncols + 3) >> 2;          // word columns in use
+#ifndef IRP_SKIP_B
       for (int col = tid & 127; col < C * kWordCols; col += 128) {
         const int plane = col / kWordCols, j = col - plane * kWordCols;
         if (j >= nwc) continue;
@@ -333,24 +390,26 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
           case 1: vpass_column<1>(sp, mp, s_vtab, r_begin, r_end); break;
           case 2: vpass_column<2>(sp, mp, s_vtab, r_begin, r_end); break;
           case 3: vpass_column<3>(sp, mp, s_vtab, r_begin, r_end); break;
-          case 4: vpass_column<4>(sp, mp, s_vtab, r_begin, r_end); break;
-          case 5: vpass_column<5>(sp, mp, s_vtab, r_begin, r_end); break;
-          case 6: vpass_column<6>(sp, mp, s_vtab, r_begin, r_end); break;
-          case 7: vpass_column<7>(sp, mp, s_vtab, r_begin, r_end); break;
-          case 8: vpass_column<8>(sp, mp, s_vtab, r_begin, r_end); break;
-          case 9: vpass_column<9>(sp, mp, s_vtab, r_begin, r_end); break;
-          case 10: vpass_column<10>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 4: vpass_rows<4>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 5: vpass_rows<5>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 6: vpass_rows<6>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 7: vpass_rows<7>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 8: vpass_rows<8>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 9: vpass_rows<9>(sp, mp, s_vtab, r_begin, r_end); break;
+          case 10: vpass_rows<10>(sp, mp, s_vtab, r_begin, r_end); break;
           case 11: vpass_column<11>(sp, mp, s_vtab, r_begin, r_end); break;
           case 12: vpass_column<12>(sp, mp, s_vtab, r_begin, r_end); break;
           default: vpass_column<13>(sp, mp, s_vtab, r_begin, r_end); break;
         }
       }
+#endif
     }
     __syncthreads();
 
     // ---- stage C: reduceh (horizontal) + normalise + store ----
     {
       const int xcol = tid & 63, rgh = tid >> 6;  // four row groups
+#ifndef IRP_SKIP_C
       if (xcol < ow) {
         const int o = ox0 + xcol;
         const int start = J.h.start[o] - sx0a;    // >= 0
@@ -371,6 +430,7 @@ resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
           default: hpass_column<C, 7>(mbase, mid_plane, hp, d, J.dst_pitch, r_begin, r_end, eg); break;
         }
       }
+#endif
     }
     __syncthreads();
   }
