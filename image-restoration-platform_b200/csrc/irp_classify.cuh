@@ -147,12 +147,9 @@ __device__ __forceinline__ void hist_add_top(const Tiles<C>& T, uint32_t t) {
 // exact floor(x / 11) for 0 <= x <= 2810  (x = 3*(l+r) + 5*c + 5)
 __device__ __forceinline__ uint32_t div11(uint32_t x) { return __umulhi(x, 390451573u); }
 
-// barrier over the 128 threads of one group (named barriers 1 / 2; barrier 0 stays __syncthreads)
+// barrier over the 128 threads of one group (named barriers 1..; barrier 0 stays __syncthreads)
 __device__ __forceinline__ void group_barrier(int group) {
-  if (group)
-    asm volatile("bar.sync 2, %0;" ::"n"(kGroupThreads) : "memory");
-  else
-    asm volatile("bar.sync 1, %0;" ::"n"(kGroupThreads) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
 }
 
 template <int C>
@@ -322,7 +319,7 @@ __device__ __forceinline__ uint32_t clip_diff(uint32_t kc, uint32_t nb) {
 
 // FULL = the tile lies strictly inside the image (x0 + 256 < W and y0 + 32 < H): no lane masks,
 // no row / column validity tests.  Edge tiles take the masked instantiation.
-template <int C, bool FULL>
+template <int C, bool FULL, int PITCH = kPlanePitch>
 __device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int tid, int x0, int y0, int W, int H) {
   const int strip = tid & (kStrips - 1), rg = tid / kStrips;
   const int x = x0 + strip * 4;
@@ -336,13 +333,13 @@ __device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int tid, in
   // byte masks for partially valid strips (pairs hold values in bytes 0 and 2)
   const uint32_t mA = nvalid >= 2 ? 0x00FF00FFu : 0x000000FFu;
   const uint32_t mB = nvalid >= 4 ? 0x00FF00FFu : (nvalid == 3 ? 0x000000FFu : 0u);
-  GreyRow up = load_grey_row(T.grey + r0 * kPlanePitch, strip), cur = load_grey_row(T.grey + (r0 + 1) * kPlanePitch, strip);
+  GreyRow up = load_grey_row(T.grey + r0 * PITCH, strip), cur = load_grey_row(T.grey + (r0 + 1) * PITCH, strip);
   uint32_t prev_t0 = 0;  // E3 > 200 at (grid row, px0), consumed by the row below
   const bool col_boundary = (strip & 1) && (FULL || x + 4 < W);  // px3 | px4 straddle an 8-px column boundary
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     if (!FULL && i >= nrows) break;
-    const GreyRow dn = load_grey_row(T.grey + (r0 + i + 2) * kPlanePitch, strip);
+    const GreyRow dn = load_grey_row(T.grey + (r0 + i + 2) * PITCH, strip);
     const uint32_t boxA = up.hA + cur.hA + dn.hA, boxB = up.hB + cur.hB + dn.hB;
     const uint32_t nineA = cur.cA * 9u, nineB = cur.cB * 9u;
     uint32_t e1A = clip_diff(nineA, boxA), e1B = clip_diff(nineB, boxB);
@@ -404,7 +401,7 @@ __device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
   return o;
 }
 
-template <int C, bool FULL>
+template <int C, bool FULL, int PITCH = kPlanePitch>
 __device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, int x0, int y0, int W, int H) {
   const int strip = tid & (kStrips - 1), rg = tid / kStrips;
   const int x = x0 + strip * 4;
@@ -418,11 +415,11 @@ __device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, in
 #pragma unroll
   for (int ch = 0; ch < C; ch++) {
     const uint8_t* pl = T.plane[ch];
-    HRow up = hpass_row(pl + r0 * kPlanePitch, strip), cur = hpass_row(pl + (r0 + 1) * kPlanePitch, strip);
+    HRow up = hpass_row(pl + r0 * PITCH, strip), cur = hpass_row(pl + (r0 + 1) * PITCH, strip);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       if (!FULL && i >= nrows) break;
-      const HRow dn = hpass_row(pl + (r0 + i + 2) * kPlanePitch, strip);
+      const HRow dn = hpass_row(pl + (r0 + i + 2) * PITCH, strip);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const uint32_t b = div11((up.h[j] + dn.h[j]) * 3u + (cur.h[j] * 5u + 5u));

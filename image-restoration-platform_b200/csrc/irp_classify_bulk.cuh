@@ -1,0 +1,348 @@
+// irp_classify_bulk.cuh — the streaming variant of the fused degradation-statistics kernel for the
+// common case (3-channel images whose base and pitch are multiples of 16 bytes: every host input
+// once staged, and tight device inputs whose row length is a multiple of 16).
+//
+// Same arithmetic and the same stage 2 / stage 3 code as classify_kernel<3> (irp_classify.cuh; the
+// reference formulas are cited there), different data movement:
+//   * one CTA per SM, six independent 4-warp groups sharing one copy of the grey tables;
+//   * each group owns a RAW tile buffer (34 rows x 416 bytes).  Warp 0 of the group fills it with
+//     one bulk async copy per row (cp.async.bulk -> UBLKCP, completion on an mbarrier) for tile n+1
+//     while the group runs the stencils of tile n, so stage 1 never waits on HBM: it reads the
+//     interleaved bytes with LDS.128, and the halo rows / halo columns come out of the same buffer
+//     instead of a byte-wise global path;
+//   * the next tile's coordinates are worked out once, by the issuing warp, and handed over in
+//     shared memory (no per-thread divisions, no per-thread descriptor reloads).
+// Row clamping (replicate top / bottom) is the choice of the copy's source row; the left / right
+// replicate columns of edge tiles are patched in the raw buffer before stage 1.
+#pragma once
+#include "irp_classify.cuh"
+
+namespace irp {
+
+constexpr int kBGroups = 6;                          // 4-warp groups per CTA
+constexpr int kBThreads = kBGroups * kGroupThreads;  // 768
+constexpr int kBPitch = 16 + kTileW;                 // plane row: [..15 = left halo][128 px]; right halo = byte 0 of the next row
+constexpr int kBPlane = kRows * kBPitch;
+constexpr int kBPlaneSet = 4 * kBPlane + 16;         // grey, R, G, B (+ the last row's right halo)
+constexpr int kRawPitch = 16 + kTileW * 3 + 16;      // [..13-15 = left halo px][384 B][right halo px = 400-402 ..]
+constexpr int kRawBytes = kRows * kRawPitch;
+
+struct TileInfo {        // written by the issuing warp, read by the whole group
+  int x0, y0, w, h;
+  int slot;              // accumulator slot of the tile's image
+  int flags;             // bit 0: tile valid (0 = end of this group's sequence); bit 1: flush the accumulators first
+  int pad[2];
+};
+
+struct BulkMap {         // .shared window addresses
+  uint32_t raw[kBGroups], planes[kBGroups], hist[kBGroups], red[kBGroups];
+  uint32_t sync;         // per group: mbarrier (8 B) + 2 x TileInfo, 80 B stride
+  uint32_t inv, lut_r, end;
+};
+constexpr int kSyncStride = 80;
+
+__host__ __device__ inline BulkMap make_bulk_map(uint32_t base) {
+  BulkMap m;
+  uint32_t p = (base + 15u) & ~15u;
+  m.raw[0] = p;
+  p += kRawBytes;
+  m.sync = (p + 15u) & ~15u;
+  p = m.sync + kBGroups * kSyncStride;
+  m.inv = (p + 16383u) & ~16383u;
+  m.lut_r = m.inv + 16384u;
+  p = m.lut_r + 3072u;
+  for (int g = 0; g < kBGroups; g++) m.hist[g] = p + 1024u * g;
+  p += 1024u * kBGroups;
+  for (int g = 0; g < kBGroups; g++) m.red[g] = p + kRedBytes * g;
+  p += kRedBytes * kBGroups;
+  p = (p + 15u) & ~15u;
+  for (int g = 0; g < kBGroups; g++) m.planes[g] = p + kBPlaneSet * g;
+  p += kBPlaneSet * kBGroups;
+  for (int g = 1; g < kBGroups; g++) m.raw[g] = p + kRawBytes * (g - 1);
+  p += kRawBytes * (kBGroups - 1);
+  m.end = p;
+  return m;
+}
+
+// ---- mbarrier / bulk-copy wrappers (shared::cta addresses) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// 4 pixels (12 interleaved bytes in w0..w2) -> planar words + grey word.
+// nvalid < 4 masks the moments / histogram (image edge); COUNTED = false for halo rows.
+template <bool COUNTED, bool MASKED>
+__device__ __forceinline__ void s1_quad(const Tiles<3>& T, Acc<3>& a, uint32_t w0, uint32_t w1, uint32_t w2, int nvalid,
+                                        uint32_t& R, uint32_t& G, uint32_t& B, uint32_t& Y) {
+  // w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3
+  R = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+  G = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+  B = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+  if (COUNTED) {
+    uint32_t r = R, g = G, b = B;
+    if (MASKED) {
+      const uint32_t m = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * max(nvalid, 0))) - 1u);
+      r &= m; g &= m; b &= m;
+    }
+    a.s[0] = __dp4a(r, 0x01010101u, a.s[0]);
+    a.s[1] = __dp4a(g, 0x01010101u, a.s[1]);
+    a.s[2] = __dp4a(b, 0x01010101u, a.s[2]);
+    a.q[0] = __dp4a(r, r, a.q[0]);
+    a.q[1] = __dp4a(g, g, a.q[1]);
+    a.q[2] = __dp4a(b, b, a.q[2]);
+  }
+  uint32_t t[4];
+  t[0] = grey_top_off(T, byte_off4<0>(R), byte_off4<0>(G), byte_off4<0>(B));
+  t[1] = grey_top_off(T, byte_off4<1>(R), byte_off4<1>(G), byte_off4<1>(B));
+  t[2] = grey_top_off(T, byte_off4<2>(R), byte_off4<2>(G), byte_off4<2>(B));
+  t[3] = grey_top_off(T, byte_off4<3>(R), byte_off4<3>(G), byte_off4<3>(B));
+  if (COUNTED) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (!MASKED || j < nvalid) hist_add_top(T, t[j]);
+  }
+  Y = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x0073), 0x5410);
+}
+
+// one 16-pixel segment of a core row: 3 x LDS.128 from the raw tile -> 4 x STS.128 to the planes
+template <bool COUNTED, bool MASKED>
+__device__ __forceinline__ void s1_segment(const Tiles<3>& T, Acc<3>& a, uint32_t raw_addr, uint32_t plane_addr, int nvalid) {
+  const uint4 v0 = lds_v4(raw_addr), v1 = lds_v4(raw_addr + 16), v2 = lds_v4(raw_addr + 32);
+  const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+  uint32_t R[4], G[4], B[4], Y[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    s1_quad<COUNTED, MASKED>(T, a, w[3 * k], w[3 * k + 1], w[3 * k + 2], nvalid - 4 * k, R[k], G[k], B[k], Y[k]);
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr), "r"(Y[0]), "r"(Y[1]), "r"(Y[2]), "r"(Y[3]) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + kBPlane), "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + 2 * kBPlane), "r"(G[0]), "r"(G[1]), "r"(G[2]), "r"(G[3]) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + 3 * kBPlane), "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]) : "memory");
+}
+
+// the issuing warp: describe this group's next tile and start its row copies
+struct Issuer {
+  int next_tile, stride, img, last_img, since_flush;
+};
+
+__device__ __forceinline__ void issue_tile(Issuer& is, const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, uint32_t bar,
+                                           uint32_t info_addr, uint32_t raw_addr, int lane) {
+  const int tile = is.next_tile;
+  is.next_tile += is.stride;
+  if (tile >= total_tiles) {
+    if (lane == 0) {
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(info_addr + 20), "r"(0) : "memory");
+      mbar_arrive(bar);
+    }
+    return;
+  }
+  while (is.img + 1 < n_imgs && tile >= __ldg(&imgs[is.img + 1].tile_base)) is.img++;
+  const ImgDev* im = imgs + is.img;
+  const int w = __ldg(&im->w), h = __ldg(&im->h), tiles_x = __ldg(&im->tiles_x), slot = __ldg(&im->slot);
+  const unsigned long long pitch = __ldg(&im->pitch);
+  const uint8_t* px = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&im->px)));
+  const int t = tile - __ldg(&im->tile_base);
+  const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  const int x0 = tx * kTileW, y0 = ty * kTileH;
+  const bool flush = is.last_img >= 0 && (is.img != is.last_img || is.since_flush >= kFlushTiles);
+  if (is.img != is.last_img || is.since_flush >= kFlushTiles) is.since_flush = 0;
+  is.since_flush++;
+  is.last_img = is.img;
+  // bytes of each row: from 16 bytes left of the tile (when there is a left neighbour) to 16 bytes
+  // right of it, cut at the 16-byte-rounded end of the image row (inside the pitch: pitch % 16 == 0)
+  const int row_end = (w * 3 + 15) & ~15;
+  const int b0 = x0 ? x0 * 3 - 16 : 0;
+  const int b1 = min(x0 * 3 + kTileW * 3 + 16, row_end);
+  const uint32_t nbytes = (uint32_t)(b1 - b0);
+  const uint32_t doff = x0 ? 0u : 16u;
+  if (lane == 0) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr), "r"(x0), "r"(y0), "r"(w), "r"(h) : "memory");
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(info_addr + 16), "r"(slot), "r"(1 | (flush ? 2 : 0)) : "memory");
+    mbar_arrive_expect_tx(bar, nbytes * kRows);
+  }
+  __syncwarp();
+  for (int r = lane; r < kRows; r += 32) {
+    const int gy = min(max(y0 - 1 + r, 0), h - 1);
+    bulk_g2s(raw_addr + r * kRawPitch + doff, px + (size_t)gy * pitch + b0, nbytes, bar);
+  }
+}
+
+__global__ void __launch_bounds__(kBThreads, 1)
+classify_bulk_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
+                     unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist, uint32_t dyn_smem_bytes,
+                     int* __restrict__ error_flag) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const BulkMap map = make_bulk_map(sbase);
+  if (map.end - sbase > dyn_smem_bytes) {
+    if (threadIdx.x == 0) atomicExch(error_flag, 1);
+    return;
+  }
+  const int group = threadIdx.x / kGroupThreads, tid = threadIdx.x & (kGroupThreads - 1);
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t a_raw = map.raw[0], a_planes = map.planes[0], a_hist = map.hist[0], a_red = map.red[0];
+#pragma unroll
+  for (int g = 1; g < kBGroups; g++)
+    if (group == g) {
+      a_raw = map.raw[g]; a_planes = map.planes[g]; a_hist = map.hist[g]; a_red = map.red[g];
+    }
+  const uint32_t a_bar = map.sync + group * kSyncStride, a_info = a_bar + 16;
+  Tiles<3> T;
+  T.grey = smem_raw + (a_planes - sbase);
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) T.plane[ch] = T.grey + (ch + 1) * kBPlane;
+  T.hist = reinterpret_cast<uint32_t*>(smem_raw + (a_hist - sbase));
+  T.red = reinterpret_cast<uint32_t*>(smem_raw + (a_red - sbase));
+  T.a_lut_r = map.lut_r; T.a_lut_g = map.lut_r + 1024u; T.a_lut_b = map.lut_r + 2048u; T.a_inv = map.inv;
+  T.a_hist = a_hist;
+  {
+    uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (map.lut_r - sbase));
+    uint32_t* inv = reinterpret_cast<uint32_t*>(smem_raw + (map.inv - sbase));
+    for (int i = threadIdx.x; i < 3 * 256; i += kBThreads) lut[i] = (&tab->lut[0][0])[i];
+    for (int i = threadIdx.x; i < 4096; i += kBThreads) inv[i] = tab->inv[i];
+    for (int b = tid; b < 256; b += kGroupThreads) T.hist[b] = 0;
+    if (tid == 0) mbar_init(a_bar, 1);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  Issuer is;
+  is.next_tile = blockIdx.x * kBGroups + group;
+  is.stride = gridDim.x * kBGroups;
+  is.img = 0; is.last_img = -1; is.since_flush = 0;
+  if (warp == 0) issue_tile(is, imgs, n_imgs, total_tiles, a_bar, a_info, a_raw, lane);
+
+  Acc<3> acc;
+  acc.clear();
+  int cur_slot = -1;
+  for (uint32_t it = 0;; it++) {
+    mbar_wait(a_bar, it & 1u);
+    const uint32_t ia = a_info + (it & 1u) * 32u;
+    int x0, y0, W, H, slot, flags;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(y0), "=r"(W), "=r"(H) : "r"(ia));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(slot), "=r"(flags) : "r"(ia + 16));
+    if (!(flags & 1)) break;
+    if (flags & 2) flush_acc<3>(T, acc, gacc + (size_t)cur_slot * ACC_COUNT, ghist + (size_t)cur_slot * 256, tid, group);
+    cur_slot = slot;
+    const int vw = min(kTileW, W - x0);          // valid columns of this tile
+    const bool full = x0 + kTileW < W && y0 + kTileH < H;
+
+    // ---- replicate columns of edge tiles, patched in the raw buffer ----
+    if (x0 == 0 || x0 + kTileW >= W) {
+      if (tid < kRows) {
+        const uint32_t rr = a_raw + tid * kRawPitch;
+        if (x0 == 0)
+          for (int k = 0; k < 3; k++) sts_u8(rr + 13 + k, lds_u8(rr + 16 + k));
+        if (x0 + kTileW >= W)
+          for (int k = 0; k < 3; k++) sts_u8(rr + 16 + 3 * vw + k, lds_u8(rr + 16 + 3 * (vw - 1) + k));
+      }
+      group_barrier(group);
+    }
+
+    // ---- stage 1: raw tile -> planar R/G/B + grey tiles, channel moments, histogram ----
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) {  // core rows 1..32: 256 segments, two per thread
+        const int item = tid + i * kGroupThreads;
+        const int row = 1 + (item >> 3), seg = item & 7;
+        s1_segment<true, false>(T, acc, a_raw + row * kRawPitch + 16 + seg * 48, a_planes + row * kBPitch + 16 + seg * 16, 16);
+      }
+    } else {
+      for (int i = 0; i < 2; i++) {
+        const int item = tid + i * kGroupThreads;
+        const int row = 1 + (item >> 3), seg = item & 7;
+        const int nvalid = vw - seg * 16;
+        if (nvalid <= -1) continue;  // right of the replicate column: nothing reads it
+        const uint32_t ra = a_raw + row * kRawPitch + 16 + seg * 48, pa = a_planes + row * kBPitch + 16 + seg * 16;
+        if (y0 - 1 + row < H)
+          s1_segment<true, true>(T, acc, ra, pa, nvalid);
+        else
+          s1_segment<false, false>(T, acc, ra, pa, 0);
+      }
+    }
+    // halo rows (0 and 33) as 4-pixel pieces, halo columns as single pixels: spread over the group
+    if (tid >= 64) {
+      const int q = tid - 64;
+      const int row = (q >> 5) ? kRows - 1 : 0, c4 = q & 31;
+      if (full || c4 * 4 <= vw) {
+        const uint32_t ra = a_raw + row * kRawPitch + 16 + c4 * 12, pa = a_planes + row * kBPitch + 16 + c4 * 4;
+        uint32_t R, G, B, Y;
+        s1_quad<false, false>(T, acc, lds_b32(ra), lds_b32(ra + 4), lds_b32(ra + 8), 0, R, G, B, Y);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(Y) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + kBPlane), "r"(R) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + 2 * kBPlane), "r"(G) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + 3 * kBPlane), "r"(B) : "memory");
+      }
+    }
+    if (tid < 2 * kRows) {
+      const int row = tid >> 1, right = tid & 1;
+      // left halo: raw bytes 13..15 -> plane byte 15; right halo (pixel vw of the tile): raw 16 + 3 vw -> next row's byte 0
+      const uint32_t ra = a_raw + row * kRawPitch + (right ? 16 + 3 * vw : 13);
+      const uint32_t pa = a_planes + (right ? row * kBPitch + 16 + vw : row * kBPitch + 15);
+      const uint32_t r = lds_u8(ra), g = lds_u8(ra + 1), b = lds_u8(ra + 2);
+      const uint32_t y = grey_top_off(T, r << 2, g << 2, b << 2) >> 24;
+      sts_u8(pa, y);
+      sts_u8(pa + kBPlane, r);
+      sts_u8(pa + 2 * kBPlane, g);
+      sts_u8(pa + 3 * kBPlane, b);
+    }
+    group_barrier(group);
+
+    // ---- the raw buffer is free: start the copies of this group's next tile ----
+    if (warp == 0) issue_tile(is, imgs, n_imgs, total_tiles, a_bar, a_info + ((it + 1) & 1u) * 32u, a_raw, lane);
+
+    // ---- stage 2 + 3 on the planes ----
+    if (full) {
+      stage2<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
+      stage3<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
+    } else {
+      stage2<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
+      stage3<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
+    }
+    group_barrier(group);
+  }
+  if (cur_slot >= 0) flush_acc<3>(T, acc, gacc + (size_t)cur_slot * ACC_COUNT, ghist + (size_t)cur_slot * 256, tid, group);
+}
+
+}  // namespace irp

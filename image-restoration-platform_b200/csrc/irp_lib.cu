@@ -22,6 +22,7 @@
 #include "../../include/irp_spec.h"
 #include "grey_tables.inc"
 #include "irp_classify.cuh"
+#include "irp_classify_bulk.cuh"
 #include "irp_resize.cuh"
 
 using namespace irp;
@@ -103,6 +104,7 @@ struct irp_ctx {
   size_t smem_optin = 0;             // opt-in dynamic shared memory limit of the device
   uint32_t smem_base = 0; // .shared address where dynamic shared memory starts (probed once)
   int* d_error_flag = nullptr;
+  bool bulk_ok = false;   // the streaming classify kernel's shared-memory map fits this device
   int* h_error_flag = nullptr;
 };
 
@@ -416,19 +418,38 @@ int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, 
   return IRP_OK;
 }
 
+// the streaming kernel: 3-channel images with 16-byte aligned base and pitch (irp_classify_bulk.cuh)
+int launch_classify_bulk(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, unsigned long long* d_acc, uint32_t* d_hist) {
+  if (!n) return IRP_OK;
+  const BulkMap map = make_bulk_map(ctx->smem_base);
+  const size_t smem = map.end - ctx->smem_base;
+  int grid = std::min((total_tiles + kBGroups - 1) / kBGroups, ctx->sm_count);
+  classify_bulk_kernel<<<grid, kBThreads, smem, ctx->stream>>>(d_imgs, n, total_tiles, ctx->d_tables, d_acc, d_hist, (uint32_t)smem,
+                                                              ctx->d_error_flag);
+  CK(cudaGetLastError());
+  ctx->timing.kernel_launches++;
+  return IRP_OK;
+}
+
 inline size_t acc_bytes_for(int n) { return round_up(sizeof(unsigned long long) * ACC_COUNT * n, 256); }
 
 // classify images [b, e): their descriptors occupy slots [b, e) of the batch-wide arrays, grouped by
-// channel count; each group is one launch over all of its tiles
+// kernel (1 channel, 3 channels generic, 4 channels, 3 channels streaming); each group is one launch
+// over all of its tiles
 int classify_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int n, int b, int e) {
-  const int chans[3] = {1, 3, 4};
   ImgDev* h_imgs = (ImgDev*)ctx->h_desc.p;
-  int pos = b, group_begin[4], group_tiles[3];
-  for (int g = 0; g < 3; g++) {
+  int pos = b, group_begin[5], group_tiles[4];
+  auto kernel_of = [&](int i) {
+    const bool aligned = (((uintptr_t)st[i].px | st[i].pitch) & 15) == 0;
+    if (imgs[i].channels == 1) return 0;
+    if (imgs[i].channels == 4) return 2;
+    return (aligned && ctx->bulk_ok) ? 3 : 1;
+  };
+  for (int g = 0; g < 4; g++) {
     group_begin[g] = pos;
     int tiles = 0;
     for (int i = b; i < e; i++) {
-      if (imgs[i].channels != chans[g]) continue;
+      if (kernel_of(i) != g) continue;
       ImgDev& d = h_imgs[pos++];
       d.px = st[i].px;
       d.pitch = st[i].pitch;
@@ -444,7 +465,7 @@ int classify_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<S
     }
     group_tiles[g] = tiles;
   }
-  group_begin[3] = pos;
+  group_begin[4] = pos;
   ImgDev* d_imgs = (ImgDev*)ctx->d_desc.p;
   CK(cudaMemcpyAsync(d_imgs + b, h_imgs + b, sizeof(ImgDev) * (e - b), cudaMemcpyHostToDevice, ctx->stream));
   unsigned long long* d_acc = (unsigned long long*)ctx->d_acc.p;
@@ -453,6 +474,7 @@ int classify_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<S
   if ((rc = launch_classify<1>(ctx, d_imgs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0], d_acc, d_hist))) return rc;
   if ((rc = launch_classify<3>(ctx, d_imgs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1], d_acc, d_hist))) return rc;
   if ((rc = launch_classify<4>(ctx, d_imgs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2], d_acc, d_hist))) return rc;
+  if ((rc = launch_classify_bulk(ctx, d_imgs + group_begin[3], group_begin[4] - group_begin[3], group_tiles[3], d_acc, d_hist))) return rc;
   return IRP_OK;
 }
 
@@ -861,6 +883,15 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
   for (const void* k : kernels)
     if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)) != cudaSuccess)
       return bail("cudaFuncSetAttribute(max dynamic shared memory)", e);
+  {  // the streaming kernel has no static shared memory and takes the whole opt-in limit
+    const BulkMap bm = make_bulk_map(ctx->smem_base);
+    const char* off = getenv("IRP_NO_BULK");
+    ctx->bulk_ok = bm.end - ctx->smem_base <= prop.sharedMemPerBlockOptin && !(off && off[0] == '1');
+    if (ctx->bulk_ok &&
+        (e = cudaFuncSetAttribute((const void*)classify_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)prop.sharedMemPerBlockOptin)) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(classify_bulk_kernel)", e);
+  }
   return ctx;
 }
 
