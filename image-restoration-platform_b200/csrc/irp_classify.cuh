@@ -412,9 +412,9 @@ __device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, in
     nvalid = min(4, W - x);
     nrows = min(8, H - (y0 + r0));
   }
-#pragma unroll
+#pragma unroll 1   // one copy of the row loop: the hot code has to stay inside the instruction cache
   for (int ch = 0; ch < C; ch++) {
-    const uint8_t* pl = T.plane[ch];
+    const uint8_t* pl = T.plane[0] + ch * (kRows * PITCH);
     HRow up = hpass_row(pl + r0 * PITCH, strip), cur = hpass_row(pl + (r0 + 1) * PITCH, strip);
 #pragma unroll
     for (int i = 0; i < 8; i++) {

@@ -282,7 +282,7 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tile
 
     // ---- stage 1: raw tile -> planar R/G/B + grey tiles, channel moments, histogram ----
     if (full) {
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < 2; i++) {  // core rows 1..32: 256 segments, two per thread
         const int item = tid + i * kGroupThreads;
         const int row = 1 + (item >> 3), seg = item & 7;
