@@ -144,8 +144,6 @@ __device__ __forceinline__ void hist_add_top(const Tiles<C>& T, uint32_t t) {
   red_inc_shared(((t >> 22) & 0x3FCu) | T.a_hist);
 }
 
-// exact floor(x / 11) for 0 <= x <= 2810  (x = 3*(l+r) + 5*c + 5)
-__device__ __forceinline__ uint32_t div11(uint32_t x) { return __umulhi(x, 390451573u); }
 
 // barrier over the 128 threads of one group (named barriers 1..; barrier 0 stays __syncthreads)
 __device__ __forceinline__ void group_barrier(int group) {
@@ -336,7 +334,7 @@ __device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int tid, in
   GreyRow up = load_grey_row(T.grey + r0 * PITCH, strip), cur = load_grey_row(T.grey + (r0 + 1) * PITCH, strip);
   uint32_t prev_t0 = 0;  // E3 > 200 at (grid row, px0), consumed by the row below
   const bool col_boundary = (strip & 1) && (FULL || x + 4 < W);  // px3 | px4 straddle an 8-px column boundary
-#pragma unroll
+#pragma unroll 4
   for (int i = 0; i < 8; i++) {
     if (!FULL && i >= nrows) break;
     const GreyRow dn = load_grey_row(T.grey + (r0 + i + 2) * PITCH, strip);
@@ -386,7 +384,10 @@ __device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int tid, in
 // stage 3: separable [12,20,12]/44 blur == floor((3(l+r)+5c+5)/11), H then V,
 // u8 between passes; only pooled sum / sumsq of the result are kept.
 // ---------------------------------------------------------------------------
-struct HRow { uint32_t h[4]; };
+// Division: floor(x / 11) for 0 <= x <= 2810 is byte 2 of x * 5958 (5958 * 11 = 2^16 + 2, and
+// 2810 * 2 < 2^16; the product stays below 2^24), so a quotient never has to be shifted out: the
+// next step picks it with PRMT.
+struct HRow { uint32_t z[4]; };   // per column: (3(l+r) + 5c + 5) * 5958, the blurred byte is byte 2
 
 __device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
   const uint32_t* rp = reinterpret_cast<const uint32_t*>(plane_row) + 3 + strip;
@@ -394,10 +395,10 @@ __device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
   HRow o;
   const uint32_t w0 = __funnelshift_r(l, c, 24);  // (l3, c0, c1, c2)
   const uint32_t w3 = __funnelshift_r(c, r, 16);  // (c2, c3, r0, r1)
-  o.h[0] = div11(__dp4a(w0, 0x00030503u, 5u));
-  o.h[1] = div11(__dp4a(c, 0x00030503u, 5u));
-  o.h[2] = div11(__dp4a(c, 0x03050300u, 5u));
-  o.h[3] = div11(__dp4a(w3, 0x00030503u, 5u));
+  o.z[0] = __dp4a(w0, 0x00030503u, 5u) * 5958u;
+  o.z[1] = __dp4a(c, 0x00030503u, 5u) * 5958u;
+  o.z[2] = __dp4a(c, 0x03050300u, 5u) * 5958u;
+  o.z[3] = __dp4a(w3, 0x00030503u, 5u) * 5958u;
   return o;
 }
 
@@ -412,24 +413,31 @@ __device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, in
     nvalid = min(4, W - x);
     nrows = min(8, H - (y0 + r0));
   }
+  const uint32_t vmask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
 #pragma unroll 1   // one copy of the row loop: the hot code has to stay inside the instruction cache
   for (int ch = 0; ch < C; ch++) {
     const uint8_t* pl = T.plane[0] + ch * (kRows * PITCH);
-    HRow up = hpass_row(pl + r0 * PITCH, strip), cur = hpass_row(pl + (r0 + 1) * PITCH, strip);
+    // per column a sliding window of horizontal results: bytes (up, cur, dn, 0)
+    uint32_t win[4];
+    {
+      const HRow up = hpass_row(pl + r0 * PITCH, strip), cur = hpass_row(pl + (r0 + 1) * PITCH, strip);
 #pragma unroll
+      for (int j = 0; j < 4; j++) win[j] = __byte_perm(up.z[j], cur.z[j], 0x7620);  // (-, up, cur, 0)
+    }
+#pragma unroll 4
     for (int i = 0; i < 8; i++) {
       if (!FULL && i >= nrows) break;
       const HRow dn = hpass_row(pl + (r0 + i + 2) * PITCH, strip);
+      uint32_t zz[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const uint32_t b = div11((up.h[j] + dn.h[j]) * 3u + (cur.h[j] * 5u + 5u));
-        if (FULL || j < nvalid) {
-          a.bs += b;
-          a.bq += b * b;
-        }
+        win[j] = __byte_perm(win[j], dn.z[j], 0x7621);                 // (up, cur, dn, 0)
+        zz[j] = __dp4a(win[j], 0x00030503u, 5u) * 5958u;               // vertical result in byte 2
       }
-      up = cur;
-      cur = dn;
+      uint32_t b4 = __byte_perm(__byte_perm(zz[0], zz[1], 0x0062), __byte_perm(zz[2], zz[3], 0x0062), 0x5410);
+      if (!FULL) b4 &= vmask;
+      a.bs = __dp4a(b4, 0x01010101u, a.bs);
+      a.bq = __dp4a(b4, b4, a.bq);
     }
   }
 }
