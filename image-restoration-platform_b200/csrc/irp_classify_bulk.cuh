@@ -5,15 +5,16 @@
 // Same arithmetic and the same stage 2 / stage 3 code as classify_kernel<3> (irp_classify.cuh; the
 // reference formulas are cited there), different data movement:
 //   * one CTA per SM, six independent 4-warp groups sharing one copy of the grey tables;
-//   * each group owns a RAW tile buffer (34 rows x 416 bytes).  Warp 0 of the group fills it with
-//     one bulk async copy per row (cp.async.bulk -> UBLKCP, completion on an mbarrier) for tile n+1
-//     while the group runs the stencils of tile n, so stage 1 never waits on HBM: it reads the
+//   * each group owns a RAW tile buffer (34 rows x 416 bytes).  One lane of the group fills it with
+//     ONE 2-D TMA tile load (cp.async.bulk.tensor -> UTMALDG, completion on an mbarrier) for tile
+//     n+1 while the group runs the stencils of tile n, so stage 1 never waits on HBM: it reads the
 //     interleaved bytes with LDS.128, and the halo rows / halo columns come out of the same buffer
 //     instead of a byte-wise global path;
 //   * the next tile's coordinates are worked out once, by the issuing warp, and handed over in
 //     shared memory (no per-thread divisions, no per-thread descriptor reloads).
-// Row clamping (replicate top / bottom) is the choice of the copy's source row; the left / right
-// replicate columns of edge tiles are patched in the raw buffer before stage 1.
+// The image is described to the TMA unit as a 2-D tensor of u16 elements (box 208 x 34); bytes
+// outside the image arrive as zeros, and the replicate rows / columns of edge tiles are patched in
+// the raw buffer before stage 1.
 #pragma once
 #include "irp_classify.cuh"
 
@@ -25,9 +26,11 @@ constexpr int kBPitch = 16 + kTileW;                 // plane row: [..15 = left 
 constexpr int kBPlane = kRows * kBPitch;
 constexpr int kBPlaneSet = 4 * kBPlane + 16;         // grey, R, G, B (+ the last row's right halo)
 constexpr int kRawPitch = 16 + kTileW * 3 + 16;      // [..13-15 = left halo px][384 B][right halo px = 400-402 ..]
-constexpr int kRawBytes = kRows * kRawPitch;
+constexpr int kRawBytes = (kRows * kRawPitch + 127) & ~127;   // the TMA box (208 u16 x 34 rows), 128-byte aligned slots
 
-struct TileInfo {        // written by the issuing warp, read by the whole group
+struct __align__(64) TmaDesc { unsigned long long opaque[16]; };   // a CUtensorMap (cuda.h), 128 bytes
+
+struct TileInfo {        // written by the issuing lane, read by the whole group
   int x0, y0, w, h;
   int slot;              // accumulator slot of the tile's image
   int flags;             // bit 0: tile valid (0 = end of this group's sequence); bit 1: flush the accumulators first
@@ -43,7 +46,7 @@ constexpr int kSyncStride = 80;
 
 __host__ __device__ inline BulkMap make_bulk_map(uint32_t base) {
   BulkMap m;
-  uint32_t p = (base + 15u) & ~15u;
+  uint32_t p = (base + 127u) & ~127u;
   m.raw[0] = p;
   p += kRawBytes;
   m.sync = (p + 15u) & ~15u;
@@ -58,6 +61,7 @@ __host__ __device__ inline BulkMap make_bulk_map(uint32_t base) {
   p = (p + 15u) & ~15u;
   for (int g = 0; g < kBGroups; g++) m.planes[g] = p + kBPlaneSet * g;
   p += kBPlaneSet * kBGroups;
+  p = (p + 127u) & ~127u;
   for (int g = 1; g < kBGroups; g++) m.raw[g] = p + kRawBytes * (g - 1);
   p += kRawBytes * (kBGroups - 1);
   m.end = p;
@@ -87,9 +91,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
+// one 2-D TMA tile load (box = the whole raw tile), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
@@ -166,50 +171,37 @@ struct Issuer {
   int next_tile, stride, img, last_img, since_flush;
 };
 
-__device__ __forceinline__ void issue_tile(Issuer& is, const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, uint32_t bar,
-                                           uint32_t info_addr, uint32_t raw_addr, int lane) {
+// One lane describes the group's next tile and starts its load: a single TMA instruction brings the
+// 34 x 416-byte box whose first column is 16 bytes left of the tile.  Whatever lies outside the
+// image arrives as zeros and is replaced by replicate rows / columns before stage 1.
+__device__ __forceinline__ void issue_tile(Issuer& is, const ImgDev* __restrict__ imgs, const TmaDesc* __restrict__ tmaps, int n_imgs,
+                                           int total_tiles, uint32_t bar, uint32_t info_addr, uint32_t raw_addr) {
   const int tile = is.next_tile;
   is.next_tile += is.stride;
   if (tile >= total_tiles) {
-    if (lane == 0) {
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(info_addr + 20), "r"(0) : "memory");
-      mbar_arrive(bar);
-    }
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(info_addr + 20), "r"(0) : "memory");
+    mbar_arrive(bar);
     return;
   }
   while (is.img + 1 < n_imgs && tile >= __ldg(&imgs[is.img + 1].tile_base)) is.img++;
   const ImgDev* im = imgs + is.img;
   const int w = __ldg(&im->w), h = __ldg(&im->h), tiles_x = __ldg(&im->tiles_x), slot = __ldg(&im->slot);
-  const unsigned long long pitch = __ldg(&im->pitch);
-  const uint8_t* px = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&im->px)));
   const int t = tile - __ldg(&im->tile_base);
   const int ty = t / tiles_x, tx = t - ty * tiles_x;
   const int x0 = tx * kTileW, y0 = ty * kTileH;
-  const bool flush = is.last_img >= 0 && (is.img != is.last_img || is.since_flush >= kFlushTiles);
-  if (is.img != is.last_img || is.since_flush >= kFlushTiles) is.since_flush = 0;
+  const bool fresh = is.img != is.last_img || is.since_flush >= kFlushTiles;
+  const bool flush = is.last_img >= 0 && fresh;
+  if (fresh) is.since_flush = 0;
   is.since_flush++;
   is.last_img = is.img;
-  // bytes of each row: from 16 bytes left of the tile (when there is a left neighbour) to 16 bytes
-  // right of it, cut at the 16-byte-rounded end of the image row (inside the pitch: pitch % 16 == 0)
-  const int row_end = (w * 3 + 15) & ~15;
-  const int b0 = x0 ? x0 * 3 - 16 : 0;
-  const int b1 = min(x0 * 3 + kTileW * 3 + 16, row_end);
-  const uint32_t nbytes = (uint32_t)(b1 - b0);
-  const uint32_t doff = x0 ? 0u : 16u;
-  if (lane == 0) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr), "r"(x0), "r"(y0), "r"(w), "r"(h) : "memory");
-    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(info_addr + 16), "r"(slot), "r"(1 | (flush ? 2 : 0)) : "memory");
-    mbar_arrive_expect_tx(bar, nbytes * kRows);
-  }
-  __syncwarp();
-  for (int r = lane; r < kRows; r += 32) {
-    const int gy = min(max(y0 - 1 + r, 0), h - 1);
-    bulk_g2s(raw_addr + r * kRawPitch + doff, px + (size_t)gy * pitch + b0, nbytes, bar);
-  }
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr), "r"(x0), "r"(y0), "r"(w), "r"(h) : "memory");
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(info_addr + 16), "r"(slot), "r"(1 | (flush ? 2 : 0)) : "memory");
+  mbar_arrive_expect_tx(bar, kRows * kRawPitch);
+  tma_load_2d(raw_addr, tmaps + is.img, (x0 * 3 - 16) >> 1, y0 - 1, bar);   // coordinates in u16 elements, rows
 }
 
 __global__ void __launch_bounds__(kBThreads, 1)
-classify_bulk_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
+classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict__ tmaps, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
                      unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist, uint32_t dyn_smem_bytes,
                      int* __restrict__ error_flag) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -220,7 +212,6 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tile
     return;
   }
   const int group = threadIdx.x / kGroupThreads, tid = threadIdx.x & (kGroupThreads - 1);
-  const int lane = tid & 31, warp = tid >> 5;
   uint32_t a_raw = map.raw[0], a_planes = map.planes[0], a_hist = map.hist[0], a_red = map.red[0];
 #pragma unroll
   for (int g = 1; g < kBGroups; g++)
@@ -251,7 +242,7 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tile
   is.next_tile = blockIdx.x * kBGroups + group;
   is.stride = gridDim.x * kBGroups;
   is.img = 0; is.last_img = -1; is.since_flush = 0;
-  if (warp == 0) issue_tile(is, imgs, n_imgs, total_tiles, a_bar, a_info, a_raw, lane);
+  if (tid == 0) issue_tile(is, imgs, tmaps, n_imgs, total_tiles, a_bar, a_info, a_raw);
 
   Acc<3> acc;
   acc.clear();
@@ -268,7 +259,18 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tile
     const int vw = min(kTileW, W - x0);          // valid columns of this tile
     const bool full = x0 + kTileW < W && y0 + kTileH < H;
 
-    // ---- replicate columns of edge tiles, patched in the raw buffer ----
+    // ---- replicate rows and columns of edge tiles, patched in the raw buffer (TMA filled them with zeros) ----
+    if (y0 == 0 || y0 + kTileH >= H) {
+      const int last = H - y0;                       // tile row holding image row H - 1
+      for (int r = 0; r < kRows; r++) {
+        const int sr = r == 0 ? (y0 == 0 ? 1 : 0) : min(r, last);
+        if (sr != r && tid < kRawPitch / 4) {
+          const uint32_t v = lds_b32(a_raw + sr * kRawPitch + tid * 4);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_raw + r * kRawPitch + tid * 4), "r"(v) : "memory");
+        }
+      }
+      group_barrier(group);
+    }
     if (x0 == 0 || x0 + kTileW >= W) {
       if (tid < kRows) {
         const uint32_t rr = a_raw + tid * kRawPitch;
@@ -330,7 +332,7 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tile
     group_barrier(group);
 
     // ---- the raw buffer is free: start the copies of this group's next tile ----
-    if (warp == 0) issue_tile(is, imgs, n_imgs, total_tiles, a_bar, a_info + ((it + 1) & 1u) * 32u, a_raw, lane);
+    if (tid == 0) issue_tile(is, imgs, tmaps, n_imgs, total_tiles, a_bar, a_info + ((it + 1) & 1u) * 32u, a_raw);
 
     // ---- stage 2 + 3 on the planes ----
     if (full) {

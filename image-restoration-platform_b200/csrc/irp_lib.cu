@@ -21,6 +21,7 @@
 #include "../../include/irp.h"
 #include "../../include/irp_spec.h"
 #include "grey_tables.inc"
+#include <cuda.h>   // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
 #include "irp_classify.cuh"
 #include "irp_classify_bulk.cuh"
 #include "irp_resize.cuh"
@@ -90,8 +91,9 @@ struct irp_ctx {
   std::mutex mu;
   std::string err;
   ClassifyTables* d_tables = nullptr;
-  DevBuf d_desc, d_acc, d_stage_in, d_stage_out, d_orient, d_jobs;
-  PinBuf h_desc, h_acc, h_jobs;
+  DevBuf d_desc, d_acc, d_stage_in, d_stage_out, d_orient, d_jobs, d_tmaps;
+  PinBuf h_desc, h_acc, h_jobs, h_tmaps;
+  void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   std::vector<void*> plan_chunks;
   size_t plan_used = 0, plan_cap = 0;
   std::map<std::tuple<int, int, double>, PlanDev> plans;
@@ -419,15 +421,32 @@ int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, 
 }
 
 // the streaming kernel: 3-channel images with 16-byte aligned base and pitch (irp_classify_bulk.cuh)
-int launch_classify_bulk(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, unsigned long long* d_acc, uint32_t* d_hist) {
+int launch_classify_bulk(irp_ctx* ctx, const ImgDev* d_imgs, const TmaDesc* d_tmaps, int n, int total_tiles, unsigned long long* d_acc,
+                         uint32_t* d_hist) {
   if (!n) return IRP_OK;
   const BulkMap map = make_bulk_map(ctx->smem_base);
   const size_t smem = map.end - ctx->smem_base;
   int grid = std::min((total_tiles + kBGroups - 1) / kBGroups, ctx->sm_count);
-  classify_bulk_kernel<<<grid, kBThreads, smem, ctx->stream>>>(d_imgs, n, total_tiles, ctx->d_tables, d_acc, d_hist, (uint32_t)smem,
-                                                              ctx->d_error_flag);
+  classify_bulk_kernel<<<grid, kBThreads, smem, ctx->stream>>>(d_imgs, d_tmaps, n, total_tiles, ctx->d_tables, d_acc, d_hist,
+                                                              (uint32_t)smem, ctx->d_error_flag);
   CK(cudaGetLastError());
   ctx->timing.kernel_launches++;
+  return IRP_OK;
+}
+
+// the image as the TMA unit sees it: rows of u16 elements, box = one raw tile (208 x 34)
+int encode_image_tmap(irp_ctx* ctx, const ImgDev& d, TmaDesc* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+  static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "TmaDesc must mirror CUtensorMap");
+  const cuuint64_t dims[2] = {(cuuint64_t)(d.w * 3 + 1) / 2, (cuuint64_t)d.h};
+  const cuuint64_t strides[1] = {(cuuint64_t)d.pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)kRawPitch / 2, (cuuint32_t)kRows}, estr[2] = {1, 1};
+  CUresult r = ((EncodeFn)ctx->encode_tiled)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)d.px, dims,
+                                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, IRP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d image, pitch %llu", (int)r, d.w, d.h, d.pitch);
   return IRP_OK;
 }
 
@@ -438,6 +457,8 @@ inline size_t acc_bytes_for(int n) { return round_up(sizeof(unsigned long long) 
 // over all of its tiles
 int classify_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int n, int b, int e) {
   ImgDev* h_imgs = (ImgDev*)ctx->h_desc.p;
+  TmaDesc* h_tmaps = (TmaDesc*)(((uintptr_t)ctx->h_tmaps.p + 63) & ~(uintptr_t)63);
+  TmaDesc* d_tmaps = (TmaDesc*)(((uintptr_t)ctx->d_tmaps.p + 63) & ~(uintptr_t)63);
   int pos = b, group_begin[5], group_tiles[4];
   auto kernel_of = [&](int i) {
     const bool aligned = (((uintptr_t)st[i].px | st[i].pitch) & 15) == 0;
@@ -462,19 +483,28 @@ int classify_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<S
       d.aligned16 = (((uintptr_t)d.px | d.pitch) & 15) == 0;
       d.slot = i;
       tiles += d.tiles_x * d.tiles_y;
+      if (g == 3) {
+        int rc = encode_image_tmap(ctx, d, h_tmaps + (pos - 1));
+        if (rc) return rc;
+      }
     }
     group_tiles[g] = tiles;
   }
   group_begin[4] = pos;
   ImgDev* d_imgs = (ImgDev*)ctx->d_desc.p;
   CK(cudaMemcpyAsync(d_imgs + b, h_imgs + b, sizeof(ImgDev) * (e - b), cudaMemcpyHostToDevice, ctx->stream));
+  if (group_begin[4] > group_begin[3])
+    CK(cudaMemcpyAsync(d_tmaps + group_begin[3], h_tmaps + group_begin[3], sizeof(TmaDesc) * (group_begin[4] - group_begin[3]),
+                       cudaMemcpyHostToDevice, ctx->stream));
   unsigned long long* d_acc = (unsigned long long*)ctx->d_acc.p;
   uint32_t* d_hist = (uint32_t*)((char*)ctx->d_acc.p + acc_bytes_for(n));
   int rc;
   if ((rc = launch_classify<1>(ctx, d_imgs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0], d_acc, d_hist))) return rc;
   if ((rc = launch_classify<3>(ctx, d_imgs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1], d_acc, d_hist))) return rc;
   if ((rc = launch_classify<4>(ctx, d_imgs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2], d_acc, d_hist))) return rc;
-  if ((rc = launch_classify_bulk(ctx, d_imgs + group_begin[3], group_begin[4] - group_begin[3], group_tiles[3], d_acc, d_hist))) return rc;
+  if ((rc = launch_classify_bulk(ctx, d_imgs + group_begin[3], d_tmaps + group_begin[3], group_begin[4] - group_begin[3], group_tiles[3],
+                                 d_acc, d_hist)))
+    return rc;
   return IRP_OK;
 }
 
@@ -711,6 +741,8 @@ int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* resul
   if (results) {
     CK(ctx->d_desc.reserve(sizeof(ImgDev) * n));
     CK(ctx->h_desc.reserve(sizeof(ImgDev) * n));
+    CK(ctx->d_tmaps.reserve(sizeof(TmaDesc) * n + 64));
+    CK(ctx->h_tmaps.reserve(sizeof(TmaDesc) * n + 64));
     CK(ctx->d_acc.reserve(acc_bytes_for(n) + sizeof(uint32_t) * 256 * n));
     CK(ctx->h_acc.reserve(acc_bytes_for(n) + sizeof(uint32_t) * 256 * n));
   }
@@ -886,7 +918,11 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
   {  // the streaming kernel has no static shared memory and takes the whole opt-in limit
     const BulkMap bm = make_bulk_map(ctx->smem_base);
     const char* off = getenv("IRP_NO_BULK");
-    ctx->bulk_ok = bm.end - ctx->smem_base <= prop.sharedMemPerBlockOptin && !(off && off[0] == '1');
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      ctx->encode_tiled = nullptr;
+    ctx->bulk_ok = ctx->encode_tiled && bm.end - ctx->smem_base <= prop.sharedMemPerBlockOptin && !(off && off[0] == '1');
     if (ctx->bulk_ok &&
         (e = cudaFuncSetAttribute((const void*)classify_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)prop.sharedMemPerBlockOptin)) != cudaSuccess)
@@ -905,8 +941,8 @@ void irp_destroy(irp_ctx* ctx) {
   for (auto& ev : ctx->timing_events) cudaEventDestroy(ev);
   if (ctx->copy_in_stream) cudaStreamDestroy(ctx->copy_in_stream);
   if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
-  for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs}) b->release();
-  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs}) b->release();
+  for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps}) b->release();
+  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);
