@@ -24,6 +24,7 @@
 #include <cuda.h>   // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
 #include "irp_classify.cuh"
 #include "irp_classify_bulk.cuh"
+#include "irp_resize_tma.cuh"
 #include "irp_resize.cuh"
 
 using namespace irp;
@@ -78,7 +79,10 @@ struct PlanDev {
   int16_t* coef;
   uint32_t* vpairs;
   uint32_t* hpairs;
+  uint32_t* vrows;   // [out][16]  the streaming kernel's per-output-row vertical table
+  uint32_t* hcols;   // [out][16]  ... and per-output-column horizontal table
   int n;
+  std::vector<int32_t> h_start;   // host copy: tile footprints are sized on the host
 };
 
 }  // namespace
@@ -91,8 +95,9 @@ struct irp_ctx {
   std::mutex mu;
   std::string err;
   ClassifyTables* d_tables = nullptr;
-  DevBuf d_desc, d_acc, d_stage_in, d_stage_out, d_orient, d_jobs, d_tmaps;
-  PinBuf h_desc, h_acc, h_jobs, h_tmaps;
+  DevBuf d_desc, d_acc, d_stage_in, d_stage_out, d_orient, d_jobs, d_tmaps, d_rtjobs, d_rtmaps;
+  PinBuf h_desc, h_acc, h_jobs, h_tmaps, h_rtjobs, h_rtmaps;
+  size_t smem_optin_full = 0;     // the device's opt-in shared memory per block
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   std::vector<void*> plan_chunks;
   size_t plan_used = 0, plan_cap = 0;
@@ -106,6 +111,7 @@ struct irp_ctx {
   size_t smem_optin = 0;             // opt-in dynamic shared memory limit of the device
   uint32_t smem_base = 0; // .shared address where dynamic shared memory starts (probed once)
   int* d_error_flag = nullptr;
+  bool rtma_ok = true;    // IRP_NO_RTMA=1 keeps the generic resize kernel (A/B runs)
   bool bulk_ok = false;   // the streaming classify kernel's shared-memory map fits this device
   int* h_error_flag = nullptr;
 };
@@ -264,7 +270,7 @@ int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
   return IRP_OK;
 }
 
-int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* ap) {
+int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* ap, const PlanDev** pdev = nullptr) {
   const bool identity = in_size == out_size;
   auto key = std::make_tuple(in_size, out_size, identity ? 1.0 : shrink);
   auto it = ctx->plans.find(key);
@@ -305,6 +311,24 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
     pd.vpairs = (uint32_t*)p;
     if ((rc = plan_alloc(ctx, hq.size() * 4, &p))) return rc;
     pd.hpairs = (uint32_t*)p;
+    {  // one 16-word row per output row / column: its coefficient pairs and where its window starts
+      const size_t no = hp.start.size();
+      std::vector<uint32_t> vr(no * 16, 0), hc(no * 16, 0);
+      for (size_t o = 0; o < no; o++) {
+        const int s0 = hp.start[o], ph = hp.phase[o];
+        for (int k = 0; k < kMaxPairs; k++) vr[o * 16 + k] = vp[((size_t)ph * 2 + (s0 & 1)) * 16 + k];
+        vr[o * 16 + 15] = (uint32_t)(s0 >> 1);
+        for (int k = 0; k < kMaxHPairs; k++) hc[o * 16 + k] = hq[((size_t)ph * 4 + (s0 & 3)) * 16 + k];
+        hc[o * 16 + 15] = (uint32_t)(s0 >> 2);
+      }
+      if ((rc = plan_alloc(ctx, vr.size() * 4, &p))) return rc;
+      pd.vrows = (uint32_t*)p;
+      if ((rc = plan_alloc(ctx, hc.size() * 4, &p))) return rc;
+      pd.hcols = (uint32_t*)p;
+      CK(cudaMemcpy(pd.vrows, vr.data(), vr.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pd.hcols, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+      pd.h_start = hp.start;
+    }
     CK(cudaMemcpy(pd.vpairs, vp.data(), vp.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pd.hpairs, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice));
     // synchronous copies: plans are built once per geometry and cached
@@ -314,6 +338,7 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
     it = ctx->plans.emplace(key, pd).first;
   }
   *ap = AxisPlan{it->second.start, it->second.phase, it->second.coef, it->second.vpairs, it->second.hpairs, it->second.n, 0};
+  if (pdev) *pdev = &it->second;
   return IRP_OK;
 }
 
@@ -633,42 +658,152 @@ int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* 
   return IRP_OK;
 }
 
-// orient + resize images [b, e); job slots [b, e) of the batch-wide arrays
+// the streaming kernel (irp_resize_tma.cuh): smallest tile footprint that serves every tile of a job
+struct RtFoot { int tow, toh, ncols, nrows; };
+bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, RtFoot* f) {
+  int tow = kRTow, toh = kRToh;
+  for (;;) {
+    int ncols = 0, nrows = 0;
+    for (int ox0 = 0; ox0 < dw; ox0 += tow) {
+      const int last = std::min(ox0 + tow, dw) - 1;
+      ncols = std::max(ncols, h.h_start[last] + h.n - (h.h_start[ox0] & ~3));
+    }
+    for (int oy0 = 0; oy0 < dh; oy0 += toh) {
+      const int last = std::min(oy0 + toh, dh) - 1;
+      nrows = std::max(nrows, v.h_start[last] + v.n - (v.h_start[oy0] & ~1));
+    }
+    const int ntr = (ncols + 3) / 4;
+    if (ntr * 12 + 12 > 512 && tow > 8) { tow >>= 1; continue; }
+    if (nrows + 1 > 256 && toh > 4) { toh >>= 1; continue; }
+    if (ntr * 12 + 12 > 512 || nrows + 1 > 256) return false;
+    *f = RtFoot{tow, toh, ntr * 4, (nrows + 1) & ~1};
+    return true;
+  }
+}
+
+RtLayout rt_layout(int ncols_px, int nrows) {
+  RtLayout L;
+  L.box_cols = (int)round_up((size_t)ncols_px * 3 + 12, 16);   // + the sub-16-byte offset of the first pixel
+  L.box_rows = nrows;
+  L.mid_pitch = (int)round_up((size_t)ncols_px + 8, 16);
+  size_t p = round_up((size_t)L.box_cols * L.box_rows, 128);
+  L.off_mid = (int)p;
+  p += (size_t)3 * kRToh * L.mid_pitch;
+  p = round_up(p, 128);
+  L.off_vtab = (int)p;
+  p += (size_t)kRToh * kTabWords * 4;
+  L.off_hcols = (int)p;
+  p += (size_t)kRTow * kTabWords * 4;
+  L.off_sync = (int)p;
+  p += 128;
+  L.group_bytes = (int)round_up(p, 128);
+  return L;
+}
+
+int encode_source_tmap(irp_ctx* ctx, const uint8_t* px, size_t pitch, int w, int h, int box_cols, int box_rows, TmaDesc* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+  const cuuint64_t dims[2] = {(cuuint64_t)(w * 3 + 1) / 2, (cuuint64_t)h};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols / 2, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  CUresult r = ((EncodeFn)ctx->encode_tiled)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)px, dims, strides,
+                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, IRP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d source, pitch %zu", (int)r, w, h, pitch);
+  return IRP_OK;
+}
+
+// orient + resize images [b, e); job slots [b, e) of the batch-wide arrays.  Jobs are grouped by
+// kernel: 1 / 3 / 4 channels on the generic kernel, and the streaming kernel for 3-channel sources
+// with aligned rows and a real shrink.
 int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, const std::vector<Geo>& geo,
                  const std::vector<OutPlan>& oplans, irp_out_desc* outs, int mode, int b, int e) {
   ResizeJob* h_jobs = (ResizeJob*)ctx->h_jobs.p;
-  const int chans[3] = {1, 3, 4};
-  int pos = b, group_begin[4], group_tiles[3];
-  for (int gi = 0; gi < 3; gi++) {
+  RtJob* h_rt = (RtJob*)ctx->h_rtjobs.p;
+  TmaDesc* h_tm = (TmaDesc*)(((uintptr_t)ctx->h_rtmaps.p + 63) & ~(uintptr_t)63);
+  TmaDesc* d_tm = (TmaDesc*)(((uintptr_t)ctx->d_rtmaps.p + 63) & ~(uintptr_t)63);
+  struct Src { const uint8_t* px; size_t pitch; };
+  std::vector<Src> src(e - b);
+  std::vector<int> kern(e - b, -1);
+  std::vector<RtFoot> foot(e - b);
+  std::vector<AxisPlan> pv(e - b), ph(e - b);
+  std::vector<const PlanDev*> dv(e - b), dh(e - b);
+  int rc;
+  // pass 1: orientation, plans, kernel choice
+  int box_cols_px = 0, box_rows = 0;
+  const size_t budget = ((size_t)ctx->smem_optin_full - 4096) / kRGroups;
+  for (int i = b; i < e; i++) {
+    if (!imgs[i].pixels) continue;
+    const irp_image_desc& d = imgs[i];
+    const Geo& g = geo[i];
+    Src& s = src[i - b];
+    if (g.o != 1) {
+      uint8_t* op = (uint8_t*)ctx->d_orient.p + g.orient_off;
+      size_t opitch = round_up((size_t)g.wo * d.channels, 16);
+      switch (d.channels) {
+        case 1: rc = launch_orient<1>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
+        case 3: rc = launch_orient<3>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
+        default: rc = launch_orient<4>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
+      }
+      if (rc) return rc;
+      s = Src{op, opitch};
+    } else {
+      s = Src{st[i].px, st[i].pitch};
+    }
+    if ((rc = get_plan(ctx, g.ho, g.dh, g.f, &pv[i - b], &dv[i - b]))) return rc;
+    if ((rc = get_plan(ctx, g.wo, g.dw, g.f, &ph[i - b], &dh[i - b]))) return rc;
+    int k = d.channels == 1 ? 0 : (d.channels == 4 ? 2 : 1);
+    if (k == 1 && ctx->bulk_ok && ctx->rtma_ok && ((((uintptr_t)s.px | s.pitch) & 15) == 0) && pv[i - b].n > 1 && ph[i - b].n > 1 &&
+        rt_footprint(*dv[i - b], *dh[i - b], g.dw, g.dh, &foot[i - b])) {
+      const RtLayout L = rt_layout(std::max(box_cols_px, foot[i - b].ncols), std::max(box_rows, foot[i - b].nrows));
+      if ((size_t)L.group_bytes <= budget && L.box_cols <= 512 && L.box_rows <= 256) {
+        k = 3;
+        box_cols_px = std::max(box_cols_px, foot[i - b].ncols);
+        box_rows = std::max(box_rows, foot[i - b].nrows);
+      }
+    }
+    kern[i - b] = k;
+  }
+  const RtLayout L = rt_layout(std::max(box_cols_px, 4), std::max(box_rows, 2));
+  // pass 2: job descriptors, grouped by kernel
+  int pos = b, group_begin[5], group_tiles[4];
+  for (int gi = 0; gi < 4; gi++) {
     group_begin[gi] = pos;
     int tiles = 0;
     for (int i = b; i < e; i++) {
-      if (!imgs[i].pixels) continue;
+      if (!imgs[i].pixels || kern[i - b] != gi) continue;
       const irp_image_desc& d = imgs[i];
-      if (d.channels != chans[gi]) continue;
       const Geo& g = geo[i];
-      ResizeJob& J = h_jobs[pos++];
-      memset(&J, 0, sizeof J);
-      if (g.o != 1) {
-        uint8_t* op = (uint8_t*)ctx->d_orient.p + g.orient_off;
-        size_t opitch = round_up((size_t)g.wo * d.channels, 16);
-        int rc;
-        switch (d.channels) {
-          case 1: rc = launch_orient<1>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
-          case 3: rc = launch_orient<3>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
-          default: rc = launch_orient<4>(ctx, st[i].px, st[i].pitch, d.width, d.height, g.o, op, opitch, g.wo, g.ho); break;
-        }
-        if (rc) return rc;
-        J.src = op;
-        J.src_pitch = opitch;
-      } else {
-        J.src = st[i].px;
-        J.src_pitch = st[i].pitch;
-      }
       const irp_out_desc& od = outs[i];
       const OutPlan& op = oplans[i];
       if (mode == 1)  // black pad: clear the whole canvas, the tiles then write the image once
         CK(cudaMemset2DAsync(op.dev, op.dev_pitch, 0, (size_t)od.width * g.dc, od.height, ctx->stream));
+      if (gi == 3) {
+        RtJob& R = h_rt[pos];
+        memset(&R, 0, sizeof R);
+        R.dst = op.dev;
+        R.dst_pitch = op.dev_pitch;
+        R.vrows = dv[i - b]->vrows;
+        R.hcols = dh[i - b]->hcols;
+        R.vstart = dv[i - b]->start;
+        R.hstart = dh[i - b]->start;
+        R.sw = g.wo; R.sh = g.ho; R.dw = g.dw; R.dh = g.dh;
+        R.dst_x0 = g.ox; R.dst_y0 = g.oy;
+        R.tow = foot[i - b].tow; R.toh = foot[i - b].toh;
+        R.tiles_x = (g.dw + R.tow - 1) / R.tow;
+        R.tiles_y = (g.dh + R.toh - 1) / R.toh;
+        R.tile_base = tiles;
+        R.vn = pv[i - b].n; R.hn = ph[i - b].n;
+        tiles += R.tiles_x * R.tiles_y;
+        if ((rc = encode_source_tmap(ctx, src[i - b].px, src[i - b].pitch, g.wo, g.ho, L.box_cols, L.box_rows, h_tm + pos))) return rc;
+        pos++;
+        continue;
+      }
+      ResizeJob& J = h_jobs[pos++];
+      memset(&J, 0, sizeof J);
+      J.src = src[i - b].px;
+      J.src_pitch = src[i - b].pitch;
       J.dst = op.dev;
       J.dst_pitch = op.dev_pitch;
       J.sw = g.wo;
@@ -681,9 +816,8 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       J.dst_y0 = g.oy;
       J.expand_grey = (d.channels == 1 && g.dc == 3);
       J.aligned16 = (((uintptr_t)J.src | J.src_pitch) & 15) == 0;
-      int rc;
-      if ((rc = get_plan(ctx, g.ho, g.dh, g.f, &J.v))) return rc;
-      if ((rc = get_plan(ctx, g.wo, g.dw, g.f, &J.h))) return rc;
+      J.v = pv[i - b];
+      J.h = ph[i - b];
       choose_tile(g.f, J.v.n, J.h.n, d.channels, &J.tow, &J.toh, &J.pairrows_max);
       J.tiles_x = (J.dw + J.tow - 1) / J.tow;
       J.tiles_y = (J.dh + J.toh - 1) / J.toh;
@@ -692,14 +826,25 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     }
     group_tiles[gi] = tiles;
   }
-  group_begin[3] = pos;
+  group_begin[4] = pos;
   if (pos == b) return IRP_OK;
   ResizeJob* d_jobs = (ResizeJob*)ctx->d_jobs.p;
-  CK(cudaMemcpyAsync(d_jobs + b, h_jobs + b, sizeof(ResizeJob) * (pos - b), cudaMemcpyHostToDevice, ctx->stream));
-  int rc;
+  if (group_begin[3] > b)
+    CK(cudaMemcpyAsync(d_jobs + b, h_jobs + b, sizeof(ResizeJob) * (group_begin[3] - b), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = launch_resize<1>(ctx, d_jobs + group_begin[0], h_jobs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0]))) return rc;
   if ((rc = launch_resize<3>(ctx, d_jobs + group_begin[1], h_jobs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1]))) return rc;
   if ((rc = launch_resize<4>(ctx, d_jobs + group_begin[2], h_jobs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2]))) return rc;
+  if (const int nrt = group_begin[4] - group_begin[3]) {
+    RtJob* d_rt = (RtJob*)ctx->d_rtjobs.p;
+    const int g3 = group_begin[3];
+    CK(cudaMemcpyAsync(d_rt + g3, h_rt + g3, sizeof(RtJob) * nrt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tm + g3, h_tm + g3, sizeof(TmaDesc) * nrt, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t smem = (size_t)L.group_bytes * kRGroups + 128;
+    const int grid = std::min((group_tiles[3] + kRGroups - 1) / kRGroups, ctx->sm_count);
+    resize_tma_kernel<<<grid, kRThreads, smem, ctx->stream>>>(d_rt + g3, d_tm + g3, nrt, group_tiles[3], L);
+    CK(cudaGetLastError());
+    ctx->timing.kernel_launches++;
+  }
   return IRP_OK;
 }
 
@@ -749,6 +894,10 @@ int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* resul
   if (outs) {
     CK(ctx->d_jobs.reserve(sizeof(ResizeJob) * n));
     CK(ctx->h_jobs.reserve(sizeof(ResizeJob) * n));
+    CK(ctx->d_rtjobs.reserve(sizeof(RtJob) * n));
+    CK(ctx->h_rtjobs.reserve(sizeof(RtJob) * n));
+    CK(ctx->d_rtmaps.reserve(sizeof(TmaDesc) * n + 64));
+    CK(ctx->h_rtmaps.reserve(sizeof(TmaDesc) * n + 64));
   }
   // chunk boundaries
   std::vector<int> cuts{0};
@@ -923,6 +1072,12 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
         qres != cudaDriverEntryPointSuccess)
       ctx->encode_tiled = nullptr;
     ctx->bulk_ok = ctx->encode_tiled && bm.end - ctx->smem_base <= prop.sharedMemPerBlockOptin && !(off && off[0] == '1');
+    ctx->smem_optin_full = prop.sharedMemPerBlockOptin;
+    const char* off2 = getenv("IRP_NO_RTMA");
+    ctx->rtma_ok = !(off2 && off2[0] == '1');
+    if (ctx->bulk_ok && (e = cudaFuncSetAttribute((const void*)resize_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(resize_tma_kernel)", e);
     if (ctx->bulk_ok &&
         (e = cudaFuncSetAttribute((const void*)classify_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)prop.sharedMemPerBlockOptin)) != cudaSuccess)
@@ -941,8 +1096,8 @@ void irp_destroy(irp_ctx* ctx) {
   for (auto& ev : ctx->timing_events) cudaEventDestroy(ev);
   if (ctx->copy_in_stream) cudaStreamDestroy(ctx->copy_in_stream);
   if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
-  for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps}) b->release();
-  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps}) b->release();
+  for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps, &ctx->d_rtjobs, &ctx->d_rtmaps}) b->release();
+  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);
