@@ -313,13 +313,13 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
     pd.hpairs = (uint32_t*)p;
     {  // one 16-word row per output row / column: its coefficient pairs and where its window starts
       const size_t no = hp.start.size();
-      std::vector<uint32_t> vr(no * 16, 0), hc(no * 16, 0);
+      std::vector<uint32_t> vr(no * 16, 0), hc(no * kHTabWords, 0);
       for (size_t o = 0; o < no; o++) {
         const int s0 = hp.start[o], ph = hp.phase[o];
         for (int k = 0; k < kMaxPairs; k++) vr[o * 16 + k] = vp[((size_t)ph * 2 + (s0 & 1)) * 16 + k];
         vr[o * 16 + 15] = (uint32_t)(s0 >> 1);
-        for (int k = 0; k < kMaxHPairs; k++) hc[o * 16 + k] = hq[((size_t)ph * 4 + (s0 & 3)) * 16 + k];
-        hc[o * 16 + 15] = (uint32_t)(s0 >> 2);
+        for (int k = 0; k < kMaxHPairs; k++) hc[o * kHTabWords + k] = hq[((size_t)ph * 4 + (s0 & 3)) * 16 + k];
+        hc[o * kHTabWords + 15] = (uint32_t)(s0 >> 2);
       }
       if ((rc = plan_alloc(ctx, vr.size() * 4, &p))) return rc;
       pd.vrows = (uint32_t*)p;
@@ -693,7 +693,7 @@ RtLayout rt_layout(int ncols_px, int nrows) {
   L.off_vtab = (int)p;
   p += (size_t)kRToh * kTabWords * 4;
   L.off_hcols = (int)p;
-  p += (size_t)kRTow * kTabWords * 4;
+  p += (size_t)kRTow * kHTabWords * 4;
   L.off_sync = (int)p;
   p += 128;
   L.group_bytes = (int)round_up(p, 128);

@@ -24,13 +24,14 @@ namespace irp {
 constexpr int kRGroups = 4;                          // 4-warp groups per CTA
 constexpr int kRThreads = kRGroups * 128;
 constexpr int kRTow = 64, kRToh = 32;                // largest output tile
-constexpr int kTabWords = 16;                        // words per row of the vertical / horizontal tables
+constexpr int kTabWords = 16;                        // words per row of the vertical table
+constexpr int kHTabWords = 20;                       // ... of the horizontal table: 80-byte rows keep the per-lane LDS.128 conflict-free
 
 struct RtJob {                   // one image of a streaming resize launch
   uint8_t* dst;
   unsigned long long dst_pitch;
   const uint32_t* vrows;         // [dh][16]: 13 vertical coefficient pairs (even-row aligned), word 15 = first pair-row
-  const uint32_t* hcols;         // [dw][16]: 14 horizontal coefficient pairs (word aligned),   word 15 = first word column
+  const uint32_t* hcols;         // [dw][20]: 14 horizontal coefficient pairs (word aligned),   word 15 = first word column
   const int32_t* vstart;         // [dh] first tap row (unclamped)
   const int32_t* hstart;         // [dw] first tap column (unclamped)
   int sw, sh, dw, dh;
@@ -208,8 +209,8 @@ __device__ __forceinline__ void rt_issue_tile(RtIssuer& is, const RtJob* __restr
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_vtab),
                "l"(vrows + (size_t)oy0 * kTabWords), "r"(oh * kTabWords * 4), "r"(bar_tile)
                : "memory");
-  is.hsrc = hcols + (size_t)ox0 * kTabWords;
-  is.hbytes = ow * kTabWords * 4;
+  is.hsrc = hcols + (size_t)ox0 * kHTabWords;
+  is.hbytes = ow * kHTabWords * 4;
 }
 // part B (the horizontal table is free too): the pending tile's horizontal-table columns
 __device__ __forceinline__ void rt_issue_hcols(const RtIssuer& is, uint32_t bar_h, uint32_t a_hcols) {
@@ -322,8 +323,23 @@ resize_tma_kernel(const RtJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
       const int npv = (SJ.vn + 2) >> 1;
       const int nrp = (oh + 1) >> 1;
       const int sy0_pair = sy0 >> 1;
-      for (int item = tid; item < ntr * nrp; item += 128) {
-        const int rp = item / ntr, tr = item - rp * ntr;
+      // A warp takes one row pair at a time and its lanes the first 32 columns, so the window distance
+      // d is uniform in the warp and the LDS.64 stream is conflict-free; columns beyond 32 (a 64-wide
+      // tile at shrink 1.95 has 35) are left-over items spread over the group afterwards.
+      const int nmain = min(ntr, 32), nleft = ntr - nmain;
+      const int main_rounds = (nrp + 3) >> 2;
+      for (int k = 0;; k++) {
+        int rp, tr;
+        if (k < main_rounds) {
+          rp = warp + 4 * k;
+          tr = lane;
+          if (rp >= nrp || lane >= nmain) continue;
+        } else {
+          const int j = tid + (k - main_rounds) * 128;
+          if (j >= nleft * nrp) break;
+          rp = j / nleft;
+          tr = 32 + j - rp * nleft;
+        }
         const int r = 2 * rp;
         const bool two = r + 1 < oh;
         const uint32_t sp = a_src + 2 * delta + tr * 24;
@@ -356,7 +372,7 @@ resize_tma_kernel(const RtJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
       const int xcol = tid & 63, rgh = tid >> 6;
       const int rows_per = (oh + 1) >> 1;
       const int r_begin = rgh * rows_per, r_end = min(oh, r_begin + rows_per);
-      const uint32_t* hp = s_hcols + xcol * kTabWords;
+      const uint32_t* hp = s_hcols + xcol * kHTabWords;
       const int hn = SJ.hn;
       const int nwh = (hn + 3 + 3) >> 2;
       uint8_t* d = SJ.dst + (size_t)(SJ.dst_y0 + oy0) * SJ.dst_pitch + (size_t)(SJ.dst_x0 + ox0 + xcol) * 3;
