@@ -241,9 +241,9 @@ def main() -> int:
     bytes_cls = B * W * H * 3  # one read of the source
     bytes_pre = B * (W * H * 3 + ow * oh * 3)  # one read of the source + one write of the output
     if cls_ms >= pre_ms:
-        kname, kbytes, kms = "classify_kernel<3>", bytes_cls, cls_ms
+        kname, kbytes, kms = "classify_bulk_kernel", bytes_cls, cls_ms
     else:
-        kname, kbytes, kms = "resize_kernel<3>", bytes_pre, pre_ms
+        kname, kbytes, kms = "resize_tma_kernel", bytes_pre, pre_ms
     achieved = kbytes / (kms * 1e-3) / 1e9
     step_bytes = B * (W * H * 3 + ow * oh * 3)  # fused figure: source once + output once
     roofline = {

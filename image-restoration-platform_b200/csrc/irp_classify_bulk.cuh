@@ -116,10 +116,28 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// A multiplier the compiler must not see as a constant: a kernel parameter.  ptxas turns x * 4 + b
+// with a literal 4 into LEA, which runs on the half-rate ALU pipe — the pipe that bounds this kernel;
+// with an opaque operand it stays an IMAD on the FMA pipe.  (IMAD.HI as a right shift was measured
+// too: slower than SHF + LOP3, so the inverse-table and histogram addresses keep those.)
+struct MulConsts { uint32_t four; };
+
+template <int J>
+__device__ __forceinline__ uint32_t byte_idx(uint32_t w) {   // byte J of w, zero-extended (one ALU-pipe op)
+  return J == 3 ? (w >> 24) : (J == 0 ? (w & 0xFFu) : __byte_perm(w, 0u, 0x4440 + J));
+}
+__device__ __forceinline__ uint32_t grey_top_fma(const Tiles<3>& T, const MulConsts& mc, uint32_t ri, uint32_t gi, uint32_t bi) {
+  const uint32_t I = lds_u32(ri * mc.four + T.a_lut_r) + lds_u32(gi * mc.four + T.a_lut_g) + lds_u32(bi * mc.four + T.a_lut_b);
+  return lds_u32(((I >> 18) & 0x3FFCu) | T.a_inv) + (I & 0xFFFFFu);
+}
+__device__ __forceinline__ void hist_add_fma(const Tiles<3>& T, const MulConsts& mc, uint32_t t) {
+  red_inc_shared(((t >> 22) & 0x3FCu) | T.a_hist);
+}
+
 // 4 pixels (12 interleaved bytes in w0..w2) -> planar words + grey word.
 // nvalid < 4 masks the moments / histogram (image edge); COUNTED = false for halo rows.
 template <bool COUNTED, bool MASKED>
-__device__ __forceinline__ void s1_quad(const Tiles<3>& T, Acc<3>& a, uint32_t w0, uint32_t w1, uint32_t w2, int nvalid,
+__device__ __forceinline__ void s1_quad(const Tiles<3>& T, const MulConsts& mc, Acc<3>& a, uint32_t w0, uint32_t w1, uint32_t w2, int nvalid,
                                         uint32_t& R, uint32_t& G, uint32_t& B, uint32_t& Y) {
   // w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3
   R = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
@@ -139,27 +157,27 @@ __device__ __forceinline__ void s1_quad(const Tiles<3>& T, Acc<3>& a, uint32_t w
     a.q[2] = __dp4a(b, b, a.q[2]);
   }
   uint32_t t[4];
-  t[0] = grey_top_off(T, byte_off4<0>(R), byte_off4<0>(G), byte_off4<0>(B));
-  t[1] = grey_top_off(T, byte_off4<1>(R), byte_off4<1>(G), byte_off4<1>(B));
-  t[2] = grey_top_off(T, byte_off4<2>(R), byte_off4<2>(G), byte_off4<2>(B));
-  t[3] = grey_top_off(T, byte_off4<3>(R), byte_off4<3>(G), byte_off4<3>(B));
+  t[0] = grey_top_fma(T, mc, byte_idx<0>(R), byte_idx<0>(G), byte_idx<0>(B));
+  t[1] = grey_top_fma(T, mc, byte_idx<1>(R), byte_idx<1>(G), byte_idx<1>(B));
+  t[2] = grey_top_fma(T, mc, byte_idx<2>(R), byte_idx<2>(G), byte_idx<2>(B));
+  t[3] = grey_top_fma(T, mc, byte_idx<3>(R), byte_idx<3>(G), byte_idx<3>(B));
   if (COUNTED) {
 #pragma unroll
     for (int j = 0; j < 4; j++)
-      if (!MASKED || j < nvalid) hist_add_top(T, t[j]);
+      if (!MASKED || j < nvalid) hist_add_fma(T, mc, t[j]);
   }
   Y = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x0073), 0x5410);
 }
 
 // one 16-pixel segment of a core row: 3 x LDS.128 from the raw tile -> 4 x STS.128 to the planes
 template <bool COUNTED, bool MASKED>
-__device__ __forceinline__ void s1_segment(const Tiles<3>& T, Acc<3>& a, uint32_t raw_addr, uint32_t plane_addr, int nvalid) {
+__device__ __forceinline__ void s1_segment(const Tiles<3>& T, const MulConsts& mc, Acc<3>& a, uint32_t raw_addr, uint32_t plane_addr, int nvalid) {
   const uint4 v0 = lds_v4(raw_addr), v1 = lds_v4(raw_addr + 16), v2 = lds_v4(raw_addr + 32);
   const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
   uint32_t R[4], G[4], B[4], Y[4];
 #pragma unroll
   for (int k = 0; k < 4; k++)
-    s1_quad<COUNTED, MASKED>(T, a, w[3 * k], w[3 * k + 1], w[3 * k + 2], nvalid - 4 * k, R[k], G[k], B[k], Y[k]);
+    s1_quad<COUNTED, MASKED>(T, mc, a, w[3 * k], w[3 * k + 1], w[3 * k + 2], nvalid - 4 * k, R[k], G[k], B[k], Y[k]);
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr), "r"(Y[0]), "r"(Y[1]), "r"(Y[2]), "r"(Y[3]) : "memory");
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + kBPlane), "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]) : "memory");
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + 2 * kBPlane), "r"(G[0]), "r"(G[1]), "r"(G[2]), "r"(G[3]) : "memory");
@@ -203,7 +221,7 @@ __device__ __forceinline__ void issue_tile(Issuer& is, const ImgDev* __restrict_
 __global__ void __launch_bounds__(kBThreads, 1)
 classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict__ tmaps, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
                      unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist, uint32_t dyn_smem_bytes,
-                     int* __restrict__ error_flag) {
+                     int* __restrict__ error_flag, MulConsts mc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const BulkMap map = make_bulk_map(sbase);
@@ -288,7 +306,7 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
       for (int i = 0; i < 2; i++) {  // core rows 1..32: 256 segments, two per thread
         const int item = tid + i * kGroupThreads;
         const int row = 1 + (item >> 3), seg = item & 7;
-        s1_segment<true, false>(T, acc, a_raw + row * kRawPitch + 16 + seg * 48, a_planes + row * kBPitch + 16 + seg * 16, 16);
+        s1_segment<true, false>(T, mc, acc, a_raw + row * kRawPitch + 16 + seg * 48, a_planes + row * kBPitch + 16 + seg * 16, 16);
       }
     } else {
       for (int i = 0; i < 2; i++) {
@@ -298,9 +316,9 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
         if (nvalid <= -1) continue;  // right of the replicate column: nothing reads it
         const uint32_t ra = a_raw + row * kRawPitch + 16 + seg * 48, pa = a_planes + row * kBPitch + 16 + seg * 16;
         if (y0 - 1 + row < H)
-          s1_segment<true, true>(T, acc, ra, pa, nvalid);
+          s1_segment<true, true>(T, mc, acc, ra, pa, nvalid);
         else
-          s1_segment<false, false>(T, acc, ra, pa, 0);
+          s1_segment<false, false>(T, mc, acc, ra, pa, 0);
       }
     }
     // halo rows (0 and 33) as 4-pixel pieces, halo columns as single pixels: spread over the group
@@ -310,7 +328,7 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
       if (full || c4 * 4 <= vw) {
         const uint32_t ra = a_raw + row * kRawPitch + 16 + c4 * 12, pa = a_planes + row * kBPitch + 16 + c4 * 4;
         uint32_t R, G, B, Y;
-        s1_quad<false, false>(T, acc, lds_b32(ra), lds_b32(ra + 4), lds_b32(ra + 8), 0, R, G, B, Y);
+        s1_quad<false, false>(T, mc, acc, lds_b32(ra), lds_b32(ra + 4), lds_b32(ra + 8), 0, R, G, B, Y);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(Y) : "memory");
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + kBPlane), "r"(R) : "memory");
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + 2 * kBPlane), "r"(G) : "memory");

@@ -107,7 +107,7 @@ struct irp_ctx {
   int occ_classify[5]{};  // CTAs per SM for C = 1, 3, 4
   cudaStream_t copy_in_stream = nullptr, copy_out_stream = nullptr;  // H2D / D2H of pipelined host batches
   std::vector<cudaEvent_t> sync_events, timing_events;
-  size_t chunk_bytes = 256u << 20;   // pixels per pipeline chunk of a host-resident batch
+  size_t chunk_bytes = 96u << 20;    // pixels per pipeline chunk of a host-resident batch (tools/pcie_probe.py: 64-128 MiB is the flat optimum)
   size_t smem_optin = 0;             // opt-in dynamic shared memory limit of the device
   uint32_t smem_base = 0; // .shared address where dynamic shared memory starts (probed once)
   int* d_error_flag = nullptr;
@@ -453,7 +453,7 @@ int launch_classify_bulk(irp_ctx* ctx, const ImgDev* d_imgs, const TmaDesc* d_tm
   const size_t smem = map.end - ctx->smem_base;
   int grid = std::min((total_tiles + kBGroups - 1) / kBGroups, ctx->sm_count);
   classify_bulk_kernel<<<grid, kBThreads, smem, ctx->stream>>>(d_imgs, d_tmaps, n, total_tiles, ctx->d_tables, d_acc, d_hist,
-                                                              (uint32_t)smem, ctx->d_error_flag);
+                                                              (uint32_t)smem, ctx->d_error_flag, MulConsts{4u});
   CK(cudaGetLastError());
   ctx->timing.kernel_launches++;
   return IRP_OK;

@@ -63,7 +63,7 @@ typedef struct irp_opts {
   int32_t luma_mode;    /* IRP_LUMA_*                                   */
   int32_t coef_mode;    /* IRP_COEF_*                                   */
   int32_t reserved0;
-  uint64_t staging_bytes; /* pixels per pipeline chunk of a host-resident batch; 0 = 256 MiB */
+  uint64_t staging_bytes; /* pixels per pipeline chunk of a host-resident batch; 0 = 96 MiB */
 } irp_opts;
 
 typedef struct irp_image_desc {
