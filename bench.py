@@ -202,8 +202,20 @@ def main() -> int:
     d_out = [eng.alloc_device(ow, oh, 3) for _ in imgs]
     mpix_step = B * W * H / 1e6
 
+    # descriptors are built once: the timed call is the C ABI itself (irp_analyze_batch), as a host
+    # binding would issue it, not the Python convenience wrapper
+    from irp_b200 import _ffi
+    import ctypes as C
+
+    dev_descs, _keep_dev = eng._descs(d_in, True, None)
+    dev_outs = (_ffi.OutDesc * B)()
+    dev_res = (_ffi.Result * B)()
+
     def step_device():
-        return eng.analyze_batch(d_in, device_outputs=d_out, raw=True)
+        for i, d in enumerate(d_out):
+            dev_outs[i] = _ffi.OutDesc(d.ptr, d.pitch, d.nbytes, 0, 0, 0, 1)
+        eng._check(eng._lib.irp_analyze_batch(eng._ctx, dev_descs, B, dev_res, dev_outs))
+        return dev_res[0].score[0]
 
     # ---- device-resident timing -------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -253,6 +265,21 @@ def main() -> int:
         "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
                  "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "frac_of_8000_nominal": step_bytes / (ms_step * 1e-3) / 1e9 / 8000.0},
     }
+    # the bound that actually binds: thread-instructions issued per source pixel (ncu, profiles/) against
+    # the SMs' issue rate (148 SMs x 4 schedulers x 32 lanes x SM clock) — DESIGN.md §4
+    ipp = os.path.join(ROOT, "profiles", "instr_per_pixel.json")
+    if os.path.exists(ipp):
+        try:
+            with open(ipp) as f:
+                ip = json.load(f)
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            peak_tips = 148 * 4 * 32 * sm_hz / 1e12
+            tot = (ip["classify_bulk_kernel"] + ip["resize_tma_kernel"]) * mpix_step * 1e6
+            roofline["issue"] = {"thread_instr_per_px": {"classify_bulk_kernel": ip["classify_bulk_kernel"], "resize_tma_kernel": ip["resize_tma_kernel"]},
+                                 "achieved_tera_instr_s": tot / ((cls_ms + pre_ms) * 1e-3) / 1e12, "peak_tera_instr_s": peak_tips,
+                                 "frac": tot / ((cls_ms + pre_ms) * 1e-3) / 1e12 / peak_tips, "source": "profiles/instr_per_pixel.json (ncu smsp__inst_executed.sum)"}
+        except Exception:
+            pass
     tr = os.path.join(ROOT, "profiles", "traffic.json")  # filled in from an ncu --set full capture, per launch
     if os.path.exists(tr):
         try:
@@ -270,9 +297,6 @@ def main() -> int:
             p[...] = im
             h_in.append(p)
         h_out = [eng.pinned_empty((oh, ow, 3)) for _ in imgs]
-        from irp_b200 import _ffi
-        import ctypes as C
-
         descs, keep = eng._descs(h_in, True, None)
         outs = (_ffi.OutDesc * B)()
         res = (_ffi.Result * B)()
@@ -302,7 +326,25 @@ def main() -> int:
             tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
+        # what the host link alone allows: the step's H2D and D2H bytes copied concurrently, nothing else
+        hi = torch.empty(B * W * H * 3, dtype=torch.uint8).pin_memory()
+        ho = torch.empty(B * ow * oh * 3, dtype=torch.uint8).pin_memory()
+        di, do = torch.empty_like(hi, device="cuda"), torch.empty_like(ho, device="cuda")
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        floor_ms = None
+        for rep in range(3):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            with torch.cuda.stream(sa):
+                di.copy_(hi, non_blocking=True)
+            with torch.cuda.stream(sb):
+                ho.copy_(do, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t1) * 1e3
+            floor_ms = dt if floor_ms is None else min(floor_ms, dt)
+        del hi, ho, di, do
         e2e = {"value": world * mpix_step / (ms / n_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": B * W * H * 3,
+               "link_floor_ms_per_step": floor_ms, "frac_of_link_floor": floor_ms / (ms / n_e2e),
                "d2h_bytes_per_step": B * ow * oh * 3 + B * C.sizeof(_ffi.Result), "steps": n_e2e, "ms_per_step": ms / n_e2e,
                "wall_ms_per_step": wall_ms / n_e2e, "host_memory": "pinned (irp_host_alloc_pinned)"}
 
