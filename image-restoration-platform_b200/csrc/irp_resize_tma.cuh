@@ -147,7 +147,36 @@ __device__ __forceinline__ void hpass_column_s(uint32_t mbase, int mid_pitch, in
     if (4 * q4 + 2 < 2 * NWH + 2) cph[4 * q4 + 2] = c4.z;
     if (4 * q4 + 3 < 2 * NWH + 2) cph[4 * q4 + 3] = c4.w;
   }
-  for (int r = r_begin; r < r_end; r++) {
+  // two rows per iteration: six independent IDP chains hide the dot-product latency
+  int r = r_begin;
+  for (; r + 1 < r_end; r += 2) {
+    uint32_t v[2][3];
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const uint32_t ma = mbase + ch * mid_plane + (r + rr) * mid_pitch;
+        uint32_t w[NWH];
+#pragma unroll
+        for (int wv = 0; wv < NWH; wv++) w[wv] = lds_b32(ma + 4 * wv);
+        int acc = 1 << (IRP_INTERP_SHIFT - 1);
+#pragma unroll
+        for (int wv = 0; wv < NWH; wv++) {
+          acc = dp2a_lo_s16_u8(cph[2 * wv], w[wv], acc);
+          acc = dp2a_hi_s16_u8(cph[2 * wv + 1], w[wv], acc);
+        }
+        v[rr][ch] = pack_sat_u8(0, acc >> IRP_INTERP_SHIFT, 0u);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      uint8_t* dp = d + (size_t)(r + rr) * dst_pitch;
+      dp[0] = (uint8_t)v[rr][0];
+      dp[1] = (uint8_t)v[rr][1];
+      dp[2] = (uint8_t)v[rr][2];
+    }
+  }
+  if (r < r_end) {
     uint32_t v[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
@@ -325,26 +354,15 @@ resize_tma_kernel(const RtJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
       const int sy0_pair = sy0 >> 1;
       // A warp takes one row pair at a time and its lanes the first 32 columns, so the window distance
       // d is uniform in the warp and the LDS.64 stream is conflict-free; columns beyond 32 (a 64-wide
-      // tile at shrink 1.95 has 35) are left-over items spread over the group afterwards.
+      // tile at shrink 1.95 has 35) are left-over items handled afterwards.
       const int nmain = min(ntr, 32), nleft = ntr - nmain;
-      const int main_rounds = (nrp + 3) >> 2;
-      for (int k = 0;; k++) {
-        int rp, tr;
-        if (k < main_rounds) {
-          rp = warp + 4 * k;
-          tr = lane;
-          if (rp >= nrp || lane >= nmain) continue;
-        } else {
-          const int j = tid + (k - main_rounds) * 128;
-          if (j >= nleft * nrp) break;
-          rp = j / nleft;
-          tr = 32 + j - rp * nleft;
-        }
+      for (int rp = warp; rp < nrp; rp += 4) {
+        if (lane >= nmain) continue;
         const int r = 2 * rp;
         const bool two = r + 1 < oh;
-        const uint32_t sp = a_src + 2 * delta + tr * 24;
+        const uint32_t sp = a_src + 2 * delta + lane * 24;
         const uint32_t* vt0 = s_vtab + r * kTabWords;
-        const uint32_t ma = a_mid + r * L.mid_pitch + tr * 4;
+        const uint32_t ma = a_mid + r * L.mid_pitch + lane * 4;
         switch (npv) {
           case 2: vpass_item<2>(sp, pair_pitch, vt0, two, sy0_pair, ma, L.mid_pitch, mid_plane); break;
           case 3: vpass_item<3>(sp, pair_pitch, vt0, two, sy0_pair, ma, L.mid_pitch, mid_plane); break;
@@ -358,6 +376,27 @@ resize_tma_kernel(const RtJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           case 11: vpass_item<11>(sp, pair_pitch, vt0, two, sy0_pair, ma, L.mid_pitch, mid_plane); break;
           case 12: vpass_item<12>(sp, pair_pitch, vt0, two, sy0_pair, ma, L.mid_pitch, mid_plane); break;
           default: vpass_item<13>(sp, pair_pitch, vt0, two, sy0_pair, ma, L.mid_pitch, mid_plane); break;
+        }
+      }
+      // left-over columns, one output ROW per item so that they spread over the whole group
+      for (int j = tid; j < nleft * oh; j += 128) {
+        const int r = j / nleft, tr = 32 + j - r * nleft;
+        const uint32_t* vt0 = s_vtab + r * kTabWords;
+        const uint32_t sp = a_src + 2 * delta + tr * 24 + ((int)vt0[15] - sy0_pair) * pair_pitch;
+        const uint32_t ma = a_mid + r * L.mid_pitch + tr * 4;
+        switch (npv) {
+          case 2: vpass_triple<2, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 3: vpass_triple<3, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 4: vpass_triple<4, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 5: vpass_triple<5, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 6: vpass_triple<6, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 7: vpass_triple<7, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 8: vpass_triple<8, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 9: vpass_triple<9, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 10: vpass_triple<10, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 11: vpass_triple<11, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          case 12: vpass_triple<12, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
+          default: vpass_triple<13, 0, false>(sp, pair_pitch, vt0, ma, L.mid_pitch, mid_plane); break;
         }
       }
     }
