@@ -594,8 +594,13 @@ int launch_resize(irp_ctx* ctx, const ResizeJob* d_jobs, const ResizeJob* h_jobs
 template <int C>
 int launch_orient(irp_ctx* ctx, const uint8_t* src, size_t spitch, int w, int h, int o, uint8_t* dst, size_t dpitch, int ow,
                   int oh) {
-  dim3 b(32, 8), g((ow + 31) / 32, (oh + 7) / 8);
-  orient_kernel<C><<<g, b, 0, ctx->stream>>>(src, spitch, w, h, o, dst, dpitch, ow, oh);
+  if (C == 3 && ((((uintptr_t)src | spitch | (uintptr_t)dst | dpitch) & 3) == 0) && dpitch >= round_up((size_t)ow * 3, 4)) {
+    dim3 g((ow + kOrTw - 1) / kOrTw, (oh + kOrTh - 1) / kOrTh);
+    orient3_kernel<<<g, kOrThreads, 0, ctx->stream>>>(src, spitch, w, h, o, dst, dpitch, ow, oh);
+  } else {
+    dim3 b(32, 8), g((ow + 31) / 32, (oh + 7) / 8);
+    orient_kernel<C><<<g, b, 0, ctx->stream>>>(src, spitch, w, h, o, dst, dpitch, ow, oh);
+  }
   CK(cudaGetLastError());
   ctx->timing.kernel_launches++;
   return IRP_OK;

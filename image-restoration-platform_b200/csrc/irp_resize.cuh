@@ -254,6 +254,63 @@ __global__ void orient_kernel(const uint8_t* __restrict__ src, unsigned long lon
   for (int ch = 0; ch < C; ch++) d[ch] = s[ch];
 }
 
+// Orientation for 3-channel images through a shared-memory tile (the gather above reads one source
+// ROW per lane for the transposing orientations 5-8: 32 sectors per load).  A CTA owns a 64x32-pixel
+// DESTINATION tile: phase 1 pulls the matching source region (64x32, or 32x64 when transposed) with
+// coalesced 32-bit loads into a tile whose odd word pitch makes column walks conflict-free; phase 2
+// lets every thread build whole destination words (4 bytes = parts of 2 pixels) from byte reads of
+// that tile and store them coalesced.  The destination scratch has a 16-byte pitch, so the word that
+// straddles the right edge of the image spills into padding, never into the next row's pixels.
+constexpr int kOrTw = 64, kOrTh = 32, kOrThreads = 192, kOrPitchW = 51;   // 51 words = 204 bytes per tile row
+
+__global__ void __launch_bounds__(kOrThreads)
+orient3_kernel(const uint8_t* __restrict__ src, unsigned long long spitch, int w, int h, int orientation, uint8_t* __restrict__ dst,
+               unsigned long long dpitch, int ow, int oh) {
+  __shared__ uint32_t tile[64 * kOrPitchW];
+  const int x0 = blockIdx.x * kOrTw, y0 = blockIdx.y * kOrTh;
+  const int tw = min(kOrTw, ow - x0), th = min(kOrTh, oh - y0);
+  const bool transposed = orientation >= 5;
+  // destination (x, y) -> source (sx, sy); flip_x / flip_y act on the SOURCE axes
+  const bool flip_sx = orientation == 2 || orientation == 3 || orientation == 7 || orientation == 8;
+  const bool flip_sy = orientation == 3 || orientation == 4 || orientation == 6 || orientation == 7;
+  // source region of this tile: columns [sx0, sx0 + ncx), rows [sy0, sy0 + ncy)
+  const int ncx = transposed ? th : tw, ncy = transposed ? tw : th;
+  const int dx0 = transposed ? y0 : x0, dy0 = transposed ? x0 : y0;       // tile origin along source x / y before flips
+  const int sx0 = flip_sx ? w - dx0 - ncx : dx0, sy0 = flip_sy ? h - dy0 - ncy : dy0;
+  // phase 1: rows of the region as words, from the word that holds its first byte
+  const int b0 = sx0 * 3, wb0 = b0 & ~3, nwords = ((b0 + ncx * 3 + 3) >> 2) - (wb0 >> 2);
+  const int boff = b0 - wb0;
+  for (int e = threadIdx.x; e < ncy * nwords; e += kOrThreads) {
+    const int r = e / nwords, k = e - r * nwords;
+    tile[r * kOrPitchW + k] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(sy0 + r) * spitch + wb0) + k);
+  }
+  __syncthreads();
+  // phase 2: thread = one word column of the destination tile (48 per row) x one of 4 row groups
+  const int wq = threadIdx.x % 48, rg = threadIdx.x / 48;
+  if (wq * 4 >= tw * 3) return;
+  const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+  int off[4], step;   // byte offset inside the tile of the word's four bytes for destination row 0, and the per-row step
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const int B = wq * 4 + b;
+    const int p = min(B / 3, tw - 1), ch = B - (B / 3) * 3;               // destination pixel (clamped into the tile) and channel
+    if (!transposed) {
+      const int cx = flip_sx ? ncx - 1 - p : p;
+      off[b] = boff + cx * 3 + ch + (flip_sy ? (ncy - 1) * kOrPitchW * 4 : 0);
+    } else {                                                              // destination x walks source rows
+      const int cy = flip_sy ? ncy - 1 - p : p;
+      off[b] = boff + cy * kOrPitchW * 4 + ch + (flip_sx ? (ncx - 1) * 3 : 0);
+    }
+  }
+  step = !transposed ? (flip_sy ? -kOrPitchW * 4 : kOrPitchW * 4) : (flip_sx ? -3 : 3);   // destination y walks source rows / columns
+  uint8_t* drow = dst + (size_t)y0 * dpitch + (size_t)x0 * 3 + wq * 4;
+  for (int ty = rg; ty < th; ty += 4) {
+    const int o = ty * step;
+    const uint32_t v = tb[off[0] + o] | (tb[off[1] + o] << 8) | (tb[off[2] + o] << 16) | (tb[off[3] + o] << 24);
+    *reinterpret_cast<uint32_t*>(drow + (size_t)ty * dpitch) = v;
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(kResizeThreads)
 resize_kernel(const ResizeJob* __restrict__ jobs, int n_jobs, int total_tiles) {
