@@ -665,9 +665,13 @@ int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* 
 
 // the streaming kernel (irp_resize_tma.cuh): smallest tile footprint that serves every tile of a job
 struct RtFoot { int tow, toh, ncols, nrows; };
-bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, RtFoot* f) {
-  int tow = kRTow, toh = kRToh;
-  for (;;) {
+RtLayout rt_layout(int ncols_px, int nrows);
+// Largest output tile whose source footprint fits the TMA box limits (512 bytes x 256 rows) and, together
+// with the boxes already chosen for this launch, one group's share of shared memory.
+bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, int launch_cols, int launch_rows, size_t budget, RtFoot* f) {
+  static const int cand[][2] = {{64, 32}, {64, 24}, {64, 16}, {32, 32}, {32, 16}, {64, 8}, {16, 32}, {32, 8}, {16, 16}, {16, 8}};
+  for (const auto& c : cand) {
+    const int tow = c[0], toh = c[1];
     int ncols = 0, nrows = 0;
     for (int ox0 = 0; ox0 < dw; ox0 += tow) {
       const int last = std::min(ox0 + tow, dw) - 1;
@@ -677,13 +681,14 @@ bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, RtFoot* f)
       const int last = std::min(oy0 + toh, dh) - 1;
       nrows = std::max(nrows, v.h_start[last] + v.n - (v.h_start[oy0] & ~1));
     }
-    const int ntr = (ncols + 3) / 4;
-    if (ntr * 12 + 12 > 512 && tow > 8) { tow >>= 1; continue; }
-    if (nrows + 1 > 256 && toh > 4) { toh >>= 1; continue; }
-    if (ntr * 12 + 12 > 512 || nrows + 1 > 256) return false;
-    *f = RtFoot{tow, toh, ntr * 4, (nrows + 1) & ~1};
+    const int ntr = (ncols + 3) / 4, rows = (nrows + 1) & ~1;
+    if (ntr * 12 + 12 > 512 || rows > 256) continue;
+    const RtLayout L = rt_layout(std::max(launch_cols, ntr * 4), std::max(launch_rows, rows));
+    if ((size_t)L.group_bytes > budget || L.box_cols > 512 || L.box_rows > 256) continue;
+    *f = RtFoot{tow, toh, ntr * 4, rows};
     return true;
   }
+  return false;
 }
 
 RtLayout rt_layout(int ncols_px, int nrows) {
@@ -760,20 +765,19 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     if ((rc = get_plan(ctx, g.wo, g.dw, g.f, &ph[i - b], &dh[i - b]))) return rc;
     int k = d.channels == 1 ? 0 : (d.channels == 4 ? 2 : 1);
     if (k == 1 && ctx->bulk_ok && ctx->rtma_ok && ((((uintptr_t)s.px | s.pitch) & 15) == 0) && pv[i - b].n > 1 && ph[i - b].n > 1 &&
-        rt_footprint(*dv[i - b], *dh[i - b], g.dw, g.dh, &foot[i - b])) {
-      const RtLayout L = rt_layout(std::max(box_cols_px, foot[i - b].ncols), std::max(box_rows, foot[i - b].nrows));
-      if ((size_t)L.group_bytes <= budget && L.box_cols <= 512 && L.box_rows <= 256) {
-        k = 3;
-        box_cols_px = std::max(box_cols_px, foot[i - b].ncols);
-        box_rows = std::max(box_rows, foot[i - b].nrows);
-      }
+        rt_footprint(*dv[i - b], *dh[i - b], g.dw, g.dh, box_cols_px, box_rows, budget, &foot[i - b])) {
+      k = 3;
+      box_cols_px = std::max(box_cols_px, foot[i - b].ncols);
+      box_rows = std::max(box_rows, foot[i - b].nrows);
     }
+    // no geometry change and nothing to normalise: the oriented pixels ARE the result, a 2-D copy
+    if (pv[i - b].n == 1 && ph[i - b].n == 1 && g.dc == d.channels && g.dw == g.wo && g.dh == g.ho) k = 4;
     kern[i - b] = k;
   }
   const RtLayout L = rt_layout(std::max(box_cols_px, 4), std::max(box_rows, 2));
   // pass 2: job descriptors, grouped by kernel
-  int pos = b, group_begin[5], group_tiles[4];
-  for (int gi = 0; gi < 4; gi++) {
+  int pos = b, group_begin[6], group_tiles[5];
+  for (int gi = 0; gi < 5; gi++) {
     group_begin[gi] = pos;
     int tiles = 0;
     for (int i = b; i < e; i++) {
@@ -784,6 +788,21 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       const OutPlan& op = oplans[i];
       if (mode == 1)  // black pad: clear the whole canvas, the tiles then write the image once
         CK(cudaMemset2DAsync(op.dev, op.dev_pitch, 0, (size_t)od.width * g.dc, od.height, ctx->stream));
+      if (gi == 4) {   // identity geometry: a row copy (into the canvas window for fusion); descriptors share the job buffer
+        CopyJob& K = reinterpret_cast<CopyJob*>(h_jobs + pos)[0];
+        static_assert(sizeof(CopyJob) <= sizeof(ResizeJob), "copy descriptors are stored in resize-job slots");
+        K.src = src[i - b].px;
+        K.spitch = src[i - b].pitch;
+        K.dst = op.dev + (size_t)g.oy * op.dev_pitch + (size_t)g.ox * g.dc;
+        K.dpitch = op.dev_pitch;
+        K.row_bytes = g.dw * g.dc;
+        K.rows = g.dh;
+        K.row_base = tiles;
+        K.pad = 0;
+        tiles += g.dh;
+        pos++;
+        continue;
+      }
       if (gi == 3) {
         RtJob& R = h_rt[pos];
         memset(&R, 0, sizeof R);
@@ -801,7 +820,9 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         R.tile_base = tiles;
         R.vn = pv[i - b].n; R.hn = ph[i - b].n;
         tiles += R.tiles_x * R.tiles_y;
-        if ((rc = encode_source_tmap(ctx, src[i - b].px, src[i - b].pitch, g.wo, g.ho, L.box_cols, L.box_rows, h_tm + pos))) return rc;
+        R.box_cols = (int)round_up((size_t)foot[i - b].ncols * 3 + 12, 16);
+        R.box_rows = foot[i - b].nrows;
+        if ((rc = encode_source_tmap(ctx, src[i - b].px, src[i - b].pitch, g.wo, g.ho, R.box_cols, R.box_rows, h_tm + pos))) return rc;
         pos++;
         continue;
       }
@@ -831,7 +852,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     }
     group_tiles[gi] = tiles;
   }
-  group_begin[4] = pos;
+  group_begin[5] = pos;
   if (pos == b) return IRP_OK;
   ResizeJob* d_jobs = (ResizeJob*)ctx->d_jobs.p;
   if (group_begin[3] > b)
@@ -839,6 +860,19 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
   if ((rc = launch_resize<1>(ctx, d_jobs + group_begin[0], h_jobs + group_begin[0], group_begin[1] - group_begin[0], group_tiles[0]))) return rc;
   if ((rc = launch_resize<3>(ctx, d_jobs + group_begin[1], h_jobs + group_begin[1], group_begin[2] - group_begin[1], group_tiles[1]))) return rc;
   if ((rc = launch_resize<4>(ctx, d_jobs + group_begin[2], h_jobs + group_begin[2], group_begin[3] - group_begin[2], group_tiles[2]))) return rc;
+  if (const int ncp = group_begin[5] - group_begin[4]) {
+    // copy jobs sit in ResizeJob-sized slots: compact them into a dense CopyJob array at the front of their range
+    const int g4 = group_begin[4];
+    CopyJob* hc = reinterpret_cast<CopyJob*>(h_jobs + g4);
+    for (int k = 1; k < ncp; k++) hc[k] = reinterpret_cast<CopyJob*>(h_jobs + g4 + k)[0];
+    CopyJob* dc = reinterpret_cast<CopyJob*>(d_jobs + g4);
+    CK(cudaMemcpyAsync(dc, hc, sizeof(CopyJob) * ncp, cudaMemcpyHostToDevice, ctx->stream));
+    const int rows = group_tiles[4];
+    const int grid = std::min((rows + 7) / 8, ctx->sm_count * 8);
+    copy_rows_kernel<<<grid, 256, 0, ctx->stream>>>(dc, ncp, rows);
+    CK(cudaGetLastError());
+    ctx->timing.kernel_launches++;
+  }
   if (const int nrt = group_begin[4] - group_begin[3]) {
     RtJob* d_rt = (RtJob*)ctx->d_rtjobs.p;
     const int g3 = group_begin[3];

@@ -254,6 +254,42 @@ __global__ void orient_kernel(const uint8_t* __restrict__ src, unsigned long lon
   for (int ch = 0; ch < C; ch++) d[ch] = s[ch];
 }
 
+// Identity geometry (source already <= 2048 px and 3 -> 3 or 1 -> 1 channels): the preprocess output
+// is the oriented source, so the whole batch's identity jobs are one launch of row copies (one warp per
+// row, the widest access both addresses allow).
+struct CopyJob {
+  const uint8_t* src;
+  unsigned long long spitch;
+  uint8_t* dst;
+  unsigned long long dpitch;
+  int row_bytes, rows, row_base, pad;
+};
+
+__global__ void __launch_bounds__(256) copy_rows_kernel(const CopyJob* __restrict__ jobs, int n_jobs, int total_rows) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  int ji = 0;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < total_rows; row += nwarps) {
+    while (ji + 1 < n_jobs && row >= __ldg(&jobs[ji + 1].row_base)) ji++;
+    const CopyJob J = jobs[ji];
+    const int r = row - J.row_base;
+    const uint8_t* sp = J.src + (size_t)r * J.spitch;
+    uint8_t* dp = J.dst + (size_t)r * J.dpitch;
+    const uintptr_t both = (uintptr_t)sp | (uintptr_t)dp;
+    int done = 0;
+    if ((both & 15) == 0) {
+      const int nv = J.row_bytes >> 4;
+      for (int k = lane; k < nv; k += 32) reinterpret_cast<uint4*>(dp)[k] = __ldg(reinterpret_cast<const uint4*>(sp) + k);
+      done = nv << 4;
+    } else if ((both & 3) == 0) {
+      const int nv = J.row_bytes >> 2;
+      for (int k = lane; k < nv; k += 32) reinterpret_cast<uint32_t*>(dp)[k] = __ldg(reinterpret_cast<const uint32_t*>(sp) + k);
+      done = nv << 2;
+    }
+    for (int k = done + lane; k < J.row_bytes; k += 32) dp[k] = __ldg(sp + k);
+  }
+}
+
 // Orientation for 3-channel images through a shared-memory tile (the gather above reads one source
 // ROW per lane for the transposing orientations 5-8: 32 sectors per load).  A CTA owns a 64x32-pixel
 // DESTINATION tile: phase 1 pulls the matching source region (64x32, or 32x64 when transposed) with

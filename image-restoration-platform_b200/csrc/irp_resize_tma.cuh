@@ -38,11 +38,12 @@ struct RtJob {                   // one image of a streaming resize launch
   int dst_x0, dst_y0;
   int tow, toh, tiles_x, tiles_y, tile_base;
   int vn, hn;
-  int pad[3];
+  int box_cols, box_rows;        // this job's TMA box: bytes per row (multiple of 16), rows (even); <= the launch-wide layout
+  int pad[1];
 };
 
 struct RtLayout {                // byte offsets inside one group's shared-memory slice (uniform per launch)
-  int box_cols, box_rows;        // TMA box: bytes per row (multiple of 16), rows (even)
+  int box_cols, box_rows;        // largest TMA box of the launch: bytes per row (multiple of 16), rows (even)
   int mid_pitch;                 // bytes per row per plane of the intermediate tile
   int off_mid, off_vtab, off_hcols, off_sync, group_bytes;
 };
@@ -233,7 +234,7 @@ __device__ __forceinline__ void rt_issue_tile(RtIssuer& is, const RtJob* __restr
   const int ntr = (__ldg(hstart + ox0 + ow - 1) + __ldg(&J->hn) - sx0 + 3) >> 2;
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr), "r"(is.job), "r"(ox0), "r"(oy0), "r"(ow) : "memory");
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr + 16), "r"(oh), "r"(sx0), "r"(sy0), "r"(ntr) : "memory");
-  mbar_arrive_expect_tx(bar_tile, (uint32_t)(L.box_rows * L.box_cols + oh * kTabWords * 4));
+  mbar_arrive_expect_tx(bar_tile, (uint32_t)(__ldg(&J->box_rows) * __ldg(&J->box_cols) + oh * kTabWords * 4));
   tma_load_2d(a_src, tmaps + is.job, ((sx0 * 3) & ~15) >> 1, sy0, bar_tile);   // a box row must start on a 16-byte boundary
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_vtab),
                "l"(vrows + (size_t)oy0 * kTabWords), "r"(oh * kTabWords * 4), "r"(bar_tile)
@@ -282,7 +283,7 @@ resize_tma_kernel(const RtJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
     rt_issue_hcols(is, a_barh, a_hcols);
   }
 
-  const int pair_pitch = 2 * L.box_cols, mid_plane = kRToh * L.mid_pitch;
+  const int mid_plane = kRToh * L.mid_pitch;
   int loaded_job = -1;
   for (uint32_t it = 0;; it++) {
     mbar_wait(a_bar, it & 1u);
@@ -298,26 +299,27 @@ resize_tma_kernel(const RtJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
       group_barrier(group);
     }
     const int sw = SJ.sw, sh = SJ.sh;
+    const int box_cols = SJ.box_cols, box_rows = SJ.box_rows, pair_pitch = 2 * box_cols;
     const int delta = (sx0 * 3) & 15;   // byte offset of pixel sx0 inside a box row (0, 4, 8 or 12)
 
     // ---- replicate rows / columns that fell outside the image (TMA wrote zeros there) ----
-    if (sy0 < 0 || sy0 + L.box_rows > sh) {
-      const int lo = max(-sy0, 0), hi = min(sh - 1 - sy0, L.box_rows - 1);   // box rows holding image rows 0 and sh - 1
-      for (int r = warp; r < L.box_rows; r += 4) {
+    if (sy0 < 0 || sy0 + box_rows > sh) {
+      const int lo = max(-sy0, 0), hi = min(sh - 1 - sy0, box_rows - 1);   // box rows holding image rows 0 and sh - 1
+      for (int r = warp; r < box_rows; r += 4) {
         const int sr = min(max(r, lo), hi);
         if (sr != r)
-          for (int k = lane; k < L.box_cols / 4; k += 32) {
-            const uint32_t v = lds_b32(a_src + sr * L.box_cols + 4 * k);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_src + r * L.box_cols + 4 * k), "r"(v) : "memory");
+          for (int k = lane; k < box_cols / 4; k += 32) {
+            const uint32_t v = lds_b32(a_src + sr * box_cols + 4 * k);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_src + r * box_cols + 4 * k), "r"(v) : "memory");
           }
       }
       group_barrier(group);
     }
-    if (sx0 < 0 || sx0 + (L.box_cols - delta) / 3 > sw) {
-      const int ncol = (L.box_cols - delta) / 3;
+    if (sx0 < 0 || sx0 + (box_cols - delta) / 3 > sw) {
+      const int ncol = (box_cols - delta) / 3;
       const int lo = max(-sx0, 0), hi = min(sw - 1 - sx0, ncol - 1);          // box columns holding image columns 0 and sw - 1
-      for (int r = tid; r < L.box_rows; r += 128) {
-        const uint32_t rr = a_src + r * L.box_cols + delta;
+      for (int r = tid; r < box_rows; r += 128) {
+        const uint32_t rr = a_src + r * box_cols + delta;
         for (int j = 0; j < lo; j++)
           for (int k = 0; k < 3; k++) sts_u8(rr + 3 * j + k, lds_u8(rr + 3 * lo + k));
         for (int j = hi + 1; j < ncol; j++)
@@ -327,13 +329,13 @@ resize_tma_kernel(const RtJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
     }
 
     // ---- rows (2q, 2q+1) -> pair-interleaved words (a_k, b_k, a_k+1, b_k+1), in place, one warp per pair-row ----
-    for (int q = warp; q < L.box_rows / 2; q += 4) {
+    for (int q = warp; q < box_rows / 2; q += 4) {
       const uint32_t ra = a_src + q * pair_pitch;
       uint4 va = make_uint4(0, 0, 0, 0), vb = va;
-      const bool on = lane * 16 < L.box_cols;
+      const bool on = lane * 16 < box_cols;
       if (on) {
         va = lds_v4(ra + 16 * lane);
-        vb = lds_v4(ra + L.box_cols + 16 * lane);
+        vb = lds_v4(ra + box_cols + 16 * lane);
       }
       __syncwarp();
       if (on) {
