@@ -212,10 +212,13 @@ def main() -> int:
     dev_outs = (_ffi.OutDesc * B)()
     dev_res = (_ffi.Result * B)()
 
+    for i, d in enumerate(d_out):
+        dev_outs[i] = _ffi.OutDesc(d.ptr, d.pitch, d.nbytes, 0, 0, 0, 1)
+
     def step_device():
-        for i, d in enumerate(d_out):
-            dev_outs[i] = _ffi.OutDesc(d.ptr, d.pitch, d.nbytes, 0, 0, 0, 1)
-        eng._check(eng._lib.irp_analyze_batch(eng._ctx, dev_descs, B, dev_res, dev_outs))
+        rc = eng._lib.irp_analyze_batch(eng._ctx, dev_descs, B, dev_res, dev_outs)
+        if rc:
+            eng._check(rc)
         return dev_res[0].score[0]
 
     # ---- device-resident timing -------------------------------------------------------------
