@@ -214,6 +214,9 @@ __device__ __forceinline__ void issue_tile(Issuer& is, const ImgDev* __restrict_
   is.last_img = is.img;
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr), "r"(x0), "r"(y0), "r"(w), "r"(h) : "memory");
   asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(info_addr + 16), "r"(slot), "r"(1 | (flush ? 2 : 0)) : "memory");
+  // generic-proxy accesses to the raw buffer (stage 1 reads, edge patches) were ordered before this
+  // lane by the group barrier; order them before the async-proxy write of the next tile as well
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   mbar_arrive_expect_tx(bar, kRows * kRawPitch);
   tma_load_2d(raw_addr, tmaps + is.img, (x0 * 3 - 16) >> 1, y0 - 1, bar);   // coordinates in u16 elements, rows
 }

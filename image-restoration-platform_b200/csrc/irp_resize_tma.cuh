@@ -234,6 +234,7 @@ __device__ __forceinline__ void rt_issue_tile(RtIssuer& is, const RtJob* __restr
   const int ntr = (__ldg(hstart + ox0 + ow - 1) + __ldg(&J->hn) - sx0 + 3) >> 2;
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr), "r"(is.job), "r"(ox0), "r"(oy0), "r"(ow) : "memory");
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info_addr + 16), "r"(oh), "r"(sx0), "r"(sy0), "r"(ntr) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes (in-place interleave) before the async-proxy refill
   mbar_arrive_expect_tx(bar_tile, (uint32_t)(__ldg(&J->box_rows) * __ldg(&J->box_cols) + oh * kTabWords * 4));
   tma_load_2d(a_src, tmaps + is.job, ((sx0 * 3) & ~15) >> 1, sy0, bar_tile);   // a box row must start on a 16-byte boundary
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_vtab),
