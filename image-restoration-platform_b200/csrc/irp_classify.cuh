@@ -133,11 +133,12 @@ template <int J>
 __device__ __forceinline__ uint32_t byte_off4(uint32_t w) {
   return J == 0 ? ((w << 2) & 0x3FCu) : ((w >> (8 * J - 2)) & 0x3FCu);
 }
-// integer restatement of libvips colourspace(B_W): returns inv[I >> 20] + (I & 0xFFFFF); grey = top byte
+// integer restatement of libvips colourspace(B_W): returns inv[I >> 20] + (I & 0xFFFFF); grey = top byte.
+// I = (I >> 20 << 20) + (I & 0xFFFFF), so with inv'[k] = inv[k] - (k << 20) the same value is inv'[I >> 20] + I.
 template <int C>
 __device__ __forceinline__ uint32_t grey_top_off(const Tiles<C>& T, uint32_t ro, uint32_t go, uint32_t bo) {
   const uint32_t I = lds_u32(ro | T.a_lut_r) + lds_u32(go | T.a_lut_g) + lds_u32(bo | T.a_lut_b);
-  return lds_u32(((I >> 18) & 0x3FFCu) | T.a_inv) + (I & 0xFFFFFu);
+  return lds_u32(((I >> 18) & 0x3FFCu) | T.a_inv) + I;   // the shared copy of inv[k] has k << 20 subtracted: no masking of I
 }
 template <int C>
 __device__ __forceinline__ void hist_add_top(const Tiles<C>& T, uint32_t t) {
@@ -470,7 +471,7 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (map.lut_r - sbase));
     uint32_t* inv = reinterpret_cast<uint32_t*>(smem_raw + (map.inv - sbase));
     for (int i = threadIdx.x; i < 3 * 256; i += kClassifyThreads) lut[i] = (&tab->lut[0][0])[i];
-    for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) inv[i] = tab->inv[i];
+    for (int i = threadIdx.x; i < 4096; i += kClassifyThreads) inv[i] = tab->inv[i] - ((uint32_t)i << 20);
     for (int b = tid; b < 256; b += kGroupThreads) T.hist[b] = 0;
   }
   __syncthreads();

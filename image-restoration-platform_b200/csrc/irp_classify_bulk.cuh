@@ -128,7 +128,7 @@ __device__ __forceinline__ uint32_t byte_idx(uint32_t w) {   // byte J of w, zer
 }
 __device__ __forceinline__ uint32_t grey_top_fma(const Tiles<3>& T, const MulConsts& mc, uint32_t ri, uint32_t gi, uint32_t bi) {
   const uint32_t I = lds_u32(ri * mc.four + T.a_lut_r) + lds_u32(gi * mc.four + T.a_lut_g) + lds_u32(bi * mc.four + T.a_lut_b);
-  return lds_u32(((I >> 18) & 0x3FFCu) | T.a_inv) + (I & 0xFFFFFu);
+  return lds_u32(((I >> 18) & 0x3FFCu) | T.a_inv) + I;
 }
 __device__ __forceinline__ void hist_add_fma(const Tiles<3>& T, const MulConsts& mc, uint32_t t) {
   red_inc_shared(((t >> 22) & 0x3FCu) | T.a_hist);
@@ -252,7 +252,7 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
     uint32_t* lut = reinterpret_cast<uint32_t*>(smem_raw + (map.lut_r - sbase));
     uint32_t* inv = reinterpret_cast<uint32_t*>(smem_raw + (map.inv - sbase));
     for (int i = threadIdx.x; i < 3 * 256; i += kBThreads) lut[i] = (&tab->lut[0][0])[i];
-    for (int i = threadIdx.x; i < 4096; i += kBThreads) inv[i] = tab->inv[i];
+    for (int i = threadIdx.x; i < 4096; i += kBThreads) inv[i] = tab->inv[i] - ((uint32_t)i << 20);
     for (int b = tid; b < 256; b += kGroupThreads) T.hist[b] = 0;
     if (tid == 0) mbar_init(a_bar, 1);
   }
