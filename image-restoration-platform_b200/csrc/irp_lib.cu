@@ -665,11 +665,12 @@ int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* 
 
 // the streaming kernel (irp_resize_tma.cuh): smallest tile footprint that serves every tile of a job
 struct RtFoot { int tow, toh, ncols, nrows; };
-RtLayout rt_layout(int ncols_px, int nrows);
+RtLayout rt_layout(int ncols_px, int nrows, int groups, int mid_rows);
 // Largest output tile whose source footprint fits the TMA box limits (512 bytes x 256 rows) and, together
 // with the boxes already chosen for this launch, one group's share of shared memory.
-bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, int launch_cols, int launch_rows, size_t budget, RtFoot* f) {
-  static const int cand[][2] = {{64, 32}, {64, 24}, {64, 16}, {32, 32}, {32, 16}, {64, 8}, {16, 32}, {32, 8}, {16, 16}, {16, 8}};
+bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, int launch_cols, int launch_rows, size_t budget, int groups, int toh_max,
+                  RtFoot* f) {
+  const int cand[][2] = {{64, toh_max}, {64, 16}, {32, toh_max}, {32, 16}, {64, 8}, {16, toh_max}, {32, 8}, {16, 16}, {16, 8}};
   for (const auto& c : cand) {
     const int tow = c[0], toh = c[1];
     int ncols = 0, nrows = 0;
@@ -683,7 +684,7 @@ bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, int launch
     }
     const int ntr = (ncols + 3) / 4, rows = (nrows + 1) & ~1;
     if (ntr * 12 + 12 > 512 || rows > 256) continue;
-    const RtLayout L = rt_layout(std::max(launch_cols, ntr * 4), std::max(launch_rows, rows));
+    const RtLayout L = rt_layout(std::max(launch_cols, ntr * 4), std::max(launch_rows, rows), groups, toh_max);
     if ((size_t)L.group_bytes > budget || L.box_cols > 512 || L.box_rows > 256) continue;
     *f = RtFoot{tow, toh, ntr * 4, rows};
     return true;
@@ -691,17 +692,19 @@ bool rt_footprint(const PlanDev& v, const PlanDev& h, int dw, int dh, int launch
   return false;
 }
 
-RtLayout rt_layout(int ncols_px, int nrows) {
+RtLayout rt_layout(int ncols_px, int nrows, int groups, int mid_rows) {
   RtLayout L;
+  L.groups = groups;
+  L.mid_rows = mid_rows;
   L.box_cols = (int)round_up((size_t)ncols_px * 3 + 12, 16);   // + the sub-16-byte offset of the first pixel
   L.box_rows = nrows;
   L.mid_pitch = (int)round_up((size_t)ncols_px + 8, 16);
   size_t p = round_up((size_t)L.box_cols * L.box_rows, 128);
   L.off_mid = (int)p;
-  p += (size_t)3 * kRToh * L.mid_pitch;
+  p += (size_t)3 * mid_rows * L.mid_pitch;
   p = round_up(p, 128);
   L.off_vtab = (int)p;
-  p += (size_t)kRToh * kTabWords * 4;
+  p += (size_t)mid_rows * kTabWords * 4;
   L.off_hcols = (int)p;
   p += (size_t)kRTow * kHTabWords * 4;
   L.off_sync = (int)p;
@@ -740,9 +743,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
   std::vector<AxisPlan> pv(e - b), ph(e - b);
   std::vector<const PlanDev*> dv(e - b), dh(e - b);
   int rc;
-  // pass 1: orientation, plans, kernel choice
-  int box_cols_px = 0, box_rows = 0;
-  const size_t budget = ((size_t)ctx->smem_optin_full - 4096) / kRGroups;
+  // pass 1: orientation, plans
   for (int i = b; i < e; i++) {
     if (!imgs[i].pixels) continue;
     const irp_image_desc& d = imgs[i];
@@ -763,18 +764,40 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     }
     if ((rc = get_plan(ctx, g.ho, g.dh, g.f, &pv[i - b], &dv[i - b]))) return rc;
     if ((rc = get_plan(ctx, g.wo, g.dw, g.f, &ph[i - b], &dh[i - b]))) return rc;
-    int k = d.channels == 1 ? 0 : (d.channels == 4 ? 2 : 1);
-    if (k == 1 && ctx->bulk_ok && ctx->rtma_ok && ((((uintptr_t)s.px | s.pitch) & 15) == 0) && pv[i - b].n > 1 && ph[i - b].n > 1 &&
-        rt_footprint(*dv[i - b], *dh[i - b], g.dw, g.dh, box_cols_px, box_rows, budget, &foot[i - b])) {
-      k = 3;
-      box_cols_px = std::max(box_cols_px, foot[i - b].ncols);
-      box_rows = std::max(box_rows, foot[i - b].nrows);
-    }
-    // no geometry change and nothing to normalise: the oriented pixels ARE the result, a 2-D copy
-    if (pv[i - b].n == 1 && ph[i - b].n == 1 && g.dc == d.channels && g.dw == g.wo && g.dh == g.ho) k = 4;
-    kern[i - b] = k;
   }
-  const RtLayout L = rt_layout(std::max(box_cols_px, 4), std::max(box_rows, 2));
+  // kernel choice.  The streaming kernel runs 5 groups x 24-row tiles per CTA when every eligible job keeps
+  // a full-size tile inside a fifth of the shared memory, else 4 groups x 32-row tiles.
+  int box_cols_px = 0, box_rows = 0, rt_groups = kRMaxGroups, rt_toh = 24;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    box_cols_px = box_rows = 0;
+    const size_t budget = ((size_t)ctx->smem_optin_full - 4096) / rt_groups;
+    bool degraded = false;
+    for (int i = b; i < e; i++) {
+      if (!imgs[i].pixels) continue;
+      const irp_image_desc& d = imgs[i];
+      const Geo& g = geo[i];
+      const Src& s = src[i - b];
+      int k = d.channels == 1 ? 0 : (d.channels == 4 ? 2 : 1);
+      if (k == 1 && ctx->bulk_ok && ctx->rtma_ok && ((((uintptr_t)s.px | s.pitch) & 15) == 0) && pv[i - b].n > 1 && ph[i - b].n > 1) {
+        if (rt_footprint(*dv[i - b], *dh[i - b], g.dw, g.dh, box_cols_px, box_rows, budget, rt_groups, rt_toh, &foot[i - b])) {
+          k = 3;
+          box_cols_px = std::max(box_cols_px, foot[i - b].ncols);
+          box_rows = std::max(box_rows, foot[i - b].nrows);
+          degraded |= foot[i - b].tow < kRTow || foot[i - b].toh < rt_toh;
+        } else {
+          degraded = true;
+        }
+      }
+      // no geometry change and nothing to normalise: the oriented pixels ARE the result, a row copy
+      if (pv[i - b].n == 1 && ph[i - b].n == 1 && g.dc == d.channels && g.dw == g.wo && g.dh == g.ho) k = 4;
+      kern[i - b] = k;
+    }
+    if (!degraded || attempt == 1) break;
+    rt_groups = 4;
+    rt_toh = kRTohMax;
+  }
+  const RtLayout L = rt_layout(std::max(box_cols_px, 4), std::max(box_rows, 2), rt_groups, rt_toh);
+  if (getenv("IRP_TRACE")) fprintf(stderr, "resize_tma: groups %d toh %d box %d x %d group_bytes %d\n", L.groups, rt_toh, L.box_cols, L.box_rows, L.group_bytes);
   // pass 2: job descriptors, grouped by kernel
   int pos = b, group_begin[6], group_tiles[5];
   for (int gi = 0; gi < 5; gi++) {
@@ -878,9 +901,9 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     const int g3 = group_begin[3];
     CK(cudaMemcpyAsync(d_rt + g3, h_rt + g3, sizeof(RtJob) * nrt, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_tm + g3, h_tm + g3, sizeof(TmaDesc) * nrt, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t smem = (size_t)L.group_bytes * kRGroups + 128;
-    const int grid = std::min((group_tiles[3] + kRGroups - 1) / kRGroups, ctx->sm_count);
-    resize_tma_kernel<<<grid, kRThreads, smem, ctx->stream>>>(d_rt + g3, d_tm + g3, nrt, group_tiles[3], L);
+    const size_t smem = (size_t)L.group_bytes * L.groups + 128;
+    const int grid = std::min((group_tiles[3] + L.groups - 1) / L.groups, ctx->sm_count);
+    resize_tma_kernel<<<grid, L.groups * 128, smem, ctx->stream>>>(d_rt + g3, d_tm + g3, nrt, group_tiles[3], L);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches++;
   }
