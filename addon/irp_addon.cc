@@ -45,12 +45,20 @@ void Execute(napi_env, void* data) {
       j->out.pixels = static_cast<uint8_t*>(std::malloc(j->out.capacity));
       j->out.pitch = 0;
       j->out.on_device = 0;
-      j->rc = j->out.pixels ? irp_preprocess_batch(j->ctx, &j->desc, 1, &j->out) : IRP_ERR_NOMEM;
+      if (!j->out.pixels) j->rc = IRP_ERR_NOMEM;
     }
-  } else {
-    j->rc = irp_classify_batch(j->ctx, &j->desc, 1, &j->result);
   }
-  if (j->rc != IRP_OK) j->error = irp_last_error(j->ctx);
+  if (j->rc == IRP_OK) {
+    // one image per promise, several promises in flight (restorator.js:196-211): queue it and let the
+    // context's dispatcher batch it with whatever the other libuv workers submitted meanwhile
+    irp_ticket ticket = nullptr;
+    char err[256] = {0};
+    j->rc = irp_submit(j->ctx, &j->desc, j->preprocess ? nullptr : &j->result, j->preprocess ? &j->out : nullptr, &ticket);
+    if (j->rc == IRP_OK) j->rc = irp_wait(j->ctx, ticket, err, sizeof err);
+    if (j->rc != IRP_OK) j->error = err[0] ? err : "irp request failed";
+  } else {
+    j->error = "unsupported geometry or out of memory";
+  }
 }
 
 void Complete(napi_env env, napi_status, void* data) {

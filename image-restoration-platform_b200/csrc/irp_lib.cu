@@ -21,6 +21,9 @@
 #include "../../include/irp.h"
 #include "../../include/irp_spec.h"
 #include "grey_tables.inc"
+#include <condition_variable>
+#include <deque>
+#include <thread>
 #include <cuda.h>   // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
 #include "irp_classify.cuh"
 #include "irp_classify_bulk.cuh"
@@ -87,6 +90,15 @@ struct PlanDev {
 
 }  // namespace
 
+struct irp_request {
+  irp_image_desc img;
+  irp_result* result;
+  irp_out_desc* out;
+  int status = 0;
+  bool done = false;
+  std::string err;
+};
+
 struct irp_ctx {
   int device = 0;
   int sm_count = 0;
@@ -111,6 +123,12 @@ struct irp_ctx {
   size_t smem_optin = 0;             // opt-in dynamic shared memory limit of the device
   uint32_t smem_base = 0; // .shared address where dynamic shared memory starts (probed once)
   int* d_error_flag = nullptr;
+  // concurrent single-image requests (irp_submit / irp_wait)
+  std::thread dispatcher;
+  std::mutex qmu;
+  std::condition_variable qcv, done_cv;
+  std::deque<struct irp_request*> queue;
+  bool stop = false, dispatcher_started = false;
   bool rtma_ok = true;    // IRP_NO_RTMA=1 keeps the generic resize kernel (A/B runs)
   bool bulk_ok = false;   // the streaming classify kernel's shared-memory map fits this device
   int* h_error_flag = nullptr;
@@ -1150,6 +1168,12 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
 
 void irp_destroy(irp_ctx* ctx) {
   if (!ctx) return;
+  {
+    std::lock_guard<std::mutex> lk(ctx->qmu);
+    ctx->stop = true;
+  }
+  ctx->qcv.notify_all();
+  if (ctx->dispatcher_started && ctx->dispatcher.joinable()) ctx->dispatcher.join();
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   for (auto& ev : ctx->ev)
@@ -1278,6 +1302,111 @@ int irp_analyze_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_resul
 int irp_fusion_prepare_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n_groups, irp_out_desc* canvases) {
   if (!canvases) return ctx ? fail(ctx, IRP_ERR_BAD_ARG, "null canvases") : IRP_ERR_BAD_ARG;
   return run_batch(ctx, imgs, n_groups * IRP_FUSION_MAX_IMAGES, nullptr, canvases, 1);
+}
+
+// ---- concurrent single-image requests ----
+static void run_requests(irp_ctx* ctx, std::vector<irp_request*>& reqs) {
+  // three kinds of request share the queue; each kind is one batched submission
+  for (int kind = 0; kind < 3; kind++) {
+    std::vector<irp_request*> sel;
+    for (irp_request* r : reqs) {
+      const int k = (r->result && r->out) ? 0 : (r->result ? 1 : 2);
+      if (k == kind) sel.push_back(r);
+    }
+    if (sel.empty()) continue;
+    const int n = (int)sel.size();
+    std::vector<irp_image_desc> descs(n);
+    std::vector<irp_result> results(n);
+    std::vector<irp_out_desc> outs(n);
+    for (int i = 0; i < n; i++) {
+      descs[i] = sel[i]->img;
+      if (sel[i]->out) outs[i] = *sel[i]->out;
+    }
+    auto call = [&](int b, int cnt) {
+      return run_batch(ctx, descs.data() + b, cnt, kind == 2 ? nullptr : results.data() + b, kind == 1 ? nullptr : outs.data() + b, 0);
+    };
+    int rc = call(0, n);
+    if (rc == IRP_OK) {
+      for (int i = 0; i < n; i++) sel[i]->status = IRP_OK;
+    } else if (n == 1) {
+      sel[0]->status = rc;
+      sel[0]->err = ctx->err;
+    } else {  // isolate the request(s) that fail: one bad upload must not fail its batch-mates
+      for (int i = 0; i < n; i++) {
+        sel[i]->status = call(i, 1);
+        if (sel[i]->status != IRP_OK) sel[i]->err = ctx->err;
+      }
+    }
+    for (int i = 0; i < n; i++) {
+      if (sel[i]->status != IRP_OK) continue;
+      if (sel[i]->result) *sel[i]->result = results[i];
+      if (sel[i]->out) *sel[i]->out = outs[i];
+    }
+  }
+}
+
+static void dispatcher_main(irp_ctx* ctx) {
+  const size_t max_batch = 64;
+  for (;;) {
+    std::vector<irp_request*> reqs;
+    {
+      std::unique_lock<std::mutex> lk(ctx->qmu);
+      ctx->qcv.wait(lk, [&] { return ctx->stop || !ctx->queue.empty(); });
+      if (ctx->queue.empty()) return;  // stop requested and nothing left
+      if (ctx->queue.size() < max_batch && !ctx->stop)  // a short window for concurrent callers to join the batch
+        ctx->qcv.wait_for(lk, std::chrono::microseconds(100), [&] { return ctx->stop || ctx->queue.size() >= max_batch; });
+      while (!ctx->queue.empty() && reqs.size() < max_batch) {
+        reqs.push_back(ctx->queue.front());
+        ctx->queue.pop_front();
+      }
+    }
+    run_requests(ctx, reqs);
+    {
+      std::lock_guard<std::mutex> lk(ctx->qmu);
+      for (irp_request* r : reqs) r->done = true;
+    }
+    ctx->done_cv.notify_all();
+  }
+}
+
+int irp_submit(irp_ctx* ctx, const irp_image_desc* img, irp_result* result, irp_out_desc* out, irp_ticket* ticket) {
+  if (!ctx || !img || !ticket || (!result && !out)) return IRP_ERR_BAD_ARG;
+  irp_request* r = new irp_request();
+  r->img = *img;
+  r->result = result;
+  r->out = out;
+  {
+    std::lock_guard<std::mutex> lk(ctx->qmu);
+    if (ctx->stop) {
+      delete r;
+      return IRP_ERR_BAD_ARG;
+    }
+    if (!ctx->dispatcher_started) {
+      ctx->dispatcher = std::thread(dispatcher_main, ctx);
+      ctx->dispatcher_started = true;
+    }
+    ctx->queue.push_back(r);
+  }
+  ctx->qcv.notify_all();
+  *ticket = r;
+  return IRP_OK;
+}
+
+int irp_wait(irp_ctx* ctx, irp_ticket ticket, char* err, size_t err_capacity) {
+  if (!ctx || !ticket) return IRP_ERR_BAD_ARG;
+  irp_request* r = ticket;
+  {
+    std::unique_lock<std::mutex> lk(ctx->qmu);
+    ctx->done_cv.wait(lk, [&] { return r->done; });
+  }
+  const int rc = r->status;
+  if (err && err_capacity) {
+    const size_t nb = std::min(err_capacity - 1, r->err.size());
+    memcpy(err, r->err.data(), nb);
+    err[nb] = 0;
+  }
+  delete r;
+  return rc;
 }
 
 void* irp_dev_alloc(irp_ctx* ctx, size_t bytes) {

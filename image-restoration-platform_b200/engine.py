@@ -251,6 +251,32 @@ class Engine:
             return results, device_outputs
         return results, arrays
 
+    # -- concurrent single-image requests (irp_submit / irp_wait) -------------
+    def submit(self, image: ImageLike, is_jpeg: bool = True, orientation: int = 1, classify: bool = True, preprocess: bool = True):
+        """Queue ONE image (as the reference's callers do, one analyze() per promise) and return a handle at
+        once; concurrent submissions are batched by the context's dispatcher thread. Thread-safe."""
+        descs, keep = self._descs([image], is_jpeg, [orientation])
+        outs, arrays = (self._outs([image], [orientation], None, fusion=False) if preprocess else (None, [None]))
+        res = _ffi.Result() if classify else None
+        ticket = C.c_void_p()
+        rc = self._lib.irp_submit(self._ctx, descs, C.byref(res) if classify else None, outs if preprocess else None, C.byref(ticket))
+        if rc:
+            raise IrpError(rc, "irp_submit rejected the request")
+        return {"ticket": ticket, "descs": descs, "keep": keep, "outs": outs, "array": arrays[0], "res": res}
+
+    def wait(self, handle, raw: bool = False):
+        """Block until the request is done; returns (result dict or None, output array or None)."""
+        err = C.create_string_buffer(512)
+        rc = self._lib.irp_wait(self._ctx, handle["ticket"], err, len(err))
+        if rc:
+            raise IrpError(rc, err.value.decode(errors="replace"))
+        res = handle["res"]
+        out = handle["array"]
+        if out is not None:
+            o = handle["outs"][0]
+            out = out.reshape(-1)[: o.height * o.width * o.channels].reshape(o.height, o.width, o.channels)
+        return (None if res is None else (res if raw else result_to_dict(res))), out
+
     def fusion_prepare_batch(self, groups: Sequence[Sequence[Optional[ImageLike]]], orientations=None, device_outputs=None):
         """Each group of <= 3 images -> aligned 2048x2048x3 canvases."""
         flat: List[Optional[ImageLike]] = []

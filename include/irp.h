@@ -152,6 +152,23 @@ int irp_analyze_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_resul
 int irp_fusion_prepare_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n_groups,
                              irp_out_desc *canvases);
 
+/* ---- concurrent single-image requests --------------------------------- */
+/* The reference's callers issue ONE image per call from several in-flight
+ * promises (ClassifierService.analyze is async, classifier.js:40; restoreBatch
+ * fans out with pLimit(3), restorator.js:196-211).  irp_submit queues one
+ * image and returns at once; a dispatcher thread owned by the context gathers
+ * whatever is queued (up to 64 requests, waiting at most ~100 us for company)
+ * into ONE batched submission, so concurrent callers share launches and the
+ * H2D / kernel / D2H pipeline instead of serialising on the context.  `result`
+ * and / or `out` select classify, preprocess or both; the pointers (and the
+ * pixels) must stay valid until irp_wait returns.  irp_wait blocks until that
+ * request is done, returns its status, copies its error text (if any) and
+ * releases the ticket.  A failing request does not fail its batch-mates. */
+typedef struct irp_request *irp_ticket;
+int irp_submit(irp_ctx *ctx, const irp_image_desc *img, irp_result *result, irp_out_desc *out,
+               irp_ticket *ticket);
+int irp_wait(irp_ctx *ctx, irp_ticket ticket, char *err, size_t err_capacity);
+
 /* ---- memory helpers (so non-CUDA hosts can stage device-resident data) -- */
 void *irp_dev_alloc(irp_ctx *ctx, size_t bytes);
 int irp_dev_free(irp_ctx *ctx, void *p);
