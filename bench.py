@@ -180,6 +180,17 @@ def main() -> int:
         print("bench.py: no CUDA device; irp_b200 has no CPU fallback", file=sys.stderr)
         return 2
     torch.cuda.set_device(local_rank)
+    numa = None
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:  # run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU: H2D/D2H cross no socket link
+        import pynvml
+
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda._get_nvml_device_index(local_rank) if hasattr(torch.cuda, "_get_nvml_device_index") else local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(hnd)
+        numa = f"{len(os.sched_getaffinity(0))} CPUs local to GPU {local_rank}"
+    except Exception as ex:  # affinity is an optimisation, never a requirement
+        numa = f"unchanged ({type(ex).__name__})"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -350,7 +361,7 @@ def main() -> int:
         e2e = {"value": world * mpix_step / (ms / n_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": B * W * H * 3,
                "link_floor_ms_per_step": floor_ms, "frac_of_link_floor": floor_ms / (ms / n_e2e),
                "d2h_bytes_per_step": B * ow * oh * 3 + B * C.sizeof(_ffi.Result), "steps": n_e2e, "ms_per_step": ms / n_e2e,
-               "wall_ms_per_step": wall_ms / n_e2e, "host_memory": "pinned (irp_host_alloc_pinned)"}
+               "wall_ms_per_step": wall_ms / n_e2e, "host_memory": "pinned (irp_host_alloc_pinned)", "cpu_affinity": numa}
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) --------
     cpu = None
@@ -358,6 +369,8 @@ def main() -> int:
         from oracle import oracle
 
         oracle.build()
+        if all_cpus:  # the CPU arm gets every host core back, not just the ones next to the GPU
+            os.sched_setaffinity(0, all_cpus)
         T = host_threads()
         sample = a.cpu_sample or min(B, max(2, min(T, 16)))
         t0 = time.perf_counter()
