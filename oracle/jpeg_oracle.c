@@ -1,0 +1,542 @@
+/*
+ * jpeg_oracle.c — TEST INFRASTRUCTURE ONLY (like irp_oracle.c): a CPU restatement of baseline JPEG
+ * decoding as libjpeg-turbo performs it with its default settings (JDCT_ISLOW, fancy upsampling), the
+ * decoder inside libvips / sharp that runs in front of every pipeline of the hot path
+ * (reference: server-node/src/services/classifier.js:51-52,107,135,199,296 `sharp(imageBuffer)`,
+ *  server-node/src/middleware/imagePreprocess.js:40-42; accepted uploads uploadValidation.js:7).
+ * SURVEY.md §8f rank 1 ("JPEG bitstream decode on device") is the next row of the hot-path table; this
+ * file is its oracle.  Unlike the rest of oracle/, it IS pinned: tests/test_jpeg_oracle.py compares
+ * it bit for bit with Pillow's decoder, which is libjpeg-turbo itself (the same library, the same
+ * defaults as libvips).
+ *
+ * Follows, by algorithm (nothing is copied; libjpeg-turbo is not in /root/reference):
+ *   jdmarker.c  marker parsing (SOF0, DQT, DHT, DRI, SOS, RSTn)
+ *   jdhuff.c    Huffman entropy decoding, HUFF_EXTEND, restart handling
+ *   jidctint.c  jpeg_idct_islow (CONST_BITS 13, PASS1_BITS 2)
+ *   jdsample.c  h2v1 / h2v2 / h1v2 fancy (triangle) upsampling, replicated edges
+ *   jdcolor.c   YCbCr -> RGB with the 16-bit fixed-point tables
+ * Scope: 8-bit baseline sequential (SOF0 / SOF1 Huffman), 1 or 3 components, sampling factors 1 or 2.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum { JO_OK = 0, JO_ERR_FORMAT = -1, JO_ERR_UNSUPPORTED = -2, JO_ERR_NOMEM = -4 };
+
+static const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+typedef struct {
+  int maxcode[18], valptr[17], mincode[17];
+  uint8_t bits[17], vals[256];
+  int present;
+} HuffTab;
+
+typedef struct {
+  int id, h, v, tq, td, ta;
+  int bw, bh;        /* blocks per row / block rows, MCU padded */
+  int dw, dh;        /* downsampled (real) width / height in samples */
+  int16_t* coef;     /* [bh][bw][64] natural order, DC already integrated */
+  uint8_t* plane;    /* [bh*8][bw*8] */
+} Comp;
+
+typedef struct {
+  int w, h, ncomp, hmax, vmax, mcux, mcuy, restart;
+  uint16_t q[4][64]; /* natural order */
+  int qpresent[4];
+  HuffTab dc[4], ac[4];
+  Comp comp[3];
+  const uint8_t* scan;
+  size_t scan_len;
+  int adobe_transform;  /* -1 none */
+} Jpeg;
+
+static int build_huff(HuffTab* t) {
+  int code = 0, k = 0;
+  for (int l = 1; l <= 16; l++) {
+    t->valptr[l] = k;
+    t->mincode[l] = code;
+    code += t->bits[l];
+    k += t->bits[l];
+    t->maxcode[l] = t->bits[l] ? code - 1 : -1;
+    code <<= 1;
+  }
+  t->maxcode[17] = 0xFFFFF;
+  t->present = 1;
+  return k <= 256 ? JO_OK : JO_ERR_FORMAT;
+}
+
+static int parse(const uint8_t* d, size_t n, Jpeg* J) {
+  memset(J, 0, sizeof *J);
+  J->adobe_transform = -1;
+  if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return JO_ERR_FORMAT;
+  size_t p = 2;
+  for (;;) {
+    if (p + 4 > n) return JO_ERR_FORMAT;
+    if (d[p] != 0xFF) return JO_ERR_FORMAT;
+    while (p < n && d[p] == 0xFF) p++;
+    if (p >= n) return JO_ERR_FORMAT;
+    const int m = d[p++];
+    if (m == 0xD9) return JO_ERR_FORMAT; /* EOI before SOS */
+    if (p + 2 > n) return JO_ERR_FORMAT;
+    const size_t len = ((size_t)d[p] << 8) | d[p + 1];
+    if (len < 2 || p + len > n) return JO_ERR_FORMAT;
+    const uint8_t* s = d + p + 2;
+    const size_t sl = len - 2;
+    if (m == 0xDB) { /* DQT */
+      size_t o = 0;
+      while (o < sl) {
+        const int pq = s[o] >> 4, tq = s[o] & 15;
+        o++;
+        if (tq > 3) return JO_ERR_FORMAT;
+        for (int i = 0; i < 64; i++) {
+          int v;
+          if (pq) {
+            if (o + 2 > sl) return JO_ERR_FORMAT;
+            v = (s[o] << 8) | s[o + 1];
+            o += 2;
+          } else {
+            if (o + 1 > sl) return JO_ERR_FORMAT;
+            v = s[o++];
+          }
+          J->q[tq][kZigzag[i]] = (uint16_t)v;
+        }
+        J->qpresent[tq] = 1;
+      }
+    } else if (m == 0xC0 || m == 0xC1) { /* SOF0 / SOF1 */
+      if (sl < 6 || s[0] != 8) return JO_ERR_UNSUPPORTED;
+      J->h = (s[1] << 8) | s[2];
+      J->w = (s[3] << 8) | s[4];
+      J->ncomp = s[5];
+      if ((J->ncomp != 1 && J->ncomp != 3) || sl < (size_t)(6 + 3 * J->ncomp) || J->w == 0 || J->h == 0) return JO_ERR_UNSUPPORTED;
+      for (int i = 0; i < J->ncomp; i++) {
+        J->comp[i].id = s[6 + 3 * i];
+        J->comp[i].h = s[7 + 3 * i] >> 4;
+        J->comp[i].v = s[7 + 3 * i] & 15;
+        J->comp[i].tq = s[8 + 3 * i];
+        if (J->comp[i].h < 1 || J->comp[i].h > 2 || J->comp[i].v < 1 || J->comp[i].v > 2 || J->comp[i].tq > 3) return JO_ERR_UNSUPPORTED;
+      }
+    } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
+      return JO_ERR_UNSUPPORTED; /* progressive, lossless, arithmetic */
+    } else if (m == 0xC4) { /* DHT */
+      size_t o = 0;
+      while (o < sl) {
+        if (o + 17 > sl) return JO_ERR_FORMAT;
+        const int tc = s[o] >> 4, th = s[o] & 15;
+        if (tc > 1 || th > 3) return JO_ERR_FORMAT;
+        HuffTab* t = tc ? &J->ac[th] : &J->dc[th];
+        int cnt = 0;
+        t->bits[0] = 0;
+        for (int l = 1; l <= 16; l++) {
+          t->bits[l] = s[o + l];
+          cnt += t->bits[l];
+        }
+        o += 17;
+        if (cnt > 256 || o + cnt > sl) return JO_ERR_FORMAT;
+        memcpy(t->vals, s + o, cnt);
+        o += cnt;
+        if (build_huff(t)) return JO_ERR_FORMAT;
+      }
+    } else if (m == 0xDD) { /* DRI */
+      if (sl < 2) return JO_ERR_FORMAT;
+      J->restart = (s[0] << 8) | s[1];
+    } else if (m == 0xEE && sl >= 12 && !memcmp(s, "Adobe", 5)) {
+      J->adobe_transform = s[11];
+    } else if (m == 0xDA) { /* SOS */
+      if (!J->w || sl < 1) return JO_ERR_FORMAT;
+      const int ns = s[0];
+      if (ns != J->ncomp || sl < (size_t)(1 + 2 * ns + 3)) return JO_ERR_UNSUPPORTED; /* non-interleaved scans not handled */
+      for (int i = 0; i < ns; i++) {
+        int ci = -1;
+        for (int k = 0; k < J->ncomp; k++)
+          if (J->comp[k].id == s[1 + 2 * i]) ci = k;
+        if (ci != i) return JO_ERR_UNSUPPORTED;
+        J->comp[ci].td = s[2 + 2 * i] >> 4;
+        J->comp[ci].ta = s[2 + 2 * i] & 15;
+      }
+      if (s[1 + 2 * ns] != 0 || s[2 + 2 * ns] != 63 || s[3 + 2 * ns] != 0) return JO_ERR_UNSUPPORTED;
+      J->scan = d + p + len;
+      J->scan_len = n - (p + len);
+      break;
+    }
+    p += len;
+  }
+  J->hmax = J->vmax = 1;
+  for (int i = 0; i < J->ncomp; i++) {
+    if (J->comp[i].h > J->hmax) J->hmax = J->comp[i].h;
+    if (J->comp[i].v > J->vmax) J->vmax = J->comp[i].v;
+  }
+  if (J->ncomp == 1) J->comp[0].h = J->comp[0].v = J->hmax = J->vmax = 1; /* single-component scans are never interleaved */
+  J->mcux = (J->w + 8 * J->hmax - 1) / (8 * J->hmax);
+  J->mcuy = (J->h + 8 * J->vmax - 1) / (8 * J->vmax);
+  for (int i = 0; i < J->ncomp; i++) {
+    Comp* c = &J->comp[i];
+    c->bw = J->mcux * c->h;
+    c->bh = J->mcuy * c->v;
+    c->dw = (J->w * c->h + J->hmax - 1) / J->hmax;
+    c->dh = (J->h * c->v + J->vmax - 1) / J->vmax;
+    if (!J->qpresent[c->tq] || !J->dc[c->td].present || !J->ac[c->ta].present) return JO_ERR_FORMAT;
+  }
+  return JO_OK;
+}
+
+/* ---- entropy decoding (jdhuff.c) ---- */
+typedef struct {
+  const uint8_t* d;
+  size_t n, p;
+  uint32_t acc;
+  int cnt;
+  int marker; /* pending marker byte, 0 none */
+} Bits;
+
+static void fill(Bits* b) {
+  while (b->cnt <= 24) {
+    int byte = 0;
+    if (!b->marker && b->p < b->n) {
+      byte = b->d[b->p++];
+      if (byte == 0xFF) {
+        int nx = b->p < b->n ? b->d[b->p] : 0xD9;
+        while (nx == 0xFF && b->p + 1 < b->n) { /* fill bytes */
+          b->p++;
+          nx = b->d[b->p];
+        }
+        if (nx == 0) {
+          b->p++;
+        } else {
+          b->marker = nx;
+          b->p++;
+          byte = 0;
+        }
+      }
+    }
+    b->acc |= (uint32_t)byte << (24 - b->cnt);
+    b->cnt += 8;
+  }
+}
+static int getbits(Bits* b, int n) {
+  if (!n) return 0;
+  if (b->cnt < n) fill(b);
+  const int v = (int)(b->acc >> (32 - n));
+  b->acc <<= n;
+  b->cnt -= n;
+  return v;
+}
+static int decode_sym(Bits* b, const HuffTab* t) {
+  int code = getbits(b, 1), l = 1;
+  while (l <= 16 && code > t->maxcode[l]) {
+    code = (code << 1) | getbits(b, 1);
+    l++;
+  }
+  if (l > 16) return 0;
+  return t->vals[t->valptr[l] + code - t->mincode[l]];
+}
+static int extend(int x, int s) { return x < (1 << (s - 1)) ? x + (int)((~0u) << s) + 1 : x; }
+
+static int decode_scan(Jpeg* J) {
+  Bits b = {J->scan, J->scan_len, 0, 0, 0, 0};
+  int pred[3] = {0, 0, 0};
+  int togo = J->restart;
+  for (int my = 0; my < J->mcuy; my++)
+    for (int mx = 0; mx < J->mcux; mx++) {
+      if (J->restart && togo == 0) {
+        /* byte-align, expect RSTn */
+        b.acc = 0;
+        b.cnt = 0;
+        if (!b.marker) { /* the marker has not been reached by the bit reader yet: scan for it */
+          while (b.p + 1 < b.n && !(b.d[b.p] == 0xFF && b.d[b.p + 1] >= 0xD0 && b.d[b.p + 1] <= 0xD7)) b.p++;
+          if (b.p + 1 >= b.n) return JO_ERR_FORMAT;
+          b.p += 2;
+        }
+        b.marker = 0;
+        pred[0] = pred[1] = pred[2] = 0;
+        togo = J->restart;
+      }
+      for (int ci = 0; ci < J->ncomp; ci++) {
+        Comp* c = &J->comp[ci];
+        for (int by = 0; by < c->v; by++)
+          for (int bx = 0; bx < c->h; bx++) {
+            int16_t* blk = c->coef + ((size_t)(my * c->v + by) * c->bw + (mx * c->h + bx)) * 64;
+            int s = decode_sym(&b, &J->dc[c->td]);
+            if (s) pred[ci] += extend(getbits(&b, s), s);
+            blk[0] = (int16_t)pred[ci];
+            for (int k = 1; k < 64; k++) {
+              const int rs = decode_sym(&b, &J->ac[c->ta]);
+              const int r = rs >> 4;
+              s = rs & 15;
+              if (s) {
+                k += r;
+                if (k > 63) break;
+                blk[kZigzag[k]] = (int16_t)extend(getbits(&b, s), s);
+              } else {
+                if (r != 15) break;
+                k += 15;
+              }
+            }
+          }
+      }
+      togo--;
+    }
+  return JO_OK;
+}
+
+/* ---- jidctint.c ---- */
+#define CONST_BITS 13
+#define PASS1_BITS 2
+#define DESCALE(x, n) (((x) + ((int32_t)1 << ((n)-1))) >> (n))
+static uint8_t range_limit(int32_t x) {
+  int v = x & 1023;
+  if (v >= 512) v -= 1024;
+  v += 128;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+static void idct_islow(const int16_t* in, const uint16_t* q, uint8_t* out, int stride) {
+  int32_t ws[64];
+  for (int c = 0; c < 8; c++) {
+    const int16_t* ip = in + c;
+    const uint16_t* qp = q + c;
+    int32_t* wp = ws + c;
+    int32_t z2 = ip[16] * qp[16], z3 = ip[48] * qp[48];
+    int32_t z1 = (z2 + z3) * 4433;
+    int32_t tmp2 = z1 + z3 * (-15137), tmp3 = z1 + z2 * 6270;
+    z2 = ip[0] * qp[0];
+    z3 = ip[32] * qp[32];
+    int32_t tmp0 = (z2 + z3) * (1 << CONST_BITS), tmp1 = (z2 - z3) * (1 << CONST_BITS);
+    const int32_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = ip[56] * qp[56];
+    tmp1 = ip[40] * qp[40];
+    tmp2 = ip[24] * qp[24];
+    tmp3 = ip[8] * qp[8];
+    z1 = tmp0 + tmp3;
+    z2 = tmp1 + tmp2;
+    z3 = tmp0 + tmp2;
+    int32_t z4 = tmp1 + tmp3;
+    const int32_t z5 = (z3 + z4) * 9633;
+    tmp0 *= 2446;
+    tmp1 *= 16819;
+    tmp2 *= 25172;
+    tmp3 *= 12299;
+    z1 *= -7373;
+    z2 *= -20995;
+    z3 *= -16069;
+    z4 *= -3196;
+    z3 += z5;
+    z4 += z5;
+    tmp0 += z1 + z3;
+    tmp1 += z2 + z4;
+    tmp2 += z2 + z3;
+    tmp3 += z1 + z4;
+    wp[0] = DESCALE(tmp10 + tmp3, CONST_BITS - PASS1_BITS);
+    wp[56] = DESCALE(tmp10 - tmp3, CONST_BITS - PASS1_BITS);
+    wp[8] = DESCALE(tmp11 + tmp2, CONST_BITS - PASS1_BITS);
+    wp[48] = DESCALE(tmp11 - tmp2, CONST_BITS - PASS1_BITS);
+    wp[16] = DESCALE(tmp12 + tmp1, CONST_BITS - PASS1_BITS);
+    wp[40] = DESCALE(tmp12 - tmp1, CONST_BITS - PASS1_BITS);
+    wp[24] = DESCALE(tmp13 + tmp0, CONST_BITS - PASS1_BITS);
+    wp[32] = DESCALE(tmp13 - tmp0, CONST_BITS - PASS1_BITS);
+  }
+  for (int r = 0; r < 8; r++) {
+    const int32_t* wp = ws + 8 * r;
+    uint8_t* op = out + (size_t)r * stride;
+    int32_t z2 = wp[2], z3 = wp[6];
+    int32_t z1 = (z2 + z3) * 4433;
+    int32_t tmp2 = z1 + z3 * (-15137), tmp3 = z1 + z2 * 6270;
+    int32_t tmp0 = (wp[0] + wp[4]) * (1 << CONST_BITS), tmp1 = (wp[0] - wp[4]) * (1 << CONST_BITS);
+    const int32_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = wp[7];
+    tmp1 = wp[5];
+    tmp2 = wp[3];
+    tmp3 = wp[1];
+    z1 = tmp0 + tmp3;
+    z2 = tmp1 + tmp2;
+    z3 = tmp0 + tmp2;
+    int32_t z4 = tmp1 + tmp3;
+    const int32_t z5 = (z3 + z4) * 9633;
+    tmp0 *= 2446;
+    tmp1 *= 16819;
+    tmp2 *= 25172;
+    tmp3 *= 12299;
+    z1 *= -7373;
+    z2 *= -20995;
+    z3 *= -16069;
+    z4 *= -3196;
+    z3 += z5;
+    z4 += z5;
+    tmp0 += z1 + z3;
+    tmp1 += z2 + z4;
+    tmp2 += z2 + z3;
+    tmp3 += z1 + z4;
+    const int sh = CONST_BITS + PASS1_BITS + 3;
+    op[0] = range_limit(DESCALE(tmp10 + tmp3, sh));
+    op[7] = range_limit(DESCALE(tmp10 - tmp3, sh));
+    op[1] = range_limit(DESCALE(tmp11 + tmp2, sh));
+    op[6] = range_limit(DESCALE(tmp11 - tmp2, sh));
+    op[2] = range_limit(DESCALE(tmp12 + tmp1, sh));
+    op[5] = range_limit(DESCALE(tmp12 - tmp1, sh));
+    op[3] = range_limit(DESCALE(tmp13 + tmp0, sh));
+    op[4] = range_limit(DESCALE(tmp13 - tmp0, sh));
+  }
+}
+
+/* ---- jdsample.c: fancy upsampling of one component to full resolution (at least w x h) ---- */
+static uint8_t* upsample(const Jpeg* J, const Comp* c, int* out_stride) {
+  const int hx = J->hmax / c->h, vx = J->vmax / c->v;
+  const int pw = c->bw * 8; /* padded plane width */
+  const int ow = c->dw * hx, oh = c->dh * vx;
+  uint8_t* o = (uint8_t*)malloc((size_t)(ow + 2) * (oh + 2));
+  if (!o) return NULL;
+  *out_stride = ow;
+#define ROW(r) (c->plane + (size_t)((r) < 0 ? 0 : ((r) >= c->dh ? c->dh - 1 : (r))) * pw)
+  if (hx == 1 && vx == 1) {
+    for (int y = 0; y < oh; y++) memcpy(o + (size_t)y * ow, ROW(y), ow);
+  } else if (hx == 2 && vx == 1) {
+    for (int y = 0; y < oh; y++) {
+      const uint8_t* in = ROW(y);
+      uint8_t* op = o + (size_t)y * ow;
+      const int n = c->dw;
+      if (n == 1) {
+        op[0] = in[0];
+        op[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2); /* libjpeg reads the padded column here */
+        continue;
+      }
+      op[0] = in[0];
+      op[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
+      for (int x = 1; x < n - 1; x++) {
+        op[2 * x] = (uint8_t)((in[x] * 3 + in[x - 1] + 1) >> 2);
+        op[2 * x + 1] = (uint8_t)((in[x] * 3 + in[x + 1] + 2) >> 2);
+      }
+      op[2 * (n - 1)] = (uint8_t)((in[n - 1] * 3 + in[n - 2] + 1) >> 2);
+      op[2 * (n - 1) + 1] = in[n - 1];
+    }
+  } else if (hx == 2 && vx == 2) {
+    for (int r = 0; r < c->dh; r++)
+      for (int v = 0; v < 2; v++) {
+        const uint8_t* in0 = ROW(r);
+        const uint8_t* in1 = v == 0 ? ROW(r - 1) : ROW(r + 1);
+        uint8_t* op = o + (size_t)(2 * r + v) * ow;
+        const int n = c->dw;
+        int thiscol = in0[0] * 3 + in1[0], nextcol = in0[1] * 3 + in1[1], lastcol;
+        op[0] = (uint8_t)((thiscol * 4 + 8) >> 4);
+        op[1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
+        if (n == 1) continue;
+        lastcol = thiscol;
+        thiscol = nextcol;
+        for (int x = 1; x < n - 1; x++) {
+          nextcol = in0[x + 1] * 3 + in1[x + 1];
+          op[2 * x] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
+          op[2 * x + 1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
+          lastcol = thiscol;
+          thiscol = nextcol;
+        }
+        op[2 * (n - 1)] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
+        op[2 * (n - 1) + 1] = (uint8_t)((thiscol * 4 + 7) >> 4);
+      }
+  } else if (hx == 1 && vx == 2) {
+    for (int r = 0; r < c->dh; r++)
+      for (int v = 0; v < 2; v++) {
+        const uint8_t* in0 = ROW(r);
+        const uint8_t* in1 = v == 0 ? ROW(r - 1) : ROW(r + 1);
+        uint8_t* op = o + (size_t)(2 * r + v) * ow;
+        const int bias = v == 0 ? 1 : 2;
+        for (int x = 0; x < ow; x++) op[x] = (uint8_t)((in0[x] * 3 + in1[x] + bias) >> 2);
+      }
+  } else {
+    free(o);
+    return NULL;
+  }
+#undef ROW
+  return o;
+}
+
+static void free_all(Jpeg* J) {
+  for (int i = 0; i < 3; i++) {
+    free(J->comp[i].coef);
+    free(J->comp[i].plane);
+  }
+}
+
+int irp_jpeg_info(const uint8_t* data, size_t len, int* w, int* h, int* ncomp, int* restart, int sampling[6]) {
+  Jpeg J;
+  const int rc = parse(data, len, &J);
+  if (rc) return rc;
+  *w = J.w;
+  *h = J.h;
+  *ncomp = J.ncomp;
+  *restart = J.restart;
+  for (int i = 0; i < 3; i++) {
+    sampling[2 * i] = i < J.ncomp ? J.comp[i].h : 0;
+    sampling[2 * i + 1] = i < J.ncomp ? J.comp[i].v : 0;
+  }
+  return JO_OK;
+}
+
+/* out: w*h*3 (RGB) for 3 components, w*h for 1.  coef_out (optional): the quantised coefficients of
+ * component `coef_comp`, [block rows][blocks per row][64] natural order (for the device stages' tests). */
+int irp_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out, int16_t* coef_out, int coef_comp) {
+  Jpeg J;
+  int rc = parse(data, len, &J);
+  if (rc) return rc;
+  for (int i = 0; i < J.ncomp; i++) {
+    Comp* c = &J.comp[i];
+    c->coef = (int16_t*)calloc((size_t)c->bw * c->bh * 64, sizeof(int16_t));
+    c->plane = (uint8_t*)malloc((size_t)c->bw * c->bh * 64);
+    if (!c->coef || !c->plane) {
+      free_all(&J);
+      return JO_ERR_NOMEM;
+    }
+  }
+  if ((rc = decode_scan(&J))) {
+    free_all(&J);
+    return rc;
+  }
+  if (coef_out && coef_comp >= 0 && coef_comp < J.ncomp)
+    memcpy(coef_out, J.comp[coef_comp].coef, (size_t)J.comp[coef_comp].bw * J.comp[coef_comp].bh * 64 * sizeof(int16_t));
+  for (int i = 0; i < J.ncomp; i++) {
+    Comp* c = &J.comp[i];
+    for (int by = 0; by < c->bh; by++)
+      for (int bx = 0; bx < c->bw; bx++)
+        idct_islow(c->coef + ((size_t)by * c->bw + bx) * 64, J.q[c->tq], c->plane + ((size_t)by * 8 * c->bw + bx) * 8, c->bw * 8);
+  }
+  if (!out) {
+    free_all(&J);
+    return JO_OK;
+  }
+  if (J.ncomp == 1) {
+    for (int y = 0; y < J.h; y++) memcpy(out + (size_t)y * J.w, J.comp[0].plane + (size_t)y * J.comp[0].bw * 8, J.w);
+    free_all(&J);
+    return JO_OK;
+  }
+  uint8_t* up[3] = {0, 0, 0};
+  int st[3];
+  for (int i = 0; i < 3; i++) {
+    up[i] = upsample(&J, &J.comp[i], &st[i]);
+    if (!up[i]) {
+      for (int k = 0; k < 3; k++) free(up[k]);
+      free_all(&J);
+      return JO_ERR_UNSUPPORTED;
+    }
+  }
+  const int rgb_passthrough = J.adobe_transform == 0;
+  for (int y = 0; y < J.h; y++)
+    for (int x = 0; x < J.w; x++) {
+      const int Y = up[0][(size_t)y * st[0] + x], cb = up[1][(size_t)y * st[1] + x], cr = up[2][(size_t)y * st[2] + x];
+      uint8_t* o = out + ((size_t)y * J.w + x) * 3;
+      if (rgb_passthrough) {
+        o[0] = (uint8_t)Y;
+        o[1] = (uint8_t)cb;
+        o[2] = (uint8_t)cr;
+        continue;
+      }
+      /* jdcolor.c build_ycc_rgb_table, SCALEBITS 16 */
+      const int xb = cb - 128, xr = cr - 128;
+      const int r = Y + (int)((91881 * (int64_t)xr + 32768) >> 16);
+      const int g = Y + (int)(((-22554) * (int64_t)xb + 32768 + (-46802) * (int64_t)xr) >> 16);
+      const int bl = Y + (int)((116130 * (int64_t)xb + 32768) >> 16);
+      o[0] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+      o[1] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
+      o[2] = (uint8_t)(bl < 0 ? 0 : (bl > 255 ? 255 : bl));
+    }
+  for (int k = 0; k < 3; k++) free(up[k]);
+  free_all(&J);
+  return JO_OK;
+}

@@ -1,0 +1,80 @@
+"""The JPEG oracle (oracle/jpeg_oracle.c) against libjpeg-turbo itself, through Pillow: bit-exact decoded
+pixels for baseline JPEGs of every chroma subsampling, odd sizes, restart intervals, qualities and content.
+This is the one PINNED oracle of the repository — Pillow links the same library with the same defaults
+(JDCT_ISLOW, fancy upsampling) as the libvips decoder behind the reference's sharp calls
+(classifier.js:51-52,107,135,199,296; imagePreprocess.js:40-42)."""
+import io
+
+import numpy as np
+import pytest
+from PIL import Image, features
+
+from conftest import rand_image
+from oracle import jpeg_oracle
+
+pytestmark = pytest.mark.skipif(not features.check_feature("libjpeg_turbo"), reason="Pillow without libjpeg-turbo")
+
+
+def _encode(img, **kw):
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+def _pillow(data):
+    return np.asarray(Image.open(io.BytesIO(data)))
+
+
+SHAPES = [(8, 8), (16, 16), (1, 1), (3, 5), (17, 33), (37, 53), (64, 48), (100, 161), (241, 319)]
+
+
+@pytest.mark.parametrize("h,w", SHAPES)
+@pytest.mark.parametrize("subsampling", [0, 1, 2])
+def test_rgb_matches_libjpeg_turbo(h, w, subsampling):
+    for kind, q in (("smooth", 85), ("noise", 60), ("edges", 95)):
+        img = rand_image(h, w, 3, seed=h * 7 + w + subsampling, kind=kind)
+        data = _encode(img, quality=q, subsampling=subsampling)
+        got, ref = jpeg_oracle.decode(data), _pillow(data)
+        assert got.shape == ref.shape and np.array_equal(got, ref), f"{h}x{w} subsampling {subsampling} {kind} q{q}: {np.abs(got.astype(int) - ref).max()}"
+
+
+@pytest.mark.parametrize("h,w", [(8, 8), (5, 9), (37, 53), (130, 70)])
+def test_greyscale_matches(h, w):
+    img = rand_image(h, w, 1, seed=h + w, kind="smooth")[:, :, 0]
+    data = _encode(img, quality=80)
+    assert np.array_equal(jpeg_oracle.decode(data), _pillow(data))
+
+
+@pytest.mark.parametrize("kw", [dict(restart_marker_rows=1), dict(restart_marker_blocks=3), dict(restart_marker_blocks=1), dict(restart_marker_rows=2)])
+@pytest.mark.parametrize("subsampling", [0, 2])
+def test_restart_intervals(kw, subsampling):
+    img = rand_image(75, 131, 3, seed=3, kind="smooth")
+    data = _encode(img, quality=75, subsampling=subsampling, **kw)
+    assert jpeg_oracle.info(data)["restart_interval"] > 0
+    assert np.array_equal(jpeg_oracle.decode(data), _pillow(data))
+
+
+def test_extreme_content_and_qualities():
+    rng = np.random.default_rng(1)
+    for q in (1, 10, 50, 100):
+        for img in (np.zeros((40, 56, 3), np.uint8), np.full((40, 56, 3), 255, np.uint8), rng.integers(0, 2, (40, 56, 3), dtype=np.uint8) * 255):
+            data = _encode(img, quality=q, subsampling=2)
+            assert np.array_equal(jpeg_oracle.decode(data), _pillow(data)), f"q{q}"
+
+
+def test_a_megapixel_photo_like_image():
+    img = rand_image(768, 1024, 3, seed=9, kind="smooth")
+    data = _encode(img, quality=90, subsampling=2, optimize=True)
+    assert np.array_equal(jpeg_oracle.decode(data), _pillow(data))
+
+
+def test_progressive_is_reported_unsupported():
+    data = _encode(rand_image(32, 32, 3, seed=1), quality=80, progressive=True)
+    with pytest.raises(ValueError):
+        jpeg_oracle.decode(data)
+
+
+def test_coefficients_hook_shape():
+    data = _encode(rand_image(37, 53, 3, seed=2, kind="smooth"), quality=85, subsampling=2)
+    y, cb = jpeg_oracle.coefficients(data, 0), jpeg_oracle.coefficients(data, 1)
+    assert y.shape == (6, 8, 64) and cb.shape == (3, 4, 64) and y.any()
