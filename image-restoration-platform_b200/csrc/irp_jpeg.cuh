@@ -1,0 +1,466 @@
+// irp_jpeg.cuh — baseline JPEG decode on the device (sm_100a): the decoder that sits in front of every
+// sharp pipeline of the hot path (reference: server-node/src/services/classifier.js:51-52,107,135,199,296
+// `sharp(imageBuffer)`; server-node/src/middleware/imagePreprocess.js:40-42), so
+// that compressed bytes instead of raw pixels cross PCIe.  Pixel-exact with libjpeg-turbo's default
+// decode (JDCT_ISLOW, fancy upsampling), the decoder inside libvips; the parity tests compare it with a CPU
+// restatement that is itself held bit-exact against libjpeg-turbo (tests/test_jpeg_*.py).
+//
+// Stages (one launch each over the whole batch; the host has parsed the headers and removed the byte
+// stuffing while it copied the entropy-coded segments into one upload buffer):
+//   huffman   Huffman decoding is sequential by nature: a code can only be found once the previous one
+//             ended.  It is parallelised the self-synchronising way: the stream is cut into 1024-bit
+//             subsequences, every thread decodes its own from the guess "a block starts here", and
+//             JPEG's code tables make a wrong guess fall into step with the true decode within a few
+//             symbols.  `huff_sync_kernel` iterates state(i) = f_i(state(i-1)) until nothing changes —
+//             then every subsequence's start state is the true one — an exclusive scan over the
+//             coefficient slots each subsequence advanced gives its place in the output, and
+//             `huff_write_kernel` decodes once more, writing coefficients.  Restart intervals, when a
+//             file has them, are independent streams with known start states.
+//   dc        the DC coefficients are coded as differences: one running sum per component and stream.
+//   idct      dequantise + jidctint (13-bit constants, two passes), 8 lanes per block, u8 planes.
+//   colour    fancy (triangle) chroma upsampling h2v1 / h2v2 / h1v2 + YCbCr -> RGB (16-bit fixed point),
+//             written as interleaved u8 rows with a 16-byte pitch: the classify / resize kernels' input.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace irp {
+
+constexpr int kSubBits = 1024;         // bits per subsequence
+constexpr int kHuffThreads = 128;      // subsequences per CTA (a CTA never spans two images)
+constexpr int kLutBits = 9;
+
+struct HuffDev {                       // one Huffman table
+  uint16_t lut[1 << kLutBits];         // (length << 8) | symbol for codes of <= 9 bits, 0 otherwise
+  int32_t maxcode[18];                 // canonical decode for longer codes
+  int32_t valoff[17];                  // valptr[l] - mincode[l]
+  uint8_t vals[256];
+};
+
+struct JpegImg {                       // one image of a decode launch (device copy)
+  int w, h, ncomp, hmax, vmax, mcux, mcuy, bpm;
+  int comp_h[3], comp_v[3], comp_bw[3], comp_bh[3], comp_dw[3], comp_dh[3];
+  int blk_comp[8], blk_bx[8], blk_by[8];   // block k of an MCU: component, offset inside the MCU (in blocks)
+  int dc_tab[3], ac_tab[3];                // table index (0..3) per component
+  uint16_t q[3][64];                       // natural order
+  int restart;                             // MCUs per restart interval (0: none)
+  int nstreams;                            // restart intervals (1 if none)
+  int stream_base;                         // first entry of this image in the stream arrays
+  int sub_base, nsub;                      // first subsequence (multiple of kHuffThreads), count
+  unsigned long long coef_off[3];          // int16 offsets into the coefficient arena
+  unsigned long long plane_off[3];         // byte offsets into the plane arena
+  unsigned long long out_off;              // byte offset of the RGB / grey output in the pixel arena
+  unsigned long long out_pitch;
+  int huff_base;                           // first of this image's 8 tables (DC 0..3, AC 0..3)
+  int pad;
+};
+
+struct JpegStream {                        // one restart interval (or the whole scan)
+  unsigned long long bit_off;              // first bit in the unstuffed batch buffer (multiple of 32)
+  unsigned long long nbits;
+  int img;
+  int first_mcu, n_mcu;
+  int sub_first;                           // first subsequence (global index), and how many
+  int nsub;
+  int pad;
+};
+
+struct SubState {                          // state AFTER a subsequence: where the next symbol starts
+  uint32_t p;                              // bit position relative to the stream
+  uint32_t slot;                           // coefficient slot modulo (64 * bpm): block in MCU * 64 + zigzag index
+};
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0u, 0x0123); }
+
+// A 64-bit window over a big-endian bit stream of 32-bit words.
+struct BitWin {
+  const uint32_t* d;
+  long long w;        // index of the word in `hi` (-2: nothing loaded; -1 would look like the predecessor of word 0)
+  uint32_t hi, lo;
+  __device__ __forceinline__ uint32_t peek16(unsigned long long p) {   // 16 bits starting at bit p
+    const long long wi = (long long)(p >> 5);
+    if (wi != w) {
+      if (wi == w + 1) {
+        hi = lo;
+      } else {
+        hi = bswap32(__ldg(d + wi));
+      }
+      lo = bswap32(__ldg(d + wi + 1));
+      w = wi;
+    }
+    const unsigned sh = (unsigned)(p & 31);
+    const unsigned long long win = ((unsigned long long)hi << 32) | lo;
+    return (uint32_t)((win << sh) >> 48);
+  }
+};
+
+struct HuffSmem {
+  HuffDev t[8];
+};
+
+__device__ __forceinline__ int huff_decode(const HuffDev& t, uint32_t bits16, int& len) {
+  const uint32_t e = t.lut[bits16 >> (16 - kLutBits)];
+  if (e) {
+    len = (int)(e >> 8);
+    return (int)(e & 0xFF);
+  }
+  int l = kLutBits + 1;
+  int code = (int)(bits16 >> (16 - l));
+  while (l <= 16 && code > t.maxcode[l]) {
+    l++;
+    code = (int)(bits16 >> (16 - l));
+  }
+  if (l > 16) {   // not a code (only reachable while out of sync): consume one bit, harmless symbol
+    len = 1;
+    return 0;
+  }
+  len = l;
+  return t.vals[(code + t.valoff[l]) & 255];
+}
+
+__device__ __forceinline__ int huff_extend(int x, int s) { return x < (1 << (s - 1)) ? x - (1 << s) + 1 : x; }
+
+// Decode the symbols that START in [p, p_end) of one stream, from slot state `slot` (mod 64 * bpm).
+// WRITE: store coefficients (zigzag -> natural) at absolute slot `abs_slot`.  Returns the state after.
+template <bool WRITE>
+__device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, BitWin& bw, unsigned long long stream_bit0,
+                                         unsigned long long stream_bits, uint32_t& p, uint32_t p_end, uint32_t& slot, uint32_t& advanced,
+                                         int16_t* __restrict__ const* coef, unsigned long long abs_slot, unsigned long long slot_limit,
+                                         const uint8_t* __restrict__ zigzag) {
+  const uint32_t period = 64u * (uint32_t)im.bpm;
+  while (p < p_end && p < stream_bits && (!WRITE || abs_slot < slot_limit)) {
+    const uint32_t z = slot & 63u, k = slot >> 6;
+    const int comp = im.blk_comp[k];
+    uint32_t bits = bw.peek16(stream_bit0 + p);
+    int len;
+    uint32_t adv;
+    if (z == 0) {
+      const int s = huff_decode(hs.t[im.dc_tab[comp]], bits, len) & 15;
+      p += len;
+      if (WRITE) {
+        int v = 0;
+        if (s) {
+          bits = bw.peek16(stream_bit0 + p);
+          v = huff_extend((int)(bits >> (16 - s)), s);
+        }
+        const unsigned long long blk = abs_slot >> 6;
+        const unsigned long long mcu = blk / im.bpm;
+        const int my = (int)(mcu / im.mcux), mx = (int)(mcu - (unsigned long long)my * im.mcux);
+        const size_t bidx = (size_t)(my * im.comp_v[comp] + im.blk_by[k]) * im.comp_bw[comp] + (mx * im.comp_h[comp] + im.blk_bx[k]);
+        coef[comp][bidx * 64] = (int16_t)v;
+      }
+      p += s;
+      adv = 1;
+    } else {
+      const int rs = huff_decode(hs.t[4 + im.ac_tab[comp]], bits, len);
+      p += len;
+      const int r = rs >> 4, s = rs & 15;
+      if (s == 0) {
+        adv = (r == 15) ? 16u : (64u - z);               // ZRL : EOB
+        if (z + adv > 64u) adv = 64u - z;
+      } else {
+        uint32_t zz = z + r;
+        if (zz > 63u) zz = 63u;                           // only while out of sync / on corrupt data
+        if (WRITE) {
+          bits = bw.peek16(stream_bit0 + p);
+          const int v = huff_extend((int)(bits >> (16 - s)), s);
+          const unsigned long long blk = abs_slot >> 6;
+          const unsigned long long mcu = blk / im.bpm;
+          const int my = (int)(mcu / im.mcux), mx = (int)(mcu - (unsigned long long)my * im.mcux);
+          const size_t bidx = (size_t)(my * im.comp_v[comp] + im.blk_by[k]) * im.comp_bw[comp] + (mx * im.comp_h[comp] + im.blk_bx[k]);
+          coef[comp][bidx * 64 + zigzag[zz]] = (int16_t)v;
+        }
+        p += s;
+        adv = zz - z + 1;
+      }
+    }
+    slot += adv;
+    if (slot >= period) slot -= period;
+    advanced += adv;
+    if (WRITE) abs_slot += adv;
+  }
+}
+
+__device__ __forceinline__ void load_huff(HuffSmem& hs, const HuffDev* __restrict__ tabs, int base) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(tabs + base);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&hs);
+  for (int i = threadIdx.x; i < (int)(sizeof(HuffSmem) / 4); i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+// which stream of the image does subsequence `sub` (global index) belong to: streams are in order
+__device__ __forceinline__ int find_stream(const JpegStream* __restrict__ streams, int lo, int n, int sub) {
+  int a = lo, b = lo + n - 1;
+  while (a < b) {
+    const int m = (a + b + 1) >> 1;
+    if (__ldg(&streams[m].sub_first) <= sub) a = m; else b = m - 1;
+  }
+  return a;
+}
+
+// One sweep of the fixed-point iteration.  first == 1: every subsequence starts from the guess "a DC symbol
+// of block 0 starts at my first bit" (true for the first subsequence of a stream).
+__global__ void __launch_bounds__(kHuffThreads)
+huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_img, const JpegStream* __restrict__ streams,
+                 const HuffDev* __restrict__ tabs, const uint32_t* __restrict__ data, SubState* __restrict__ state,
+                 uint32_t* __restrict__ advanced, int first, int* __restrict__ changed) {
+  __shared__ HuffSmem hs;
+  __shared__ JpegImg im;
+  const int img = cta_img[blockIdx.x];
+  for (int i = threadIdx.x; i < (int)(sizeof(JpegImg) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&im)[i] = reinterpret_cast<const uint32_t*>(imgs + img)[i];
+  load_huff(hs, tabs, imgs[img].huff_base);
+  __syncthreads();
+  const int sub = blockIdx.x * kHuffThreads + threadIdx.x;
+  if (sub >= im.sub_base + im.nsub) return;
+  const int si = find_stream(streams, im.stream_base, im.nstreams, sub);
+  const JpegStream st = streams[si];
+  const int local = sub - st.sub_first;
+  uint32_t p, slot;
+  if (local == 0) {
+    p = 0;
+    slot = 0;
+    if (!first) return;          // the first subsequence of a stream never changes
+  } else if (first) {
+    p = (uint32_t)local * kSubBits;
+    slot = 0;
+  } else {
+    const unsigned long long pv = reinterpret_cast<const volatile unsigned long long*>(state)[sub - 1];   // one 64-bit read: never torn
+    p = (uint32_t)pv;
+    slot = (uint32_t)(pv >> 32);
+  }
+  BitWin bw{data, -2, 0, 0};
+  uint32_t adv = 0;
+  const uint32_t p_end = (uint32_t)(local + 1) * kSubBits;
+  huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, p_end, slot, adv, nullptr, 0, 0, nullptr);
+  const unsigned long long nv = (unsigned long long)p | ((unsigned long long)slot << 32);
+  const unsigned long long ov = reinterpret_cast<const volatile unsigned long long*>(state)[sub];
+  if (first || ov != nv || advanced[sub] != adv) {
+    reinterpret_cast<volatile unsigned long long*>(state)[sub] = nv;
+    advanced[sub] = adv;
+    if (!first) atomicOr(changed, 1);
+  }
+}
+
+// exclusive scan of `advanced` inside every stream (one warp per stream; streams hold at most a few 10^4 subsequences)
+__global__ void huff_scan_kernel(const JpegStream* __restrict__ streams, int n_streams, const uint32_t* __restrict__ advanced,
+                                 unsigned long long* __restrict__ slot_start) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= n_streams) return;
+  const JpegStream st = streams[s];
+  unsigned long long run = 0;
+  for (int base = 0; base < st.nsub; base += 32) {
+    const int i = base + lane;
+    const unsigned long long v = i < st.nsub ? advanced[st.sub_first + i] : 0;
+    unsigned long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (i < st.nsub) slot_start[st.sub_first + i] = run + x - v;
+    run += __shfl_sync(0xffffffffu, x, 31);
+  }
+}
+
+__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+__global__ void __launch_bounds__(kHuffThreads)
+huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_img, const JpegStream* __restrict__ streams,
+                  const HuffDev* __restrict__ tabs, const uint32_t* __restrict__ data, const SubState* __restrict__ state,
+                  const unsigned long long* __restrict__ slot_start, int16_t* __restrict__ coef_arena) {
+  __shared__ HuffSmem hs;
+  __shared__ JpegImg im;
+  __shared__ uint8_t zz[64];
+  const int img = cta_img[blockIdx.x];
+  for (int i = threadIdx.x; i < (int)(sizeof(JpegImg) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&im)[i] = reinterpret_cast<const uint32_t*>(imgs + img)[i];
+  if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+  load_huff(hs, tabs, imgs[img].huff_base);
+  __syncthreads();
+  const int sub = blockIdx.x * kHuffThreads + threadIdx.x;
+  if (sub >= im.sub_base + im.nsub) return;
+  const int si = find_stream(streams, im.stream_base, im.nstreams, sub);
+  const JpegStream st = streams[si];
+  const int local = sub - st.sub_first;
+  uint32_t p = 0, slot = 0;
+  if (local) {
+    const SubState prev = state[sub - 1];
+    p = prev.p;
+    slot = prev.slot;
+  }
+  int16_t* coef[3] = {coef_arena + im.coef_off[0], coef_arena + im.coef_off[1], coef_arena + im.coef_off[2]};
+  const unsigned long long base_slot = (unsigned long long)st.first_mcu * im.bpm * 64;
+  const unsigned long long limit = base_slot + (unsigned long long)st.n_mcu * im.bpm * 64;
+  BitWin bw{data, -2, 0, 0};
+  uint32_t adv = 0;
+  huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef, base_slot + slot_start[sub], limit, zz);
+}
+
+// DC differences -> DC values: one warp per (stream, component); a round takes 128 blocks in MCU order
+// (4 per lane, loads in flight together), scans them with shuffles and carries the running prediction.
+__global__ void dc_kernel(const JpegImg* __restrict__ imgs, const JpegStream* __restrict__ streams, int n_streams, int16_t* __restrict__ coef_arena) {
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int s = wg / 3, c = wg - s * 3;
+  if (s >= n_streams) return;
+  const JpegStream st = streams[s];
+  const JpegImg& im = imgs[st.img];
+  if (c >= im.ncomp) return;
+  int16_t* coef = coef_arena + im.coef_off[c];
+  const int ch = im.comp_h[c], cv = im.comp_v[c], bw = im.comp_bw[c], per = ch * cv;
+  const int nblk = st.n_mcu * per;
+  int pred = 0;
+  for (int base = 0; base < nblk; base += 128) {
+    int v[4];
+    size_t addr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i = base + lane * 4 + k;
+      v[k] = 0;
+      addr[k] = 0;
+      if (i < nblk) {
+        const int m = st.first_mcu + i / per, j = i % per;
+        const int my = m / im.mcux, mx = m - my * im.mcux;
+        addr[k] = ((size_t)(my * cv + j / ch) * bw + (mx * ch + j % ch)) * 64;
+        v[k] = coef[addr[k]];
+      }
+    }
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    int x = v[3];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    const int off = pred + x - v[3];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (base + lane * 4 + k < nblk) coef[addr[k]] = (int16_t)(v[k] + off);
+    pred += __shfl_sync(0xffffffffu, x, 31);
+  }
+}
+
+// jidctint: 8 lanes per block, lane = column in pass 1, row in pass 2 (transpose through shared memory)
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+__device__ __forceinline__ uint32_t range_limit(int x) {
+  int v = x & 1023;
+  if (v >= 512) v -= 1024;
+  return (uint32_t)min(max(v + 128, 0), 255);
+}
+__device__ __forceinline__ void idct_1d(const int in[8], int out[8], int shift) {
+  int z2 = in[2], z3 = in[6];
+  int z1 = (z2 + z3) * 4433;
+  int tmp2 = z1 + z3 * (-15137), tmp3 = z1 + z2 * 6270;
+  int tmp0 = (in[0] + in[4]) * 8192, tmp1 = (in[0] - in[4]) * 8192;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+  z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+  int z4 = tmp1 + tmp3;
+  const int z5 = (z3 + z4) * 9633;
+  tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;
+  z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+  z3 += z5; z4 += z5;
+  tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+  out[0] = descale(tmp10 + tmp3, shift); out[7] = descale(tmp10 - tmp3, shift);
+  out[1] = descale(tmp11 + tmp2, shift); out[6] = descale(tmp11 - tmp2, shift);
+  out[2] = descale(tmp12 + tmp1, shift); out[5] = descale(tmp12 - tmp1, shift);
+  out[3] = descale(tmp13 + tmp0, shift); out[4] = descale(tmp13 - tmp0, shift);
+}
+
+struct IdctJob {                // one component of one image
+  unsigned long long coef_off, plane_off;
+  int nblocks, bw;              // blocks, blocks per row
+  int block_base;               // first global block index of this job
+  int qidx;                     // index into the quantisation-table array (64 x u16 each)
+};
+
+__global__ void __launch_bounds__(256)
+idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, const int16_t* __restrict__ coef_arena,
+            const uint16_t* __restrict__ qtabs, uint8_t* __restrict__ plane_arena) {
+  __shared__ int ws[32][65];
+  const int lane8 = threadIdx.x & 7, bl = threadIdx.x >> 3;       // 32 blocks per CTA
+  const int gb = blockIdx.x * 32 + bl;
+  const bool on = gb < total_blocks;
+  int ji = 0;
+  if (on)
+    while (ji + 1 < n_jobs && gb >= __ldg(&jobs[ji + 1].block_base)) ji++;
+  const IdctJob J = jobs[ji];
+  const int b = gb - J.block_base;
+  int v[8], o[8];
+  if (on) {
+    const int16_t* c = coef_arena + J.coef_off + (size_t)b * 64;
+    const uint16_t* q = qtabs + J.qidx * 64;
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = (int)c[r * 8 + lane8] * (int)__ldg(q + r * 8 + lane8);
+    idct_1d(v, o, 11);
+#pragma unroll
+    for (int r = 0; r < 8; r++) ws[bl][r * 8 + lane8] = o[r];
+  }
+  __syncwarp();
+  if (on) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = ws[bl][lane8 * 8 + k];
+    idct_1d(v, o, 18);
+    const int by = b / J.bw, bx = b - by * J.bw;
+    uint8_t* p = plane_arena + J.plane_off + ((size_t)(by * 8 + lane8) * J.bw + bx) * 8;
+    const uint32_t lo = range_limit(o[0]) | (range_limit(o[1]) << 8) | (range_limit(o[2]) << 16) | (range_limit(o[3]) << 24);
+    const uint32_t hi = range_limit(o[4]) | (range_limit(o[5]) << 8) | (range_limit(o[6]) << 16) | (range_limit(o[7]) << 24);
+    *reinterpret_cast<uint2*>(p) = make_uint2(lo, hi);
+  }
+}
+
+// fancy upsampling of one chroma sample position + colour conversion, one thread per output pixel
+__device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ pl, int pw, int dw, int dh, int hx, int vx, int x, int y) {
+  if (hx == 1 && vx == 1) return pl[(size_t)y * pw + x];
+  if (hx == 2 && vx == 1) {
+    const uint8_t* in = pl + (size_t)y * pw;
+    const int i = x >> 1;
+    if (x & 1) {
+      if (i == dw - 1 && dw > 1) return in[i];
+      return (in[i] * 3 + in[i + 1] + 2) >> 2;
+    }
+    if (i == 0) return in[0];
+    return (in[i] * 3 + in[i - 1] + 1) >> 2;
+  }
+  const int r = y >> 1;
+  const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+  const uint8_t* in0 = pl + (size_t)r * pw;
+  const uint8_t* in1 = pl + (size_t)rn * pw;
+  if (hx == 1) return (in0[x] * 3 + in1[x] + ((y & 1) ? 2 : 1)) >> 2;
+  const int i = x >> 1;
+  const int thiscol = in0[i] * 3 + in1[i];
+  if (x & 1) {
+    if (i == dw - 1 && dw > 1) return (thiscol * 4 + 7) >> 4;
+    return (thiscol * 3 + in0[i + 1] * 3 + in1[i + 1] + 7) >> 4;
+  }
+  if (i == 0) return (thiscol * 4 + 8) >> 4;
+  return (thiscol * 3 + in0[i - 1] * 3 + in1[i - 1] + 8) >> 4;
+}
+
+__global__ void __launch_bounds__(256)
+colour_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __restrict__ plane_arena, uint8_t* __restrict__ pix_arena) {
+  const int img = blockIdx.z;
+  const JpegImg& im = imgs[img];
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= im.w || y >= im.h) return;
+  uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch;
+  const uint8_t* p0 = plane_arena + im.plane_off[0];
+  const int pw0 = im.comp_bw[0] * 8;
+  if (im.ncomp == 1) {
+    out[x] = p0[(size_t)y * pw0 + x];
+    return;
+  }
+  const int Y = p0[(size_t)y * pw0 + x];
+  const int cb = chroma_at(plane_arena + im.plane_off[1], im.comp_bw[1] * 8, im.comp_dw[1], im.comp_dh[1], im.hmax / im.comp_h[1],
+                           im.vmax / im.comp_v[1], x, y);
+  const int cr = chroma_at(plane_arena + im.plane_off[2], im.comp_bw[2] * 8, im.comp_dw[2], im.comp_dh[2], im.hmax / im.comp_h[2],
+                           im.vmax / im.comp_v[2], x, y);
+  const int xb = cb - 128, xr = cr - 128;
+  const int r = Y + ((91881 * xr + 32768) >> 16);
+  const int g = Y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);
+  const int b = Y + ((116130 * xb + 32768) >> 16);
+  out[3 * x] = (uint8_t)min(max(r, 0), 255);
+  out[3 * x + 1] = (uint8_t)min(max(g, 0), 255);
+  out[3 * x + 2] = (uint8_t)min(max(b, 0), 255);
+}
+
+}  // namespace irp

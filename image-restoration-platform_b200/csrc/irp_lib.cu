@@ -28,6 +28,7 @@
 #include "irp_classify.cuh"
 #include "irp_classify_bulk.cuh"
 #include "irp_resize_tma.cuh"
+#include "irp_jpeg.cuh"
 #include "irp_resize.cuh"
 
 using namespace irp;
@@ -110,6 +111,9 @@ struct irp_ctx {
   DevBuf d_desc, d_acc, d_stage_in, d_stage_out, d_orient, d_jobs, d_tmaps, d_rtjobs, d_rtmaps;
   PinBuf h_desc, h_acc, h_jobs, h_tmaps, h_rtjobs, h_rtmaps;
   size_t smem_optin_full = 0;     // the device's opt-in shared memory per block
+  DevBuf d_jdata, d_jmeta, d_jstate, d_jcoef, d_jplane, d_jpix;   // device JPEG decode (irp_jpeg.cuh)
+  PinBuf h_jdata, h_jmeta;
+  int jpeg_sweeps = 0;            // synchronisation sweeps of the last JPEG batch
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   std::vector<void*> plan_chunks;
   size_t plan_used = 0, plan_cap = 0;
@@ -945,10 +949,14 @@ int copy_outputs(irp_ctx* ctx, const irp_image_desc* imgs, irp_out_desc* outs, c
 // H2D of chunk c+1, the kernels of chunk c and the D2H of chunk c-1 overlap, so the call is bound by
 // the slower PCIe direction rather than by the sum of copies and kernels.  Device-resident batches
 // are one chunk: one launch per kernel and channel count.
+int run_batch_locked(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode);
 int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode) {
   if (!ctx) return IRP_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->err.clear();
+  return run_batch_locked(ctx, imgs, n, results, outs, resize_mode);
+}
+int run_batch_locked(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode) {
   if (n < 0 || (n > 0 && !imgs)) return fail(ctx, IRP_ERR_BAD_ARG, "bad batch arguments");
   if (n == 0) return IRP_OK;
   CK(cudaSetDevice(ctx->device));
@@ -1066,6 +1074,8 @@ int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* resul
   return IRP_OK;
 }
 
+#include "irp_jpeg_host.inc"
+
 }  // namespace
 
 // ============================================================================
@@ -1182,8 +1192,10 @@ void irp_destroy(irp_ctx* ctx) {
   for (auto& ev : ctx->timing_events) cudaEventDestroy(ev);
   if (ctx->copy_in_stream) cudaStreamDestroy(ctx->copy_in_stream);
   if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
-  for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps, &ctx->d_rtjobs, &ctx->d_rtmaps}) b->release();
-  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps}) b->release();
+  for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps, &ctx->d_rtjobs, &ctx->d_rtmaps,
+                    &ctx->d_jdata, &ctx->d_jmeta, &ctx->d_jstate, &ctx->d_jcoef, &ctx->d_jplane, &ctx->d_jpix})
+    b->release();
+  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);
@@ -1302,6 +1314,60 @@ int irp_analyze_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_resul
 int irp_fusion_prepare_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n_groups, irp_out_desc* canvases) {
   if (!canvases) return ctx ? fail(ctx, IRP_ERR_BAD_ARG, "null canvases") : IRP_ERR_BAD_ARG;
   return run_batch(ctx, imgs, n_groups * IRP_FUSION_MAX_IMAGES, nullptr, canvases, 1);
+}
+
+// ---- compressed input: baseline JPEG decoded on the device ----
+int irp_jpeg_info(const uint8_t* data, size_t size, int* width, int* height, int* channels) {
+  if (!data || !width || !height || !channels) return IRP_ERR_BAD_ARG;
+  HostJpeg J;
+  const char* why = "";
+  const int rc = jpeg_parse(data, size, &J, &why);
+  if (rc) return rc;
+  *width = J.w;
+  *height = J.h;
+  *channels = J.ncomp == 1 ? 1 : 3;
+  return IRP_OK;
+}
+
+int irp_decode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_out_desc* outs) {
+  if (!ctx || n < 0 || (n && (!jpegs || !outs))) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->err.clear();
+  if (!n) return IRP_OK;
+  ctx->timing = irp_timing{};
+  std::vector<JpegPlaced> pl;
+  int rc = decode_jpegs_locked(ctx, jpegs, n, &pl);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    irp_out_desc& od = outs[i];
+    const size_t tight = (size_t)pl[i].w * pl[i].c, pitch = od.pitch ? od.pitch : tight;
+    if (!od.pixels || pitch < tight || od.capacity < pitch * (size_t)(pl[i].h - 1) + tight)
+      return fail(ctx, IRP_ERR_CAPACITY, "output %d: capacity %zu too small for %dx%dx%d", i, od.capacity, pl[i].w, pl[i].h, pl[i].c);
+    od.width = pl[i].w;
+    od.height = pl[i].h;
+    od.channels = pl[i].c;
+    CK(cudaMemcpy2DAsync(od.pixels, pitch, pl[i].px, pl[i].pitch, tight, pl[i].h, od.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                         ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return IRP_OK;
+}
+
+int irp_analyze_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, irp_out_desc* outs) {
+  if (!ctx || n < 0 || (n && (!jpegs || (!results && !outs)))) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->err.clear();
+  if (!n) return IRP_OK;
+  std::vector<JpegPlaced> pl;
+  int rc = decode_jpegs_locked(ctx, jpegs, n, &pl);
+  if (rc) return rc;
+  const uint32_t decode_launches = ctx->timing.kernel_launches;
+  std::vector<irp_image_desc> descs(n);
+  for (int i = 0; i < n; i++)
+    descs[i] = irp_image_desc{pl[i].px, pl[i].pitch, pl[i].w, pl[i].h, pl[i].c, 1, jpegs[i].exif_orientation, 1};
+  rc = run_batch_locked(ctx, descs.data(), n, results, outs, 0);
+  ctx->timing.kernel_launches += decode_launches;
+  return rc;
 }
 
 // ---- concurrent single-image requests ----

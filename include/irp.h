@@ -152,6 +152,32 @@ int irp_analyze_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_resul
 int irp_fusion_prepare_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n_groups,
                              irp_out_desc *canvases);
 
+/* ---- compressed input ------------------------------------------------- */
+/* What the reference's callers actually hold is the FILE: analyze(imageBuffer)
+ * and preprocessImage(req.file.buffer) hand sharp compressed bytes
+ * (classifier.js:40,51-52; imagePreprocess.js:36-42), and sharp decodes them
+ * with libjpeg-turbo (JDCT_ISLOW, fancy upsampling).  These entry points take
+ * baseline JPEG bytes, decode them ON THE DEVICE pixel-exact with that decoder
+ * (parallel Huffman decode, integer IDCT, triangle chroma upsampling, YCbCr ->
+ * RGB) and feed the pixels to the same kernels — ~4 MB instead of 36 MB per
+ * 12 MP photo crosses PCIe and the host decodes nothing.  8-bit baseline
+ * (SOF0/SOF1 Huffman), 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, with or
+ * without restart markers; anything else returns IRP_ERR_UNSUPPORTED (no CPU
+ * fallback). */
+typedef struct irp_jpeg_desc {
+  const uint8_t *data;      /* host pointer to the JPEG file bytes          */
+  size_t size;
+  int32_t exif_orientation; /* 1..8 (from the caller's header parse), else 1 */
+  int32_t reserved;
+} irp_jpeg_desc;
+/* header only: stored dims and channels (1 grey, 3 colour) — sharp(buf).metadata(), classifier.js:51 */
+int irp_jpeg_info(const uint8_t *data, size_t size, int *width, int *height, int *channels);
+/* decoded pixels (u8 RGB or grey), to host or device buffers */
+int irp_decode_jpeg_batch(irp_ctx *ctx, const irp_jpeg_desc *jpegs, int n, irp_out_desc *outs);
+/* decode + classify (is_jpeg = 1) + preprocess; `results` or `outs` may be NULL */
+int irp_analyze_jpeg_batch(irp_ctx *ctx, const irp_jpeg_desc *jpegs, int n, irp_result *results,
+                           irp_out_desc *outs);
+
 /* ---- concurrent single-image requests --------------------------------- */
 /* The reference's callers issue ONE image per call from several in-flight
  * promises (ClassifierService.analyze is async, classifier.js:40; restoreBatch

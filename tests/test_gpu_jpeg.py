@@ -1,0 +1,113 @@
+"""Device JPEG decode (irp_decode_jpeg_batch / irp_analyze_jpeg_batch) against libjpeg-turbo itself (Pillow)
+and against the pinned CPU restatement: decoded pixels bit-exact for every chroma subsampling, odd sizes,
+restart intervals, optimised Huffman tables, and batches; then the classify / preprocess results computed from
+the compressed bytes must equal those computed from Pillow's pixels."""
+import ctypes as C
+import io
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import assert_result_parity, rand_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _encode(img, **kw):
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+def _pillow(data):
+    return np.asarray(Image.open(io.BytesIO(data)))
+
+
+def _decode_batch(engine, blobs):
+    from irp_b200 import _ffi
+
+    n = len(blobs)
+    keep = [np.frombuffer(b, np.uint8) for b in blobs]
+    descs = (_ffi.JpegDesc * n)()
+    outs = (_ffi.OutDesc * n)()
+    arrays = []
+    for i, k in enumerate(keep):
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        assert engine._lib.irp_jpeg_info(k.ctypes.data, k.size, C.byref(w), C.byref(h), C.byref(c)) == 0
+        a = np.empty((h.value, w.value, c.value), np.uint8)
+        arrays.append(a)
+        descs[i] = _ffi.JpegDesc(k.ctypes.data, k.size, 1, 0)
+        outs[i] = _ffi.OutDesc(a.ctypes.data, 0, a.nbytes, 0, 0, 0, 0)
+    engine._check(engine._lib.irp_decode_jpeg_batch(engine._ctx, descs, n, outs))
+    return [a[:, :, 0] if a.shape[2] == 1 else a for a in arrays]
+
+
+SHAPES = [(8, 8), (1, 1), (3, 5), (17, 33), (37, 53), (64, 48), (100, 161), (241, 319), (600, 900)]
+
+
+@pytest.mark.parametrize("subsampling", [0, 1, 2])
+def test_decode_matches_libjpeg_turbo(engine, subsampling):
+    blobs = []
+    for i, (h, w) in enumerate(SHAPES):
+        for kind, q in (("smooth", 85), ("noise", 60), ("edges", 95)):
+            blobs.append(_encode(rand_image(h, w, 3, seed=31 * i + subsampling, kind=kind), quality=q, subsampling=subsampling))
+    got = _decode_batch(engine, blobs)
+    for i, (g, b) in enumerate(zip(got, blobs)):
+        ref = _pillow(b)
+        assert g.shape == ref.shape and np.array_equal(g, ref), f"blob {i} shape {ref.shape}: max diff {np.abs(g.astype(int) - ref).max()}"
+
+
+def test_greyscale_restart_intervals_and_optimised_tables(engine):
+    blobs = [_encode(rand_image(130, 70, 1, seed=1, kind="smooth")[:, :, 0], quality=80),
+             _encode(rand_image(75, 131, 3, seed=2, kind="smooth"), quality=75, subsampling=2, restart_marker_rows=1),
+             _encode(rand_image(75, 131, 3, seed=3, kind="noise"), quality=75, subsampling=0, restart_marker_blocks=3),
+             _encode(rand_image(211, 333, 3, seed=4, kind="smooth"), quality=90, subsampling=2, optimize=True),
+             _encode(rand_image(40, 56, 3, seed=5, kind="edges"), quality=1, subsampling=1),
+             _encode(np.zeros((33, 47, 3), np.uint8), quality=50), _encode(np.full((33, 47, 3), 255, np.uint8), quality=100)]
+    for g, b in zip(_decode_batch(engine, blobs), blobs):
+        ref = _pillow(b)
+        assert g.shape == ref.shape and np.array_equal(g, ref)
+
+
+def test_a_large_photo_sized_image_synchronises(engine):
+    """Many thousand subsequences in one stream: the self-synchronising decode must converge and match."""
+    img = rand_image(1500, 2000, 3, seed=8, kind="smooth")
+    blob = _encode(img, quality=88, subsampling=2)
+    got = _decode_batch(engine, [blob])[0]
+    assert np.array_equal(got, _pillow(blob))
+
+
+def test_analyze_from_compressed_bytes_equals_analyze_from_pixels(engine, oracle):
+    from irp_b200 import _ffi
+
+    imgs = [rand_image(900, 1300, 3, seed=11, kind="smooth"), rand_image(2300, 2100, 3, seed=12, kind="smooth")]
+    blobs = [_encode(im, quality=85, subsampling=2) for im in imgs]
+    orients = [1, 6]
+    keep = [np.frombuffer(b, np.uint8) for b in blobs]
+    n = len(blobs)
+    descs = (_ffi.JpegDesc * n)(*[_ffi.JpegDesc(k.ctypes.data, k.size, o, 0) for k, o in zip(keep, orients)])
+    res = (_ffi.Result * n)()
+    outs = (_ffi.OutDesc * n)()
+    arrays = []
+    for i, b in enumerate(blobs):
+        px = _pillow(b)
+        ow, oh = engine.preprocess_dims(px.shape[1], px.shape[0], orients[i])
+        a = np.empty((oh, ow, 3), np.uint8)
+        arrays.append(a)
+        outs[i] = _ffi.OutDesc(a.ctypes.data, 0, a.nbytes, 0, 0, 0, 0)
+    engine._check(engine._lib.irp_analyze_jpeg_batch(engine._ctx, descs, n, res, outs))
+    from irp_b200.engine import result_to_dict
+
+    for i, b in enumerate(blobs):
+        px = np.ascontiguousarray(_pillow(b))
+        assert_result_parity(result_to_dict(res[i]), oracle.classify(px), 3, f"jpeg {i}")
+        assert np.array_equal(arrays[i], oracle.preprocess(px, orients[i]))
+
+
+def test_progressive_is_refused_loudly(engine):
+    from irp_b200 import _ffi
+
+    blob = np.frombuffer(_encode(rand_image(64, 64, 3, seed=1), quality=80, progressive=True), np.uint8)
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    assert engine._lib.irp_jpeg_info(blob.ctypes.data, blob.size, C.byref(w), C.byref(h), C.byref(c)) == _ffi.IRP_ERR_UNSUPPORTED
