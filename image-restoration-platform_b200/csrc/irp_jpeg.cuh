@@ -197,12 +197,16 @@ __device__ __forceinline__ int find_stream(const JpegStream* __restrict__ stream
   return a;
 }
 
-// One sweep of the fixed-point iteration.  first == 1: every subsequence starts from the guess "a DC symbol
-// of block 0 starts at my first bit" (true for the first subsequence of a stream).
+// The fixed-point iteration.  in_state[i] is the start state subsequence i was last decoded from and
+// state[i] the state it ended in.  first == 1: every subsequence starts from the guess "a DC symbol of block
+// 0 starts at my first bit" (true for the first subsequence of a stream).  Later launches run `rounds` rounds:
+// a thread re-decodes only when its predecessor's end state differs from the start state it used, and a CTA
+// barrier between rounds lets a correction travel up to `rounds` subsequences per launch.  A launch in which
+// nobody re-decoded leaves `changed` at 0: state[i] == f_i(state[i-1]) everywhere, i.e. all states are true.
 __global__ void __launch_bounds__(kHuffThreads)
 huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_img, const JpegStream* __restrict__ streams,
                  const HuffDev* __restrict__ tabs, const uint32_t* __restrict__ data, SubState* __restrict__ state,
-                 uint32_t* __restrict__ advanced, int first, int* __restrict__ changed) {
+                 SubState* __restrict__ in_state, uint32_t* __restrict__ advanced, int first, int rounds, int* __restrict__ changed) {
   __shared__ HuffSmem hs;
   __shared__ JpegImg im;
   const int img = cta_img[blockIdx.x];
@@ -210,33 +214,38 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
   load_huff(hs, tabs, imgs[img].huff_base);
   __syncthreads();
   const int sub = blockIdx.x * kHuffThreads + threadIdx.x;
-  if (sub >= im.sub_base + im.nsub) return;
-  const int si = find_stream(streams, im.stream_base, im.nstreams, sub);
-  const JpegStream st = streams[si];
-  const int local = sub - st.sub_first;
-  uint32_t p, slot;
-  if (local == 0) {
-    p = 0;
-    slot = 0;
-    if (!first) return;          // the first subsequence of a stream never changes
-  } else if (first) {
-    p = (uint32_t)local * kSubBits;
-    slot = 0;
-  } else {
-    const unsigned long long pv = reinterpret_cast<const volatile unsigned long long*>(state)[sub - 1];   // one 64-bit read: never torn
-    p = (uint32_t)pv;
-    slot = (uint32_t)(pv >> 32);
+  const bool active = sub < im.sub_base + im.nsub;
+  JpegStream st;
+  int local = 0;
+  if (active) {
+    st = streams[find_stream(streams, im.stream_base, im.nstreams, sub)];
+    local = sub - st.sub_first;
   }
+  volatile unsigned long long* vstate = reinterpret_cast<volatile unsigned long long*>(state);
+  unsigned long long* vin = reinterpret_cast<unsigned long long*>(in_state);
   BitWin bw{data, -2, 0, 0};
-  uint32_t adv = 0;
-  const uint32_t p_end = (uint32_t)(local + 1) * kSubBits;
-  huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, p_end, slot, adv, nullptr, 0, 0, nullptr);
-  const unsigned long long nv = (unsigned long long)p | ((unsigned long long)slot << 32);
-  const unsigned long long ov = reinterpret_cast<const volatile unsigned long long*>(state)[sub];
-  if (first || ov != nv || advanced[sub] != adv) {
-    reinterpret_cast<volatile unsigned long long*>(state)[sub] = nv;
-    advanced[sub] = adv;
-    if (!first) atomicOr(changed, 1);
+  for (int round = 0; round < rounds; round++) {
+    if (active && (first || local > 0)) {
+      unsigned long long start;
+      if (local == 0)
+        start = 0;
+      else if (first)
+        start = (unsigned long long)((uint32_t)local * kSubBits);
+      else
+        start = vstate[sub - 1];
+      if (first || start != vin[sub]) {
+        uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
+        huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0, 0, nullptr);
+        vin[sub] = start;
+        vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
+        advanced[sub] = adv;
+        if (!first) *changed = 1;
+      }
+    }
+    if (round + 1 < rounds) {
+      __threadfence_block();
+      __syncthreads();
+    }
   }
 }
 
@@ -296,46 +305,74 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
   huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef, base_slot + slot_start[sub], limit, zz);
 }
 
-// DC differences -> DC values: one warp per (stream, component); a round takes 128 blocks in MCU order
-// (4 per lane, loads in flight together), scans them with shuffles and carries the running prediction.
-__global__ void dc_kernel(const JpegImg* __restrict__ imgs, const JpegStream* __restrict__ streams, int n_streams, int16_t* __restrict__ coef_arena) {
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int s = wg / 3, c = wg - s * 3;
-  if (s >= n_streams) return;
-  const JpegStream st = streams[s];
+// DC differences -> DC values: a scan per (stream, component) over its blocks in MCU order, in three
+// steps over 2048-block chunks: chunk sums, an exclusive scan of the sums of each (stream, component),
+// then every chunk is scanned again from its offset and written back.
+constexpr int kDcChunk = 2048, kDcThreads = 256;   // 8 blocks per thread
+struct DcChunk {
+  int stream, comp;
+  int first, count;      // blocks of this (stream, component), in MCU order
+  int group_first;       // index of the first chunk of the same (stream, component)
+  int pad;
+};
+__device__ __forceinline__ size_t dc_addr(const JpegImg& im, const JpegStream& st, int c, int i) {
+  const int ch = im.comp_h[c], cv = im.comp_v[c], per = ch * cv;
+  const int m = st.first_mcu + i / per, j = i % per;
+  const int my = m / im.mcux, mx = m - my * im.mcux;
+  return ((size_t)(my * cv + j / ch) * im.comp_bw[c] + (mx * ch + j % ch)) * 64;
+}
+template <bool APPLY>
+__global__ void __launch_bounds__(kDcThreads)
+dc_chunk_kernel(const JpegImg* __restrict__ imgs, const JpegStream* __restrict__ streams, const DcChunk* __restrict__ chunks,
+                int* __restrict__ sums, int16_t* __restrict__ coef_arena) {
+  __shared__ int warp_tot[kDcThreads / 32];
+  const DcChunk ck = chunks[blockIdx.x];
+  const JpegStream st = streams[ck.stream];
   const JpegImg& im = imgs[st.img];
-  if (c >= im.ncomp) return;
-  int16_t* coef = coef_arena + im.coef_off[c];
-  const int ch = im.comp_h[c], cv = im.comp_v[c], bw = im.comp_bw[c], per = ch * cv;
-  const int nblk = st.n_mcu * per;
-  int pred = 0;
-  for (int base = 0; base < nblk; base += 128) {
-    int v[4];
-    size_t addr[4];
+  int16_t* coef = coef_arena + im.coef_off[ck.comp];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v[8];
+  size_t addr[8];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int i = base + lane * 4 + k;
-      v[k] = 0;
-      addr[k] = 0;
-      if (i < nblk) {
-        const int m = st.first_mcu + i / per, j = i % per;
-        const int my = m / im.mcux, mx = m - my * im.mcux;
-        addr[k] = ((size_t)(my * cv + j / ch) * bw + (mx * ch + j % ch)) * 64;
-        v[k] = coef[addr[k]];
-      }
+  for (int k = 0; k < 8; k++) {
+    const int i = threadIdx.x * 8 + k;
+    v[k] = 0;
+    addr[k] = 0;
+    if (i < ck.count) {
+      addr[k] = dc_addr(im, st, ck.comp, ck.first + i);
+      v[k] = coef[addr[k]];
     }
-    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
-    int x = v[3];
+  }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    const int off = pred + x - v[3];
+  for (int k = 1; k < 8; k++) v[k] += v[k - 1];
+  int x = v[7];
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (base + lane * 4 + k < nblk) coef[addr[k]] = (int16_t)(v[k] + off);
-    pred += __shfl_sync(0xffffffffu, x, 31);
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[warp] = x;
+  __syncthreads();
+  int before = 0;
+  for (int w2 = 0; w2 < warp; w2++) before += warp_tot[w2];
+  if (!APPLY) {
+    if (threadIdx.x == kDcThreads - 1) sums[blockIdx.x] = before + x;
+    return;
+  }
+  const int off = sums[blockIdx.x] + before + x - v[7];   // sums[] now holds the exclusive prefix of the chunk
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (threadIdx.x * 8 + k < ck.count) coef[addr[k]] = (int16_t)(v[k] + off);
+}
+// exclusive scan of the chunk sums inside each (stream, component): the first chunk of a group does it
+__global__ void dc_offsets_kernel(const DcChunk* __restrict__ chunks, int n_chunks, int* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks || chunks[c].group_first != c) return;
+  int run = 0;
+  for (int k = c; k < n_chunks && chunks[k].group_first == c; k++) {
+    const int t = sums[k];
+    sums[k] = run;
+    run += t;
   }
 }
 
@@ -436,31 +473,54 @@ __device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ pl, int pw,
   return (thiscol * 3 + in0[i - 1] * 3 + in1[i - 1] + 8) >> 4;
 }
 
+// four output pixels per thread: one word of Y, twelve bytes of RGB
 __global__ void __launch_bounds__(256)
 colour_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __restrict__ plane_arena, uint8_t* __restrict__ pix_arena) {
   const int img = blockIdx.z;
   const JpegImg& im = imgs[img];
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x >= im.w || y >= im.h) return;
+  const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x0 >= im.w || y >= im.h) return;
   uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch;
   const uint8_t* p0 = plane_arena + im.plane_off[0];
   const int pw0 = im.comp_bw[0] * 8;
+  const uint32_t yw = *reinterpret_cast<const uint32_t*>(p0 + (size_t)y * pw0 + x0);   // plane rows are multiples of 8 wide
+  const int nvalid = min(4, im.w - x0);
   if (im.ncomp == 1) {
-    out[x] = p0[(size_t)y * pw0 + x];
+    if (nvalid == 4 && (im.out_pitch & 3) == 0)
+      *reinterpret_cast<uint32_t*>(out + x0) = yw;
+    else
+      for (int k = 0; k < nvalid; k++) out[x0 + k] = (uint8_t)(yw >> (8 * k));
     return;
   }
-  const int Y = p0[(size_t)y * pw0 + x];
-  const int cb = chroma_at(plane_arena + im.plane_off[1], im.comp_bw[1] * 8, im.comp_dw[1], im.comp_dh[1], im.hmax / im.comp_h[1],
-                           im.vmax / im.comp_v[1], x, y);
-  const int cr = chroma_at(plane_arena + im.plane_off[2], im.comp_bw[2] * 8, im.comp_dw[2], im.comp_dh[2], im.hmax / im.comp_h[2],
-                           im.vmax / im.comp_v[2], x, y);
-  const int xb = cb - 128, xr = cr - 128;
-  const int r = Y + ((91881 * xr + 32768) >> 16);
-  const int g = Y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);
-  const int b = Y + ((116130 * xb + 32768) >> 16);
-  out[3 * x] = (uint8_t)min(max(r, 0), 255);
-  out[3 * x + 1] = (uint8_t)min(max(g, 0), 255);
-  out[3 * x + 2] = (uint8_t)min(max(b, 0), 255);
+  const uint8_t* p1 = plane_arena + im.plane_off[1];
+  const uint8_t* p2 = plane_arena + im.plane_off[2];
+  const int pw1 = im.comp_bw[1] * 8, pw2 = im.comp_bw[2] * 8;
+  const int hx1 = im.hmax / im.comp_h[1], vx1 = im.vmax / im.comp_v[1], hx2 = im.hmax / im.comp_h[2], vx2 = im.vmax / im.comp_v[2];
+  uint32_t px[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = min(x0 + k, im.w - 1);
+    const int Y = (yw >> (8 * k)) & 0xFF;
+    const int cb = chroma_at(p1, pw1, im.comp_dw[1], im.comp_dh[1], hx1, vx1, x, y);
+    const int cr = chroma_at(p2, pw2, im.comp_dw[2], im.comp_dh[2], hx2, vx2, x, y);
+    const int xb = cb - 128, xr = cr - 128;
+    const int r = Y + ((91881 * xr + 32768) >> 16);
+    const int g = Y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);
+    const int b = Y + ((116130 * xb + 32768) >> 16);
+    px[k] = (uint32_t)min(max(r, 0), 255) | ((uint32_t)min(max(g, 0), 255) << 8) | ((uint32_t)min(max(b, 0), 255) << 16);
+  }
+  if (nvalid == 4) {   // out_pitch is a multiple of 16 and x0 of 4: three aligned words
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + 3 * x0);
+    o[0] = px[0] | (px[1] << 24);
+    o[1] = (px[1] >> 8) | (px[2] << 16);
+    o[2] = (px[2] >> 16) | (px[3] << 8);
+  } else {
+    for (int k = 0; k < nvalid; k++) {
+      out[3 * (x0 + k)] = (uint8_t)px[k];
+      out[3 * (x0 + k) + 1] = (uint8_t)(px[k] >> 8);
+      out[3 * (x0 + k) + 2] = (uint8_t)(px[k] >> 16);
+    }
+  }
 }
 
 }  // namespace irp

@@ -21,6 +21,8 @@
 #include "../../include/irp.h"
 #include "../../include/irp_spec.h"
 #include "grey_tables.inc"
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <thread>
