@@ -1360,15 +1360,20 @@ int irp_analyze_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->err.clear();
   if (!n) return IRP_OK;
+  ctx->timing = irp_timing{};
+  cudaEventRecord(ctx->ev[1], ctx->stream);
   std::vector<JpegPlaced> pl;
   int rc = decode_jpegs_locked(ctx, jpegs, n, &pl);
   if (rc) return rc;
+  cudaEventRecord(ctx->ev[2], ctx->stream);
   const uint32_t decode_launches = ctx->timing.kernel_launches;
   std::vector<irp_image_desc> descs(n);
   for (int i = 0; i < n; i++)
     descs[i] = irp_image_desc{pl[i].px, pl[i].pitch, pl[i].w, pl[i].h, pl[i].c, 1, jpegs[i].exif_orientation, 1};
   rc = run_batch_locked(ctx, descs.data(), n, results, outs, 0);
   ctx->timing.kernel_launches += decode_launches;
+  float ms = 0;
+  if (rc == IRP_OK && cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) ctx->timing.h2d_ms = ms;   // upload of the compressed bytes + device decode
   return rc;
 }
 
