@@ -473,11 +473,72 @@ __device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ pl, int pw,
   return (thiscol * 3 + in0[i - 1] * 3 + in1[i - 1] + 8) >> 4;
 }
 
+// is this image the common camera layout (3 components, 4:2:0, not tiny)?  Those take colour420_kernel.
+__device__ __forceinline__ bool is_plain_420(const JpegImg& im) {
+  return im.ncomp == 3 && im.hmax == 2 && im.vmax == 2 && im.comp_h[1] == 1 && im.comp_v[1] == 1 && im.comp_h[2] == 1 &&
+         im.comp_v[2] == 1 && im.w >= 16;
+}
+
+// 4:2:0: eight output pixels of one row per thread.  Replicating the first / last chroma column turns
+// libjpeg's special first- and last-column formulas into the general one ((4c + 8) >> 4 == (3c + c + 8) >> 4).
+__global__ void __launch_bounds__(256)
+colour420_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __restrict__ plane_arena, uint8_t* __restrict__ pix_arena) {
+  const JpegImg& im = imgs[blockIdx.z];
+  if (!is_plain_420(im)) return;
+  const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 8, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x0 >= im.w || y >= im.h) return;
+  const uint2 yw = *reinterpret_cast<const uint2*>(plane_arena + im.plane_off[0] + (size_t)y * (im.comp_bw[0] * 8) + x0);
+  const int r = y >> 1, i0 = x0 >> 1;
+  int up[2][8];
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const int dw = im.comp_dw[c + 1], dh = im.comp_dh[c + 1], pw = im.comp_bw[c + 1] * 8;
+    const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
+    const uint8_t* in0 = plane_arena + im.plane_off[c + 1] + (size_t)r * pw;
+    const uint8_t* in1 = plane_arena + im.plane_off[c + 1] + (size_t)rn * pw;
+    int cs[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int i = min(max(i0 - 1 + k, 0), dw - 1);
+      cs[k] = in0[i] * 3 + in1[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      up[c][2 * j] = (cs[j + 1] * 3 + cs[j] + 8) >> 4;
+      up[c][2 * j + 1] = (cs[j + 1] * 3 + cs[j + 2] + 7) >> 4;
+    }
+  }
+  uint32_t px[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int Y = (int)(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xFF);
+    const int xb = up[0][k] - 128, xr = up[1][k] - 128;
+    const int rr = Y + ((91881 * xr + 32768) >> 16);
+    const int g = Y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);
+    const int b = Y + ((116130 * xb + 32768) >> 16);
+    px[k] = (uint32_t)min(max(rr, 0), 255) | ((uint32_t)min(max(g, 0), 255) << 8) | ((uint32_t)min(max(b, 0), 255) << 16);
+  }
+  uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch + 3 * (size_t)x0;
+  if (x0 + 8 <= im.w) {   // 24 bytes, 8-byte aligned
+    uint2* o = reinterpret_cast<uint2*>(out);
+    o[0] = make_uint2(px[0] | (px[1] << 24), (px[1] >> 8) | (px[2] << 16));
+    o[1] = make_uint2((px[2] >> 16) | (px[3] << 8), px[4] | (px[5] << 24));
+    o[2] = make_uint2((px[5] >> 8) | (px[6] << 16), (px[6] >> 16) | (px[7] << 8));
+  } else {
+    for (int k = 0; k < im.w - x0; k++) {
+      out[3 * k] = (uint8_t)px[k];
+      out[3 * k + 1] = (uint8_t)(px[k] >> 8);
+      out[3 * k + 2] = (uint8_t)(px[k] >> 16);
+    }
+  }
+}
+
 // four output pixels per thread: one word of Y, twelve bytes of RGB
 __global__ void __launch_bounds__(256)
 colour_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __restrict__ plane_arena, uint8_t* __restrict__ pix_arena) {
   const int img = blockIdx.z;
   const JpegImg& im = imgs[img];
+  if (is_plain_420(im)) return;   // colour420_kernel's
   const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
   if (x0 >= im.w || y >= im.h) return;
   uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch;

@@ -35,6 +35,13 @@ with irp_b200.Engine(0) as eng:
     dt = (time.perf_counter() - t0) / 5
     tm = eng.timing()
     print(f"analyze from JPEG bytes: {dt * 1e3:.1f} ms per {B} images  {B * W * H / dt / 1e9:.2f} GPix/s  (classify {tm['classify_ms']:.2f} ms, preprocess {tm['preprocess_ms']:.2f} ms, launches {tm['kernel_launches']})")
+    # the same pixels, decoded by Pillow and uploaded: is the classify / preprocess time a matter of content?
+    d_px = [eng.upload(np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(b))))) for b in blobs[:8]]
+    d_px = [d_px[i % 8] for i in range(B)]
+    d_o2 = [eng.alloc_device(ow, oh, 3) for _ in range(B)]
+    for _ in range(3): eng.analyze_batch(d_px, device_outputs=d_o2, raw=True)
+    tm = eng.timing()
+    print(f"analyze of the Pillow-decoded pixels (device resident): classify {tm['classify_ms']:.2f} ms, preprocess {tm['preprocess_ms']:.2f} ms")
     # decode only, to device buffers
     d_out = [eng.alloc_device(W, H, 3) for _ in range(B)]
     douts = (_ffi.OutDesc * B)(*[_ffi.OutDesc(d.ptr, d.pitch, d.nbytes, 0, 0, 0, 1) for d in d_out])
