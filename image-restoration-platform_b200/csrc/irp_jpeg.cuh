@@ -121,16 +121,26 @@ __device__ __forceinline__ int huff_decode(const HuffDev& t, uint32_t bits16, in
 __device__ __forceinline__ int huff_extend(int x, int s) { return x < (1 << (s - 1)) ? x - (1 << s) + 1 : x; }
 
 // Decode the symbols that START in [p, p_end) of one stream, from slot state `slot` (mod 64 * bpm).
-// WRITE: store coefficients (zigzag -> natural) at absolute slot `abs_slot`.  Returns the state after.
+// WRITE: store coefficients (zigzag -> natural); `abs_blk` is the absolute block index (MCU order) the
+// run starts in and `blk_limit` one past the stream's last block.  The block's address is worked out
+// once per block, not per coefficient.
 template <bool WRITE>
 __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, BitWin& bw, unsigned long long stream_bit0,
                                          unsigned long long stream_bits, uint32_t& p, uint32_t p_end, uint32_t& slot, uint32_t& advanced,
-                                         int16_t* __restrict__ const* coef, unsigned long long abs_slot, unsigned long long slot_limit,
+                                         int16_t* __restrict__ const* coef, uint32_t abs_blk, uint32_t blk_limit,
                                          const uint8_t* __restrict__ zigzag) {
   const uint32_t period = 64u * (uint32_t)im.bpm;
-  while (p < p_end && p < stream_bits && (!WRITE || abs_slot < slot_limit)) {
+  int16_t* blk_ptr = nullptr;
+  uint32_t ptr_blk = 0xFFFFFFFFu;
+  while (p < p_end && p < stream_bits && (!WRITE || abs_blk < blk_limit)) {
     const uint32_t z = slot & 63u, k = slot >> 6;
     const int comp = im.blk_comp[k];
+    if (WRITE && ptr_blk != abs_blk) {
+      const uint32_t mcu = abs_blk / (uint32_t)im.bpm;
+      const uint32_t my = mcu / (uint32_t)im.mcux, mx = mcu - my * (uint32_t)im.mcux;
+      blk_ptr = coef[comp] + ((size_t)(my * im.comp_v[comp] + im.blk_by[k]) * im.comp_bw[comp] + (mx * im.comp_h[comp] + im.blk_bx[k])) * 64;
+      ptr_blk = abs_blk;
+    }
     uint32_t bits = bw.peek16(stream_bit0 + p);
     int len;
     uint32_t adv;
@@ -143,11 +153,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
           bits = bw.peek16(stream_bit0 + p);
           v = huff_extend((int)(bits >> (16 - s)), s);
         }
-        const unsigned long long blk = abs_slot >> 6;
-        const unsigned long long mcu = blk / im.bpm;
-        const int my = (int)(mcu / im.mcux), mx = (int)(mcu - (unsigned long long)my * im.mcux);
-        const size_t bidx = (size_t)(my * im.comp_v[comp] + im.blk_by[k]) * im.comp_bw[comp] + (mx * im.comp_h[comp] + im.blk_bx[k]);
-        coef[comp][bidx * 64] = (int16_t)v;
+        blk_ptr[0] = (int16_t)v;
       }
       p += s;
       adv = 1;
@@ -163,12 +169,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
         if (zz > 63u) zz = 63u;                           // only while out of sync / on corrupt data
         if (WRITE) {
           bits = bw.peek16(stream_bit0 + p);
-          const int v = huff_extend((int)(bits >> (16 - s)), s);
-          const unsigned long long blk = abs_slot >> 6;
-          const unsigned long long mcu = blk / im.bpm;
-          const int my = (int)(mcu / im.mcux), mx = (int)(mcu - (unsigned long long)my * im.mcux);
-          const size_t bidx = (size_t)(my * im.comp_v[comp] + im.blk_by[k]) * im.comp_bw[comp] + (mx * im.comp_h[comp] + im.blk_bx[k]);
-          coef[comp][bidx * 64 + zigzag[zz]] = (int16_t)v;
+          blk_ptr[zigzag[zz]] = (int16_t)huff_extend((int)(bits >> (16 - s)), s);
         }
         p += s;
         adv = zz - z + 1;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
     slot += adv;
     if (slot >= period) slot -= period;
     advanced += adv;
-    if (WRITE) abs_slot += adv;
+    if (WRITE && z + adv >= 64u) abs_blk++;
   }
 }
 
@@ -235,7 +236,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
         start = vstate[sub - 1];
       if (first || start != vin[sub]) {
         uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
-        huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0, 0, nullptr);
+        huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0u, 0u, nullptr);
         vin[sub] = start;
         vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
         advanced[sub] = adv;
@@ -298,11 +299,11 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
     slot = prev.slot;
   }
   int16_t* coef[3] = {coef_arena + im.coef_off[0], coef_arena + im.coef_off[1], coef_arena + im.coef_off[2]};
-  const unsigned long long base_slot = (unsigned long long)st.first_mcu * im.bpm * 64;
-  const unsigned long long limit = base_slot + (unsigned long long)st.n_mcu * im.bpm * 64;
+  const uint32_t base_blk = (uint32_t)st.first_mcu * (uint32_t)im.bpm;
   BitWin bw{data, -2, 0, 0};
   uint32_t adv = 0;
-  huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef, base_slot + slot_start[sub], limit, zz);
+  huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef,
+                 base_blk + (uint32_t)(slot_start[sub] >> 6), base_blk + (uint32_t)st.n_mcu * (uint32_t)im.bpm, zz);
 }
 
 // DC differences -> DC values: a scan per (stream, component) over its blocks in MCU order, in three
