@@ -26,7 +26,7 @@
 
 namespace irp {
 
-constexpr int kSubBits = 1024;         // bits per subsequence
+constexpr int kSubBits = 2048;         // bits per subsequence
 constexpr int kHuffThreads = 128;      // subsequences per CTA (a CTA never spans two images)
 constexpr int kLutBits = 9;
 
@@ -214,19 +214,39 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
   for (int i = threadIdx.x; i < (int)(sizeof(JpegImg) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&im)[i] = reinterpret_cast<const uint32_t*>(imgs + img)[i];
   load_huff(hs, tabs, imgs[img].huff_base);
   __syncthreads();
-  const int sub = blockIdx.x * kHuffThreads + threadIdx.x;
-  const bool active = sub < im.sub_base + im.nsub;
-  JpegStream st;
-  int local = 0;
-  if (active) {
-    st = streams[find_stream(streams, im.stream_base, im.nstreams, sub)];
-    local = sub - st.sub_first;
-  }
+  const int sub0 = blockIdx.x * kHuffThreads;
+  const int sub_end = im.sub_base + im.nsub;
   volatile unsigned long long* vstate = reinterpret_cast<volatile unsigned long long*>(state);
   unsigned long long* vin = reinterpret_cast<unsigned long long*>(in_state);
-  BitWin bw{data, -2, 0, 0};
+  __shared__ int queue[kHuffThreads];
+  __shared__ int qn;
   for (int round = 0; round < rounds; round++) {
-    if (active && (first || local > 0)) {
+    // which subsequences of this CTA must be decoded (again)?  Their indices are packed into a queue so
+    // that the decoding threads fill whole warps: a warp with one busy lane costs as much as a full one.
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
+    const int mine = sub0 + threadIdx.x;
+    bool need = false;
+    if (mine < sub_end) {
+      if (first) {
+        need = true;
+      } else {
+        const JpegStream s0 = streams[find_stream(streams, im.stream_base, im.nstreams, mine)];
+        need = mine > s0.sub_first && vstate[mine - 1] != vin[mine];
+      }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, need);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && ballot) base = atomicAdd(&qn, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) queue[base + __popc(ballot & ((1u << (threadIdx.x & 31)) - 1u))] = mine;
+    __syncthreads();
+    const int n = qn;
+    if (n == 0) break;     // uniform: nothing to do here now (a change arriving from the previous CTA is caught by the next launch)
+    if ((int)threadIdx.x < n) {
+      const int sub = queue[threadIdx.x];
+      const JpegStream st = streams[find_stream(streams, im.stream_base, im.nstreams, sub)];
+      const int local = sub - st.sub_first;
       unsigned long long start;
       if (local == 0)
         start = 0;
@@ -234,39 +254,49 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
         start = (unsigned long long)((uint32_t)local * kSubBits);
       else
         start = vstate[sub - 1];
-      if (first || start != vin[sub]) {
-        uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
-        huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0u, 0u, nullptr);
-        vin[sub] = start;
-        vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
-        advanced[sub] = adv;
-        if (!first) *changed = 1;
-      }
+      uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
+      BitWin bw{data, -2, 0, 0};
+      huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0u, 0u, nullptr);
+      vin[sub] = start;
+      vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
+      advanced[sub] = adv;
+      if (!first) *changed = 1;
     }
-    if (round + 1 < rounds) {
-      __threadfence_block();
-      __syncthreads();
-    }
+    __threadfence_block();
+    __syncthreads();
   }
 }
 
-// exclusive scan of `advanced` inside every stream (one warp per stream; streams hold at most a few 10^4 subsequences)
+// exclusive scan of `advanced` inside every stream (one warp per stream, 8 entries per lane per round)
 __global__ void huff_scan_kernel(const JpegStream* __restrict__ streams, int n_streams, const uint32_t* __restrict__ advanced,
                                  unsigned long long* __restrict__ slot_start) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= n_streams) return;
   const JpegStream st = streams[s];
   unsigned long long run = 0;
-  for (int base = 0; base < st.nsub; base += 32) {
-    const int i = base + lane;
-    const unsigned long long v = i < st.nsub ? advanced[st.sub_first + i] : 0;
-    unsigned long long x = v;
+  for (int base = 0; base < st.nsub; base += 256) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = base + lane * 8 + k;
+      v[k] = i < st.nsub ? advanced[st.sub_first + i] : 0u;
+    }
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tot += v[k];
+    unsigned long long x = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
       if (lane >= o) x += y;
     }
-    if (i < st.nsub) slot_start[st.sub_first + i] = run + x - v;
+    unsigned long long acc = run + x - tot;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = base + lane * 8 + k;
+      if (i < st.nsub) slot_start[st.sub_first + i] = acc;
+      acc += v[k];
+    }
     run += __shfl_sync(0xffffffffu, x, 31);
   }
 }
