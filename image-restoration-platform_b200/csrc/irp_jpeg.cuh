@@ -260,7 +260,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
       vin[sub] = start;
       vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
       advanced[sub] = adv;
-      if (!first) *changed = 1;
+      if (!first) { *changed = 1; atomicAdd(changed + 1, 1); }
     }
     __threadfence_block();
     __syncthreads();
@@ -445,21 +445,40 @@ __global__ void __launch_bounds__(256)
 idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, const int16_t* __restrict__ coef_arena,
             const uint16_t* __restrict__ qtabs, uint8_t* __restrict__ plane_arena) {
   __shared__ int ws[32][65];
-  const int lane8 = threadIdx.x & 7, bl = threadIdx.x >> 3;       // 32 blocks per CTA
+  const int lane8 = threadIdx.x & 7, bl = threadIdx.x >> 3;       // 32 blocks per CTA, 8 lanes per block
   const int gb = blockIdx.x * 32 + bl;
   const bool on = gb < total_blocks;
   int ji = 0;
-  if (on)
-    while (ji + 1 < n_jobs && gb >= __ldg(&jobs[ji + 1].block_base)) ji++;
+  if (on) {   // binary search: a batch has three jobs per image
+    int hi = n_jobs - 1;
+    while (ji < hi) {
+      const int m = (ji + hi + 1) >> 1;
+      if (__ldg(&jobs[m].block_base) <= gb) ji = m; else hi = m - 1;
+    }
+  }
   const IdctJob J = jobs[ji];
   const int b = gb - J.block_base;
   int v[8], o[8];
   if (on) {
-    const int16_t* c = coef_arena + J.coef_off + (size_t)b * 64;
-    const uint16_t* q = qtabs + J.qidx * 64;
+    // a lane fetches ROW lane8 of the block with one 128-bit load (the 8 lanes of a block read its 128 bytes
+    // contiguously), dequantises it and parks it in shared memory; pass 1 then reads its column from there
+    const uint4 cw = __ldg(reinterpret_cast<const uint4*>(coef_arena + J.coef_off + (size_t)b * 64) + lane8);
+    const uint4 qw = __ldg(reinterpret_cast<const uint4*>(qtabs + J.qidx * 64) + lane8);
+    const uint32_t cc[4] = {cw.x, cw.y, cw.z, cw.w}, qq[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = (int)c[r * 8 + lane8] * (int)__ldg(q + r * 8 + lane8);
+    for (int k = 0; k < 4; k++) {
+      ws[bl][lane8 * 8 + 2 * k] = (int)(int16_t)(cc[k] & 0xFFFFu) * (int)(qq[k] & 0xFFFFu);
+      ws[bl][lane8 * 8 + 2 * k + 1] = (int)(int16_t)(cc[k] >> 16) * (int)(qq[k] >> 16);
+    }
+  }
+  __syncwarp();
+  if (on) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = ws[bl][r * 8 + lane8];
     idct_1d(v, o, 11);
+  }
+  __syncwarp();
+  if (on) {
 #pragma unroll
     for (int r = 0; r < 8; r++) ws[bl][r * 8 + lane8] = o[r];
   }
