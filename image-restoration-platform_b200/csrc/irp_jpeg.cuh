@@ -260,7 +260,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
       vin[sub] = start;
       vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
       advanced[sub] = adv;
-      if (!first) { *changed = 1; atomicAdd(changed + 1, 1); }
+      if (!first) *changed = 1;
     }
     __threadfence_block();
     __syncthreads();
