@@ -4,8 +4,9 @@ Same constructor option (`logger`), same `analyze(imageBuffer)` coroutine return
 seven scores in the reference's key order (classifier.js:62-70), same static
 `getDegradationTypes()` and `createClassifierService(options)` factory (classifier.js:342-349).
 What changed is underneath: instead of six sharp pipelines and JS reductions, the decoded
-pixels make ONE trip through libirp_b200.so (hand-written sm_100a kernels).  Container decode
-(JPEG/PNG/WebP -> raw u8) stays on the host, as §8(f) of SURVEY.md ranks it "next".
+pixels make ONE trip through libirp_b200.so (hand-written sm_100a kernels).  Baseline JPEG files are
+decoded on the device too (bit-exact with libjpeg-turbo, sharp's decoder); PNG / WebP / progressive JPEG
+containers are decoded on the host first.
 
 The reference's per-analysis fallback constants (classifier.js:123-126 ...) have no analogue:
 the fused kernel either produces all moments or the whole call fails, which the reference
@@ -86,6 +87,11 @@ class ClassifierService:
             if isinstance(image_buffer, np.ndarray):
                 px, fmt = image_buffer, "raw"
             else:
+                # a baseline JPEG never touches a host decoder: the file bytes go to the device, which decodes
+                # them bit-exactly as libjpeg-turbo (sharp's decoder) would; other containers decode on the host
+                if self.engine.jpeg_info(image_buffer) is not None:
+                    res, _ = self.engine.analyze_jpeg_batch([bytes(image_buffer)], preprocess=False)
+                    return self._finish([res[0]], [self.engine.jpeg_info(image_buffer)[:2]], [True])[0]
                 px, fmt, _ = decode_image(image_buffer)
             return self.analyze_pixels([px], [fmt == "jpeg"])[0]
         except Exception as error:  # classifier.js:91-95
@@ -104,11 +110,23 @@ class ClassifierService:
                                  "Integrate Hough transforms for better accuracy.")
             _scratch_warning_logged = True
         results = self.engine.classify_batch(list(images), is_jpeg=list(is_jpeg))
+        sizes = [((im.width, im.height) if hasattr(im, "ptr") else (im.shape[1], im.shape[0])) for im in images]
+        return self._finish(results, sizes, is_jpeg)
+
+    def _finish(self, results, sizes, is_jpeg) -> list:
+        global _blockiness_warning_logged, _scratch_warning_logged
+        if any(is_jpeg) and not _blockiness_warning_logged:  # classifier.js:289-292
+            self._log("warning", "[classifier] Blockiness detection is using a simplified heuristic. "
+                                 "Enhance with DCT-based analysis for production accuracy.")
+            _blockiness_warning_logged = True
+        if not _scratch_warning_logged:  # classifier.js:311-314
+            self._log("warning", "[classifier] Scratch detection is using a simplified heuristic. "
+                                 "Integrate Hough transforms for better accuracy.")
+            _scratch_warning_logged = True
         out = []
-        for im, r in zip(images, results):
+        for (w, h), r in zip(sizes, results):
             analysis = {k: r["scores"][k] for k in SCORE_KEYS}
             top = sorted(((k, v) for k, v in analysis.items() if v > 0.3), key=lambda kv: -kv[1])[:3]  # classifier.js:73-76
-            h, w = (im.height, im.width) if hasattr(im, "ptr") else im.shape[:2]
             self._log("debug", "[classifier] Analysis complete",
                       {"topIssues": [{"type": k, "score": f"{v:.2f}"} for k, v in top], "imageSize": f"{w}x{h}"})
             out.append(analysis)

@@ -251,6 +251,55 @@ class Engine:
             return results, device_outputs
         return results, arrays
 
+    # -- compressed input: baseline JPEG decoded on the device ------------------
+    def jpeg_info(self, data) -> Optional[Tuple[int, int, int]]:
+        """(width, height, channels) if `data` is a baseline JPEG the device decoder takes, else None."""
+        k = np.frombuffer(bytes(data) if not isinstance(data, (bytes, np.ndarray)) else data, np.uint8)
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        if self._lib.irp_jpeg_info(k.ctypes.data, k.size, C.byref(w), C.byref(h), C.byref(c)):
+            return None
+        return w.value, h.value, c.value
+
+    def analyze_jpeg_batch(self, blobs: Sequence[bytes], orientations=None, classify: bool = True, preprocess: bool = True, raw: bool = False):
+        """JPEG file bytes -> (score dicts, resized images): decode, classify and preprocess on the device."""
+        n = len(blobs)
+        keep = [np.frombuffer(b, np.uint8) for b in blobs]
+        descs = (_ffi.JpegDesc * n)()
+        outs = (_ffi.OutDesc * n)() if preprocess else None
+        arrays = []
+        for i, k in enumerate(keep):
+            o = 1 if orientations is None else int(orientations[i])
+            descs[i] = _ffi.JpegDesc(k.ctypes.data, k.size, o, 0)
+            if preprocess:
+                info = self.jpeg_info(k)
+                if info is None:
+                    raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a baseline JPEG the device decoder takes")
+                ow, oh = self.preprocess_dims(info[0], info[1], o)
+                a = np.empty((oh, ow, 1 if info[2] == 1 else 3), np.uint8)
+                arrays.append(a)
+                outs[i] = _ffi.OutDesc(a.ctypes.data, 0, a.nbytes, 0, 0, 0, 0)
+        res = (_ffi.Result * n)() if classify else None
+        self._check(self._lib.irp_analyze_jpeg_batch(self._ctx, descs, n, res, outs))
+        results = None if res is None else (list(res) if raw else [result_to_dict(r) for r in res])
+        return results, (arrays if preprocess else None)
+
+    def decode_jpeg_batch(self, blobs: Sequence[bytes]):
+        """JPEG file bytes -> decoded u8 images (HxWx3 or HxW), bit-exact with libjpeg-turbo's default decode."""
+        n = len(blobs)
+        keep = [np.frombuffer(b, np.uint8) for b in blobs]
+        descs = (_ffi.JpegDesc * n)(*[_ffi.JpegDesc(k.ctypes.data, k.size, 1, 0) for k in keep])
+        outs = (_ffi.OutDesc * n)()
+        arrays = []
+        for i, k in enumerate(keep):
+            info = self.jpeg_info(k)
+            if info is None:
+                raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a baseline JPEG the device decoder takes")
+            a = np.empty((info[1], info[0], info[2]), np.uint8)
+            arrays.append(a)
+            outs[i] = _ffi.OutDesc(a.ctypes.data, 0, a.nbytes, 0, 0, 0, 0)
+        self._check(self._lib.irp_decode_jpeg_batch(self._ctx, descs, n, outs))
+        return [a[:, :, 0] if a.shape[2] == 1 else a for a in arrays]
+
     # -- concurrent single-image requests (irp_submit / irp_wait) -------------
     def submit(self, image: ImageLike, is_jpeg: bool = True, orientation: int = 1, classify: bool = True, preprocess: bool = True):
         """Queue ONE image (as the reference's callers do, one analyze() per promise) and return a handle at
