@@ -111,3 +111,37 @@ def test_progressive_is_refused_loudly(engine):
     blob = np.frombuffer(_encode(rand_image(64, 64, 3, seed=1), quality=80, progressive=True), np.uint8)
     w, h, c = C.c_int(), C.c_int(), C.c_int()
     assert engine._lib.irp_jpeg_info(blob.ctypes.data, blob.size, C.byref(w), C.byref(h), C.byref(c)) == _ffi.IRP_ERR_UNSUPPORTED
+
+
+def test_truncated_and_corrupted_streams_do_not_poison_the_context(engine):
+    """Damaged entropy data may decode to anything (or be refused) but must neither crash nor hang, and the
+    next clean file must still decode exactly."""
+    import irp_b200
+
+    good = _encode(rand_image(300, 420, 3, seed=21, kind="smooth"), quality=85, subsampling=2)
+    cut = good[: int(len(good) * 0.6)]
+    rng = np.random.default_rng(3)
+    noisy = bytearray(good)
+    for i in rng.integers(len(good) // 2, len(good) - 4, 40):
+        noisy[i] = int(rng.integers(0, 256))
+    for bad in (cut, bytes(noisy)):
+        try:
+            out = engine.decode_jpeg_batch([bad])[0]
+            assert out.shape == (300, 420, 3)
+        except irp_b200.IrpError:
+            pass
+    assert np.array_equal(engine.decode_jpeg_batch([good])[0], _pillow(good))
+
+
+def test_engine_wrappers_and_mixed_batch(engine, oracle):
+    blobs = [_encode(rand_image(120, 200, 3, seed=1, kind="smooth"), quality=90, subsampling=2),
+             _encode(rand_image(97, 131, 1, seed=2, kind="smooth")[:, :, 0], quality=70),
+             _encode(rand_image(2300, 180, 3, seed=3, kind="edges"), quality=80, subsampling=1, restart_marker_rows=2)]
+    assert engine.jpeg_info(blobs[0]) == (200, 120, 3) and engine.jpeg_info(blobs[1]) == (131, 97, 1)
+    assert engine.jpeg_info(b"not a jpeg at all") is None
+    res, outs = engine.analyze_jpeg_batch(blobs, orientations=[1, 3, 4])
+    for i, b in enumerate(blobs):
+        px = np.ascontiguousarray(_pillow(b))
+        assert_result_parity(res[i], oracle.classify(px), 1 if px.ndim == 2 else 3, f"blob {i}")
+        ref = oracle.preprocess(px, [1, 3, 4][i])
+        assert np.array_equal(outs[i].reshape(ref.shape), ref)
