@@ -422,7 +422,22 @@ def main() -> int:
         t0 = time.perf_counter()
         oracle.analyze_batch(imgs[:sample], threads=T, with_preprocess=True)
         dt = time.perf_counter() - t0
-        cpu = {"value": sample * W * H / 1e6 / dt, "unit": UNIT, "cores": T, "kind": "port",
+        jpeg_cpu = None
+        try:  # what the host would spend BEFORE any of this if it had to decode the files itself (libjpeg-turbo via Pillow)
+            import io
+            from concurrent.futures import ThreadPoolExecutor
+            from PIL import Image
+
+            bio = io.BytesIO()
+            Image.fromarray(imgs[0]).save(bio, "JPEG", quality=90, subsampling=2)
+            blob = bio.getvalue()
+            with ThreadPoolExecutor(T) as ex:
+                tj0 = time.perf_counter()
+                list(ex.map(lambda _: np.asarray(Image.open(io.BytesIO(blob))).shape, range(2 * T)))
+                jpeg_cpu = 2 * T * W * H / 1e6 / (time.perf_counter() - tj0)
+        except Exception:
+            pass
+        cpu = {"value": sample * W * H / 1e6 / dt, "unit": UNIT, "cores": T, "kind": "port", "host_jpeg_decode_mpix_s": jpeg_cpu,
                "sample": f"{sample} of the {B} images, {T} threads, one image per thread, {dt:.1f} s wall",
                "note": "oracle port of the reference arithmetic; the real sharp path adds 6 decodes and ~16 N JS closure visits per image"}
 
