@@ -130,22 +130,26 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
                                          int16_t* __restrict__ const* coef, uint32_t abs_blk, uint32_t blk_limit,
                                          const uint8_t* __restrict__ zigzag) {
   const uint32_t period = 64u * (uint32_t)im.bpm;
-  int16_t* blk_ptr = nullptr;
-  uint32_t ptr_blk = 0xFFFFFFFFu;
-  while (p < p_end && p < stream_bits && (!WRITE || abs_blk < blk_limit)) {
-    const uint32_t z = slot & 63u, k = slot >> 6;
+  const uint32_t stop = (uint32_t)min((unsigned long long)p_end, stream_bits);
+  // block by block: the component, its two tables and (when writing) the block's address are looked up once
+  // per block; the inner loop over the AC symbols touches one table and the bit window only
+  while (p < stop && (!WRITE || abs_blk < blk_limit)) {
+    uint32_t z = slot & 63u;
+    const uint32_t k = slot >> 6;
     const int comp = im.blk_comp[k];
-    if (WRITE && ptr_blk != abs_blk) {
+    const HuffDev& dct = hs.t[im.dc_tab[comp]];
+    const HuffDev& act = hs.t[4 + im.ac_tab[comp]];
+    int16_t* blk_ptr = nullptr;
+    if (WRITE) {
       const uint32_t mcu = abs_blk / (uint32_t)im.bpm;
       const uint32_t my = mcu / (uint32_t)im.mcux, mx = mcu - my * (uint32_t)im.mcux;
       blk_ptr = coef[comp] + ((size_t)(my * im.comp_v[comp] + im.blk_by[k]) * im.comp_bw[comp] + (mx * im.comp_h[comp] + im.blk_bx[k])) * 64;
-      ptr_blk = abs_blk;
     }
-    uint32_t bits = bw.peek16(stream_bit0 + p);
-    int len;
-    uint32_t adv;
+    const uint32_t z_in = z;
     if (z == 0) {
-      const int s = huff_decode(hs.t[im.dc_tab[comp]], bits, len) & 15;
+      uint32_t bits = bw.peek16(stream_bit0 + p);
+      int len;
+      const int s = huff_decode(dct, bits, len) & 15;
       p += len;
       if (WRITE) {
         int v = 0;
@@ -156,14 +160,16 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
         blk_ptr[0] = (int16_t)v;
       }
       p += s;
-      adv = 1;
-    } else {
-      const int rs = huff_decode(hs.t[4 + im.ac_tab[comp]], bits, len);
+      z = 1;
+    }
+    while (z < 64u && p < stop) {
+      uint32_t bits = bw.peek16(stream_bit0 + p);
+      int len;
+      const int rs = huff_decode(act, bits, len);
       p += len;
       const int r = rs >> 4, s = rs & 15;
       if (s == 0) {
-        adv = (r == 15) ? 16u : (64u - z);               // ZRL : EOB
-        if (z + adv > 64u) adv = 64u - z;
+        z = (r == 15) ? min(z + 16u, 64u) : 64u;          // ZRL : EOB
       } else {
         uint32_t zz = z + r;
         if (zz > 63u) zz = 63u;                           // only while out of sync / on corrupt data
@@ -172,13 +178,14 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
           blk_ptr[zigzag[zz]] = (int16_t)huff_extend((int)(bits >> (16 - s)), s);
         }
         p += s;
-        adv = zz - z + 1;
+        z = zz + 1;
       }
     }
+    const uint32_t adv = z - z_in;
     slot += adv;
     if (slot >= period) slot -= period;
     advanced += adv;
-    if (WRITE && z + adv >= 64u) abs_blk++;
+    if (WRITE && z >= 64u) abs_blk++;
   }
 }
 
