@@ -72,27 +72,62 @@ struct SubState {                          // state AFTER a subsequence: where t
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0u, 0x0123); }
 
-// A 64-bit window over a big-endian bit stream of 32-bit words.
+// A 64-bit window over a big-endian bit stream of 32-bit words.  The words of a subsequence (and 16 bytes
+// beyond: a symbol that starts in it may end there) are staged in shared memory by its owner thread with
+// independent 128-bit loads before any decoding, so the dependent chain "position -> word -> code" never
+// waits on global memory.
+constexpr int kSubWords = kSubBits / 32 + 4;
 struct BitWin {
-  const uint32_t* d;
-  long long w;        // index of the word in `hi` (-2: nothing loaded; -1 would look like the predecessor of word 0)
+  const uint32_t* d;  // staged words of ONE subsequence
+  uint32_t bit0;      // stream-relative bit position of its first word
+  int w;              // index of the word in `hi` (-2: nothing loaded)
   uint32_t hi, lo;
-  __device__ __forceinline__ uint32_t peek16(unsigned long long p) {   // 16 bits starting at bit p
-    const long long wi = (long long)(p >> 5);
+  __device__ __forceinline__ uint32_t peek16(uint32_t p) {   // 16 bits starting at stream bit p
+    const uint32_t q = p - bit0;
+    const int wi = min((int)(q >> 5), kSubWords - 2);        // (a position past the staged words only occurs on corrupt data)
     if (wi != w) {
-      if (wi == w + 1) {
-        hi = lo;
-      } else {
-        hi = bswap32(__ldg(d + wi));
-      }
+      hi = (wi == w + 1) ? lo : d[wi];
+      lo = d[wi + 1];
+      w = wi;
+    }
+    const unsigned long long win = ((unsigned long long)hi << 32) | lo;
+    return (uint32_t)((win << (q & 31)) >> 48);
+  }
+};
+// the same window straight over global memory (read-only path, L1-cached): the synchronisation launches
+// decode little after the first sweep, and staging would cost them their occupancy
+struct BitWinG {
+  const uint32_t* d;   // the batch buffer
+  unsigned long long base;   // stream_bit0
+  long long w;
+  uint32_t hi, lo;
+  __device__ __forceinline__ uint32_t peek16(uint32_t p) {
+    const unsigned long long q = base + p;
+    const long long wi = (long long)(q >> 5);
+    if (wi != w) {
+      hi = (wi == w + 1) ? lo : bswap32(__ldg(d + wi));
       lo = bswap32(__ldg(d + wi + 1));
       w = wi;
     }
-    const unsigned sh = (unsigned)(p & 31);
     const unsigned long long win = ((unsigned long long)hi << 32) | lo;
-    return (uint32_t)((win << sh) >> 48);
+    return (uint32_t)((win << (unsigned)(q & 31)) >> 48);
   }
 };
+// stage subsequence `local` of a stream: words are byte-swapped once here
+__device__ __forceinline__ void stage_sub(uint32_t* dst, const uint32_t* __restrict__ data, unsigned long long stream_bit0, int local) {
+  const uint4* src = reinterpret_cast<const uint4*>(data + (stream_bit0 >> 5) + (size_t)local * (kSubBits / 32));
+  // stream starts are 4-byte aligned only: 128-bit loads need 16; fall back to words when they are not
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll 4
+    for (int k = 0; k < kSubWords / 4; k++) {
+      const uint4 v = __ldg(src + k);
+      dst[4 * k] = bswap32(v.x); dst[4 * k + 1] = bswap32(v.y); dst[4 * k + 2] = bswap32(v.z); dst[4 * k + 3] = bswap32(v.w);
+    }
+  } else {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+    for (int k = 0; k < kSubWords; k++) dst[k] = bswap32(__ldg(s32 + k));
+  }
+}
 
 struct HuffSmem {
   HuffDev t[8];
@@ -124,8 +159,8 @@ __device__ __forceinline__ int huff_extend(int x, int s) { return x < (1 << (s -
 // WRITE: store coefficients (zigzag -> natural); `abs_blk` is the absolute block index (MCU order) the
 // run starts in and `blk_limit` one past the stream's last block.  The block's address is worked out
 // once per block, not per coefficient.
-template <bool WRITE>
-__device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, BitWin& bw, unsigned long long stream_bit0,
+template <bool WRITE, class Reader>
+__device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, Reader& bw, unsigned long long stream_bit0,
                                          unsigned long long stream_bits, uint32_t& p, uint32_t p_end, uint32_t& slot, uint32_t& advanced,
                                          int16_t* __restrict__ const* coef, uint32_t abs_blk, uint32_t blk_limit,
                                          const uint8_t* __restrict__ zigzag) {
@@ -147,14 +182,14 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
     }
     const uint32_t z_in = z;
     if (z == 0) {
-      uint32_t bits = bw.peek16(stream_bit0 + p);
+      uint32_t bits = bw.peek16(p);
       int len;
       const int s = huff_decode(dct, bits, len) & 15;
       p += len;
       if (WRITE) {
         int v = 0;
         if (s) {
-          bits = bw.peek16(stream_bit0 + p);
+          bits = bw.peek16(p);
           v = huff_extend((int)(bits >> (16 - s)), s);
         }
         blk_ptr[0] = (int16_t)v;
@@ -163,7 +198,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
       z = 1;
     }
     while (z < 64u && p < stop) {
-      uint32_t bits = bw.peek16(stream_bit0 + p);
+      uint32_t bits = bw.peek16(p);
       int len;
       const int rs = huff_decode(act, bits, len);
       p += len;
@@ -174,7 +209,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
         uint32_t zz = z + r;
         if (zz > 63u) zz = 63u;                           // only while out of sync / on corrupt data
         if (WRITE) {
-          bits = bw.peek16(stream_bit0 + p);
+          bits = bw.peek16(p);
           blk_ptr[zigzag[zz]] = (int16_t)huff_extend((int)(bits >> (16 - s)), s);
         }
         p += s;
@@ -227,6 +262,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
   unsigned long long* vin = reinterpret_cast<unsigned long long*>(in_state);
   __shared__ int queue[kHuffThreads];
   __shared__ int qn;
+
   for (int round = 0; round < rounds; round++) {
     // which subsequences of this CTA must be decoded (again)?  Their indices are packed into a queue so
     // that the decoding threads fill whole warps: a warp with one busy lane costs as much as a full one.
@@ -262,7 +298,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
       else
         start = vstate[sub - 1];
       uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
-      BitWin bw{data, -2, 0, 0};
+      BitWinG bw{data, st.bit_off, -2, 0, 0};
       huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0u, 0u, nullptr);
       vin[sub] = start;
       vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
@@ -329,6 +365,8 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
   const int si = find_stream(streams, im.stream_base, im.nstreams, sub);
   const JpegStream st = streams[si];
   const int local = sub - st.sub_first;
+  extern __shared__ uint32_t staged[];   // [kHuffThreads][kSubWords]
+  stage_sub(staged + threadIdx.x * kSubWords, data, st.bit_off, local);
   uint32_t p = 0, slot = 0;
   if (local) {
     const SubState prev = state[sub - 1];
@@ -337,7 +375,7 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
   }
   int16_t* coef[3] = {coef_arena + im.coef_off[0], coef_arena + im.coef_off[1], coef_arena + im.coef_off[2]};
   const uint32_t base_blk = (uint32_t)st.first_mcu * (uint32_t)im.bpm;
-  BitWin bw{data, -2, 0, 0};
+  BitWin bw{staged + threadIdx.x * kSubWords, (uint32_t)local * kSubBits, -2, 0, 0};
   uint32_t adv = 0;
   huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef,
                  base_blk + (uint32_t)(slot_start[sub] >> 6), base_blk + (uint32_t)st.n_mcu * (uint32_t)im.bpm, zz);
