@@ -1,7 +1,7 @@
 // Drop-in for server-node/src/services/classifier.js — SOURCE ONLY / UNVERIFIED (no Node here).
 // Same exports, same analyze() key order, same logging and span calls; the six sharp pipelines
-// and the JS reductions are replaced by ONE native call on the decoded pixels.  Container decode
-// stays with sharp (one decode instead of six) until the nvJPEG stage of SURVEY.md §8f lands.
+// and the JS reductions are replaced by ONE native call.  Baseline JPEG files are handed over as they
+// are (decoded on the device); other containers are decoded by sharp once instead of six times.
 import { trace, SpanStatusCode } from '@opentelemetry/api';
 import sharp from 'sharp';
 import { createRequire } from 'node:module';
@@ -34,8 +34,16 @@ export class ClassifierService {
     try {
       ctx ??= native.createContext(this.device);
       const metadata = await sharp(imageBuffer).metadata();
-      const { data, info } = await sharp(imageBuffer).raw().toBuffer({ resolveWithObject: true });
-      const scores = await native.analyzeRaw(ctx, data, info.width, info.height, info.channels, metadata.format === 'jpeg');
+      let scores;
+      try {
+        // a baseline JPEG goes to the GPU as it is: decoded there bit-exactly as libjpeg-turbo (sharp's decoder) would
+        scores = await native.analyzeFile(ctx, imageBuffer);
+      } catch (e) {
+        if (e.message !== 'unsupported') throw e;
+        // PNG / WebP / progressive JPEG: one sharp decode (instead of six), then the raw entry point
+        const { data, info } = await sharp(imageBuffer).raw().toBuffer({ resolveWithObject: true });
+        scores = await native.analyzeRaw(ctx, data, info.width, info.height, info.channels, metadata.format === 'jpeg');
+      }
       const analysis = Object.fromEntries(KEYS.map((k, i) => [k, scores[i]]));
       const topIssues = Object.entries(analysis).filter(([, s]) => s > 0.3).sort((a, b) => b[1] - a[1]).slice(0, 3);
       span.setAttributes({

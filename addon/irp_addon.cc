@@ -7,6 +7,7 @@
 //
 // JS surface (used by addon/classifier.js and addon/imagePreprocess.js):
 //   createContext(device:number) -> external
+//   analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>   (baseline JPEG bytes, decoded on the device)
 //   analyzeRaw(ctx, pixels:Buffer, width, height, channels, isJpeg:boolean) -> Promise<Float64Array(7)>
 //   preprocessRaw(ctx, pixels:Buffer, width, height, channels, orientation) -> Promise<{data:Buffer,width,height,channels}>
 // Work runs on the libuv pool through napi_create_async_work, so the event loop never blocks
@@ -28,6 +29,8 @@ struct Job {
   irp_ctx* ctx = nullptr;
   irp_image_desc desc{};
   bool preprocess = false;
+  bool file = false;            // the input Buffer is a JPEG FILE, decoded on the device (irp_submit_jpeg)
+  irp_jpeg_desc jpeg{};
   irp_result result{};
   irp_out_desc out{};
   int rc = 0;
@@ -53,7 +56,8 @@ void Execute(napi_env, void* data) {
     // context's dispatcher batch it with whatever the other libuv workers submitted meanwhile
     irp_ticket ticket = nullptr;
     char err[256] = {0};
-    j->rc = irp_submit(j->ctx, &j->desc, j->preprocess ? nullptr : &j->result, j->preprocess ? &j->out : nullptr, &ticket);
+    j->rc = j->file ? irp_submit_jpeg(j->ctx, &j->jpeg, &j->result, nullptr, &ticket)
+                    : irp_submit(j->ctx, &j->desc, j->preprocess ? nullptr : &j->result, j->preprocess ? &j->out : nullptr, &ticket);
     if (j->rc == IRP_OK) j->rc = irp_wait(j->ctx, ticket, err, sizeof err);
     if (j->rc != IRP_OK) j->error = err[0] ? err : "irp request failed";
   } else {
@@ -145,6 +149,42 @@ napi_value Submit(napi_env env, napi_callback_info info, bool preprocess) {
   return promise;
 }
 
+// analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>; rejects with "unsupported" for anything but a baseline
+// JPEG, in which case the shim decodes with sharp and calls analyzeRaw
+napi_value AnalyzeFile(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value argv[2];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  Job* j = new Job();
+  j->file = true;
+  void* ctx = nullptr;
+  napi_get_value_external(env, argv[0], &ctx);
+  j->ctx = static_cast<irp_ctx*>(ctx);
+  void* data = nullptr;
+  size_t len = 0;
+  napi_get_buffer_info(env, argv[1], &data, &len);
+  napi_create_reference(env, argv[1], 1, &j->input_ref);
+  j->jpeg.data = static_cast<const uint8_t*>(data);
+  j->jpeg.size = len;
+  j->jpeg.exif_orientation = 1;   // the classifier never rotates (classifier.js has no .rotate())
+  napi_value promise, name;
+  napi_create_promise(env, &j->deferred, &promise);
+  int w = 0, h = 0, c = 0;
+  if (irp_jpeg_info(j->jpeg.data, len, &w, &h, &c) != IRP_OK) {
+    napi_value msg, err;
+    napi_create_string_utf8(env, "unsupported", NAPI_AUTO_LENGTH, &msg);
+    napi_create_error(env, nullptr, msg, &err);
+    napi_reject_deferred(env, j->deferred, err);
+    napi_delete_reference(env, j->input_ref);
+    delete j;
+    return promise;
+  }
+  napi_create_string_utf8(env, "irp.analyzeFile", NAPI_AUTO_LENGTH, &name);
+  napi_create_async_work(env, nullptr, name, Execute, Complete, j, &j->work);
+  napi_queue_async_work(env, j->work);
+  return promise;
+}
+
 napi_value AnalyzeRaw(napi_env env, napi_callback_info info) { return Submit(env, info, false); }
 napi_value PreprocessRaw(napi_env env, napi_callback_info info) { return Submit(env, info, true); }
 
@@ -171,10 +211,11 @@ napi_value CreateContext(napi_env env, napi_callback_info info) {
 napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor props[] = {
       {"createContext", nullptr, CreateContext, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"analyzeFile", nullptr, AnalyzeFile, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"analyzeRaw", nullptr, AnalyzeRaw, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"preprocessRaw", nullptr, PreprocessRaw, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
-  napi_define_properties(env, exports, 3, props);
+  napi_define_properties(env, exports, 4, props);
   return exports;
 }
 

@@ -95,6 +95,8 @@ struct PlanDev {
 
 struct irp_request {
   irp_image_desc img;
+  irp_jpeg_desc jpeg;      // used instead of img when is_jpeg_file
+  bool is_jpeg_file = false;
   irp_result* result;
   irp_out_desc* out;
   int status = 0;
@@ -1379,24 +1381,31 @@ int irp_analyze_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_
 
 // ---- concurrent single-image requests ----
 static void run_requests(irp_ctx* ctx, std::vector<irp_request*>& reqs) {
-  // three kinds of request share the queue; each kind is one batched submission
-  for (int kind = 0; kind < 3; kind++) {
+  // raw-pixel and JPEG-file requests, each as classify+preprocess / classify / preprocess: every kind present
+  // in the queue is one batched submission
+  for (int kind = 0; kind < 6; kind++) {
+    const bool jpeg_kind = kind >= 3;
     std::vector<irp_request*> sel;
     for (irp_request* r : reqs) {
-      const int k = (r->result && r->out) ? 0 : (r->result ? 1 : 2);
+      const int k = ((r->result && r->out) ? 0 : (r->result ? 1 : 2)) + (r->is_jpeg_file ? 3 : 0);
       if (k == kind) sel.push_back(r);
     }
     if (sel.empty()) continue;
     const int n = (int)sel.size();
     std::vector<irp_image_desc> descs(n);
+    std::vector<irp_jpeg_desc> jdescs(n);
     std::vector<irp_result> results(n);
     std::vector<irp_out_desc> outs(n);
     for (int i = 0; i < n; i++) {
       descs[i] = sel[i]->img;
+      jdescs[i] = sel[i]->jpeg;
       if (sel[i]->out) outs[i] = *sel[i]->out;
     }
+    const int k3 = kind % 3;
     auto call = [&](int b, int cnt) {
-      return run_batch(ctx, descs.data() + b, cnt, kind == 2 ? nullptr : results.data() + b, kind == 1 ? nullptr : outs.data() + b, 0);
+      irp_result* rp = k3 == 2 ? nullptr : results.data() + b;
+      irp_out_desc* op = k3 == 1 ? nullptr : outs.data() + b;
+      return jpeg_kind ? irp_analyze_jpeg_batch(ctx, jdescs.data() + b, cnt, rp, op) : run_batch(ctx, descs.data() + b, cnt, rp, op, 0);
     };
     int rc = call(0, n);
     if (rc == IRP_OK) {
@@ -1446,6 +1455,30 @@ int irp_submit(irp_ctx* ctx, const irp_image_desc* img, irp_result* result, irp_
   if (!ctx || !img || !ticket || (!result && !out)) return IRP_ERR_BAD_ARG;
   irp_request* r = new irp_request();
   r->img = *img;
+  r->result = result;
+  r->out = out;
+  {
+    std::lock_guard<std::mutex> lk(ctx->qmu);
+    if (ctx->stop) {
+      delete r;
+      return IRP_ERR_BAD_ARG;
+    }
+    if (!ctx->dispatcher_started) {
+      ctx->dispatcher = std::thread(dispatcher_main, ctx);
+      ctx->dispatcher_started = true;
+    }
+    ctx->queue.push_back(r);
+  }
+  ctx->qcv.notify_all();
+  *ticket = r;
+  return IRP_OK;
+}
+
+int irp_submit_jpeg(irp_ctx* ctx, const irp_jpeg_desc* jpeg, irp_result* result, irp_out_desc* out, irp_ticket* ticket) {
+  if (!ctx || !jpeg || !jpeg->data || !ticket || (!result && !out)) return IRP_ERR_BAD_ARG;
+  irp_request* r = new irp_request();
+  r->jpeg = *jpeg;
+  r->is_jpeg_file = true;
   r->result = result;
   r->out = out;
   {

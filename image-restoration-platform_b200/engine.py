@@ -313,6 +313,25 @@ class Engine:
             raise IrpError(rc, "irp_submit rejected the request")
         return {"ticket": ticket, "descs": descs, "keep": keep, "outs": outs, "array": arrays[0], "res": res}
 
+    def submit_jpeg(self, blob: bytes, orientation: int = 1, classify: bool = True, preprocess: bool = True):
+        """Queue ONE baseline JPEG FILE (what analyze(imageBuffer) receives); decoded on the device with its batch."""
+        k = np.frombuffer(blob, np.uint8)
+        info = self.jpeg_info(k)
+        if info is None:
+            raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, "not a baseline JPEG the device decoder takes")
+        desc = _ffi.JpegDesc(k.ctypes.data, k.size, orientation, 0)
+        outs, arr = None, None
+        if preprocess:
+            ow, oh = self.preprocess_dims(info[0], info[1], orientation)
+            arr = np.empty((oh, ow, 1 if info[2] == 1 else 3), np.uint8)
+            outs = (_ffi.OutDesc * 1)(_ffi.OutDesc(arr.ctypes.data, 0, arr.nbytes, 0, 0, 0, 0))
+        res = _ffi.Result() if classify else None
+        ticket = C.c_void_p()
+        rc = self._lib.irp_submit_jpeg(self._ctx, C.byref(desc), C.byref(res) if classify else None, outs, C.byref(ticket))
+        if rc:
+            raise IrpError(rc, "irp_submit_jpeg rejected the request")
+        return {"ticket": ticket, "descs": desc, "keep": k, "outs": outs, "array": arr, "res": res}
+
     def wait(self, handle, raw: bool = False):
         """Block until the request is done; returns (result dict or None, output array or None)."""
         err = C.create_string_buffer(512)

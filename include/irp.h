@@ -193,6 +193,10 @@ int irp_analyze_jpeg_batch(irp_ctx *ctx, const irp_jpeg_desc *jpegs, int n, irp_
 typedef struct irp_request *irp_ticket;
 int irp_submit(irp_ctx *ctx, const irp_image_desc *img, irp_result *result, irp_out_desc *out,
                irp_ticket *ticket);
+/* the same for a JPEG FILE (the bytes must stay valid until irp_wait returns): what analyze(imageBuffer)
+ * hands over, decoded on the device with the rest of its batch */
+int irp_submit_jpeg(irp_ctx *ctx, const irp_jpeg_desc *jpeg, irp_result *result, irp_out_desc *out,
+                    irp_ticket *ticket);
 int irp_wait(irp_ctx *ctx, irp_ticket ticket, char *err, size_t err_capacity);
 
 /* ---- memory helpers (so non-CUDA hosts can stage device-resident data) -- */

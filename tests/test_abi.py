@@ -118,3 +118,37 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "grey_tables.inc", f"{f} mentions the oracle"
+
+
+def test_jpeg_header_parse_runs_without_a_gpu():
+    """irp_jpeg_info is pure host code (sharp's metadata() for the device-decodable subset): baseline files give
+    their stored dims, everything else is refused with IRP_ERR_UNSUPPORTED."""
+    import ctypes as C
+    import io
+
+    import numpy as np
+    from PIL import Image
+
+    from irp_b200 import _ffi
+
+    lib = _ffi.load()
+
+    def info(blob):
+        k = np.frombuffer(blob, np.uint8)
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        rc = lib.irp_jpeg_info(k.ctypes.data, k.size, C.byref(w), C.byref(h), C.byref(c))
+        return rc, (w.value, h.value, c.value)
+
+    def enc(arr, **kw):
+        b = io.BytesIO()
+        Image.fromarray(arr).save(b, "JPEG", **kw)
+        return b.getvalue()
+
+    rgb = np.zeros((37, 53, 3), np.uint8)
+    for ss in (0, 1, 2):
+        assert info(enc(rgb, quality=80, subsampling=ss)) == (0, (53, 37, 3))
+    assert info(enc(rgb[:, :, 0], quality=80)) == (0, (53, 37, 1))
+    assert info(enc(rgb, quality=80, restart_marker_rows=1)) == (0, (53, 37, 3))
+    assert info(enc(rgb, quality=80, progressive=True))[0] == _ffi.IRP_ERR_UNSUPPORTED
+    assert info(b"\x89PNG\r\n\x1a\n" + b"\0" * 64)[0] == _ffi.IRP_ERR_UNSUPPORTED
+    assert info(enc(rgb, quality=80)[:40])[0] == _ffi.IRP_ERR_UNSUPPORTED   # truncated inside the header

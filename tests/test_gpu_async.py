@@ -86,3 +86,52 @@ def test_a_failing_request_fails_alone(engine, oracle):
         r, o = engine.wait(hd)
         assert_result_parity(r, oracle.classify(g), 3, "batch-mate of a failing request")
         assert np.array_equal(o, oracle.preprocess(g, 1))
+
+
+def test_concurrent_jpeg_file_requests(engine, oracle):
+    """JPEG files submitted one by one from several threads: decoded on the device in whatever batch the
+    dispatcher formed, each answer equal to the oracle's on libjpeg-turbo's pixels; a progressive file is refused
+    at submission by the wrapper and a mixed queue (raw + file requests) works."""
+    import io
+
+    from PIL import Image
+
+    def enc(img, **kw):
+        b = io.BytesIO()
+        Image.fromarray(img).save(b, "JPEG", **kw)
+        return b.getvalue()
+
+    blobs = [enc(rand_image(200 + 17 * i, 320 + 31 * i, 3, seed=40 + i, kind="smooth"), quality=85, subsampling=[0, 1, 2][i % 3]) for i in range(10)]
+    blobs.append(enc(rand_image(2300, 400, 3, seed=77, kind="smooth"), quality=90, subsampling=2))
+    errors, lock = [], threading.Lock()
+
+    def client(t):
+        hs = [(b, engine.submit_jpeg(b, orientation=1 + (t + j) % 4)) for j, b in enumerate(blobs[t::3])]
+        raw_img = rand_image(150, 210, 3, seed=500 + t, kind="noise")
+        hr = engine.submit(raw_img)
+        for j, (b, hd) in enumerate(hs):
+            try:
+                res, out = engine.wait(hd)
+                px = np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(b))))
+                assert_result_parity(res, oracle.classify(px), 3, f"thread {t} file {j}")
+                assert np.array_equal(out, oracle.preprocess(px, 1 + (t + j) % 4))
+            except Exception as e:
+                with lock:
+                    errors.append(repr(e))
+        try:
+            r, o = engine.wait(hr)
+            assert_result_parity(r, oracle.classify(raw_img), 3, "raw request in a mixed queue")
+        except Exception as e:
+            with lock:
+                errors.append(repr(e))
+
+    ts = [threading.Thread(target=client, args=(t,)) for t in range(3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+    import irp_b200
+
+    with pytest.raises(irp_b200.IrpError):
+        engine.submit_jpeg(enc(rand_image(64, 64, 3, seed=1), quality=80, progressive=True))
