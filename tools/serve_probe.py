@@ -41,3 +41,32 @@ with irp_b200.Engine(0) as eng:
                 dt = time.perf_counter() - t0
             n = nthreads * PER
             print(f"{nthreads:3d} clients {mode:5s}: {n / dt:7.1f} images/s  {n * W * H / dt / 1e9:6.2f} GPix/s  {dt / PER * 1e3:7.2f} ms per request round")
+
+    # the same clients holding JPEG FILES (q90 4:2:0, ~3.5 MB): nothing is decoded on the host
+    import io
+    from PIL import Image
+    blobs = []
+    for im in imgs:
+        b = io.BytesIO(); Image.fromarray(im).save(b, "JPEG", quality=90, subsampling=2); blobs.append(np.frombuffer(b.getvalue(), np.uint8))
+    for nthreads in (1, 16, 64):
+        slots = []
+        for t in range(nthreads):
+            o = eng.pinned_empty((oh, ow, 3))
+            k = blobs[t % 4]
+            jd = _ffi.JpegDesc(k.ctypes.data, k.size, 1, 0)
+            od = (_ffi.OutDesc * 1)(_ffi.OutDesc(o.ctypes.data, ow * 3, o.nbytes, 0, 0, 0, 0))
+            slots.append((o, jd, od, _ffi.Result()))
+        def jclient(t):
+            o, jd, od, res = slots[t]
+            for _ in range(PER):
+                tk = C.c_void_p()
+                rc = lib.irp_submit_jpeg(ctx, C.byref(jd), C.byref(res), od, C.byref(tk)) or lib.irp_wait(ctx, tk, None, 0)
+                assert rc == 0, rc
+        for warm in (True, False):
+            ts = [threading.Thread(target=jclient, args=(t,)) for t in range(nthreads)]
+            t0 = time.perf_counter()
+            for th in ts: th.start()
+            for th in ts: th.join()
+            dt = time.perf_counter() - t0
+        n = nthreads * PER
+        print(f"{nthreads:3d} clients JPEG files: {n / dt:7.1f} images/s  {n * W * H / dt / 1e9:6.2f} GPix/s")
