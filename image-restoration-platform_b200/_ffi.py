@@ -23,6 +23,7 @@ SYMBOLS = (
     "irp_get_timing", "irp_preprocess_dims", "irp_fusion_dims", "irp_scores_from_moments", "irp_grey_tables",
     "irp_classify_batch", "irp_preprocess_batch", "irp_analyze_batch", "irp_fusion_prepare_batch",
     "irp_submit", "irp_submit_jpeg", "irp_wait", "irp_jpeg_info", "irp_decode_jpeg_batch", "irp_analyze_jpeg_batch",
+    "irp_encode_jpeg_batch", "irp_analyze_encode_batch", "irp_transcode_jpeg_batch",
     "irp_dev_alloc", "irp_dev_free", "irp_host_alloc_pinned", "irp_host_free_pinned", "irp_memcpy_h2d",
     "irp_memcpy_d2h", "irp_synchronize",
 )
@@ -54,6 +55,11 @@ class OutDesc(C.Structure):
 
 class JpegDesc(C.Structure):
     _fields_ = [("data", C.c_void_p), ("size", C.c_size_t), ("exif_orientation", C.c_int32), ("reserved", C.c_int32)]
+
+
+class JpegOut(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("capacity", C.c_size_t), ("size", C.c_size_t), ("width", C.c_int32),
+                ("height", C.c_int32), ("channels", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -98,6 +104,9 @@ def load() -> C.CDLL:
     lib.irp_jpeg_info.argtypes = [vp, C.c_size_t, ip, ip, ip]
     lib.irp_decode_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(OutDesc)]
     lib.irp_analyze_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(Result), C.POINTER(OutDesc)]
+    lib.irp_encode_jpeg_batch.argtypes = [vp, C.POINTER(ImageDesc), i32, i32, C.POINTER(JpegOut)]
+    lib.irp_analyze_encode_batch.argtypes = [vp, C.POINTER(ImageDesc), i32, C.POINTER(Result), i32, C.POINTER(JpegOut)]
+    lib.irp_transcode_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(Result), i32, C.POINTER(JpegOut)]
     lib.irp_submit.argtypes = [vp, C.POINTER(ImageDesc), C.POINTER(Result), C.POINTER(OutDesc), C.POINTER(vp)]
     lib.irp_submit_jpeg.argtypes = [vp, C.POINTER(JpegDesc), C.POINTER(Result), C.POINTER(OutDesc), C.POINTER(vp)]
     lib.irp_wait.argtypes = [vp, vp, C.c_char_p, C.c_size_t]

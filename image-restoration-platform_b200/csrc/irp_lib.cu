@@ -31,6 +31,7 @@
 #include "irp_classify_bulk.cuh"
 #include "irp_resize_tma.cuh"
 #include "irp_jpeg.cuh"
+#include "irp_jpeg_enc.cuh"
 #include "irp_resize.cuh"
 
 using namespace irp;
@@ -117,6 +118,8 @@ struct irp_ctx {
   size_t smem_optin_full = 0;     // the device's opt-in shared memory per block
   DevBuf d_jdata, d_jmeta, d_jstate, d_jcoef, d_jplane, d_jpix;   // device JPEG decode (irp_jpeg.cuh)
   PinBuf h_jdata, h_jmeta;
+  DevBuf d_emeta, d_eblk, d_ebits, d_eout, d_epix;                 // device JPEG encode (irp_jpeg_enc.cuh)
+  PinBuf h_emeta;
   int jpeg_sweeps = 0;            // synchronisation sweeps of the last JPEG batch
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   std::vector<void*> plan_chunks;
@@ -1079,6 +1082,7 @@ int run_batch_locked(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result
 }
 
 #include "irp_jpeg_host.inc"
+#include "irp_jpeg_enc_host.inc"
 
 }  // namespace
 
@@ -1197,7 +1201,8 @@ void irp_destroy(irp_ctx* ctx) {
   if (ctx->copy_in_stream) cudaStreamDestroy(ctx->copy_in_stream);
   if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
   for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps, &ctx->d_rtjobs, &ctx->d_rtmaps,
-                    &ctx->d_jdata, &ctx->d_jmeta, &ctx->d_jstate, &ctx->d_jcoef, &ctx->d_jplane, &ctx->d_jpix})
+                    &ctx->d_jdata, &ctx->d_jmeta, &ctx->d_jstate, &ctx->d_jcoef, &ctx->d_jplane, &ctx->d_jpix, &ctx->d_emeta,
+                    &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix})
     b->release();
   for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
@@ -1376,6 +1381,103 @@ int irp_analyze_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_
   ctx->timing.kernel_launches += decode_launches;
   float ms = 0;
   if (rc == IRP_OK && cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) ctx->timing.h2d_ms = ms;   // upload of the compressed bytes + device decode
+  return rc;
+}
+
+// ---- compressed output: baseline JPEG encoded on the device ----
+int irp_encode_jpeg_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, int quality, irp_jpeg_out* outs) {
+  if (!ctx || n < 0 || (n && (!imgs || !outs))) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->err.clear();
+  if (!n) return IRP_OK;
+  ctx->timing = irp_timing{};
+  CK(cudaSetDevice(ctx->device));
+  // host-resident sources are staged once (an encode-only call is a test / tooling entry; the serving paths below
+  // encode what the resize kernels left in HBM)
+  std::vector<EncSrc> src(n);
+  size_t stage = 0;
+  for (int i = 0; i < n; i++) {
+    if (!imgs[i].pixels || imgs[i].width < 1 || imgs[i].height < 1 || (imgs[i].channels != 1 && imgs[i].channels != 3) ||
+        imgs[i].pitch < (size_t)imgs[i].width * imgs[i].channels)
+      return fail(ctx, IRP_ERR_BAD_ARG, "encode %d: bad image (1 or 3 channels of u8)", i);
+    if (!imgs[i].on_device) stage += round_up(round_up((size_t)imgs[i].width * imgs[i].channels, 16) * imgs[i].height, 256);
+  }
+  CK(ctx->d_epix.reserve(stage + 256));
+  size_t off = 0;
+  for (int i = 0; i < n; i++) {
+    const irp_image_desc& d = imgs[i];
+    if (d.on_device) {
+      src[i] = EncSrc{d.pixels, d.pitch, d.width, d.height, d.channels};
+      continue;
+    }
+    const size_t tight = (size_t)d.width * d.channels, pitch = round_up(tight, 16);
+    uint8_t* dst = (uint8_t*)ctx->d_epix.p + off;
+    CK(cudaMemcpy2DAsync(dst, pitch, d.pixels, d.pitch, tight, d.height, cudaMemcpyHostToDevice, ctx->stream));
+    src[i] = EncSrc{dst, pitch, d.width, d.height, d.channels};
+    off += round_up(pitch * d.height, 256);
+  }
+  return encode_images_locked(ctx, src.data(), n, quality, outs);
+}
+
+// preprocess into context-owned HBM, then encode from there
+static int preprocess_encode_locked(irp_ctx* ctx, const irp_image_desc* descs, int n, irp_result* results, int quality, irp_jpeg_out* outs) {
+  std::vector<irp_out_desc> od(n);
+  std::vector<EncSrc> src(n);
+  size_t total = 0;
+  for (int i = 0; i < n; i++) {
+    int ow = 0, oh = 0;
+    if (irp_preprocess_dims(descs[i].width, descs[i].height, descs[i].exif_orientation, &ow, &oh) != IRP_OK)
+      return fail(ctx, IRP_ERR_BAD_ARG, "image %d: bad dimensions %dx%d", i, descs[i].width, descs[i].height);
+    const int oc = descs[i].channels == 1 ? 1 : 3;
+    const size_t pitch = round_up((size_t)ow * oc, 16);
+    od[i] = irp_out_desc{nullptr, pitch, pitch * oh, 0, 0, 0, 1};
+    src[i] = EncSrc{nullptr, pitch, ow, oh, oc};
+    total += round_up(pitch * oh, 256);
+  }
+  CK(ctx->d_epix.reserve(total + 256));
+  size_t off = 0;
+  for (int i = 0; i < n; i++) {
+    od[i].pixels = (uint8_t*)ctx->d_epix.p + off;
+    src[i].px = od[i].pixels;
+    off += round_up(od[i].capacity, 256);
+  }
+  int rc = run_batch_locked(ctx, descs, n, results, od.data(), 0);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++)
+    if (od[i].width != src[i].w || od[i].height != src[i].h || od[i].channels != src[i].c)
+      return fail(ctx, IRP_ERR_UNSUPPORTED, "image %d: preprocess wrote %dx%dx%d, expected %dx%dx%d", i, od[i].width, od[i].height, od[i].channels, src[i].w,
+                  src[i].h, src[i].c);
+  const irp_timing t = ctx->timing;
+  rc = encode_images_locked(ctx, src.data(), n, quality, outs);
+  const uint32_t enc_launches = ctx->timing.kernel_launches - t.kernel_launches;
+  ctx->timing = t;
+  ctx->timing.kernel_launches += enc_launches;
+  return rc;
+}
+
+int irp_analyze_encode_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, int quality, irp_jpeg_out* outs) {
+  if (!ctx || n < 0 || (n && (!imgs || !outs))) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->err.clear();
+  if (!n) return IRP_OK;
+  return preprocess_encode_locked(ctx, imgs, n, results, quality, outs);
+}
+
+int irp_transcode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, int quality, irp_jpeg_out* outs) {
+  if (!ctx || n < 0 || (n && (!jpegs || !outs))) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->err.clear();
+  if (!n) return IRP_OK;
+  ctx->timing = irp_timing{};
+  std::vector<JpegPlaced> pl;
+  int rc = decode_jpegs_locked(ctx, jpegs, n, &pl);
+  if (rc) return rc;
+  const uint32_t decode_launches = ctx->timing.kernel_launches;
+  std::vector<irp_image_desc> descs(n);
+  for (int i = 0; i < n; i++)
+    descs[i] = irp_image_desc{pl[i].px, pl[i].pitch, pl[i].w, pl[i].h, pl[i].c, 1, jpegs[i].exif_orientation, 1};
+  rc = preprocess_encode_locked(ctx, descs.data(), n, results, quality, outs);
+  ctx->timing.kernel_launches += decode_launches;
   return rc;
 }
 

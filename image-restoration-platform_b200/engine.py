@@ -300,6 +300,61 @@ class Engine:
         self._check(self._lib.irp_decode_jpeg_batch(self._ctx, descs, n, outs))
         return [a[:, :, 0] if a.shape[2] == 1 else a for a in arrays]
 
+    # -- compressed output: baseline JPEG encoded on the device ---------------
+    def _encode_call(self, fn, n, caps):
+        """Run fn(outs) with host buffers of caps[i] bytes; one retry with the sizes the library asks for."""
+        for attempt in range(2):
+            bufs = [np.empty(int(c), np.uint8) for c in caps]
+            outs = (_ffi.JpegOut * n)(*[_ffi.JpegOut(b.ctypes.data, b.size, 0, 0, 0, 0, 0) for b in bufs])
+            rc = fn(outs)
+            if rc == _ffi.IRP_ERR_CAPACITY and attempt == 0:
+                caps = [max(int(c), int(o.size)) * 2 for c, o in zip(caps, outs)]
+                continue
+            self._check(rc)
+            return [bytes(memoryview(b)[:o.size]) for b, o in zip(bufs, outs)]
+
+    def encode_jpeg_batch(self, images: Sequence[ImageLike], quality: int = 85) -> List[bytes]:
+        """u8 RGB / grey images (host arrays or DeviceImages) -> baseline 4:4:4 JPEG files, byte-identical to
+        libjpeg-turbo's (imagePreprocess.js:50-53 without mozjpeg's trellis / progressive passes)."""
+        n = len(images)
+        descs, keep = self._descs(images, True, None)
+        caps = [d.width * d.height * d.channels + 4096 for d in descs]
+        return self._encode_call(lambda outs: self._lib.irp_encode_jpeg_batch(self._ctx, descs, n, quality, outs), n, caps)
+
+    def analyze_encode_batch(self, images: Sequence[ImageLike], is_jpeg=True, orientations=None, quality: int = 85, classify: bool = True,
+                             raw: bool = False):
+        """analyze() + preprocessImage() of raw pixels: (score dicts, preprocessed JPEG FILES)."""
+        n = len(images)
+        descs, keep = self._descs(images, is_jpeg, orientations)
+        res = (_ffi.Result * n)() if classify else None
+        caps = []
+        for d in descs:
+            ow, oh = self.preprocess_dims(d.width, d.height, d.exif_orientation)
+            caps.append(ow * oh * (1 if d.channels == 1 else 3) // 2 + 4096)
+        files = self._encode_call(lambda outs: self._lib.irp_analyze_encode_batch(self._ctx, descs, n, res, quality, outs), n, caps)
+        results = None if res is None else (list(res) if raw else [result_to_dict(r) for r in res])
+        return results, files
+
+    def transcode_jpeg_batch(self, blobs: Sequence[bytes], orientations=None, quality: int = 85, classify: bool = True, raw: bool = False):
+        """JPEG files in -> (score dicts, preprocessed JPEG files): decode, classify, resize and re-encode on the
+        device; only file bytes cross PCIe in either direction."""
+        n = len(blobs)
+        keep = [np.frombuffer(b, np.uint8) for b in blobs]
+        descs = (_ffi.JpegDesc * n)()
+        caps = []
+        for i, k in enumerate(keep):
+            o = 1 if orientations is None else int(orientations[i])
+            descs[i] = _ffi.JpegDesc(k.ctypes.data, k.size, o, 0)
+            info = self.jpeg_info(k)
+            if info is None:
+                raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a baseline JPEG the device decoder takes")
+            ow, oh = self.preprocess_dims(info[0], info[1], o)
+            caps.append(ow * oh * (1 if info[2] == 1 else 3) // 2 + 4096)
+        res = (_ffi.Result * n)() if classify else None
+        files = self._encode_call(lambda outs: self._lib.irp_transcode_jpeg_batch(self._ctx, descs, n, res, quality, outs), n, caps)
+        results = None if res is None else (list(res) if raw else [result_to_dict(r) for r in res])
+        return results, files
+
     # -- concurrent single-image requests (irp_submit / irp_wait) -------------
     def submit(self, image: ImageLike, is_jpeg: bool = True, orientation: int = 1, classify: bool = True, preprocess: bool = True):
         """Queue ONE image (as the reference's callers do, one analyze() per promise) and return a handle at

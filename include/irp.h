@@ -178,6 +178,33 @@ int irp_decode_jpeg_batch(irp_ctx *ctx, const irp_jpeg_desc *jpegs, int n, irp_o
 int irp_analyze_jpeg_batch(irp_ctx *ctx, const irp_jpeg_desc *jpegs, int n, irp_result *results,
                            irp_out_desc *outs);
 
+/* ---- compressed output ------------------------------------------------ */
+/* preprocessImage ends in `.jpeg({quality: 85, chromaSubsampling: '4:4:4',
+ * mozjpeg: true})` and returns the FILE (imagePreprocess.js:50-58).  These entry
+ * points encode on the device, bit-identical to libjpeg-turbo's baseline encoder
+ * (RGB->YCbCr, accurate integer DCT, reciprocal quantisation, Annex K Huffman
+ * tables, 4:4:4, JFIF header) — a 2048x1536 result leaves the GPU as ~1 MB of
+ * file bytes instead of 9.4 MB of pixels.  mozjpeg's trellis quantisation and
+ * progressive scan search are NOT reproduced (same picture, ~10 % larger file). */
+typedef struct irp_jpeg_out {
+  uint8_t *data;    /* caller-owned HOST buffer for the file                     */
+  size_t capacity;  /* in: bytes available at `data`                             */
+  size_t size;      /* out: bytes written (on IRP_ERR_CAPACITY: bytes required)  */
+  int32_t width, height, channels; /* out: dims of the encoded image             */
+  int32_t reserved;
+} irp_jpeg_out;
+/* pixels (host or device, 1 or 3 channels) -> baseline JPEG files */
+int irp_encode_jpeg_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, int quality,
+                          irp_jpeg_out *outs);
+/* classify (results may be NULL) + preprocess + encode: raw pixels in, scores and the
+ * preprocessed FILE out — analyze() and preprocessImage() of one upload */
+int irp_analyze_encode_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_result *results,
+                             int quality, irp_jpeg_out *outs);
+/* the same from JPEG FILE bytes: decode, classify, preprocess and re-encode without a
+ * pixel crossing PCIe */
+int irp_transcode_jpeg_batch(irp_ctx *ctx, const irp_jpeg_desc *jpegs, int n, irp_result *results,
+                             int quality, irp_jpeg_out *outs);
+
 /* ---- concurrent single-image requests --------------------------------- */
 /* The reference's callers issue ONE image per call from several in-flight
  * promises (ClassifierService.analyze is async, classifier.js:40; restoreBatch

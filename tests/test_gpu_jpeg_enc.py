@@ -1,0 +1,147 @@
+"""Device JPEG encode (irp_encode_jpeg_batch / irp_analyze_encode_batch / irp_transcode_jpeg_batch) against
+libjpeg-turbo itself (Pillow, the same library sharp encodes with): the FILE must be byte-identical to
+`Image.save(quality=q, subsampling=0, optimize=False)` — quantisation tables, Huffman tables, every bit of the
+entropy-coded segment including byte stuffing and the final padding — for colour and grey, odd sizes (edge blocks
+replicate), several qualities and image statistics (long zero runs, ZRL codes, 0xFF-rich noise).  Then the
+serving entry points: the file they return must be the encoder's file of the preprocess kernel's pixels."""
+import io
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import assert_result_parity, rand_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _pillow_encode(img, quality):
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", quality=quality, subsampling=0, optimize=False)
+    return b.getvalue()
+
+
+def _scan(data):
+    """(header bytes up to and including SOS, entropy-coded bytes)"""
+    p = 2
+    while True:
+        assert data[p] == 0xFF
+        m = data[p + 1]
+        ln = (data[p + 2] << 8) | data[p + 3]
+        if m == 0xDA:
+            return data[:p + 2 + ln], data[p + 2 + ln:]
+        p += 2 + ln
+
+
+def _explain(got, ref):
+    if got == ref:
+        return "identical"
+    gh, gs = _scan(got)
+    rh, rs = _scan(ref)
+    first = next((i for i, (a, b) in enumerate(zip(gs, rs)) if a != b), min(len(gs), len(rs)))
+    return f"header equal: {gh == rh} (lens {len(gh)}/{len(rh)}); scan lens {len(gs)}/{len(rs)}, first differing scan byte {first}"
+
+
+SHAPES = [(8, 8), (1, 1), (3, 5), (16, 24), (17, 33), (37, 53), (64, 48), (100, 161), (241, 319), (600, 900)]
+
+
+@pytest.mark.parametrize("channels", [3, 1])
+def test_encode_is_byte_identical_to_libjpeg_turbo(engine, channels):
+    imgs, quals = [], []
+    for i, (h, w) in enumerate(SHAPES):
+        for kind, q in (("smooth", 85), ("noise", 60), ("edges", 95), ("noise", 85), ("smooth", 30)):
+            im = rand_image(h, w, channels, seed=17 * i + q, kind=kind)
+            imgs.append(im[:, :, 0] if channels == 1 else im)
+            quals.append(q)
+    for q in sorted(set(quals)):
+        sel = [im for im, qq in zip(imgs, quals) if qq == q]
+        got = engine.encode_jpeg_batch(sel, quality=q)
+        for i, (g, im) in enumerate(zip(got, sel)):
+            ref = _pillow_encode(im, q)
+            assert g == ref, f"quality {q} image {i} shape {im.shape}: {_explain(g, ref)}"
+
+
+def test_encode_extreme_content(engine):
+    """flat black / white / saturated colours (all-zero AC: EOB only), a checkerboard at Nyquist (largest AC
+    magnitudes), sparse impulses (runs > 15: ZRL), and uniform noise at quality 100 (0xFF bytes to stuff)."""
+    h, w = 72, 104
+    imgs = [np.zeros((h, w, 3), np.uint8), np.full((h, w, 3), 255, np.uint8)]
+    sat = np.zeros((h, w, 3), np.uint8)
+    sat[..., 0] = 255
+    imgs.append(sat)
+    yy, xx = np.mgrid[0:h, 0:w]
+    imgs.append(np.repeat((((yy + xx) & 1) * 255).astype(np.uint8)[:, :, None], 3, 2))
+    sparse = np.full((h, w, 3), 128, np.uint8)
+    sparse[7::8, 7::8] = 255
+    imgs.append(sparse)
+    imgs.append(np.random.default_rng(5).integers(0, 256, (h, w, 3), dtype=np.uint8))
+    for q in (100, 97, 85, 10, 1):
+        got = engine.encode_jpeg_batch(imgs, quality=q)
+        for i, (g, im) in enumerate(zip(got, imgs)):
+            ref = _pillow_encode(im, q)
+            assert g == ref, f"quality {q} image {i}: {_explain(g, ref)}"
+
+
+def test_encode_unaligned_rows_and_device_sources(engine):
+    """A device-resident source whose pitch is not a multiple of 4 takes the byte-load path of the DCT kernel."""
+    img = rand_image(203, 301, 3, seed=3, kind="smooth")
+    ref = _pillow_encode(img, 85)
+    for align in (1, 256):
+        d = engine.upload(img, pitch_align=align)
+        assert engine.encode_jpeg_batch([d], quality=85)[0] == ref, f"pitch_align {align}"
+
+
+def test_encode_full_size_output(engine):
+    """The size preprocessImage produces (2048 x 1536 x 3): 147k blocks, bit offsets past 2^24."""
+    img = rand_image(1536, 2048, 3, seed=8, kind="smooth")
+    img[500:900, 300:1200] = np.random.default_rng(1).integers(0, 256, (400, 900, 3), dtype=np.uint8)
+    got = engine.encode_jpeg_batch([img, img[::-1].copy()], quality=85)
+    assert got[0] == _pillow_encode(img, 85), _explain(got[0], _pillow_encode(img, 85))
+    assert got[1] == _pillow_encode(img[::-1].copy(), 85)
+
+
+def test_capacity_error_reports_the_size_needed(engine):
+    from irp_b200 import _ffi
+
+    img = np.random.default_rng(2).integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    descs, keep = engine._descs([img], True, None)
+    buf = np.empty(700, np.uint8)
+    outs = (_ffi.JpegOut * 1)(_ffi.JpegOut(buf.ctypes.data, buf.size, 0, 0, 0, 0, 0))
+    assert engine._lib.irp_encode_jpeg_batch(engine._ctx, descs, 1, 85, outs) == _ffi.IRP_ERR_CAPACITY
+    need = outs[0].size
+    assert need > 700
+    buf = np.empty(need, np.uint8)
+    outs = (_ffi.JpegOut * 1)(_ffi.JpegOut(buf.ctypes.data, buf.size, 0, 0, 0, 0, 0))
+    assert engine._lib.irp_encode_jpeg_batch(engine._ctx, descs, 1, 85, outs) == 0
+    assert bytes(buf[:outs[0].size]) == _pillow_encode(img, 85)
+
+
+@pytest.mark.parametrize("orientation", [1, 6])
+def test_analyze_encode_returns_the_file_of_the_preprocessed_pixels(engine, oracle, orientation):
+    imgs = [rand_image(2300, 3100, 3, seed=1, kind="smooth"), rand_image(900, 700, 3, seed=2, kind="edges"),
+            rand_image(2500, 2500, 1, seed=3, kind="smooth")]
+    res, files = engine.analyze_encode_batch(imgs, orientations=[orientation] * 3, quality=85)
+    for i, im in enumerate(imgs):
+        assert_result_parity(res[i], oracle.classify(im), im.shape[2], f"image {i}")
+        px = oracle.preprocess(im, orientation)
+        px = px[:, :, 0] if px.shape[2] == 1 else px
+        ref = _pillow_encode(px, 85)
+        assert files[i] == ref, f"image {i}: {_explain(files[i], ref)}"
+
+
+def test_transcode_files_in_files_out(engine, oracle):
+    """File bytes in, scores + preprocessed file out: equal to (Pillow decode -> oracle -> Pillow encode)."""
+    srcs = [rand_image(2200, 3000, 3, seed=11, kind="smooth"), rand_image(1200, 1600, 3, seed=12, kind="noise"),
+            rand_image(640, 480, 3, seed=13, kind="edges")]
+    blobs = []
+    for i, s in enumerate(srcs):
+        b = io.BytesIO()
+        Image.fromarray(s).save(b, "JPEG", quality=90, subsampling=(2, 1, 0)[i])
+        blobs.append(b.getvalue())
+    res, files = engine.transcode_jpeg_batch(blobs, quality=85)
+    for i, b in enumerate(blobs):
+        px = np.asarray(Image.open(io.BytesIO(b)))
+        assert_result_parity(res[i], oracle.classify(px), 3, f"file {i}")
+        ref = _pillow_encode(oracle.preprocess(px, 1), 85)
+        assert files[i] == ref, f"file {i}: {_explain(files[i], ref)}"
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(files[i]))), np.asarray(Image.open(io.BytesIO(ref))))
