@@ -87,8 +87,10 @@ __device__ __forceinline__ void fdct_1d(int* d) {
 
 __device__ __forceinline__ int enc_nbits(int a) { return 32 - __clz(a); }   // a >= 0
 
-// One thread per MCU (= one 8x8 block of each component: 4:4:4).  grid = (ceil(max MCUs / 128), n images).
-__global__ void __launch_bounds__(kEncThreads)
+// One thread per 8x8 block of one component (4:4:4: an MCU is one block of each).  grid = (ceil(max blocks / 128), n images).
+// The three threads of an MCU read the same pixels (one L1 line) and keep only their own component: 64 live values
+// per thread instead of the packed MCU, which is what lets four CTAs share an SM.
+__global__ void __launch_bounds__(kEncThreads, 4)
 jenc_dct_kernel(const EncImg* __restrict__ imgs, const EncTables* __restrict__ tabs, int16_t* __restrict__ coef, uint32_t* __restrict__ blkinfo) {
   __shared__ EncTables T;
   __shared__ int16_t zs[kEncThreads * kEncPitchH];
@@ -96,31 +98,39 @@ jenc_dct_kernel(const EncImg* __restrict__ imgs, const EncTables* __restrict__ t
   __syncthreads();
   const EncImg& im = imgs[blockIdx.y];
   const int w = im.w, h = im.h, c = im.c, bw = im.bw;
-  const int m = blockIdx.x * kEncThreads + threadIdx.x;
-  if (m >= bw * im.bh) return;
+  const int t = blockIdx.x * kEncThreads + threadIdx.x;
+  if (t >= im.nblk) return;
+  const int m = c == 3 ? t / 3 : t, comp = t - m * c;
   const int bx = m % bw, by = m / bw, x0 = bx * 8, y0 = by * 8;
   const uint8_t* __restrict__ px = im.px;
   const size_t pitch = (size_t)im.pitch;
-
-  // the MCU's pixels, packed as they lie in memory (edge blocks replicate the last column / row: jcprepct.c)
-  uint32_t raw[8][6];
-  const bool fast = x0 + 8 <= w && (((uintptr_t)px | pitch) & 3) == 0;
+  int d[64];
   if (c == 3) {
+    // jccolor.c rgb_ycc_convert: 16-bit fixed point, the chroma rows biased by 128.5 - 1 LSB; level shift folded in
+    const int cr = comp == 0 ? 19595 : (comp == 1 ? -11059 : 32768);
+    const int cg = comp == 0 ? 38470 : (comp == 1 ? -21709 : -27439);
+    const int cb = comp == 0 ? 7471 : (comp == 1 ? 32768 : -5329);
+    const int c0 = comp == 0 ? 32768 : (128 << 16) + 32767;
+    const bool fast = x0 + 8 <= w && (((uintptr_t)px | pitch) & 3) == 0;   // whole block inside, rows 4-byte aligned
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      const uint8_t* row = px + (size_t)min(y0 + r, h - 1) * pitch;
+      const uint8_t* row = px + (size_t)min(y0 + r, h - 1) * pitch;   // edge blocks replicate the last row / column (jcprepct.c)
       if (fast) {
         const uint2* p = (const uint2*)(row + x0 * 3);
         const uint2 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
-        raw[r][0] = a.x; raw[r][1] = a.y; raw[r][2] = b.x; raw[r][3] = b.y; raw[r][4] = cc.x; raw[r][5] = cc.y;
-      } else {
+        const uint32_t raw[6] = {a.x, a.y, b.x, b.y, cc.x, cc.y};
 #pragma unroll
-        for (int k = 0; k < 6; k++) raw[r][k] = 0;
+        for (int j = 0; j < 8; j++) {
+          const int R = (raw[(3 * j) >> 2] >> (8 * ((3 * j) & 3))) & 255;
+          const int G = (raw[(3 * j + 1) >> 2] >> (8 * ((3 * j + 1) & 3))) & 255;
+          const int B = (raw[(3 * j + 2) >> 2] >> (8 * ((3 * j + 2) & 3))) & 255;
+          d[r * 8 + j] = ((cr * R + cg * G + cb * B + c0) >> 16) - 128;
+        }
+      } else {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const uint8_t* p = row + (size_t)min(x0 + j, w - 1) * 3;
-#pragma unroll
-          for (int k = 0; k < 3; k++) raw[r][(3 * j + k) >> 2] |= (uint32_t)__ldg(p + k) << (8 * ((3 * j + k) & 3));
+          d[r * 8 + j] = ((cr * (int)__ldg(p) + cg * (int)__ldg(p + 1) + cb * (int)__ldg(p + 2) + c0) >> 16) - 128;
         }
       }
     }
@@ -128,80 +138,53 @@ jenc_dct_kernel(const EncImg* __restrict__ imgs, const EncTables* __restrict__ t
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       const uint8_t* row = px + (size_t)min(y0 + r, h - 1) * pitch;
-      raw[r][0] = raw[r][1] = 0;
 #pragma unroll
-      for (int j = 0; j < 8; j++) raw[r][j >> 2] |= (uint32_t)__ldg(row + min(x0 + j, w - 1)) << (8 * (j & 3));
+      for (int j = 0; j < 8; j++) d[r * 8 + j] = (int)__ldg(row + min(x0 + j, w - 1)) - 128;
     }
   }
-
+#pragma unroll
+  for (int r = 0; r < 8; r++) fdct_1d<true, 1>(d + r * 8);
+#pragma unroll
+  for (int j = 0; j < 8; j++) fdct_1d<false, 8>(d + j);
+  // jcdctmgr.c quantize(): |x| + correction, times the 16-bit reciprocal, shifted; sign restored
   int16_t* mine = zs + threadIdx.x * kEncPitchH;
-#pragma unroll 1
-  for (int comp = 0; comp < c; comp++) {
-    int d[64];
-    if (c == 3) {
-      // jccolor.c rgb_ycc_convert: 16-bit fixed point, the chroma rows biased by 128.5 - 1 LSB
-      const int cr = comp == 0 ? 19595 : (comp == 1 ? -11059 : 32768);
-      const int cg = comp == 0 ? 38470 : (comp == 1 ? -21709 : -27439);
-      const int cb = comp == 0 ? 7471 : (comp == 1 ? 32768 : -5329);
-      const int c0 = comp == 0 ? 32768 : (128 << 16) + 32767;
+  const uint32_t* qt = T.q[comp ? 1 : 0];
 #pragma unroll
-      for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int R = (raw[r][(3 * j) >> 2] >> (8 * ((3 * j) & 3))) & 255;
-          const int G = (raw[r][(3 * j + 1) >> 2] >> (8 * ((3 * j + 1) & 3))) & 255;
-          const int B = (raw[r][(3 * j + 2) >> 2] >> (8 * ((3 * j + 2) & 3))) & 255;
-          d[r * 8 + j] = ((cr * R + cg * G + cb * B + c0) >> 16) - 128;
-        }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) d[r * 8 + j] = (int)((raw[r][j >> 2] >> (8 * (j & 3))) & 255) - 128;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; r++) fdct_1d<true, 1>(d + r * 8);
-#pragma unroll
-    for (int j = 0; j < 8; j++) fdct_1d<false, 8>(d + j);
-    // jcdctmgr.c quantize(): |x| + correction, times the 16-bit reciprocal, shifted; sign restored
-    const uint32_t* qt = T.q[comp ? 1 : 0];
-#pragma unroll
-    for (int i = 0; i < 64; i++) {
-      const uint32_t e = qt[i];
-      const int v = d[i];
-      const uint32_t prod = ((uint32_t)abs(v) + ((e >> 16) & 0x7FFu)) * (e & 0xFFFFu);
-      const int qv = (int)(prod >> ((e >> 27) + 16));
-      mine[i] = (int16_t)(v < 0 ? -qv : qv);
-    }
-    // zigzag read-back: 8 coefficients per 16-byte store; AC code lengths summed on the way (jchuff.c encode_one_block)
-    const uint32_t* act = T.ac[comp ? 1 : 0];
-    const size_t g = (size_t)im.blk0 + (size_t)m * c + comp;
-    uint4* dst = (uint4*)(coef + g * 64);
-    int run = 0, bits = 0, dcv = 0;
-#pragma unroll 1
-    for (int k8 = 0; k8 < 8; k8++) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int v = mine[c_enc_zigzag[k8 * 8 + i]];
-        if (i & 1) pk[i >> 1] |= (uint32_t)(uint16_t)v << 16;
-        else pk[i >> 1] = (uint16_t)v;
-        if (k8 == 0 && i == 0) {
-          dcv = v;
-        } else if (v == 0) {
-          run++;
-        } else {
-          bits += (run >> 4) * (int)(act[0xF0] >> 16);
-          const int nb = enc_nbits(abs(v));
-          bits += (int)(act[((run & 15) << 4) | nb] >> 16) + nb;
-          run = 0;
-        }
-      }
-      dst[k8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
-    if (run) bits += (int)(act[0] >> 16);
-    blkinfo[g] = (uint32_t)bits | ((uint32_t)(uint16_t)dcv << 16);
+  for (int i = 0; i < 64; i++) {
+    const uint32_t e = qt[i];
+    const int v = d[i];
+    const uint32_t prod = ((uint32_t)abs(v) + ((e >> 16) & 0x7FFu)) * (e & 0xFFFFu);
+    const int qv = (int)(prod >> ((e >> 27) + 16));
+    mine[i] = (int16_t)(v < 0 ? -qv : qv);
   }
+  // zigzag read-back: 8 coefficients per 16-byte store; AC code lengths summed on the way (jchuff.c encode_one_block)
+  const uint32_t* act = T.ac[comp ? 1 : 0];
+  const size_t g = (size_t)im.blk0 + t;
+  uint4* dst = (uint4*)(coef + g * 64);
+  int run = 0, bits = 0, dcv = 0;
+#pragma unroll 1
+  for (int k8 = 0; k8 < 8; k8++) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int v = mine[c_enc_zigzag[k8 * 8 + i]];
+      if (i & 1) pk[i >> 1] |= (uint32_t)(uint16_t)v << 16;
+      else pk[i >> 1] = (uint16_t)v;
+      if (k8 == 0 && i == 0) {
+        dcv = v;
+      } else if (v == 0) {
+        run++;
+      } else {
+        bits += (run >> 4) * (int)(act[0xF0] >> 16);
+        const int nb = enc_nbits(abs(v));
+        bits += (int)(act[((run & 15) << 4) | nb] >> 16) + nb;
+        run = 0;
+      }
+    }
+    dst[k8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (run) bits += (int)(act[0] >> 16);
+  blkinfo[g] = (uint32_t)bits | ((uint32_t)(uint16_t)dcv << 16);
 }
 
 // bits of every block = AC bits + the DC difference code (previous block of the same component, 0 at the start)
