@@ -72,45 +72,64 @@ struct SubState {                          // state AFTER a subsequence: where t
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0u, 0x0123); }
 
-// A 64-bit window over a big-endian bit stream of 32-bit words.  The words of a subsequence (and 16 bytes
+// A left-aligned 64-bit bit buffer over a big-endian stream of 32-bit words: seek() once per run, then per symbol
+// fill() (one predicated word load when fewer than 32 bits are left), top32() and skip().  One 32-bit look
+// covers a Huffman code (<= 16 bits) and its value bits (<= 15), so the dependent chain per symbol is
+// "buffer -> LUT -> shift", with no position -> word arithmetic.  The words of a subsequence (and 16 bytes
 // beyond: a symbol that starts in it may end there) are staged in shared memory by its owner thread with
-// independent 128-bit loads before any decoding, so the dependent chain "position -> word -> code" never
-// waits on global memory.
+// independent 128-bit loads before any decoding, so the chain never waits on global memory.
 constexpr int kSubWords = kSubBits / 32 + 4;
 struct BitWin {
   const uint32_t* d;  // staged words of ONE subsequence
   uint32_t bit0;      // stream-relative bit position of its first word
-  int w;              // index of the word in `hi` (-2: nothing loaded)
-  uint32_t hi, lo;
-  __device__ __forceinline__ uint32_t peek16(uint32_t p) {   // 16 bits starting at stream bit p
+  unsigned long long acc;
+  int avail, nw;      // valid bits in acc; index of the next word to load
+  __device__ __forceinline__ void seek(uint32_t p) {
     const uint32_t q = p - bit0;
     const int wi = min((int)(q >> 5), kSubWords - 2);        // (a position past the staged words only occurs on corrupt data)
-    if (wi != w) {
-      hi = (wi == w + 1) ? lo : d[wi];
-      lo = d[wi + 1];
-      w = wi;
+    acc = (((unsigned long long)d[wi] << 32) | d[wi + 1]) << (q & 31);
+    avail = 64 - (int)(q & 31);
+    nw = wi + 2;
+  }
+  __device__ __forceinline__ void fill() {
+    if (avail < 32) {
+      acc |= (unsigned long long)d[min(nw, kSubWords - 1)] << (32 - avail);
+      avail += 32;
+      nw++;
     }
-    const unsigned long long win = ((unsigned long long)hi << 32) | lo;
-    return (uint32_t)((win << (q & 31)) >> 48);
+  }
+  __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(acc >> 32); }
+  __device__ __forceinline__ void skip(int n) {
+    acc <<= n;
+    avail -= n;
   }
 };
-// the same window straight over global memory (read-only path, L1-cached): the synchronisation launches
+// the same buffer straight over global memory (read-only path, L1-cached): the synchronisation launches
 // decode little after the first sweep, and staging would cost them their occupancy
 struct BitWinG {
   const uint32_t* d;   // the batch buffer
   unsigned long long base;   // stream_bit0
-  long long w;
-  uint32_t hi, lo;
-  __device__ __forceinline__ uint32_t peek16(uint32_t p) {
+  unsigned long long acc;
+  int avail;
+  const uint32_t* nw;
+  __device__ __forceinline__ void seek(uint32_t p) {
     const unsigned long long q = base + p;
-    const long long wi = (long long)(q >> 5);
-    if (wi != w) {
-      hi = (wi == w + 1) ? lo : bswap32(__ldg(d + wi));
-      lo = bswap32(__ldg(d + wi + 1));
-      w = wi;
+    const uint32_t* w = d + (q >> 5);
+    acc = (((unsigned long long)bswap32(__ldg(w)) << 32) | bswap32(__ldg(w + 1))) << (unsigned)(q & 31);
+    avail = 64 - (int)(q & 31);
+    nw = w + 2;
+  }
+  __device__ __forceinline__ void fill() {
+    if (avail < 32) {
+      acc |= (unsigned long long)bswap32(__ldg(nw)) << (32 - avail);
+      avail += 32;
+      nw++;
     }
-    const unsigned long long win = ((unsigned long long)hi << 32) | lo;
-    return (uint32_t)((win << (unsigned)(q & 31)) >> 48);
+  }
+  __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(acc >> 32); }
+  __device__ __forceinline__ void skip(int n) {
+    acc <<= n;
+    avail -= n;
   }
 };
 // stage subsequence `local` of a stream: words are byte-swapped once here
@@ -166,8 +185,10 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
                                          const uint8_t* __restrict__ zigzag) {
   const uint32_t period = 64u * (uint32_t)im.bpm;
   const uint32_t stop = (uint32_t)min((unsigned long long)p_end, stream_bits);
+  if (p >= stop) return;
+  bw.seek(p);
   // block by block: the component, its two tables and (when writing) the block's address are looked up once
-  // per block; the inner loop over the AC symbols touches one table and the bit window only
+  // per block; the inner loop over the AC symbols touches one table and the bit buffer only
   while (p < stop && (!WRITE || abs_blk < blk_limit)) {
     uint32_t z = slot & 63u;
     const uint32_t k = slot >> 6;
@@ -182,39 +203,31 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
     }
     const uint32_t z_in = z;
     if (z == 0) {
-      uint32_t bits = bw.peek16(p);
+      bw.fill();
+      const uint32_t b32 = bw.top32();
       int len;
-      const int s = huff_decode(dct, bits, len) & 15;
-      p += len;
-      if (WRITE) {
-        int v = 0;
-        if (s) {
-          bits = bw.peek16(p);
-          v = huff_extend((int)(bits >> (16 - s)), s);
-        }
-        blk_ptr[0] = (int16_t)v;
-      }
-      p += s;
+      const int s = huff_decode(dct, b32 >> 16, len) & 15;
+      if (WRITE) blk_ptr[0] = (int16_t)(s ? huff_extend((int)((b32 << len) >> (32 - s)), s) : 0);
+      bw.skip(len + s);
+      p += len + s;
       z = 1;
     }
     while (z < 64u && p < stop) {
-      uint32_t bits = bw.peek16(p);
+      bw.fill();
+      const uint32_t b32 = bw.top32();
       int len;
-      const int rs = huff_decode(act, bits, len);
-      p += len;
+      const int rs = huff_decode(act, b32 >> 16, len);
       const int r = rs >> 4, s = rs & 15;
       if (s == 0) {
         z = (r == 15) ? min(z + 16u, 64u) : 64u;          // ZRL : EOB
       } else {
         uint32_t zz = z + r;
         if (zz > 63u) zz = 63u;                           // only while out of sync / on corrupt data
-        if (WRITE) {
-          bits = bw.peek16(p);
-          blk_ptr[zigzag[zz]] = (int16_t)huff_extend((int)(bits >> (16 - s)), s);
-        }
-        p += s;
+        if (WRITE) blk_ptr[zigzag[zz]] = (int16_t)huff_extend((int)((b32 << len) >> (32 - s)), s);
         z = zz + 1;
       }
+      bw.skip(len + s);
+      p += len + s;
     }
     const uint32_t adv = z - z_in;
     slot += adv;
@@ -298,7 +311,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
       else
         start = vstate[sub - 1];
       uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
-      BitWinG bw{data, st.bit_off, -2, 0, 0};
+      BitWinG bw{data, st.bit_off, 0ull, 0, nullptr};
       huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0u, 0u, nullptr);
       vin[sub] = start;
       vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
@@ -375,7 +388,7 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
   }
   int16_t* coef[3] = {coef_arena + im.coef_off[0], coef_arena + im.coef_off[1], coef_arena + im.coef_off[2]};
   const uint32_t base_blk = (uint32_t)st.first_mcu * (uint32_t)im.bpm;
-  BitWin bw{staged + threadIdx.x * kSubWords, (uint32_t)local * kSubBits, -2, 0, 0};
+  BitWin bw{staged + threadIdx.x * kSubWords, (uint32_t)local * kSubBits, 0ull, 0, 0};
   uint32_t adv = 0;
   huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef,
                  base_blk + (uint32_t)(slot_start[sub] >> 6), base_blk + (uint32_t)st.n_mcu * (uint32_t)im.bpm, zz);

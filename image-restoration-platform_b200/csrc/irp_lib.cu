@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -143,6 +144,11 @@ struct irp_ctx {
   bool rtma_ok = true;    // IRP_NO_RTMA=1 keeps the generic resize kernel (A/B runs)
   bool bulk_ok = false;   // the streaming classify kernel's shared-memory map fits this device
   int* h_error_flag = nullptr;
+  // compressed-input batches are cut into lanes: child contexts (own streams and scratch) driven by their own host
+  // threads, so one lane's marker scan / un-stuffing / uploads / size read-backs run under the other lanes' kernels
+  std::vector<irp_ctx*> lanes;
+  std::mutex lanes_mu;
+  bool is_lane = false;
 };
 
 namespace {
@@ -1186,6 +1192,8 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
 
 void irp_destroy(irp_ctx* ctx) {
   if (!ctx) return;
+  for (irp_ctx* l : ctx->lanes) irp_destroy(l);
+  ctx->lanes.clear();
   {
     std::lock_guard<std::mutex> lk(ctx->qmu);
     ctx->stop = true;
@@ -1204,7 +1212,7 @@ void irp_destroy(irp_ctx* ctx) {
                     &ctx->d_jdata, &ctx->d_jmeta, &ctx->d_jstate, &ctx->d_jcoef, &ctx->d_jplane, &ctx->d_jpix, &ctx->d_emeta,
                     &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix})
     b->release();
-  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta}) b->release();
+  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta, &ctx->h_emeta}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);
@@ -1362,8 +1370,47 @@ int irp_decode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_o
   return IRP_OK;
 }
 
+// Cut [0, n) into the context's lanes and run f(lane context, begin, count) on each from its own host thread
+// (lane 0 is the context itself, on the calling thread).  At least 8 files per lane; IRP_LANES overrides the
+// default of 4 (1 = off).  The first failing lane's status and message are returned.
+static int run_in_lanes(irp_ctx* ctx, int n, const std::function<int(irp_ctx*, int, int)>& f) {
+  static const int env_lanes = getenv("IRP_LANES") ? atoi(getenv("IRP_LANES")) : 4;
+  const int want = ctx->is_lane ? 1 : std::max(1, std::min(env_lanes, n / 8));
+  if (want == 1) return f(ctx, 0, n);
+  {
+    std::lock_guard<std::mutex> lk(ctx->lanes_mu);
+    while ((int)ctx->lanes.size() < want - 1) {
+      irp_ctx* l = irp_create(ctx->device, &ctx->opts);
+      if (!l) return f(ctx, 0, n);      // no memory for another lane: run unsplit
+      l->is_lane = true;
+      ctx->lanes.push_back(l);
+    }
+  }
+  std::vector<int> rc(want, IRP_OK);
+  std::vector<std::thread> th;
+  auto part = [&](int k) { return (int)((long long)n * k / want); };
+  for (int k = 1; k < want; k++) th.emplace_back([&, k] { rc[k] = f(ctx->lanes[k - 1], part(k), part(k + 1) - part(k)); });
+  rc[0] = f(ctx, 0, part(1));
+  for (auto& t : th) t.join();
+  for (int k = 1; k < want; k++) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->timing.kernel_launches += ctx->lanes[k - 1]->timing.kernel_launches;
+    if (rc[k] != IRP_OK && rc[0] == IRP_OK) {
+      rc[0] = rc[k];
+      ctx->err = ctx->lanes[k - 1]->err;
+    }
+  }
+  return rc[0];
+}
+
+static int analyze_jpeg_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, irp_out_desc* outs);
 int irp_analyze_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, irp_out_desc* outs) {
   if (!ctx || n < 0 || (n && (!jpegs || (!results && !outs)))) return IRP_ERR_BAD_ARG;
+  return run_in_lanes(ctx, n, [&](irp_ctx* lane, int b, int cnt) {
+    return analyze_jpeg_single(lane, jpegs + b, cnt, results ? results + b : nullptr, outs ? outs + b : nullptr);
+  });
+}
+static int analyze_jpeg_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, irp_out_desc* outs) {
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->err.clear();
   if (!n) return IRP_OK;
@@ -1463,8 +1510,14 @@ int irp_analyze_encode_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, ir
   return preprocess_encode_locked(ctx, imgs, n, results, quality, outs);
 }
 
+static int transcode_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, int quality, irp_jpeg_out* outs);
 int irp_transcode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, int quality, irp_jpeg_out* outs) {
   if (!ctx || n < 0 || (n && (!jpegs || !outs))) return IRP_ERR_BAD_ARG;
+  return run_in_lanes(ctx, n, [&](irp_ctx* lane, int b, int cnt) {
+    return transcode_single(lane, jpegs + b, cnt, results ? results + b : nullptr, quality, outs + b);
+  });
+}
+static int transcode_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_result* results, int quality, irp_jpeg_out* outs) {
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->err.clear();
   if (!n) return IRP_OK;
