@@ -8,6 +8,8 @@
 // JS surface (used by addon/classifier.js and addon/imagePreprocess.js):
 //   createContext(device:number) -> external
 //   analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>   (baseline JPEG bytes, decoded on the device)
+//   transcodeFile(ctx, file:Buffer, orientation, quality) -> Promise<{scores:Float64Array(7), file:Buffer, width, height, channels}>
+//       analyze() + preprocessImage() of one upload with files on both sides (irp_transcode_jpeg_batch)
 //   analyzeRaw(ctx, pixels:Buffer, width, height, channels, isJpeg:boolean) -> Promise<Float64Array(7)>
 //   preprocessRaw(ctx, pixels:Buffer, width, height, channels, orientation) -> Promise<{data:Buffer,width,height,channels}>
 // Work runs on the libuv pool through napi_create_async_work, so the event loop never blocks
@@ -31,6 +33,9 @@ struct Job {
   bool preprocess = false;
   bool file = false;            // the input Buffer is a JPEG FILE, decoded on the device (irp_submit_jpeg)
   irp_jpeg_desc jpeg{};
+  bool transcode = false;       // file in, scores + preprocessed file out
+  int quality = 85;
+  irp_jpeg_out enc{};
   irp_result result{};
   irp_out_desc out{};
   int rc = 0;
@@ -39,6 +44,22 @@ struct Job {
 
 void Execute(napi_env, void* data) {
   Job* j = static_cast<Job*>(data);
+  if (j->transcode) {   // capacity: half a byte per sample is ample at quality 85; one retry with the size the library reports
+    int w = 0, h = 0, c = 0, ow = 0, oh = 0;
+    j->rc = irp_jpeg_info(j->jpeg.data, j->jpeg.size, &w, &h, &c);
+    if (j->rc == IRP_OK) j->rc = irp_preprocess_dims(w, h, j->jpeg.exif_orientation, &ow, &oh);
+    for (int attempt = 0; j->rc == IRP_OK && attempt < 2; attempt++) {
+      j->enc.capacity = attempt ? j->enc.size : static_cast<size_t>(ow) * oh * (c == 1 ? 1 : 3) / 2 + 4096;
+      std::free(j->enc.data);
+      j->enc.data = static_cast<uint8_t*>(std::malloc(j->enc.capacity));
+      if (!j->enc.data) { j->rc = IRP_ERR_NOMEM; break; }
+      j->rc = irp_transcode_jpeg_batch(j->ctx, &j->jpeg, 1, &j->result, j->quality, &j->enc);
+      if (j->rc != IRP_ERR_CAPACITY) break;
+      if (attempt == 0) j->rc = IRP_OK;
+    }
+    if (j->rc != IRP_OK) j->error = j->rc == IRP_ERR_UNSUPPORTED ? "unsupported" : irp_last_error(j->ctx);
+    return;
+  }
   if (j->preprocess) {
     int ow = 0, oh = 0;
     j->rc = irp_preprocess_dims(j->desc.width, j->desc.height, j->desc.exif_orientation, &ow, &oh);
@@ -73,6 +94,25 @@ void Complete(napi_env env, napi_status, void* data) {
     napi_create_error(env, nullptr, msg, &err);
     napi_reject_deferred(env, j->deferred, err);
     std::free(j->out.pixels);
+    std::free(j->enc.data);
+  } else if (j->transcode) {
+    napi_value obj, buf, v, ab, arr;
+    void *copy = nullptr, *dst = nullptr;
+    napi_create_object(env, &obj);
+    napi_create_buffer_copy(env, j->enc.size, j->enc.data, &copy, &buf);
+    std::free(j->enc.data);
+    napi_set_named_property(env, obj, "file", buf);
+    napi_create_arraybuffer(env, sizeof(double) * IRP_NUM_SCORES, &dst, &ab);
+    std::memcpy(dst, j->result.score, sizeof(double) * IRP_NUM_SCORES);
+    napi_create_typedarray(env, napi_float64_array, IRP_NUM_SCORES, ab, 0, &arr);
+    napi_set_named_property(env, obj, "scores", arr);
+    napi_create_int32(env, j->enc.width, &v);
+    napi_set_named_property(env, obj, "width", v);
+    napi_create_int32(env, j->enc.height, &v);
+    napi_set_named_property(env, obj, "height", v);
+    napi_create_int32(env, j->enc.channels, &v);
+    napi_set_named_property(env, obj, "channels", v);
+    napi_resolve_deferred(env, j->deferred, obj);
   } else if (j->preprocess) {
     napi_value obj, buf, v;
     void* copy = nullptr;
@@ -185,6 +225,35 @@ napi_value AnalyzeFile(napi_env env, napi_callback_info info) {
   return promise;
 }
 
+// transcodeFile(ctx, file:Buffer, orientation, quality): rejects with "unsupported" for anything but a baseline JPEG
+napi_value TranscodeFile(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value argv[4];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  Job* j = new Job();
+  j->transcode = true;
+  void* ctx = nullptr;
+  napi_get_value_external(env, argv[0], &ctx);
+  j->ctx = static_cast<irp_ctx*>(ctx);
+  void* data = nullptr;
+  size_t len = 0;
+  napi_get_buffer_info(env, argv[1], &data, &len);
+  napi_create_reference(env, argv[1], 1, &j->input_ref);
+  int32_t orientation = 1, quality = 85;
+  if (argc > 2) napi_get_value_int32(env, argv[2], &orientation);
+  if (argc > 3) napi_get_value_int32(env, argv[3], &quality);
+  j->jpeg.data = static_cast<const uint8_t*>(data);
+  j->jpeg.size = len;
+  j->jpeg.exif_orientation = orientation;
+  j->quality = quality;
+  napi_value promise, name;
+  napi_create_promise(env, &j->deferred, &promise);
+  napi_create_string_utf8(env, "irp.transcodeFile", NAPI_AUTO_LENGTH, &name);
+  napi_create_async_work(env, nullptr, name, Execute, Complete, j, &j->work);
+  napi_queue_async_work(env, j->work);
+  return promise;
+}
+
 napi_value AnalyzeRaw(napi_env env, napi_callback_info info) { return Submit(env, info, false); }
 napi_value PreprocessRaw(napi_env env, napi_callback_info info) { return Submit(env, info, true); }
 
@@ -212,10 +281,11 @@ napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor props[] = {
       {"createContext", nullptr, CreateContext, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"analyzeFile", nullptr, AnalyzeFile, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"transcodeFile", nullptr, TranscodeFile, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"analyzeRaw", nullptr, AnalyzeRaw, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"preprocessRaw", nullptr, PreprocessRaw, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
-  napi_define_properties(env, exports, 4, props);
+  napi_define_properties(env, exports, 5, props);
   return exports;
 }
 
