@@ -499,57 +499,54 @@ struct IdctJob {                // one component of one image
   int qidx;                     // index into the quantisation-table array (64 x u16 each)
 };
 
-__global__ void __launch_bounds__(256)
+// One thread per 8x8 block: the block's 128 bytes are read as 8 x 16 bytes (the lanes of a warp read neighbouring
+// blocks, so the lines are shared through L1), dequantised, transformed in 64 registers (columns, then rows, as
+// jidctint does) and stored as 8 x 8 bytes — neighbouring lanes write neighbouring 8-byte row segments.  The job
+// search, the block address and the quantisation row loads are paid once per 64 samples.
+constexpr int kIdctThreads = 128;
+__global__ void __launch_bounds__(kIdctThreads)
 idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, const int16_t* __restrict__ coef_arena,
             const uint16_t* __restrict__ qtabs, uint8_t* __restrict__ plane_arena) {
-  __shared__ int ws[32][65];
-  const int lane8 = threadIdx.x & 7, bl = threadIdx.x >> 3;       // 32 blocks per CTA, 8 lanes per block
-  const int gb = blockIdx.x * 32 + bl;
-  const bool on = gb < total_blocks;
-  int ji = 0;
-  if (on) {   // binary search: a batch has three jobs per image
-    int hi = n_jobs - 1;
-    while (ji < hi) {
-      const int m = (ji + hi + 1) >> 1;
-      if (__ldg(&jobs[m].block_base) <= gb) ji = m; else hi = m - 1;
-    }
+  const int gb = blockIdx.x * kIdctThreads + threadIdx.x;
+  if (gb >= total_blocks) return;
+  int ji = 0, hi = n_jobs - 1;   // binary search: a batch has three jobs per image
+  while (ji < hi) {
+    const int m = (ji + hi + 1) >> 1;
+    if (__ldg(&jobs[m].block_base) <= gb) ji = m; else hi = m - 1;
   }
   const IdctJob J = jobs[ji];
   const int b = gb - J.block_base;
-  int v[8], o[8];
-  if (on) {
-    // a lane fetches ROW lane8 of the block with one 128-bit load (the 8 lanes of a block read its 128 bytes
-    // contiguously), dequantises it and parks it in shared memory; pass 1 then reads its column from there
-    const uint4 cw = __ldg(reinterpret_cast<const uint4*>(coef_arena + J.coef_off + (size_t)b * 64) + lane8);
-    const uint4 qw = __ldg(reinterpret_cast<const uint4*>(qtabs + J.qidx * 64) + lane8);
+  const uint4* src = reinterpret_cast<const uint4*>(coef_arena + J.coef_off + (size_t)b * 64);
+  const uint4* qsrc = reinterpret_cast<const uint4*>(qtabs + J.qidx * 64);
+  int d[64];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const uint4 cw = __ldg(src + r), qw = __ldg(qsrc + r);
     const uint32_t cc[4] = {cw.x, cw.y, cw.z, cw.w}, qq[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      ws[bl][lane8 * 8 + 2 * k] = (int)(int16_t)(cc[k] & 0xFFFFu) * (int)(qq[k] & 0xFFFFu);
-      ws[bl][lane8 * 8 + 2 * k + 1] = (int)(int16_t)(cc[k] >> 16) * (int)(qq[k] >> 16);
+      d[r * 8 + 2 * k] = (int)(int16_t)(cc[k] & 0xFFFFu) * (int)(qq[k] & 0xFFFFu);
+      d[r * 8 + 2 * k + 1] = (int)(int16_t)(cc[k] >> 16) * (int)(qq[k] >> 16);
     }
   }
-  __syncwarp();
-  if (on) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = ws[bl][r * 8 + lane8];
+  for (int c = 0; c < 8; c++) {
+    int v[8], o[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = d[r * 8 + c];
     idct_1d(v, o, 11);
-  }
-  __syncwarp();
-  if (on) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) ws[bl][r * 8 + lane8] = o[r];
+    for (int r = 0; r < 8; r++) d[r * 8 + c] = o[r];
   }
-  __syncwarp();
-  if (on) {
+  const int by = b / J.bw, bx = b - by * J.bw;
+  uint8_t* p = plane_arena + J.plane_off + ((size_t)(by * 8) * J.bw + bx) * 8;
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = ws[bl][lane8 * 8 + k];
-    idct_1d(v, o, 18);
-    const int by = b / J.bw, bx = b - by * J.bw;
-    uint8_t* p = plane_arena + J.plane_off + ((size_t)(by * 8 + lane8) * J.bw + bx) * 8;
+  for (int r = 0; r < 8; r++) {
+    int o[8];
+    idct_1d(d + r * 8, o, 18);
     const uint32_t lo = range_limit(o[0]) | (range_limit(o[1]) << 8) | (range_limit(o[2]) << 16) | (range_limit(o[3]) << 24);
-    const uint32_t hi = range_limit(o[4]) | (range_limit(o[5]) << 8) | (range_limit(o[6]) << 16) | (range_limit(o[7]) << 24);
-    *reinterpret_cast<uint2*>(p) = make_uint2(lo, hi);
+    const uint32_t hi2 = range_limit(o[4]) | (range_limit(o[5]) << 8) | (range_limit(o[6]) << 16) | (range_limit(o[7]) << 24);
+    *reinterpret_cast<uint2*>(p + (size_t)r * J.bw * 8) = make_uint2(lo, hi2);
   }
 }
 
