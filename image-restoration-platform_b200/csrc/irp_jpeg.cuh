@@ -49,6 +49,7 @@ struct JpegImg {                       // one image of a decode launch (device c
   int sub_base, nsub;                      // first subsequence (multiple of kHuffThreads), count
   unsigned long long coef_off[3];          // int16 offsets into the coefficient arena
   unsigned long long plane_off[3];         // byte offsets into the plane arena
+  unsigned long long dc_off[3];            // first entry of the component in the compact DC array (MCU order)
   unsigned long long out_off;              // byte offset of the RGB / grey output in the pixel arena
   unsigned long long out_pitch;
   int huff_base;                           // first of this image's 8 tables (DC 0..3, AC 0..3)
@@ -181,8 +182,8 @@ __device__ __forceinline__ int huff_extend(int x, int s) { return x < (1 << (s -
 template <bool WRITE, class Reader>
 __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, Reader& bw, unsigned long long stream_bit0,
                                          unsigned long long stream_bits, uint32_t& p, uint32_t p_end, uint32_t& slot, uint32_t& advanced,
-                                         int16_t* __restrict__ const* coef, uint32_t abs_blk, uint32_t blk_limit,
-                                         const uint8_t* __restrict__ zigzag) {
+                                         int16_t* __restrict__ const* coef, int16_t* __restrict__ dcv, uint32_t abs_blk,
+                                         uint32_t blk_limit, const uint8_t* __restrict__ zigzag) {
   const uint32_t period = 64u * (uint32_t)im.bpm;
   const uint32_t stop = (uint32_t)min((unsigned long long)p_end, stream_bits);
   if (p >= stop) return;
@@ -196,10 +197,13 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
     const HuffDev& dct = hs.t[im.dc_tab[comp]];
     const HuffDev& act = hs.t[4 + im.ac_tab[comp]];
     int16_t* blk_ptr = nullptr;
-    if (WRITE) {
+    int16_t* dc_ptr = nullptr;     // DC differences go to a compact array in MCU order: the prediction scan runs over
+    if (WRITE) {                   // contiguous values instead of one 2-byte access per 128-byte block
       const uint32_t mcu = abs_blk / (uint32_t)im.bpm;
       const uint32_t my = mcu / (uint32_t)im.mcux, mx = mcu - my * (uint32_t)im.mcux;
-      blk_ptr = coef[comp] + ((size_t)(my * im.comp_v[comp] + im.blk_by[k]) * im.comp_bw[comp] + (mx * im.comp_h[comp] + im.blk_bx[k])) * 64;
+      const int ch = im.comp_h[comp], cv = im.comp_v[comp];
+      blk_ptr = coef[comp] + ((size_t)(my * cv + im.blk_by[k]) * im.comp_bw[comp] + (mx * ch + im.blk_bx[k])) * 64;
+      dc_ptr = dcv + im.dc_off[comp] + (size_t)mcu * (ch * cv) + (im.blk_by[k] * ch + im.blk_bx[k]);
     }
     const uint32_t z_in = z;
     if (z == 0) {
@@ -207,7 +211,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
       const uint32_t b32 = bw.top32();
       int len;
       const int s = huff_decode(dct, b32 >> 16, len) & 15;
-      if (WRITE) blk_ptr[0] = (int16_t)(s ? huff_extend((int)((b32 << len) >> (32 - s)), s) : 0);
+      if (WRITE) *dc_ptr = (int16_t)(s ? huff_extend((int)((b32 << len) >> (32 - s)), s) : 0);
       bw.skip(len + s);
       p += len + s;
       z = 1;
@@ -312,7 +316,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
         start = vstate[sub - 1];
       uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
       BitWinG bw{data, st.bit_off, 0ull, 0, nullptr};
-      huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, 0u, 0u, nullptr);
+      huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, nullptr, 0u, 0u, nullptr);
       vin[sub] = start;
       vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
       advanced[sub] = adv;
@@ -364,7 +368,7 @@ __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32,
 __global__ void __launch_bounds__(kHuffThreads)
 huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_img, const JpegStream* __restrict__ streams,
                   const HuffDev* __restrict__ tabs, const uint32_t* __restrict__ data, const SubState* __restrict__ state,
-                  const unsigned long long* __restrict__ slot_start, int16_t* __restrict__ coef_arena) {
+                  const unsigned long long* __restrict__ slot_start, int16_t* __restrict__ coef_arena, int16_t* __restrict__ dcv) {
   __shared__ HuffSmem hs;
   __shared__ JpegImg im;
   __shared__ uint8_t zz[64];
@@ -390,7 +394,7 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
   const uint32_t base_blk = (uint32_t)st.first_mcu * (uint32_t)im.bpm;
   BitWin bw{staged + threadIdx.x * kSubWords, (uint32_t)local * kSubBits, 0ull, 0, 0};
   uint32_t adv = 0;
-  huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef,
+  huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef, dcv,
                  base_blk + (uint32_t)(slot_start[sub] >> 6), base_blk + (uint32_t)st.n_mcu * (uint32_t)im.bpm, zz);
 }
 
@@ -404,21 +408,16 @@ struct DcChunk {
   int group_first;       // index of the first chunk of the same (stream, component)
   int pad;
 };
-__device__ __forceinline__ size_t dc_addr(const JpegImg& im, const JpegStream& st, int c, int i) {
-  const int ch = im.comp_h[c], cv = im.comp_v[c], per = ch * cv;
-  const int m = st.first_mcu + i / per, j = i % per;
-  const int my = m / im.mcux, mx = m - my * im.mcux;
-  return ((size_t)(my * cv + j / ch) * im.comp_bw[c] + (mx * ch + j % ch)) * 64;
-}
 template <bool APPLY>
 __global__ void __launch_bounds__(kDcThreads)
 dc_chunk_kernel(const JpegImg* __restrict__ imgs, const JpegStream* __restrict__ streams, const DcChunk* __restrict__ chunks,
-                int* __restrict__ sums, int16_t* __restrict__ coef_arena) {
+                int* __restrict__ sums, int16_t* __restrict__ dcv) {
   __shared__ int warp_tot[kDcThreads / 32];
   const DcChunk ck = chunks[blockIdx.x];
   const JpegStream st = streams[ck.stream];
   const JpegImg& im = imgs[st.img];
-  int16_t* coef = coef_arena + im.coef_off[ck.comp];
+  // the blocks of (stream, component) in MCU order are contiguous in the compact DC array
+  int16_t* coef = dcv + im.dc_off[ck.comp] + (size_t)st.first_mcu * (im.comp_h[ck.comp] * im.comp_v[ck.comp]) + ck.first;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int v[8];
   size_t addr[8];
@@ -428,7 +427,7 @@ dc_chunk_kernel(const JpegImg* __restrict__ imgs, const JpegStream* __restrict__
     v[k] = 0;
     addr[k] = 0;
     if (i < ck.count) {
-      addr[k] = dc_addr(im, st, ck.comp, ck.first + i);
+      addr[k] = (size_t)i;
       v[k] = coef[addr[k]];
     }
   }
@@ -497,6 +496,8 @@ struct IdctJob {                // one component of one image
   int nblocks, bw;              // blocks, blocks per row
   int block_base;               // first global block index of this job
   int qidx;                     // index into the quantisation-table array (64 x u16 each)
+  unsigned long long dc_off;    // the component's first entry in the compact DC array
+  int ch, cv, mcux, pad;        // sampling factors and MCUs per row: block (by, bx) -> MCU-order DC index
 };
 
 // One thread per 8x8 block: the block's 128 bytes are read as 8 x 16 bytes (the lanes of a warp read neighbouring
@@ -506,7 +507,7 @@ struct IdctJob {                // one component of one image
 constexpr int kIdctThreads = 128;
 __global__ void __launch_bounds__(kIdctThreads)
 idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, const int16_t* __restrict__ coef_arena,
-            const uint16_t* __restrict__ qtabs, uint8_t* __restrict__ plane_arena) {
+            const uint16_t* __restrict__ qtabs, const int16_t* __restrict__ dcv, uint8_t* __restrict__ plane_arena) {
   const int gb = blockIdx.x * kIdctThreads + threadIdx.x;
   if (gb >= total_blocks) return;
   int ji = 0, hi = n_jobs - 1;   // binary search: a batch has three jobs per image
@@ -529,6 +530,13 @@ idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, cons
       d[r * 8 + 2 * k + 1] = (int)(int16_t)(cc[k] >> 16) * (int)(qq[k] >> 16);
     }
   }
+  const int by = b / J.bw, bx = b - by * J.bw;
+  uint8_t* p = plane_arena + J.plane_off + ((size_t)(by * 8) * J.bw + bx) * 8;
+  {   // the predicted DC value comes from the compact array (the arena's slot 0 is never written)
+    const int my = by / J.cv, mx = bx / J.ch;
+    const size_t di = (size_t)J.dc_off + ((size_t)my * J.mcux + mx) * (J.ch * J.cv) + ((by - my * J.cv) * J.ch + (bx - mx * J.ch));
+    d[0] = (int)__ldg(dcv + di) * (int)(__ldg(qtabs + J.qidx * 64));
+  }
 #pragma unroll
   for (int c = 0; c < 8; c++) {
     int v[8], o[8];
@@ -538,8 +546,6 @@ idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, cons
 #pragma unroll
     for (int r = 0; r < 8; r++) d[r * 8 + c] = o[r];
   }
-  const int by = b / J.bw, bx = b - by * J.bw;
-  uint8_t* p = plane_arena + J.plane_off + ((size_t)(by * 8) * J.bw + bx) * 8;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     int o[8];
