@@ -590,46 +590,31 @@ __device__ __forceinline__ bool is_plain_420(const JpegImg& im) {
          im.comp_v[2] == 1 && im.w >= 16;
 }
 
-// 4:2:0: eight output pixels of one row per thread.  Replicating the first / last chroma column turns
-// libjpeg's special first- and last-column formulas into the general one ((4c + 8) >> 4 == (3c + c + 8) >> 4).
-__global__ void __launch_bounds__(256)
-colour420_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __restrict__ plane_arena, uint8_t* __restrict__ pix_arena) {
-  const JpegImg& im = imgs[blockIdx.z];
-  if (!is_plain_420(im)) return;
-  const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 8, y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x0 >= im.w || y >= im.h) return;
-  const uint2 yw = *reinterpret_cast<const uint2*>(plane_arena + im.plane_off[0] + (size_t)y * (im.comp_bw[0] * 8) + x0);
-  const int r = y >> 1, i0 = x0 >> 1;
-  int up[2][8];
+// 4:2:0: a 8 x 2 patch of output pixels per thread — the two rows share their near chroma row, so each chroma
+// plane is read as three rows of (one aligned word + two edge bytes).  Replicating the first / last chroma column
+// turns libjpeg's special first- and last-column formulas into the general one ((4c + 8) >> 4 == (3c + c + 8) >> 4).
+__device__ __forceinline__ void chroma6(const uint8_t* __restrict__ row, int i0, int dw, int v[6]) {
+  if (i0 >= 1 && i0 + 4 <= dw - 1) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(row + i0);   // i0 is a multiple of 4, rows are 8-byte multiples
+    v[0] = row[i0 - 1];
+    v[1] = (int)(w & 255u); v[2] = (int)((w >> 8) & 255u); v[3] = (int)((w >> 16) & 255u); v[4] = (int)(w >> 24);
+    v[5] = row[i0 + 4];
+  } else {
 #pragma unroll
-  for (int c = 0; c < 2; c++) {
-    const int dw = im.comp_dw[c + 1], dh = im.comp_dh[c + 1], pw = im.comp_bw[c + 1] * 8;
-    const int rn = (y & 1) ? min(r + 1, dh - 1) : max(r - 1, 0);
-    const uint8_t* in0 = plane_arena + im.plane_off[c + 1] + (size_t)r * pw;
-    const uint8_t* in1 = plane_arena + im.plane_off[c + 1] + (size_t)rn * pw;
-    int cs[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      const int i = min(max(i0 - 1 + k, 0), dw - 1);
-      cs[k] = in0[i] * 3 + in1[i];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      up[c][2 * j] = (cs[j + 1] * 3 + cs[j] + 8) >> 4;
-      up[c][2 * j + 1] = (cs[j + 1] * 3 + cs[j + 2] + 7) >> 4;
-    }
+    for (int k = 0; k < 6; k++) v[k] = row[min(max(i0 - 1 + k, 0), dw - 1)];
   }
+}
+__device__ __forceinline__ void ycc_row_store(const JpegImg& im, uint2 yw, const int (&ub)[8], const int (&ur)[8], uint8_t* __restrict__ out, int x0) {
   uint32_t px[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int Y = (int)(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xFF);
-    const int xb = up[0][k] - 128, xr = up[1][k] - 128;
+    const int xb = ub[k] - 128, xr = ur[k] - 128;
     const int rr = Y + ((91881 * xr + 32768) >> 16);
     const int g = Y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);
     const int b = Y + ((116130 * xb + 32768) >> 16);
-    px[k] = (uint32_t)min(max(rr, 0), 255) | ((uint32_t)min(max(g, 0), 255) << 8) | ((uint32_t)min(max(b, 0), 255) << 16);
+    px[k] = (uint32_t)__vimin_s32_relu(rr, 255) | ((uint32_t)__vimin_s32_relu(g, 255) << 8) | ((uint32_t)__vimin_s32_relu(b, 255) << 16);
   }
-  uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch + 3 * (size_t)x0;
   if (x0 + 8 <= im.w) {   // 24 bytes, 8-byte aligned
     uint2* o = reinterpret_cast<uint2*>(out);
     o[0] = make_uint2(px[0] | (px[1] << 24), (px[1] >> 8) | (px[2] << 16));
@@ -642,6 +627,40 @@ colour420_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __
       out[3 * k + 2] = (uint8_t)(px[k] >> 16);
     }
   }
+}
+__global__ void __launch_bounds__(256)
+colour420_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __restrict__ plane_arena, uint8_t* __restrict__ pix_arena) {
+  const JpegImg& im = imgs[blockIdx.z];
+  if (!is_plain_420(im)) return;
+  const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 8, r = blockIdx.y * 4 + (threadIdx.x >> 6), y = 2 * r;
+  if (x0 >= im.w || y >= im.h) return;
+  const int i0 = x0 >> 1;
+  int up[2][2][8];   // [row of the pair][Cb / Cr][pixel]
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const int dw = im.comp_dw[c + 1], dh = im.comp_dh[c + 1], pw = im.comp_bw[c + 1] * 8;
+    const uint8_t* base = plane_arena + im.plane_off[c + 1];
+    int near_[6], above[6], below[6];
+    chroma6(base + (size_t)r * pw, i0, dw, near_);
+    chroma6(base + (size_t)max(r - 1, 0) * pw, i0, dw, above);
+    chroma6(base + (size_t)min(r + 1, dh - 1) * pw, i0, dw, below);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      int cs[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cs[k] = near_[k] * 3 + (h ? below[k] : above[k]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        up[h][c][2 * j] = (cs[j + 1] * 3 + cs[j] + 8) >> 4;
+        up[h][c][2 * j + 1] = (cs[j + 1] * 3 + cs[j + 2] + 7) >> 4;
+      }
+    }
+  }
+  const size_t ypitch = (size_t)im.comp_bw[0] * 8;
+  const uint8_t* yp = plane_arena + im.plane_off[0] + (size_t)y * ypitch + x0;
+  uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch + 3 * (size_t)x0;
+  ycc_row_store(im, *reinterpret_cast<const uint2*>(yp), up[0][0], up[0][1], out, x0);
+  if (y + 1 < im.h) ycc_row_store(im, *reinterpret_cast<const uint2*>(yp + ypitch), up[1][0], up[1][1], out + im.out_pitch, x0);
 }
 
 // four output pixels per thread: one word of Y, twelve bytes of RGB
