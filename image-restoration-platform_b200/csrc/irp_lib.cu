@@ -1372,9 +1372,9 @@ int irp_decode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_o
 
 // Cut [0, n) into the context's lanes and run f(lane context, begin, count) on each from its own host thread
 // (lane 0 is the context itself, on the calling thread).  At least 8 files per lane; IRP_LANES overrides the
-// default of 4 (1 = off).  The first failing lane's status and message are returned.
+// default of 8 (1 = off).  The first failing lane's status and message are returned.
 static int run_in_lanes(irp_ctx* ctx, int n, const std::function<int(irp_ctx*, int, int)>& f) {
-  static const int env_lanes = getenv("IRP_LANES") ? atoi(getenv("IRP_LANES")) : 4;
+  static const int env_lanes = getenv("IRP_LANES") ? atoi(getenv("IRP_LANES")) : 8;
   const int want = ctx->is_lane ? 1 : std::max(1, std::min(env_lanes, n / 8));
   if (want == 1) return f(ctx, 0, n);
   {
