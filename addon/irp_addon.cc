@@ -53,11 +53,16 @@ void Execute(napi_env, void* data) {
       std::free(j->enc.data);
       j->enc.data = static_cast<uint8_t*>(std::malloc(j->enc.capacity));
       if (!j->enc.data) { j->rc = IRP_ERR_NOMEM; break; }
-      j->rc = irp_transcode_jpeg_batch(j->ctx, &j->jpeg, 1, &j->result, j->quality, &j->enc);
+      // queued like every other request: the dispatcher batches the uploads of concurrent HTTP requests
+      irp_ticket ticket = nullptr;
+      char err[256] = {0};
+      j->rc = irp_submit_transcode(j->ctx, &j->jpeg, &j->result, j->quality, &j->enc, &ticket);
+      if (j->rc == IRP_OK) j->rc = irp_wait(j->ctx, ticket, err, sizeof err);
+      if (j->rc != IRP_OK) j->error = err[0] ? err : "irp request failed";
       if (j->rc != IRP_ERR_CAPACITY) break;
       if (attempt == 0) j->rc = IRP_OK;
     }
-    if (j->rc != IRP_OK) j->error = j->rc == IRP_ERR_UNSUPPORTED ? "unsupported" : irp_last_error(j->ctx);
+    if (j->rc == IRP_ERR_UNSUPPORTED) j->error = "unsupported";
     return;
   }
   if (j->preprocess) {

@@ -22,7 +22,7 @@ SYMBOLS = (
     "irp_abi_version", "irp_device_count", "irp_create", "irp_destroy", "irp_last_error", "irp_set_stream",
     "irp_get_timing", "irp_preprocess_dims", "irp_fusion_dims", "irp_scores_from_moments", "irp_grey_tables",
     "irp_classify_batch", "irp_preprocess_batch", "irp_analyze_batch", "irp_fusion_prepare_batch",
-    "irp_submit", "irp_submit_jpeg", "irp_wait", "irp_jpeg_info", "irp_decode_jpeg_batch", "irp_analyze_jpeg_batch",
+    "irp_submit", "irp_submit_jpeg", "irp_submit_transcode", "irp_wait", "irp_jpeg_info", "irp_decode_jpeg_batch", "irp_analyze_jpeg_batch",
     "irp_encode_jpeg_batch", "irp_analyze_encode_batch", "irp_transcode_jpeg_batch",
     "irp_dev_alloc", "irp_dev_free", "irp_host_alloc_pinned", "irp_host_free_pinned", "irp_memcpy_h2d",
     "irp_memcpy_d2h", "irp_synchronize",
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     lib.irp_transcode_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(Result), i32, C.POINTER(JpegOut)]
     lib.irp_submit.argtypes = [vp, C.POINTER(ImageDesc), C.POINTER(Result), C.POINTER(OutDesc), C.POINTER(vp)]
     lib.irp_submit_jpeg.argtypes = [vp, C.POINTER(JpegDesc), C.POINTER(Result), C.POINTER(OutDesc), C.POINTER(vp)]
+    lib.irp_submit_transcode.argtypes = [vp, C.POINTER(JpegDesc), C.POINTER(Result), i32, C.POINTER(JpegOut), C.POINTER(vp)]
     lib.irp_wait.argtypes = [vp, vp, C.c_char_p, C.c_size_t]
     lib.irp_dev_alloc.restype = vp
     lib.irp_dev_alloc.argtypes = [vp, C.c_size_t]

@@ -98,6 +98,8 @@ struct PlanDev {
 struct irp_request {
   irp_image_desc img;
   irp_jpeg_desc jpeg;      // used instead of img when is_jpeg_file
+  irp_jpeg_out* enc = nullptr;   // file in -> scores + preprocessed FILE out (irp_submit_transcode)
+  int quality = 85;
   bool is_jpeg_file = false;
   irp_result* result;
   irp_out_desc* out;
@@ -1395,6 +1397,8 @@ static int run_in_lanes(irp_ctx* ctx, int n, const std::function<int(irp_ctx*, i
   for (int k = 1; k < want; k++) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->timing.kernel_launches += ctx->lanes[k - 1]->timing.kernel_launches;
+    ctx->timing.classify_ms += ctx->lanes[k - 1]->timing.classify_ms;       // sums over lanes (they overlap in time)
+    ctx->timing.preprocess_ms += ctx->lanes[k - 1]->timing.preprocess_ms;
     if (rc[k] != IRP_OK && rc[0] == IRP_OK) {
       rc[0] = rc[k];
       ctx->err = ctx->lanes[k - 1]->err;
@@ -1535,7 +1539,40 @@ static int transcode_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp
 }
 
 // ---- concurrent single-image requests ----
-static void run_requests(irp_ctx* ctx, std::vector<irp_request*>& reqs) {
+static void run_transcode_requests(irp_ctx* ctx, std::vector<irp_request*>& sel) {
+  // one batched submission per quality present; a failing batch is retried request by request
+  while (!sel.empty()) {
+    const int quality = sel[0]->quality;
+    std::vector<irp_request*> grp, rest;
+    for (irp_request* r : sel) (r->quality == quality ? grp : rest).push_back(r);
+    sel.swap(rest);
+    const int n = (int)grp.size();
+    std::vector<irp_jpeg_desc> jd(n);
+    std::vector<irp_result> results(n);
+    std::vector<irp_jpeg_out> outs(n);
+    for (int i = 0; i < n; i++) {
+      jd[i] = grp[i]->jpeg;
+      outs[i] = *grp[i]->enc;
+    }
+    int rc = irp_transcode_jpeg_batch(ctx, jd.data(), n, results.data(), quality, outs.data());
+    for (int i = 0; i < n; i++) {
+      if (rc != IRP_OK && n > 1) {
+        outs[i] = *grp[i]->enc;
+        grp[i]->status = irp_transcode_jpeg_batch(ctx, &jd[i], 1, &results[i], quality, &outs[i]);
+      } else {
+        grp[i]->status = rc;
+      }
+      if (grp[i]->status != IRP_OK) grp[i]->err = ctx->err;
+      if (grp[i]->status == IRP_OK || grp[i]->status == IRP_ERR_CAPACITY) *grp[i]->enc = outs[i];   // size needed on a capacity error
+      if (grp[i]->status == IRP_OK && grp[i]->result) *grp[i]->result = results[i];
+    }
+  }
+}
+
+static void run_requests(irp_ctx* ctx, std::vector<irp_request*>& all) {
+  std::vector<irp_request*> reqs, trans;
+  for (irp_request* r : all) (r->enc ? trans : reqs).push_back(r);
+  run_transcode_requests(ctx, trans);
   // raw-pixel and JPEG-file requests, each as classify+preprocess / classify / preprocess: every kind present
   // in the queue is one batched submission
   for (int kind = 0; kind < 6; kind++) {
@@ -1636,6 +1673,31 @@ int irp_submit_jpeg(irp_ctx* ctx, const irp_jpeg_desc* jpeg, irp_result* result,
   r->is_jpeg_file = true;
   r->result = result;
   r->out = out;
+  {
+    std::lock_guard<std::mutex> lk(ctx->qmu);
+    if (ctx->stop) {
+      delete r;
+      return IRP_ERR_BAD_ARG;
+    }
+    if (!ctx->dispatcher_started) {
+      ctx->dispatcher = std::thread(dispatcher_main, ctx);
+      ctx->dispatcher_started = true;
+    }
+    ctx->queue.push_back(r);
+  }
+  ctx->qcv.notify_all();
+  *ticket = r;
+  return IRP_OK;
+}
+
+int irp_submit_transcode(irp_ctx* ctx, const irp_jpeg_desc* jpeg, irp_result* result, int quality, irp_jpeg_out* out, irp_ticket* ticket) {
+  if (!ctx || !jpeg || !jpeg->data || !ticket || !out || !out->data) return IRP_ERR_BAD_ARG;
+  irp_request* r = new irp_request();
+  r->jpeg = *jpeg;
+  r->is_jpeg_file = true;
+  r->result = result;
+  r->enc = out;
+  r->quality = quality;
   {
     std::lock_guard<std::mutex> lk(ctx->qmu);
     if (ctx->stop) {

@@ -387,6 +387,23 @@ class Engine:
             raise IrpError(rc, "irp_submit_jpeg rejected the request")
         return {"ticket": ticket, "descs": desc, "keep": k, "outs": outs, "array": arr, "res": res}
 
+    def submit_transcode(self, blob: bytes, orientation: int = 1, quality: int = 85, classify: bool = True):
+        """Queue ONE baseline JPEG FILE for analyze() + preprocessImage(): wait() returns (scores, preprocessed FILE bytes)."""
+        k = np.frombuffer(blob, np.uint8)
+        info = self.jpeg_info(k)
+        if info is None:
+            raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, "not a baseline JPEG the device decoder takes")
+        desc = _ffi.JpegDesc(k.ctypes.data, k.size, orientation, 0)
+        ow, oh = self.preprocess_dims(info[0], info[1], orientation)
+        buf = np.empty(ow * oh * (1 if info[2] == 1 else 3) + 4096, np.uint8)   # a file never exceeds its pixels by more than the header at q <= 95
+        enc = _ffi.JpegOut(buf.ctypes.data, buf.size, 0, 0, 0, 0, 0)
+        res = _ffi.Result() if classify else None
+        ticket = C.c_void_p()
+        rc = self._lib.irp_submit_transcode(self._ctx, C.byref(desc), C.byref(res) if classify else None, quality, C.byref(enc), C.byref(ticket))
+        if rc:
+            raise IrpError(rc, "irp_submit_transcode rejected the request")
+        return {"ticket": ticket, "descs": desc, "keep": k, "outs": None, "array": None, "res": res, "enc": enc, "file": buf}
+
     def wait(self, handle, raw: bool = False):
         """Block until the request is done; returns (result dict or None, output array or None)."""
         err = C.create_string_buffer(512)
@@ -394,6 +411,8 @@ class Engine:
         if rc:
             raise IrpError(rc, err.value.decode(errors="replace"))
         res = handle["res"]
+        if handle.get("enc") is not None:
+            return (None if res is None else (res if raw else result_to_dict(res))), bytes(memoryview(handle["file"])[:handle["enc"].size])
         out = handle["array"]
         if out is not None:
             o = handle["outs"][0]

@@ -224,6 +224,10 @@ int irp_submit(irp_ctx *ctx, const irp_image_desc *img, irp_result *result, irp_
  * hands over, decoded on the device with the rest of its batch */
 int irp_submit_jpeg(irp_ctx *ctx, const irp_jpeg_desc *jpeg, irp_result *result, irp_out_desc *out,
                     irp_ticket *ticket);
+/* the same with the preprocessed FILE as output (irp_transcode_jpeg_batch for one upload): analyze(buf) and
+ * preprocessImage(buf) of one request; `result` may be NULL; on IRP_ERR_CAPACITY out->size is the size needed */
+int irp_submit_transcode(irp_ctx *ctx, const irp_jpeg_desc *jpeg, irp_result *result, int quality,
+                         irp_jpeg_out *out, irp_ticket *ticket);
 int irp_wait(irp_ctx *ctx, irp_ticket ticket, char *err, size_t err_capacity);
 
 /* ---- memory helpers (so non-CUDA hosts can stage device-resident data) -- */

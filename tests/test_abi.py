@@ -152,3 +152,22 @@ def test_jpeg_header_parse_runs_without_a_gpu():
     assert info(enc(rgb, quality=80, progressive=True))[0] == _ffi.IRP_ERR_UNSUPPORTED
     assert info(b"\x89PNG\r\n\x1a\n" + b"\0" * 64)[0] == _ffi.IRP_ERR_UNSUPPORTED
     assert info(enc(rgb, quality=80)[:40])[0] == _ffi.IRP_ERR_UNSUPPORTED   # truncated inside the header
+
+
+def test_committed_jpeg_tables_are_what_libjpeg_turbo_writes(tmp_path):
+    """csrc/jpeg_std_tables.inc (the encoder's Annex K quantisation / Huffman tables) is generated from files
+    written by libjpeg-turbo; regenerating it must reproduce the committed file byte for byte."""
+    pytest.importorskip("PIL")
+    import shutil
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "image-restoration-platform_b200", "csrc", "jpeg_std_tables.inc")
+    committed = open(inc).read()
+    work = tmp_path / "repo"
+    (work / "tools").mkdir(parents=True)
+    (work / "image-restoration-platform_b200" / "csrc").mkdir(parents=True)
+    shutil.copy(os.path.join(root, "tools", "gen_jpeg_std_tables.py"), work / "tools" / "gen_jpeg_std_tables.py")
+    subprocess.run([sys.executable, str(work / "tools" / "gen_jpeg_std_tables.py")], check=True, capture_output=True)
+    assert open(work / "image-restoration-platform_b200" / "csrc" / "jpeg_std_tables.inc").read() == committed

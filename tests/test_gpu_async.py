@@ -135,3 +135,56 @@ def test_concurrent_jpeg_file_requests(engine, oracle):
 
     with pytest.raises(irp_b200.IrpError):
         engine.submit_jpeg(enc(rand_image(64, 64, 3, seed=1), quality=80, progressive=True))
+
+
+def test_concurrent_transcode_requests(engine, oracle):
+    """One upload per request, files on both sides (analyze + preprocessImage of the reference's upload route):
+    requests from several threads, two qualities in the queue, every returned file byte-identical to
+    libjpeg-turbo's encoding of the oracle's preprocessed pixels, scores equal to the oracle's; a request whose
+    buffer is too small fails alone with the size it needs."""
+    import ctypes as C
+    import io
+
+    from PIL import Image
+    from irp_b200 import _ffi
+
+    def enc(img, **kw):
+        b = io.BytesIO()
+        Image.fromarray(img).save(b, "JPEG", **kw)
+        return b.getvalue()
+
+    blobs = [enc(rand_image(2100 + 50 * i, 2500 - 40 * i, 3, seed=60 + i, kind="smooth"), quality=88, subsampling=[2, 1, 0][i % 3]) for i in range(6)]
+    blobs += [enc(rand_image(300 + 11 * i, 500 + 7 * i, 3, seed=80 + i, kind="edges"), quality=75, subsampling=2) for i in range(6)]
+    errors, lock = [], threading.Lock()
+
+    def client(t):
+        hs = [(b, 85 if (t + j) % 2 else 70, engine.submit_transcode(b, quality=85 if (t + j) % 2 else 70)) for j, b in enumerate(blobs[t::3])]
+        for j, (b, q, hd) in enumerate(hs):
+            try:
+                res, file = engine.wait(hd)
+                px = np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(b))))
+                assert_result_parity(res, oracle.classify(px), 3, f"thread {t} file {j}")
+                assert file == enc(oracle.preprocess(px, 1), quality=q, subsampling=0), f"thread {t} file {j} quality {q}"
+            except Exception as e:
+                with lock:
+                    errors.append(repr(e))
+
+    ts = [threading.Thread(target=client, args=(t,)) for t in range(3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+    # a too-small buffer: that request alone reports IRP_ERR_CAPACITY and the size it needs
+    k = np.frombuffer(blobs[0], np.uint8)
+    desc = _ffi.JpegDesc(k.ctypes.data, k.size, 1, 0)
+    small = np.empty(1000, np.uint8)
+    out = _ffi.JpegOut(small.ctypes.data, small.size, 0, 0, 0, 0, 0)
+    ticket = C.c_void_p()
+    good = engine.submit_transcode(blobs[1])
+    assert engine._lib.irp_submit_transcode(engine._ctx, C.byref(desc), None, 85, C.byref(out), C.byref(ticket)) == 0
+    err = C.create_string_buffer(256)
+    assert engine._lib.irp_wait(engine._ctx, ticket, err, len(err)) == _ffi.IRP_ERR_CAPACITY
+    assert out.size > 1000
+    res, file = engine.wait(good)
+    assert file[:2] == b"\xff\xd8" and file[-2:] == b"\xff\xd9"
