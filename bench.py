@@ -451,7 +451,7 @@ def main() -> int:
         t0 = time.perf_counter()
         oracle.analyze_batch(imgs[:sample], threads=T, with_preprocess=True)
         dt = time.perf_counter() - t0
-        jpeg_cpu = None
+        jpeg_cpu = jpeg_enc_cpu = None
         try:  # what the host would spend BEFORE any of this if it had to decode the files itself (libjpeg-turbo via Pillow)
             import io
             from concurrent.futures import ThreadPoolExecutor
@@ -464,9 +464,21 @@ def main() -> int:
                 tj0 = time.perf_counter()
                 list(ex.map(lambda _: np.asarray(Image.open(io.BytesIO(blob))).shape, range(2 * T)))
                 jpeg_cpu = 2 * T * W * H / 1e6 / (time.perf_counter() - tj0)
+                # ... and AFTER it, to turn the resized image into the file preprocessImage returns (per OUTPUT pixel)
+                small = np.ascontiguousarray(imgs[0][:oh, :ow])
+
+                def enc_one(_):
+                    b = io.BytesIO()
+                    Image.fromarray(small).save(b, "JPEG", quality=85, subsampling=0)
+                    return b.tell()
+
+                te0 = time.perf_counter()
+                list(ex.map(enc_one, range(2 * T)))
+                jpeg_enc_cpu = 2 * T * ow * oh / 1e6 / (time.perf_counter() - te0)
         except Exception:
             pass
         cpu = {"value": sample * W * H / 1e6 / dt, "unit": UNIT, "cores": T, "kind": "port", "host_jpeg_decode_mpix_s": jpeg_cpu,
+               "host_jpeg_encode_out_mpix_s": jpeg_enc_cpu,
                "sample": f"{sample} of the {B} images, {T} threads, one image per thread, {dt:.1f} s wall",
                "note": "oracle port of the reference arithmetic; the real sharp path adds 6 decodes and ~16 N JS closure visits per image"}
 

@@ -1492,8 +1492,12 @@ static int preprocess_encode_locked(irp_ctx* ctx, const irp_image_desc* descs, i
     src[i].px = od[i].pixels;
     off += round_up(od[i].capacity, 256);
   }
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = run_batch_locked(ctx, descs, n, results, od.data(), 0);
   if (rc) return rc;
+  if (getenv("IRP_TRACE"))
+    fprintf(stderr, "transcode: classify + preprocess returned after %.2f ms (includes waiting for the decode kernels)\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   for (int i = 0; i < n; i++)
     if (od[i].width != src[i].w || od[i].height != src[i].h || od[i].channels != src[i].c)
       return fail(ctx, IRP_ERR_UNSUPPORTED, "image %d: preprocess wrote %dx%dx%d, expected %dx%dx%d", i, od[i].width, od[i].height, od[i].channels, src[i].w,
@@ -1526,15 +1530,20 @@ static int transcode_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp
   ctx->err.clear();
   if (!n) return IRP_OK;
   ctx->timing = irp_timing{};
+  const bool trace = getenv("IRP_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   std::vector<JpegPlaced> pl;
   int rc = decode_jpegs_locked(ctx, jpegs, n, &pl);
   if (rc) return rc;
+  const double t_dec = since();
   const uint32_t decode_launches = ctx->timing.kernel_launches;
   std::vector<irp_image_desc> descs(n);
   for (int i = 0; i < n; i++)
     descs[i] = irp_image_desc{pl[i].px, pl[i].pitch, pl[i].w, pl[i].h, pl[i].c, 1, jpegs[i].exif_orientation, 1};
   rc = preprocess_encode_locked(ctx, descs.data(), n, results, quality, outs);
   ctx->timing.kernel_launches += decode_launches;
+  if (trace) fprintf(stderr, "transcode: %d files, host wall: decode enqueued at %.2f ms, call done at %.2f ms\n", n, t_dec, since());
   return rc;
 }
 

@@ -70,3 +70,25 @@ with irp_b200.Engine(0) as eng:
             dt = time.perf_counter() - t0
         n = nthreads * PER
         print(f"{nthreads:3d} clients JPEG files: {n / dt:7.1f} images/s  {n * W * H / dt / 1e9:6.2f} GPix/s")
+    # files on both sides: one upload per request, scores + the preprocessed FILE back (irp_submit_transcode)
+    for nthreads in (1, 16, 64):
+        slots = []
+        for t in range(nthreads):
+            o = eng.pinned_empty((oh, ow, 3))
+            k = blobs[t % 4]
+            jd = _ffi.JpegDesc(k.ctypes.data, k.size, 1, 0)
+            slots.append((o, jd, _ffi.JpegOut(o.ctypes.data, o.nbytes, 0, 0, 0, 0, 0), _ffi.Result()))
+        def tclient(t):
+            o, jd, enc, res = slots[t]
+            for _ in range(PER):
+                tk = C.c_void_p()
+                rc = lib.irp_submit_transcode(ctx, C.byref(jd), C.byref(res), 85, C.byref(enc), C.byref(tk)) or lib.irp_wait(ctx, tk, None, 0)
+                assert rc == 0, rc
+        for warm in (True, False):
+            ts = [threading.Thread(target=tclient, args=(t,)) for t in range(nthreads)]
+            t0 = time.perf_counter()
+            for th in ts: th.start()
+            for th in ts: th.join()
+            dt = time.perf_counter() - t0
+        n = nthreads * PER
+        print(f"{nthreads:3d} clients files in / files out: {n / dt:7.1f} images/s  {n * W * H / dt / 1e9:6.2f} GPix/s  ({slots[0][2].size / 1e6:.2f} MB per returned file)")
