@@ -604,7 +604,8 @@ __device__ __forceinline__ void chroma6(const uint8_t* __restrict__ row, int i0,
     for (int k = 0; k < 6; k++) v[k] = row[min(max(i0 - 1 + k, 0), dw - 1)];
   }
 }
-__device__ __forceinline__ void ycc_row_store(const JpegImg& im, uint2 yw, const int (&ub)[8], const int (&ur)[8], uint8_t* __restrict__ out, int x0) {
+// YCbCr -> RGB of 8 pixels into 24 bytes of a shared-memory row (the CTA's rows go out as whole 16-byte stores)
+__device__ __forceinline__ void ycc_row_stage(uint2 yw, const int (&ub)[8], const int (&ur)[8], uint2* __restrict__ o) {
   uint32_t px[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -615,52 +616,59 @@ __device__ __forceinline__ void ycc_row_store(const JpegImg& im, uint2 yw, const
     const int b = Y + ((116130 * xb + 32768) >> 16);
     px[k] = (uint32_t)__vimin_s32_relu(rr, 255) | ((uint32_t)__vimin_s32_relu(g, 255) << 8) | ((uint32_t)__vimin_s32_relu(b, 255) << 16);
   }
-  if (x0 + 8 <= im.w) {   // 24 bytes, 8-byte aligned
-    uint2* o = reinterpret_cast<uint2*>(out);
-    o[0] = make_uint2(px[0] | (px[1] << 24), (px[1] >> 8) | (px[2] << 16));
-    o[1] = make_uint2((px[2] >> 16) | (px[3] << 8), px[4] | (px[5] << 24));
-    o[2] = make_uint2((px[5] >> 8) | (px[6] << 16), (px[6] >> 16) | (px[7] << 8));
-  } else {
-    for (int k = 0; k < im.w - x0; k++) {
-      out[3 * k] = (uint8_t)px[k];
-      out[3 * k + 1] = (uint8_t)(px[k] >> 8);
-      out[3 * k + 2] = (uint8_t)(px[k] >> 16);
-    }
-  }
+  o[0] = make_uint2(px[0] | (px[1] << 24), (px[1] >> 8) | (px[2] << 16));
+  o[1] = make_uint2((px[2] >> 16) | (px[3] << 8), px[4] | (px[5] << 24));
+  o[2] = make_uint2((px[5] >> 8) | (px[6] << 16), (px[6] >> 16) | (px[7] << 8));
 }
+constexpr int kC420RowBytes = 64 * 24;   // one CTA row: 64 threads x 8 pixels x 3 bytes
 __global__ void __launch_bounds__(256)
 colour420_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __restrict__ plane_arena, uint8_t* __restrict__ pix_arena) {
+  __shared__ __align__(16) uint8_t stage[8][kC420RowBytes];
   const JpegImg& im = imgs[blockIdx.z];
   if (!is_plain_420(im)) return;
-  const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 8, r = blockIdx.y * 4 + (threadIdx.x >> 6), y = 2 * r;
-  if (x0 >= im.w || y >= im.h) return;
-  const int i0 = x0 >> 1;
-  int up[2][2][8];   // [row of the pair][Cb / Cr][pixel]
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int xc = blockIdx.x * 512, x0 = xc + tx * 8, r = blockIdx.y * 4 + ty, y = 2 * r;
+  if (xc >= im.w || blockIdx.y * 8 >= im.h) return;   // uniform per CTA
+  if (x0 < im.w && y < im.h) {
+    const int i0 = x0 >> 1;
+    int up[2][2][8];   // [row of the pair][Cb / Cr][pixel]
 #pragma unroll
-  for (int c = 0; c < 2; c++) {
-    const int dw = im.comp_dw[c + 1], dh = im.comp_dh[c + 1], pw = im.comp_bw[c + 1] * 8;
-    const uint8_t* base = plane_arena + im.plane_off[c + 1];
-    int near_[6], above[6], below[6];
-    chroma6(base + (size_t)r * pw, i0, dw, near_);
-    chroma6(base + (size_t)max(r - 1, 0) * pw, i0, dw, above);
-    chroma6(base + (size_t)min(r + 1, dh - 1) * pw, i0, dw, below);
+    for (int c = 0; c < 2; c++) {
+      const int dw = im.comp_dw[c + 1], dh = im.comp_dh[c + 1], pw = im.comp_bw[c + 1] * 8;
+      const uint8_t* base = plane_arena + im.plane_off[c + 1];
+      int near_[6], above[6], below[6];
+      chroma6(base + (size_t)r * pw, i0, dw, near_);
+      chroma6(base + (size_t)max(r - 1, 0) * pw, i0, dw, above);
+      chroma6(base + (size_t)min(r + 1, dh - 1) * pw, i0, dw, below);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      int cs[6];
+      for (int h = 0; h < 2; h++) {
+        int cs[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) cs[k] = near_[k] * 3 + (h ? below[k] : above[k]);
+        for (int k = 0; k < 6; k++) cs[k] = near_[k] * 3 + (h ? below[k] : above[k]);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        up[h][c][2 * j] = (cs[j + 1] * 3 + cs[j] + 8) >> 4;
-        up[h][c][2 * j + 1] = (cs[j + 1] * 3 + cs[j + 2] + 7) >> 4;
+        for (int j = 0; j < 4; j++) {
+          up[h][c][2 * j] = (cs[j + 1] * 3 + cs[j] + 8) >> 4;
+          up[h][c][2 * j + 1] = (cs[j + 1] * 3 + cs[j + 2] + 7) >> 4;
+        }
       }
     }
+    const size_t ypitch = (size_t)im.comp_bw[0] * 8;
+    const uint8_t* yp = plane_arena + im.plane_off[0] + (size_t)y * ypitch + x0;   // the Y plane is padded to whole blocks
+    ycc_row_stage(*reinterpret_cast<const uint2*>(yp), up[0][0], up[0][1], reinterpret_cast<uint2*>(&stage[2 * ty][tx * 24]));
+    ycc_row_stage(*reinterpret_cast<const uint2*>(yp + ((y + 1 < im.h) ? ypitch : 0)), up[1][0], up[1][1],
+                  reinterpret_cast<uint2*>(&stage[2 * ty + 1][tx * 24]));
   }
-  const size_t ypitch = (size_t)im.comp_bw[0] * 8;
-  const uint8_t* yp = plane_arena + im.plane_off[0] + (size_t)y * ypitch + x0;
-  uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch + 3 * (size_t)x0;
-  ycc_row_store(im, *reinterpret_cast<const uint2*>(yp), up[0][0], up[0][1], out, x0);
-  if (y + 1 < im.h) ycc_row_store(im, *reinterpret_cast<const uint2*>(yp + ypitch), up[1][0], up[1][1], out + im.out_pitch, x0);
+  __syncthreads();
+  // 8 rows x 96 16-byte pieces, three per thread; a row ends at its 16-byte pitch (the pad bytes are never read)
+  const size_t row_bytes = (size_t)im.out_pitch;
+  uint8_t* out0 = pix_arena + im.out_off + (size_t)xc * 3;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int piece = threadIdx.x + k * 256, row = piece / 96, col = (piece - row * 96) * 16;
+    const int yy = blockIdx.y * 8 + row;
+    if (yy < im.h && (size_t)xc * 3 + col < row_bytes)
+      *reinterpret_cast<uint4*>(out0 + (size_t)yy * row_bytes + col) = *reinterpret_cast<const uint4*>(&stage[row][col]);
+  }
 }
 
 // four output pixels per thread: one word of Y, twelve bytes of RGB
