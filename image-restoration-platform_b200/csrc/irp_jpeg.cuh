@@ -227,7 +227,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
       } else {
         uint32_t zz = z + r;
         if (zz > 63u) zz = 63u;                           // only while out of sync / on corrupt data
-        if (WRITE) blk_ptr[zigzag[zz]] = (int16_t)huff_extend((int)((b32 << len) >> (32 - s)), s);
+        if (WRITE) blk_ptr[zz] = (int16_t)huff_extend((int)((b32 << len) >> (32 - s)), s);   // the arena keeps ZIGZAG order
         z = zz + 1;
       }
       bw.skip(len + s);
@@ -519,6 +519,11 @@ idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, cons
   const int b = gb - J.block_base;
   const uint4* src = reinterpret_cast<const uint4*>(coef_arena + J.coef_off + (size_t)b * 64);
   const uint4* qsrc = reinterpret_cast<const uint4*>(qtabs + J.qidx * 64);
+  // coefficients and quantisation steps are both stored in zigzag order (the Huffman writer's order: the nonzero
+  // ones cluster in a block's first sectors); the permutation to natural order is register renaming here
+  constexpr int nat[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                           41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                           30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
   int d[64];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
@@ -526,8 +531,8 @@ idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, cons
     const uint32_t cc[4] = {cw.x, cw.y, cw.z, cw.w}, qq[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      d[r * 8 + 2 * k] = (int)(int16_t)(cc[k] & 0xFFFFu) * (int)(qq[k] & 0xFFFFu);
-      d[r * 8 + 2 * k + 1] = (int)(int16_t)(cc[k] >> 16) * (int)(qq[k] >> 16);
+      d[nat[r * 8 + 2 * k]] = (int)(int16_t)(cc[k] & 0xFFFFu) * (int)(qq[k] & 0xFFFFu);
+      d[nat[r * 8 + 2 * k + 1]] = (int)(int16_t)(cc[k] >> 16) * (int)(qq[k] >> 16);
     }
   }
   const int by = b / J.bw, bx = b - by * J.bw;
