@@ -10,6 +10,7 @@
 //   analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>   (baseline JPEG bytes, decoded on the device)
 //   transcodeFile(ctx, file:Buffer, orientation, quality) -> Promise<{scores:Float64Array(7), file:Buffer, width, height, channels}>
 //       analyze() + preprocessImage() of one upload with files on both sides (irp_transcode_jpeg_batch)
+//   setOutputIcc(ctx, profile:Buffer|null)   ICC profile attached to every file transcodeFile returns (withMetadata({icc}))
 //   analyzeRaw(ctx, pixels:Buffer, width, height, channels, isJpeg:boolean) -> Promise<Float64Array(7)>
 //   preprocessRaw(ctx, pixels:Buffer, width, height, channels, orientation) -> Promise<{data:Buffer,width,height,channels}>
 // Work runs on the libuv pool through napi_create_async_work, so the event loop never blocks
@@ -259,6 +260,20 @@ napi_value TranscodeFile(napi_env env, napi_callback_info info) {
   return promise;
 }
 
+napi_value SetOutputIcc(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value argv[2];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  void* ctx = nullptr;
+  napi_get_value_external(env, argv[0], &ctx);
+  void* data = nullptr;
+  size_t len = 0;
+  if (argc > 1) napi_get_buffer_info(env, argv[1], &data, &len);   // not a Buffer (null / undefined): clears the profile
+  if (irp_set_output_icc(static_cast<irp_ctx*>(ctx), static_cast<const uint8_t*>(data), data ? len : 0) != IRP_OK)
+    napi_throw_error(env, nullptr, "bad ICC profile");
+  return nullptr;
+}
+
 napi_value AnalyzeRaw(napi_env env, napi_callback_info info) { return Submit(env, info, false); }
 napi_value PreprocessRaw(napi_env env, napi_callback_info info) { return Submit(env, info, true); }
 
@@ -287,10 +302,11 @@ napi_value Init(napi_env env, napi_value exports) {
       {"createContext", nullptr, CreateContext, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"analyzeFile", nullptr, AnalyzeFile, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"transcodeFile", nullptr, TranscodeFile, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"setOutputIcc", nullptr, SetOutputIcc, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"analyzeRaw", nullptr, AnalyzeRaw, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"preprocessRaw", nullptr, PreprocessRaw, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
-  napi_define_properties(env, exports, 5, props);
+  napi_define_properties(env, exports, 6, props);
   return exports;
 }
 

@@ -23,7 +23,7 @@ SYMBOLS = (
     "irp_get_timing", "irp_preprocess_dims", "irp_fusion_dims", "irp_scores_from_moments", "irp_grey_tables",
     "irp_classify_batch", "irp_preprocess_batch", "irp_analyze_batch", "irp_fusion_prepare_batch",
     "irp_submit", "irp_submit_jpeg", "irp_submit_transcode", "irp_wait", "irp_jpeg_info", "irp_decode_jpeg_batch", "irp_analyze_jpeg_batch",
-    "irp_encode_jpeg_batch", "irp_analyze_encode_batch", "irp_transcode_jpeg_batch",
+    "irp_set_output_icc", "irp_encode_jpeg_batch", "irp_analyze_encode_batch", "irp_transcode_jpeg_batch",
     "irp_dev_alloc", "irp_dev_free", "irp_host_alloc_pinned", "irp_host_free_pinned", "irp_memcpy_h2d",
     "irp_memcpy_d2h", "irp_synchronize",
 )
@@ -104,6 +104,7 @@ def load() -> C.CDLL:
     lib.irp_jpeg_info.argtypes = [vp, C.c_size_t, ip, ip, ip]
     lib.irp_decode_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(OutDesc)]
     lib.irp_analyze_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(Result), C.POINTER(OutDesc)]
+    lib.irp_set_output_icc.argtypes = [vp, vp, C.c_size_t]
     lib.irp_encode_jpeg_batch.argtypes = [vp, C.POINTER(ImageDesc), i32, i32, C.POINTER(JpegOut)]
     lib.irp_analyze_encode_batch.argtypes = [vp, C.POINTER(ImageDesc), i32, C.POINTER(Result), i32, C.POINTER(JpegOut)]
     lib.irp_transcode_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(Result), i32, C.POINTER(JpegOut)]

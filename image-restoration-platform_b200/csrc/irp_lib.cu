@@ -149,6 +149,7 @@ struct irp_ctx {
   // compressed-input batches are cut into lanes: child contexts (own streams and scratch) driven by their own host
   // threads, so one lane's marker scan / un-stuffing / uploads / size read-backs run under the other lanes' kernels
   std::vector<irp_ctx*> lanes;
+  std::vector<uint8_t> icc;       // profile attached to encoded files (irp_set_output_icc)
   std::mutex lanes_mu;
   bool is_lane = false;
 };
@@ -1388,6 +1389,10 @@ static int run_in_lanes(irp_ctx* ctx, int n, const std::function<int(irp_ctx*, i
       ctx->lanes.push_back(l);
     }
   }
+  for (int k = 1; k < want; k++) {   // the lanes encode with the parent's profile
+    std::lock_guard<std::mutex> lk(ctx->lanes[k - 1]->mu);
+    if (ctx->lanes[k - 1]->icc != ctx->icc) ctx->lanes[k - 1]->icc = ctx->icc;
+  }
   std::vector<int> rc(want, IRP_OK);
   std::vector<std::thread> th;
   auto part = [&](int k) { return (int)((long long)n * k / want); };
@@ -1436,6 +1441,13 @@ static int analyze_jpeg_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, 
 }
 
 // ---- compressed output: baseline JPEG encoded on the device ----
+int irp_set_output_icc(irp_ctx* ctx, const uint8_t* profile, size_t size) {
+  if (!ctx || (size && !profile) || size > 255u * 65519u) return IRP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->icc.assign(profile, profile + size);
+  return IRP_OK;
+}
+
 int irp_encode_jpeg_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, int quality, irp_jpeg_out* outs) {
   if (!ctx || n < 0 || (n && (!imgs || !outs))) return IRP_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);

@@ -304,7 +304,8 @@ class Engine:
     def _encode_call(self, fn, n, caps):
         """Run fn(outs) with host buffers of caps[i] bytes; one retry with the sizes the library asks for."""
         for attempt in range(2):
-            bufs = [np.empty(int(c), np.uint8) for c in caps]
+            icc = getattr(self, "_icc_len", 0)
+            bufs = [np.empty(int(c) + icc + 18 * (icc // 65519 + 1), np.uint8) for c in caps]
             outs = (_ffi.JpegOut * n)(*[_ffi.JpegOut(b.ctypes.data, b.size, 0, 0, 0, 0, 0) for b in bufs])
             rc = fn(outs)
             if rc == _ffi.IRP_ERR_CAPACITY and attempt == 0:
@@ -312,6 +313,12 @@ class Engine:
                 continue
             self._check(rc)
             return [bytes(memoryview(b)[:o.size]) for b, o in zip(bufs, outs)]
+
+    def set_output_icc(self, profile: Optional[bytes]) -> None:
+        """Attach an ICC profile (`.withMetadata({icc})`, imagePreprocess.js:57-67) to every file encoded from now on; None clears it."""
+        b = np.frombuffer(profile, np.uint8) if profile else None
+        self._check(self._lib.irp_set_output_icc(self._ctx, b.ctypes.data if b is not None else None, b.size if b is not None else 0))
+        self._icc_len = 0 if b is None else int(b.size)
 
     def encode_jpeg_batch(self, images: Sequence[ImageLike], quality: int = 85) -> List[bytes]:
         """u8 RGB / grey images (host arrays or DeviceImages) -> baseline 4:4:4 JPEG files, byte-identical to

@@ -193,6 +193,11 @@ typedef struct irp_jpeg_out {
   int32_t width, height, channels; /* out: dims of the encoded image             */
   int32_t reserved;
 } irp_jpeg_out;
+/* `.withMetadata({icc: 'srgb'})` (imagePreprocess.js:57-67): an ICC profile attached to every file this context
+ * encodes from now on, as APP2 "ICC_PROFILE" segments right behind the JFIF header (jpeg_write_icc_profile's
+ * layout, 65519 bytes per segment).  The bytes are the caller's (libvips' built-in sRGB profile is not
+ * redistributed here); NULL / 0 clears it.  Output buffers must hold the profile as well. */
+int irp_set_output_icc(irp_ctx *ctx, const uint8_t *profile, size_t size);
 /* pixels (host or device, 1 or 3 channels) -> baseline JPEG files */
 int irp_encode_jpeg_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, int quality,
                           irp_jpeg_out *outs);

@@ -145,3 +145,30 @@ def test_transcode_files_in_files_out(engine, oracle):
         ref = _pillow_encode(oracle.preprocess(px, 1), 85)
         assert files[i] == ref, f"file {i}: {_explain(files[i], ref)}"
         assert np.array_equal(np.asarray(Image.open(io.BytesIO(files[i]))), np.asarray(Image.open(io.BytesIO(ref))))
+
+
+def test_icc_profile_is_attached_like_libjpeg_turbo(engine):
+    """`.withMetadata({icc})`: the APP2 "ICC_PROFILE" segments sit where Pillow / jpeg_write_icc_profile put them
+    (behind the JFIF header), one and two segments (a profile above 65519 bytes is split); clearing restores the
+    plain file; the serving entry point (lanes) attaches it to every file."""
+    img = rand_image(120, 200, 3, seed=4, kind="smooth")
+    rng = np.random.default_rng(9)
+    try:
+        for size in (3144, 70000):
+            prof = rng.integers(0, 256, size, dtype=np.uint8).tobytes()
+            engine.set_output_icc(prof)
+            got = engine.encode_jpeg_batch([img], quality=85)[0]
+            b = io.BytesIO()
+            Image.fromarray(img).save(b, "JPEG", quality=85, subsampling=0, optimize=False, icc_profile=prof)
+            assert got == b.getvalue(), f"profile of {size} bytes: {_explain(got, b.getvalue())}"
+            assert Image.open(io.BytesIO(got)).info.get("icc_profile") == prof
+        blobs = []
+        for i in range(20):
+            bb = io.BytesIO()
+            Image.fromarray(rand_image(300 + i, 400, 3, seed=i, kind="smooth")).save(bb, "JPEG", quality=90, subsampling=2)
+            blobs.append(bb.getvalue())
+        _, files = engine.transcode_jpeg_batch(blobs, quality=85)     # 20 files: two lanes
+        assert all(Image.open(io.BytesIO(f)).info.get("icc_profile") == prof for f in files)
+    finally:
+        engine.set_output_icc(None)
+    assert engine.encode_jpeg_batch([img], quality=85)[0] == _pillow_encode(img, 85)
