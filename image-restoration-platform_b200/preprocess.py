@@ -3,8 +3,10 @@
 `preprocess_image(req, _res, next)` keeps the Express-middleware shape: it reads `req.file.buffer`,
 rewrites the same `req.file` fields (imagePreprocess.js:70-78), records the same operation strings
 (:43,54,64-65) and reports failures through `next(Problem)` with the same status codes (:25-34,81-90).
-The pixel stages — EXIF auto-orient, lanczos3 fit-inside <= 2048, normalise — run in libirp_b200.so;
-container decode and the q85 4:4:4 JPEG entropy coding stay on the host.
+Everything between the upload and the returned file runs in libirp_b200.so: baseline JPEG uploads are decoded on
+the device (other containers by Pillow on the host), then EXIF auto-orient, lanczos3 fit-inside <= 2048, normalise,
+and the q85 4:4:4 JPEG encode with the sRGB profile attached (the file is libjpeg-turbo's
+baseline file of those pixels, not mozjpeg's trellis / progressive one).
 """
 from __future__ import annotations
 
@@ -51,7 +53,7 @@ _engine: Optional[Engine] = None
 
 def _get_engine(req) -> Engine:
     global _engine
-    eng = getattr(req, "engine", None)
+    eng = getattr(req, "engine", None) if req is not None else None
     if eng is not None:
         return eng
     if _engine is None:
@@ -70,15 +72,34 @@ def _set(file, key, value):
         setattr(file, key, value)
 
 
-def encode_jpeg(px: np.ndarray) -> bytes:
-    """.jpeg({quality:85, chromaSubsampling:'4:4:4'}).withMetadata({icc:'sRGB'}) — host side."""
-    from PIL import Image, ImageCms
+def _srgb_profile() -> Optional[bytes]:
+    """An sRGB profile for `.withMetadata({icc:'sRGB'})` (LittleCMS' built-in one through Pillow; libvips embeds its own)."""
+    try:
+        from PIL import ImageCms
 
-    im = Image.fromarray(px[:, :, 0] if px.shape[2] == 1 else px)
-    icc = ImageCms.ImageCmsProfile(ImageCms.createProfile("sRGB")).tobytes()
-    out = io.BytesIO()
-    im.save(out, format="JPEG", quality=JPEG_QUALITY, subsampling=0, optimize=True, progressive=True, icc_profile=icc)
-    return out.getvalue()
+        return ImageCms.ImageCmsProfile(ImageCms.createProfile("sRGB")).tobytes()
+    except Exception:
+        return None
+
+
+def encode_jpeg(px: np.ndarray, engine: Optional[Engine] = None) -> bytes:
+    """.jpeg({quality:85, chromaSubsampling:'4:4:4'}).withMetadata({icc:'sRGB'}) — on the device."""
+    eng = engine if engine is not None else _get_engine(None)
+    if not getattr(eng, "_srgb_attached", False):
+        eng.set_output_icc(_srgb_profile())
+        eng._srgb_attached = True
+    return eng.encode_jpeg_batch([px[:, :, 0] if px.shape[2] == 1 else px], quality=JPEG_QUALITY)[0]
+
+
+def _jpeg_orientation(buf) -> int:
+    """EXIF orientation from the header only (no pixel decode)."""
+    try:
+        from PIL import Image
+
+        o = int(Image.open(io.BytesIO(bytes(buf))).getexif().get(0x0112, 1))
+        return o if 1 <= o <= 8 else 1
+    except Exception:
+        return 1
 
 
 def preprocess_image(req, _res, next):  # imagePreprocess.js:24-91
@@ -89,17 +110,26 @@ def preprocess_image(req, _res, next):  # imagePreprocess.js:24-91
                             "An image file must be provided in the request."))
     try:
         operations = []
-        px, fmt, orientation = decode_image(buf)
-        h, w, c = px.shape
+        eng = _get_engine(req)
+        info = eng.jpeg_info(buf)   # (w, h, channels) when the device decoder takes the file, else None
+        if info is not None:
+            w, h, c = info
+            fmt, orientation, px = "jpeg", _jpeg_orientation(buf), None
+        else:
+            px, fmt, orientation = decode_image(buf)
+            h, w, c = px.shape
         source_metadata = {"width": w, "height": h, "format": fmt, "channels": c, "orientation": orientation}
         operations.append("auto_orient")
         if needs_resize(w, h):
             d = calculate_resize_dimensions(w, h)
             operations.append(f"resize_{d['width']}x{d['height']}")
-        out = _get_engine(req).preprocess_batch([px], orientations=[orientation])[0]
+        if px is None:
+            out = eng.analyze_jpeg_batch([bytes(buf)], orientations=[orientation], classify=False)[1][0]
+        else:
+            out = eng.preprocess_batch([px], orientations=[orientation])[0]
         operations.append(f"compress_jpeg_q{JPEG_QUALITY}")
         operations.append("attach_sRGB_icc")
-        processed = encode_jpeg(out)
+        processed = encode_jpeg(out, eng)
         _set(file, "originalBuffer", buf)
         _set(file, "originalMetadata", source_metadata)
         _set(file, "buffer", processed)

@@ -137,3 +137,31 @@ def test_preprocess_resizes_and_rotates_large_uploads(engine, oracle):
     assert np.array_equal(req.file.processedPixels, oracle.preprocess(a, 6))
     out = Image.open(io.BytesIO(req.file.buffer))
     assert out.format == "JPEG" and out.size == (1152, 1536) and out.info.get("icc_profile")
+
+
+def test_preprocess_of_a_jpeg_upload_never_touches_a_host_codec(engine, oracle):
+    """A baseline JPEG upload: decoded on the device, oriented, resized and re-encoded on the device; the returned
+    file is libjpeg-turbo's q85 4:4:4 file of the oracle's pixels with the sRGB profile attached."""
+    from PIL import Image, ImageCms
+
+    from irp_b200.preprocess import make_request, preprocess_image
+
+    y, x = np.mgrid[0:2500, 0:3300]
+    a = np.stack([(x // 11) % 256, (y // 5) % 256, (x + 2 * y) % 256], axis=2).astype(np.uint8)
+    im = Image.fromarray(a)
+    exif = im.getexif()
+    exif[0x0112] = 3
+    buf = io.BytesIO()
+    im.save(buf, format="JPEG", quality=92, subsampling=1, exif=exif.tobytes())
+    req = make_request(buf.getvalue(), engine)
+    calls = []
+    preprocess_image(req, {}, lambda *a: calls.append(a))
+    assert calls == [()]
+    assert req.file.originalMetadata["format"] == "jpeg" and req.file.originalMetadata["orientation"] == 3
+    px = np.asarray(Image.open(io.BytesIO(buf.getvalue())))
+    want_px = oracle.preprocess(px, 3)
+    assert np.array_equal(req.file.processedPixels, want_px)
+    ref = io.BytesIO()
+    icc = ImageCms.ImageCmsProfile(ImageCms.createProfile("sRGB")).tobytes()
+    Image.fromarray(want_px).save(ref, "JPEG", quality=85, subsampling=0, icc_profile=icc)
+    assert req.file.buffer == ref.getvalue()
