@@ -85,10 +85,11 @@ def _srgb_profile() -> Optional[bytes]:
 def encode_jpeg(px: np.ndarray, engine: Optional[Engine] = None) -> bytes:
     """.jpeg({quality:85, chromaSubsampling:'4:4:4'}).withMetadata({icc:'sRGB'}) — on the device."""
     eng = engine if engine is not None else _get_engine(None)
-    if not getattr(eng, "_srgb_attached", False):
-        eng.set_output_icc(_srgb_profile())
-        eng._srgb_attached = True
-    return eng.encode_jpeg_batch([px[:, :, 0] if px.shape[2] == 1 else px], quality=JPEG_QUALITY)[0]
+    eng.set_output_icc(_srgb_profile())      # the profile is a property of THIS middleware's files, not of the engine
+    try:
+        return eng.encode_jpeg_batch([px[:, :, 0] if px.shape[2] == 1 else px], quality=JPEG_QUALITY)[0]
+    finally:
+        eng.set_output_icc(None)
 
 
 def _jpeg_orientation(buf) -> int:
