@@ -1,0 +1,91 @@
+"""Damaged JPEG files (sharp is opened with failOnError: false, imagePreprocess.js:42): truncated scans, flipped
+bytes in the entropy-coded data, stray markers.  The device decoder may refuse a file or return a picture with
+damage in it, but it must not fault, hang or poison the context — a valid file decoded afterwards is still
+bit-exact — and the part of a truncated picture that precedes the damage is still libjpeg-turbo's."""
+import io
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import irp_b200
+from conftest import rand_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _encode(img, **kw):
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+def _scan_start(data):
+    p = 2
+    while True:
+        m = data[p + 1]
+        ln = (data[p + 2] << 8) | data[p + 3]
+        if m == 0xDA:
+            return p + 2 + ln
+        p += 2 + ln
+
+
+def _try_decode(engine, blob, shape):
+    try:
+        out = engine.decode_jpeg_batch([blob])[0]
+    except irp_b200.IrpError:
+        return None
+    assert out.shape == shape
+    return out
+
+
+@pytest.mark.parametrize("subsampling", [0, 2])
+def test_damaged_files_neither_fault_nor_poison_the_context(engine, subsampling):
+    rng = np.random.default_rng(100 + subsampling)
+    img = rand_image(480, 640, 3, seed=21, kind="smooth")
+    good = _encode(img, quality=85, subsampling=subsampling)
+    ref = np.asarray(Image.open(io.BytesIO(good)))
+    s0 = _scan_start(good)
+    variants = []
+    for cut in sorted(rng.integers(s0 + 1, len(good) - 2, 12)):          # truncated inside the scan
+        variants.append(good[:int(cut)])
+    for k in (1, 3, 17, 200):                                            # flipped bytes
+        b = bytearray(good)
+        for pos in rng.integers(s0, len(good) - 2, k):
+            b[int(pos)] ^= int(rng.integers(1, 256))
+        variants.append(bytes(b))
+    b = bytearray(good)                                                  # a stray restart marker and a stray 0xFF 0x00
+    mid = (s0 + len(good)) // 2
+    b[mid:mid] = b"\xff\xd3"
+    variants.append(bytes(b))
+    variants.append(good[:-2])                                           # no EOI
+    variants.append(good[:s0])                                           # no entropy-coded data at all
+    survived = 0
+    for v in variants:
+        out = _try_decode(engine, v, ref.shape)
+        survived += out is not None
+    assert survived >= 1
+    # truncation: the MCU rows that were complete before the cut are still exact
+    cut = s0 + (len(good) - s0) // 2
+    out = _try_decode(engine, good[:cut], ref.shape)
+    if out is not None:
+        rows_equal = np.all(out == ref, axis=(1, 2))
+        assert rows_equal[:64].all(), "the first MCU rows of a file cut half way must be intact"
+    # the context still works and is still exact
+    assert np.array_equal(engine.decode_jpeg_batch([good])[0], ref)
+    # a batch holding a damaged file and a good one: the good one is still exact if the batch is accepted
+    try:
+        outs = engine.decode_jpeg_batch([variants[0], good])
+        assert np.array_equal(outs[1], ref)
+    except irp_b200.IrpError:
+        pass
+    assert np.array_equal(engine.decode_jpeg_batch([good])[0], ref)
+
+
+def test_header_over_the_pixel_limit_is_refused(engine):
+    good = bytearray(_encode(rand_image(16, 16, 3, seed=1, kind="smooth"), quality=85))
+    p = 2
+    while good[p + 1] != 0xC0:
+        p += 2 + ((good[p + 2] << 8) | good[p + 3])
+    good[p + 5:p + 9] = b"\xff\xff\xff\xff"      # 65535 x 65535
+    assert engine.jpeg_info(bytes(good)) is None
