@@ -8,16 +8,19 @@
 // Stages (one launch each over the whole batch; the host has parsed the headers and removed the byte
 // stuffing while it copied the entropy-coded segments into one upload buffer):
 //   huffman   Huffman decoding is sequential by nature: a code can only be found once the previous one
-//             ended.  It is parallelised the self-synchronising way: the stream is cut into 1024-bit
+//             ended.  It is parallelised the self-synchronising way: the stream is cut into 2048-bit
 //             subsequences, every thread decodes its own from the guess "a block starts here", and
 //             JPEG's code tables make a wrong guess fall into step with the true decode within a few
 //             symbols.  `huff_sync_kernel` iterates state(i) = f_i(state(i-1)) until nothing changes —
 //             then every subsequence's start state is the true one — an exclusive scan over the
 //             coefficient slots each subsequence advanced gives its place in the output, and
-//             `huff_write_kernel` decodes once more, writing coefficients.  Restart intervals, when a
+//             `huff_write_kernel` decodes once more, writing coefficients — in ZIGZAG order, 64 int16
+//             per block, DC differences apart in a compact MCU-order array.  Restart intervals, when a
 //             file has them, are independent streams with known start states.
-//   dc        the DC coefficients are coded as differences: one running sum per component and stream.
-//   idct      dequantise + jidctint (13-bit constants, two passes), 8 lanes per block, u8 planes.
+//   dc        the DC coefficients are coded as differences: one running sum per component and stream,
+//             over the compact array.
+//   idct      dequantise + jidctint (13-bit constants, two passes), one thread per block in 64 registers
+//             (zigzag -> natural order is register renaming), u8 planes.
 //   colour    fancy (triangle) chroma upsampling h2v1 / h2v2 / h1v2 + YCbCr -> RGB (16-bit fixed point),
 //             written as interleaved u8 rows with a 16-byte pitch: the classify / resize kernels' input.
 #pragma once
@@ -176,14 +179,14 @@ __device__ __forceinline__ int huff_decode(const HuffDev& t, uint32_t bits16, in
 __device__ __forceinline__ int huff_extend(int x, int s) { return x < (1 << (s - 1)) ? x - (1 << s) + 1 : x; }
 
 // Decode the symbols that START in [p, p_end) of one stream, from slot state `slot` (mod 64 * bpm).
-// WRITE: store coefficients (zigzag -> natural); `abs_blk` is the absolute block index (MCU order) the
+// WRITE: store coefficients (in zigzag order, DC differences to the compact array); `abs_blk` is the absolute block index (MCU order) the
 // run starts in and `blk_limit` one past the stream's last block.  The block's address is worked out
 // once per block, not per coefficient.
 template <bool WRITE, class Reader>
 __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, Reader& bw, unsigned long long stream_bit0,
                                          unsigned long long stream_bits, uint32_t& p, uint32_t p_end, uint32_t& slot, uint32_t& advanced,
                                          int16_t* __restrict__ const* coef, int16_t* __restrict__ dcv, uint32_t abs_blk,
-                                         uint32_t blk_limit, const uint8_t* __restrict__ zigzag) {
+                                         uint32_t blk_limit) {
   const uint32_t period = 64u * (uint32_t)im.bpm;
   const uint32_t stop = (uint32_t)min((unsigned long long)p_end, stream_bits);
   if (p >= stop) return;
@@ -316,7 +319,7 @@ huff_sync_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_i
         start = vstate[sub - 1];
       uint32_t p = (uint32_t)start, slot = (uint32_t)(start >> 32), adv = 0;
       BitWinG bw{data, st.bit_off, 0ull, 0, nullptr};
-      huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, nullptr, 0u, 0u, nullptr);
+      huff_run<false>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, nullptr, nullptr, 0u, 0u);
       vin[sub] = start;
       vstate[sub] = (unsigned long long)p | ((unsigned long long)slot << 32);
       advanced[sub] = adv;
@@ -361,9 +364,6 @@ __global__ void huff_scan_kernel(const JpegStream* __restrict__ streams, int n_s
   }
 }
 
-__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 __global__ void __launch_bounds__(kHuffThreads)
 huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_img, const JpegStream* __restrict__ streams,
@@ -371,10 +371,8 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
                   const unsigned long long* __restrict__ slot_start, int16_t* __restrict__ coef_arena, int16_t* __restrict__ dcv) {
   __shared__ HuffSmem hs;
   __shared__ JpegImg im;
-  __shared__ uint8_t zz[64];
   const int img = cta_img[blockIdx.x];
   for (int i = threadIdx.x; i < (int)(sizeof(JpegImg) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&im)[i] = reinterpret_cast<const uint32_t*>(imgs + img)[i];
-  if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
   load_huff(hs, tabs, imgs[img].huff_base);
   __syncthreads();
   const int sub = blockIdx.x * kHuffThreads + threadIdx.x;
@@ -395,7 +393,7 @@ huff_write_kernel(const JpegImg* __restrict__ imgs, const int* __restrict__ cta_
   BitWin bw{staged + threadIdx.x * kSubWords, (uint32_t)local * kSubBits, 0ull, 0, 0};
   uint32_t adv = 0;
   huff_run<true>(im, hs, bw, st.bit_off, st.nbits, p, (uint32_t)(local + 1) * kSubBits, slot, adv, coef, dcv,
-                 base_blk + (uint32_t)(slot_start[sub] >> 6), base_blk + (uint32_t)st.n_mcu * (uint32_t)im.bpm, zz);
+                 base_blk + (uint32_t)(slot_start[sub] >> 6), base_blk + (uint32_t)st.n_mcu * (uint32_t)im.bpm);
 }
 
 // DC differences -> DC values: a scan per (stream, component) over its blocks in MCU order, in three

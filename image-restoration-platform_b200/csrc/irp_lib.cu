@@ -1378,7 +1378,8 @@ int irp_decode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_o
 // default of 8 (1 = off).  The first failing lane's status and message are returned.
 static int run_in_lanes(irp_ctx* ctx, int n, const std::function<int(irp_ctx*, int, int)>& f) {
   static const int env_lanes = getenv("IRP_LANES") ? atoi(getenv("IRP_LANES")) : 8;
-  const int want = ctx->is_lane ? 1 : std::max(1, std::min(env_lanes, n / 8));
+  static const int env_min = getenv("IRP_LANE_MIN") ? std::max(1, atoi(getenv("IRP_LANE_MIN"))) : 8;
+  const int want = ctx->is_lane ? 1 : std::max(1, std::min(env_lanes, n / env_min));
   if (want == 1) return f(ctx, 0, n);
   {
     std::lock_guard<std::mutex> lk(ctx->lanes_mu);
