@@ -44,7 +44,7 @@ struct JpegImg {                       // one image of a decode launch (device c
   int w, h, ncomp, hmax, vmax, mcux, mcuy, bpm;
   int comp_h[3], comp_v[3], comp_bw[3], comp_bh[3], comp_dw[3], comp_dh[3];
   int blk_comp[8], blk_bx[8], blk_by[8];   // block k of an MCU: component, offset inside the MCU (in blocks)
-  int dc_tab[3], ac_tab[3];                // table index (0..3) per component
+  int dc_tab[3], ac_tab[3];                // slot (0..5) of the component's DC / AC table among the image's tables
   uint16_t q[3][64];                       // natural order
   int restart;                             // MCUs per restart interval (0: none)
   int nstreams;                            // restart intervals (1 if none)
@@ -55,7 +55,7 @@ struct JpegImg {                       // one image of a decode launch (device c
   unsigned long long dc_off[3];            // first entry of the component in the compact DC array (MCU order)
   unsigned long long out_off;              // byte offset of the RGB / grey output in the pixel arena
   unsigned long long out_pitch;
-  int huff_base;                           // first of this image's 8 tables (DC 0..3, AC 0..3)
+  int huff_base;                           // first of this image's kHuffSlots tables
   int pad;
 };
 
@@ -152,8 +152,11 @@ __device__ __forceinline__ void stage_sub(uint32_t* dst, const uint32_t* __restr
   }
 }
 
+// three components use at most three DC and three AC tables: six slots instead of the eight a file may define keep
+// the write kernel (35 KB of staged stream per CTA) at five CTAs per SM
+constexpr int kHuffSlots = 6;
 struct HuffSmem {
-  HuffDev t[8];
+  HuffDev t[kHuffSlots];
 };
 
 __device__ __forceinline__ int huff_decode(const HuffDev& t, uint32_t bits16, int& len) {
@@ -198,7 +201,7 @@ __device__ __forceinline__ void huff_run(const JpegImg& im, const HuffSmem& hs, 
     const uint32_t k = slot >> 6;
     const int comp = im.blk_comp[k];
     const HuffDev& dct = hs.t[im.dc_tab[comp]];
-    const HuffDev& act = hs.t[4 + im.ac_tab[comp]];
+    const HuffDev& act = hs.t[im.ac_tab[comp]];
     int16_t* blk_ptr = nullptr;
     int16_t* dc_ptr = nullptr;     // DC differences go to a compact array in MCU order: the prediction scan runs over
     if (WRITE) {                   // contiguous values instead of one 2-byte access per 128-byte block
