@@ -615,12 +615,15 @@ __device__ __forceinline__ void ycc_row_stage(uint2 yw, const int (&ub)[8], cons
   uint32_t px[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
+    // jdcolor.c's Y + ((c * (x - 128) + 32768) >> 16) as one multiply-add chain: Y * 65536 is a multiple of the
+    // shift, and the -128 offsets fold into the constant — the additions ride on the FMA pipe, the half-rate ALU
+    // pipe keeps the byte extraction, the shifts and the clamps
     const int Y = (int)(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xFF);
-    const int xb = ub[k] - 128, xr = ur[k] - 128;
-    const int rr = Y + ((91881 * xr + 32768) >> 16);
-    const int g = Y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);
-    const int b = Y + ((116130 * xb + 32768) >> 16);
-    px[k] = (uint32_t)__vimin_s32_relu(rr, 255) | ((uint32_t)__vimin_s32_relu(g, 255) << 8) | ((uint32_t)__vimin_s32_relu(b, 255) << 16);
+    const int y16 = Y * 65536;
+    const int rr = (91881 * ur[k] + (y16 + 32768 - 128 * 91881)) >> 16;
+    const int g = (-22554 * ub[k] + (-46802 * ur[k] + (y16 + 32768 + 128 * (22554 + 46802)))) >> 16;
+    const int b = (116130 * ub[k] + (y16 + 32768 - 128 * 116130)) >> 16;
+    px[k] = (uint32_t)__vimin_s32_relu(rr, 255) + (uint32_t)__vimin_s32_relu(g, 255) * 256u + (uint32_t)__vimin_s32_relu(b, 255) * 65536u;
   }
   o[0] = make_uint2(px[0] | (px[1] << 24), (px[1] >> 8) | (px[2] << 16));
   o[1] = make_uint2((px[2] >> 16) | (px[3] << 8), px[4] | (px[5] << 24));
