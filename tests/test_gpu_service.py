@@ -162,6 +162,7 @@ def test_preprocess_of_a_jpeg_upload_never_touches_a_host_codec(engine, oracle):
     want_px = oracle.preprocess(px, 3)
     assert np.array_equal(req.file.processedPixels, want_px)
     ref = io.BytesIO()
-    icc = ImageCms.ImageCmsProfile(ImageCms.createProfile("sRGB")).tobytes()
+    icc = Image.open(io.BytesIO(req.file.buffer)).info["icc_profile"]   # (LittleCMS stamps the creation second into it)
+    assert len(icc) == len(ImageCms.ImageCmsProfile(ImageCms.createProfile("sRGB")).tobytes()) and icc[36:40] == b"acsp"
     Image.fromarray(want_px).save(ref, "JPEG", quality=85, subsampling=0, icc_profile=icc)
     assert req.file.buffer == ref.getvalue()
