@@ -190,3 +190,14 @@ def test_decoded_pixels_equal_the_progressive_optimised_encoding(engine):
     psnr = 10 * np.log10(255.0 ** 2 / mse)
     assert psnr > 30.0, psnr               # 33 dB on this noisy test picture (the noise is what q85 removes)
     assert len(ours) < 1.15 * len(theirs)      # the price of the fixed Annex K tables and sequential coding
+
+
+def test_twelve_megapixel_round_trip(engine):
+    """BASELINE.json's image size through both codecs: the device encoder's file of a 4000 x 3000 picture is
+    libjpeg-turbo's, and the device decoder gets out of it what libjpeg-turbo gets (encode -> decode round trip)."""
+    img = rand_image(3000, 4000, 3, seed=77, kind="smooth")
+    img[1000:1400, 500:3500] = np.random.default_rng(3).integers(0, 256, (400, 3000, 3), dtype=np.uint8)
+    ours = engine.encode_jpeg_batch([img], quality=85)[0]
+    assert ours == _pillow_encode(img, 85)
+    back = engine.decode_jpeg_batch([ours])[0]
+    assert np.array_equal(back, np.asarray(Image.open(io.BytesIO(ours))))
