@@ -201,3 +201,16 @@ def test_twelve_megapixel_round_trip(engine):
     assert ours == _pillow_encode(img, 85)
     back = engine.decode_jpeg_batch([ours])[0]
     assert np.array_equal(back, np.asarray(Image.open(io.BytesIO(ours))))
+
+
+def test_analyze_encode_of_a_pipelined_host_batch(engine, oracle):
+    """A host-resident batch larger than one pipeline chunk (96 MiB): uploads, kernels and the device-side
+    preprocess outputs run chunk by chunk, the encoder afterwards; spot-checked files are libjpeg-turbo's."""
+    base = [rand_image(3000, 4000, 3, seed=200 + i, kind="smooth") for i in range(3)]
+    imgs = [base[i % 3] for i in range(10)]          # 360 MB: four chunks
+    res, files = engine.analyze_encode_batch(imgs, quality=85)
+    assert engine.timing()["chunks"] > 1
+    for i in (0, 4, 9):
+        assert_result_parity(res[i], oracle.classify(imgs[i]), 3, f"image {i}")
+        assert files[i] == _pillow_encode(oracle.preprocess(imgs[i], 1), 85), f"image {i}"
+    assert files[3] == files[0] and files[5] == files[2]
