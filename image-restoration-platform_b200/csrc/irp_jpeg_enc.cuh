@@ -252,6 +252,93 @@ seg_scan_kernel(const ScanSeg* __restrict__ segs, uint32_t* __restrict__ vals, u
   if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
+// ---- optimised Huffman tables (libjpeg's optimize_coding): symbol statistics per image, tables on the host ----
+struct EncHuff {                          // per image: codes (| length << 16) in the pack pass, counts in the histogram pass
+  uint32_t dc[2][16];
+  uint32_t ac[2][256];
+};
+
+// jchuff.c htest_one_block for every block: one thread per block, counts gathered per CTA in shared memory
+__global__ void __launch_bounds__(kEncThreads)
+jenc_hist_kernel(const EncImg* __restrict__ imgs, const int16_t* __restrict__ coef, const uint32_t* __restrict__ blkinfo, EncHuff* __restrict__ hist) {
+  __shared__ EncHuff h;
+  for (int i = threadIdx.x; i < (int)(sizeof(EncHuff) / 4); i += kEncThreads) ((uint32_t*)&h)[i] = 0u;
+  __syncthreads();
+  const EncImg& im = imgs[blockIdx.y];
+  const int g = blockIdx.x * kEncThreads + threadIdx.x;
+  if (g < im.nblk) {
+    const size_t a = (size_t)im.blk0 + g;
+    const int t = (g % im.c) ? 1 : 0;
+    const int prev = g >= im.c ? (int)(int16_t)(__ldg(blkinfo + a - im.c) >> 16) : 0;
+    const uint4* src = (const uint4*)(coef + a * 64);
+    int run = 0;
+#pragma unroll 1
+    for (int k8 = 0; k8 < 8; k8++) {
+      const uint4 q = __ldg(src + k8);
+      const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int v = (int)(int16_t)(pk[i >> 1] >> ((i & 1) * 16));
+        if (k8 == 0 && i == 0) {
+          atomicAdd(&h.dc[t][enc_nbits(abs(v - prev))], 1u);
+        } else if (v == 0) {
+          run++;
+        } else {
+          if (run > 15) atomicAdd(&h.ac[t][0xF0], (uint32_t)(run >> 4));
+          atomicAdd(&h.ac[t][((run & 15) << 4) | enc_nbits(abs(v))], 1u);
+          run = 0;
+        }
+      }
+    }
+    if (run) atomicAdd(&h.ac[t][0], 1u);
+  }
+  __syncthreads();
+  uint32_t* out = (uint32_t*)(hist + blockIdx.y);
+  for (int i = threadIdx.x; i < (int)(sizeof(EncHuff) / 4); i += kEncThreads) {
+    const uint32_t v = ((uint32_t*)&h)[i];
+    if (v) atomicAdd(out + i, v);
+  }
+}
+
+// bits of every block under the image's own tables (replaces the Annex K lengths jenc_dct_kernel summed)
+__global__ void __launch_bounds__(kEncThreads)
+jenc_blocklen_kernel(const EncImg* __restrict__ imgs, const EncHuff* __restrict__ own, const int16_t* __restrict__ coef,
+                     const uint32_t* __restrict__ blkinfo, uint32_t* __restrict__ bits) {
+  __shared__ EncHuff h;
+  for (int i = threadIdx.x; i < (int)(sizeof(EncHuff) / 4); i += kEncThreads) ((uint32_t*)&h)[i] = ((const uint32_t*)(own + blockIdx.y))[i];
+  __syncthreads();
+  const EncImg& im = imgs[blockIdx.y];
+  const int g = blockIdx.x * kEncThreads + threadIdx.x;
+  if (g >= im.nblk) return;
+  const size_t a = (size_t)im.blk0 + g;
+  const int t = (g % im.c) ? 1 : 0;
+  const int prev = g >= im.c ? (int)(int16_t)(__ldg(blkinfo + a - im.c) >> 16) : 0;
+  const uint4* src = (const uint4*)(coef + a * 64);
+  int run = 0, n = 0;
+#pragma unroll 1
+  for (int k8 = 0; k8 < 8; k8++) {
+    const uint4 q = __ldg(src + k8);
+    const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int v = (int)(int16_t)(pk[i >> 1] >> ((i & 1) * 16));
+      if (k8 == 0 && i == 0) {
+        const int nb = enc_nbits(abs(v - prev));
+        n += (int)(h.dc[t][nb] >> 16) + nb;
+      } else if (v == 0) {
+        run++;
+      } else {
+        n += (run >> 4) * (int)(h.ac[t][0xF0] >> 16);
+        const int nb = enc_nbits(abs(v));
+        n += (int)(h.ac[t][((run & 15) << 4) | nb] >> 16) + nb;
+        run = 0;
+      }
+    }
+  }
+  if (run) n += (int)(h.ac[t][0] >> 16);
+  bits[a] = (uint32_t)n;
+}
+
 // bit writer of one block: MSB-first into 32-bit words, byte-swapped on the way out
 struct BitOut {
   uint32_t* wp;
@@ -282,10 +369,13 @@ struct BitOut {
 // One thread per block.  grid = (ceil(max blocks / 128), n images).  The bit stream area must be zero.
 __global__ void __launch_bounds__(kEncThreads)
 jenc_pack_kernel(const EncImg* __restrict__ imgs, const EncTables* __restrict__ tabs, const int16_t* __restrict__ coef,
-                 const uint32_t* __restrict__ blkinfo, const uint32_t* __restrict__ bitoff, uint8_t* __restrict__ rawbits) {
+                 const uint32_t* __restrict__ blkinfo, const uint32_t* __restrict__ bitoff, uint8_t* __restrict__ rawbits,
+                 const EncHuff* __restrict__ own) {
   __shared__ uint32_t s_dc[2][16], s_ac[2][256];
-  for (int i = threadIdx.x; i < 32; i += kEncThreads) (&s_dc[0][0])[i] = (&tabs->dc[0][0])[i];
-  for (int i = threadIdx.x; i < 512; i += kEncThreads) (&s_ac[0][0])[i] = (&tabs->ac[0][0])[i];
+  const uint32_t* dcs = own ? &own[blockIdx.y].dc[0][0] : &tabs->dc[0][0];   // the image's optimised tables, or Annex K
+  const uint32_t* acs = own ? &own[blockIdx.y].ac[0][0] : &tabs->ac[0][0];
+  for (int i = threadIdx.x; i < 32; i += kEncThreads) (&s_dc[0][0])[i] = dcs[i];
+  for (int i = threadIdx.x; i < 512; i += kEncThreads) (&s_ac[0][0])[i] = acs[i];
   __syncthreads();
   const EncImg& im = imgs[blockIdx.y];
   const int g = blockIdx.x * kEncThreads + threadIdx.x;

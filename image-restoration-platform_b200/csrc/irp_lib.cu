@@ -121,8 +121,8 @@ struct irp_ctx {
   size_t smem_optin_full = 0;     // the device's opt-in shared memory per block
   DevBuf d_jdata, d_jmeta, d_jstate, d_jcoef, d_jplane, d_jpix;   // device JPEG decode (irp_jpeg.cuh)
   PinBuf h_jdata, h_jmeta;
-  DevBuf d_emeta, d_eblk, d_ebits, d_eout, d_epix;                 // device JPEG encode (irp_jpeg_enc.cuh)
-  PinBuf h_emeta;
+  DevBuf d_emeta, d_eblk, d_ebits, d_eout, d_epix, d_ehuff;        // device JPEG encode (irp_jpeg_enc.cuh)
+  PinBuf h_emeta, h_ehuff;
   int jpeg_sweeps = 0;            // synchronisation sweeps of the last JPEG batch
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   std::vector<void*> plan_chunks;
@@ -1213,9 +1213,9 @@ void irp_destroy(irp_ctx* ctx) {
   if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
   for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps, &ctx->d_rtjobs, &ctx->d_rtmaps,
                     &ctx->d_jdata, &ctx->d_jmeta, &ctx->d_jstate, &ctx->d_jcoef, &ctx->d_jplane, &ctx->d_jpix, &ctx->d_emeta,
-                    &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix})
+                    &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix, &ctx->d_ehuff})
     b->release();
-  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta, &ctx->h_emeta}) b->release();
+  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta, &ctx->h_emeta, &ctx->h_ehuff}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);

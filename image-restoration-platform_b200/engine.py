@@ -320,13 +320,14 @@ class Engine:
         self._check(self._lib.irp_set_output_icc(self._ctx, b.ctypes.data if b is not None else None, b.size if b is not None else 0))
         self._icc_len = 0 if b is None else int(b.size)
 
-    def encode_jpeg_batch(self, images: Sequence[ImageLike], quality: int = 85) -> List[bytes]:
+    def encode_jpeg_batch(self, images: Sequence[ImageLike], quality: int = 85, optimize: bool = False) -> List[bytes]:
         """u8 RGB / grey images (host arrays or DeviceImages) -> baseline 4:4:4 JPEG files, byte-identical to
         libjpeg-turbo's (imagePreprocess.js:50-53 without mozjpeg's trellis / progressive passes)."""
         n = len(images)
         descs, keep = self._descs(images, True, None)
         caps = [d.width * d.height * d.channels + 4096 for d in descs]
-        return self._encode_call(lambda outs: self._lib.irp_encode_jpeg_batch(self._ctx, descs, n, quality, outs), n, caps)
+        q = quality | (0x100 if optimize else 0)   # IRP_JPEG_OPTIMIZE
+        return self._encode_call(lambda outs: self._lib.irp_encode_jpeg_batch(self._ctx, descs, n, q, outs), n, caps)
 
     def analyze_encode_batch(self, images: Sequence[ImageLike], is_jpeg=True, orientations=None, quality: int = 85, classify: bool = True,
                              raw: bool = False):

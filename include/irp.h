@@ -186,6 +186,10 @@ int irp_analyze_jpeg_batch(irp_ctx *ctx, const irp_jpeg_desc *jpegs, int n, irp_
  * tables, 4:4:4, JFIF header) — a 2048x1536 result leaves the GPU as ~1 MB of
  * file bytes instead of 9.4 MB of pixels.  mozjpeg's trellis quantisation and
  * progressive scan search are NOT reproduced (same picture, ~10 % larger file). */
+/* OR-ed into `quality`: Huffman tables optimised per image (libjpeg's optimize_coding, part of sharp's
+ * `mozjpeg: true`): one more pass over the coefficients, files ~5-10 % smaller, byte-identical to
+ * libjpeg-turbo's optimised sequential file */
+#define IRP_JPEG_OPTIMIZE 0x100
 typedef struct irp_jpeg_out {
   uint8_t *data;    /* caller-owned HOST buffer for the file                     */
   size_t capacity;  /* in: bytes available at `data`                             */

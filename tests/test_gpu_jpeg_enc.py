@@ -214,3 +214,37 @@ def test_analyze_encode_of_a_pipelined_host_batch(engine, oracle):
         assert_result_parity(res[i], oracle.classify(imgs[i]), 3, f"image {i}")
         assert files[i] == _pillow_encode(oracle.preprocess(imgs[i], 1), 85), f"image {i}"
     assert files[3] == files[0] and files[5] == files[2]
+
+
+def _pillow_encode_opt(img, quality):
+    from PIL import ImageFile
+
+    b = io.BytesIO()
+    old = ImageFile.MAXBLOCK      # an optimised file must fit Pillow's buffer in one piece; noise at q100 exceeds its guess
+    ImageFile.MAXBLOCK = max(old, 4 * img.size + 65536)
+    try:
+        Image.fromarray(img).save(b, "JPEG", quality=quality, subsampling=0, optimize=True)
+    finally:
+        ImageFile.MAXBLOCK = old
+    return b.getvalue()
+
+
+@pytest.mark.parametrize("channels", [3, 1])
+def test_optimised_huffman_tables_match_libjpeg_turbo(engine, channels):
+    """IRP_JPEG_OPTIMIZE: symbol statistics on the device, jpeg_gen_optimal_table on the host, the file is
+    libjpeg-turbo's optimize_coding file byte for byte (DHT segments included) — flat pictures (two-symbol
+    tables), noise (every symbol used, lengths limited to 16 bits), odd sizes, several qualities."""
+    imgs = []
+    for i, (h, w) in enumerate([(8, 8), (17, 33), (100, 161), (241, 319), (600, 900), (1536, 2048)]):
+        for kind in ("smooth", "noise", "edges"):
+            im = rand_image(h, w, channels, seed=5 * i + 1, kind=kind)
+            imgs.append(im[:, :, 0] if channels == 1 else im)
+    flat = np.full((64, 64, channels), 77, np.uint8)
+    imgs.append(flat[:, :, 0] if channels == 1 else flat)
+    for q in (85, 100, 25):
+        got = engine.encode_jpeg_batch(imgs, quality=q, optimize=True)
+        for i, (g, im) in enumerate(zip(got, imgs)):
+            ref = _pillow_encode_opt(im, q)
+            assert g == ref, f"quality {q} image {i} shape {im.shape}: {_explain(g, ref)}"
+    plain = engine.encode_jpeg_batch(imgs[-4:-1], quality=25)
+    assert all(len(a) <= len(b) for a, b in zip(got[-4:-1], plain))
