@@ -5,8 +5,8 @@ rewrites the same `req.file` fields (imagePreprocess.js:70-78), records the same
 (:43,54,64-65) and reports failures through `next(Problem)` with the same status codes (:25-34,81-90).
 Everything between the upload and the returned file runs in libirp_b200.so: baseline JPEG uploads are decoded on
 the device (other containers by Pillow on the host), then EXIF auto-orient, lanczos3 fit-inside <= 2048, normalise,
-and the q85 4:4:4 JPEG encode with the sRGB profile attached (the file is libjpeg-turbo's
-baseline file of those pixels, not mozjpeg's trellis / progressive one).
+and the q85 4:4:4 JPEG encode with optimised Huffman tables and the sRGB profile attached (SURVEY.md §8f rows 1-2;
+the file is libjpeg-turbo's optimised sequential file of those pixels, not mozjpeg's trellis / progressive one).
 """
 from __future__ import annotations
 
@@ -87,7 +87,7 @@ def encode_jpeg(px: np.ndarray, engine: Optional[Engine] = None) -> bytes:
     eng = engine if engine is not None else _get_engine(None)
     eng.set_output_icc(_srgb_profile())      # the profile is a property of THIS middleware's files, not of the engine
     try:
-        return eng.encode_jpeg_batch([px[:, :, 0] if px.shape[2] == 1 else px], quality=JPEG_QUALITY)[0]
+        return eng.encode_jpeg_batch([px[:, :, 0] if px.shape[2] == 1 else px], quality=JPEG_QUALITY, optimize=True)[0]
     finally:
         eng.set_output_icc(None)
 

@@ -164,5 +164,5 @@ def test_preprocess_of_a_jpeg_upload_never_touches_a_host_codec(engine, oracle):
     ref = io.BytesIO()
     icc = Image.open(io.BytesIO(req.file.buffer)).info["icc_profile"]   # (LittleCMS stamps the creation second into it)
     assert len(icc) == len(ImageCms.ImageCmsProfile(ImageCms.createProfile("sRGB")).tobytes()) and icc[36:40] == b"acsp"
-    Image.fromarray(want_px).save(ref, "JPEG", quality=85, subsampling=0, icc_profile=icc)
+    Image.fromarray(want_px).save(ref, "JPEG", quality=85, subsampling=0, optimize=True, icc_profile=icc)
     assert req.file.buffer == ref.getvalue()
