@@ -4,8 +4,8 @@
 //
 // What is reproduced bit for bit is libjpeg-turbo's BASELINE encoder (the library under sharp / libvips and
 // under Pillow): jccolor.c RGB -> YCbCr in 16-bit fixed point, jfdctint.c (accurate integer forward DCT),
-// jcdctmgr.c quantisation by 16-bit reciprocals, jchuff.c sequential Huffman coding with the Annex K tables,
-// 4:4:4, no restart markers.  mozjpeg's trellis quantisation and progressive scan optimisation (sharp's
+// jcdctmgr.c quantisation by 16-bit reciprocals, jchuff.c sequential Huffman coding with the Annex K tables or
+// with tables optimised per image (optimize_coding), 4:4:4, no restart markers.  mozjpeg's trellis quantisation and progressive scan optimisation (sharp's
 // `mozjpeg: true`) are file-size optimisations on top of the same transform; they are NOT reproduced — a
 // decoder sees the same kind of image, the file is ~10 % larger.
 //
@@ -16,6 +16,8 @@
 //                      exclusive scan per image = bit offset of every block, total bits per image
 //   jenc_pack_kernel   one thread per block: Huffman-code the block into the image's bit stream at its offset
 //                      (whole words stored, the words shared with a neighbour block OR-ed atomically)
+//   jenc_hist_kernel / jenc_blocklen_kernel   (IRP_JPEG_OPTIMIZE) symbol statistics per image for the host's
+//                      jpeg_gen_optimal_table, then the block lengths under the image's own tables
 //   jenc_ffcount_kernel / seg_scan_kernel / jenc_stuff_kernel   0xFF -> 0xFF00 byte stuffing as a stream expansion
 #pragma once
 #include <cstdint>
