@@ -6,20 +6,18 @@
 // sharp once, processed natively as raw pixels and encoded by sharp as before.
 import sharp from 'sharp';
 import { createRequire } from 'node:module';
-import { readFileSync } from 'node:fs';
 import { createProblem } from '../utils/problem.js';
 
 const native = createRequire(import.meta.url)('./build/Release/irp_addon.node');
 const MAX_DIMENSION = 2048;
 const JPEG_QUALITY = 85;
 const IRP_JPEG_OPTIMIZE = 0x100;
+const IRP_JPEG_ICC_SRGB = 1 << 16;   // IRP_JPEG_ICC(IRP_ICC_SRGB): the library's generated sRGB profile, named per call
 
 let ctx = null;
 function context() {
   if (!ctx) {
     ctx = native.createContext(Number(process.env.IRP_DEVICE ?? 0));
-    // the integrator's copy of the sRGB profile (libvips' own is not redistributed with this addon)
-    if (process.env.IRP_SRGB_ICC) native.setOutputIcc(ctx, readFileSync(process.env.IRP_SRGB_ICC));
   }
   return ctx;
 }
@@ -43,7 +41,7 @@ export async function preprocessImage(req, _res, next) {
     if (target) operations.push(`resize_${target.width}x${target.height}`);
     let processed, outInfo;
     try {
-      const r = await native.transcodeFile(context(), source, meta.orientation ?? 1, JPEG_QUALITY | IRP_JPEG_OPTIMIZE);
+      const r = await native.transcodeFile(context(), source, meta.orientation ?? 1, JPEG_QUALITY | IRP_JPEG_OPTIMIZE | IRP_JPEG_ICC_SRGB);   // 'attach_sRGB_icc' is always true
       processed = r.file;
       outInfo = { width: r.width, height: r.height, channels: r.channels };
     } catch (e) {

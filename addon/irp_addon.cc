@@ -10,7 +10,8 @@
 //   analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>   (baseline JPEG bytes, decoded on the device)
 //   transcodeFile(ctx, file:Buffer, orientation, quality) -> Promise<{scores:Float64Array(7), file:Buffer, width, height, channels}>
 //       analyze() + preprocessImage() of one upload with files on both sides (irp_transcode_jpeg_batch)
-//   setOutputIcc(ctx, profile:Buffer|null)   ICC profile attached to every file transcodeFile returns (withMetadata({icc}))
+//       `quality` carries the flags of include/irp.h: IRP_JPEG_OPTIMIZE, IRP_JPEG_ICC(id) (IRP_ICC_SRGB = the generated sRGB profile)
+//   setOutputIcc(ctx, profile:Buffer|null)   the context DEFAULT profile (files encoded without IRP_JPEG_ICC bits); set once at start-up
 //   analyzeRaw(ctx, pixels:Buffer, width, height, channels, isJpeg:boolean) -> Promise<Float64Array(7)>
 //   preprocessRaw(ctx, pixels:Buffer, width, height, channels, orientation) -> Promise<{data:Buffer,width,height,channels}>
 // Work runs on the libuv pool through napi_create_async_work, so the event loop never blocks
@@ -50,7 +51,7 @@ void Execute(napi_env, void* data) {
     j->rc = irp_jpeg_info(j->jpeg.data, j->jpeg.size, &w, &h, &c);
     if (j->rc == IRP_OK) j->rc = irp_preprocess_dims(w, h, j->jpeg.exif_orientation, &ow, &oh);
     for (int attempt = 0; j->rc == IRP_OK && attempt < 2; attempt++) {
-      j->enc.capacity = attempt ? j->enc.size : static_cast<size_t>(ow) * oh * (c == 1 ? 1 : 3) / 2 + 4096;
+      j->enc.capacity = attempt ? j->enc.size : static_cast<size_t>(ow) * oh * (c == 1 ? 1 : 3) / 2 + 8192;   // + header and a small profile
       std::free(j->enc.data);
       j->enc.data = static_cast<uint8_t*>(std::malloc(j->enc.capacity));
       if (!j->enc.data) { j->rc = IRP_ERR_NOMEM; break; }

@@ -14,6 +14,15 @@ LIB_PATH = os.environ.get("IRP_LIB_PATH") or os.path.join(_HERE, "libirp_b200.so
 
 IRP_OK = 0
 IRP_ERR_BAD_ARG, IRP_ERR_UNSUPPORTED, IRP_ERR_CUDA, IRP_ERR_NOMEM, IRP_ERR_NO_DEVICE, IRP_ERR_CAPACITY = -1, -2, -3, -4, -5, -6
+ICC_SRGB = 1              # IRP_ICC_SRGB: the library's generated sRGB profile
+JPEG_OPTIMIZE = 0x100     # IRP_JPEG_OPTIMIZE
+
+
+def jpeg_icc(profile_id: int) -> int:
+    """IRP_JPEG_ICC(id): the profile of one encode call, OR-ed into `quality`."""
+    return (profile_id & 0xFF) << 16
+
+
 FUSION_CANVAS = 2048
 FUSION_MAX_IMAGES = 3
 
@@ -23,7 +32,7 @@ SYMBOLS = (
     "irp_get_timing", "irp_preprocess_dims", "irp_fusion_dims", "irp_scores_from_moments", "irp_grey_tables",
     "irp_classify_batch", "irp_preprocess_batch", "irp_analyze_batch", "irp_fusion_prepare_batch",
     "irp_submit", "irp_submit_jpeg", "irp_submit_transcode", "irp_wait", "irp_jpeg_info", "irp_decode_jpeg_batch", "irp_analyze_jpeg_batch",
-    "irp_set_output_icc", "irp_encode_jpeg_batch", "irp_analyze_encode_batch", "irp_transcode_jpeg_batch",
+    "irp_set_output_icc", "irp_register_icc", "irp_get_icc", "irp_encode_jpeg_batch", "irp_analyze_encode_batch", "irp_transcode_jpeg_batch",
     "irp_dev_alloc", "irp_dev_free", "irp_host_alloc_pinned", "irp_host_free_pinned", "irp_memcpy_h2d",
     "irp_memcpy_d2h", "irp_synchronize",
 )
@@ -105,6 +114,8 @@ def load() -> C.CDLL:
     lib.irp_decode_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(OutDesc)]
     lib.irp_analyze_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(Result), C.POINTER(OutDesc)]
     lib.irp_set_output_icc.argtypes = [vp, vp, C.c_size_t]
+    lib.irp_register_icc.argtypes = [vp, vp, C.c_size_t]
+    lib.irp_get_icc.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.irp_encode_jpeg_batch.argtypes = [vp, C.POINTER(ImageDesc), i32, i32, C.POINTER(JpegOut)]
     lib.irp_analyze_encode_batch.argtypes = [vp, C.POINTER(ImageDesc), i32, C.POINTER(Result), i32, C.POINTER(JpegOut)]
     lib.irp_transcode_jpeg_batch.argtypes = [vp, C.POINTER(JpegDesc), i32, C.POINTER(Result), i32, C.POINTER(JpegOut)]

@@ -6,11 +6,13 @@
 // One context per GPU; calls on one context are serialised by a mutex (the Node
 // addon / Python mirror give each worker its own context or batch their jobs).
 // No CPU fallback: every entry point that touches pixels needs the device.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -149,9 +151,16 @@ struct irp_ctx {
   // compressed-input batches are cut into lanes: child contexts (own streams and scratch) driven by their own host
   // threads, so one lane's marker scan / un-stuffing / uploads / size read-backs run under the other lanes' kernels
   std::vector<irp_ctx*> lanes;
-  std::vector<uint8_t> icc;       // profile attached to encoded files (irp_set_output_icc)
+  // ICC profiles an encode call can name (IRP_JPEG_ICC(id) in `quality`): slot 0 = the context default
+  // (irp_set_output_icc), slot IRP_ICC_SRGB = the generated sRGB profile, then irp_register_icc's.  Entries are
+  // immutable once published; a call holds a shared_ptr to the one it encodes with.  Lanes resolve through `parent`.
+  std::mutex icc_mu;
+  std::vector<std::shared_ptr<const std::vector<uint8_t>>> icc_profiles;
+  irp_ctx* parent = nullptr;
   std::mutex lanes_mu;
   bool is_lane = false;
+  std::mutex pin_mu;
+  std::vector<void*> pinned;      // irp_host_alloc_pinned allocations still alive: freed with the context
 };
 
 namespace {
@@ -972,7 +981,20 @@ int run_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* resul
   ctx->err.clear();
   return run_batch_locked(ctx, imgs, n, results, outs, resize_mode);
 }
+// A failing call must not leave copies to or from the caller's buffers (or reads of the context's pinned
+// scratch) in flight: the caller may free or reuse them as soon as the call returns.
+void drain_streams(irp_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_in_stream) cudaStreamSynchronize(ctx->copy_in_stream);
+  if (ctx->copy_out_stream) cudaStreamSynchronize(ctx->copy_out_stream);
+}
+int run_batch_inner(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode);
 int run_batch_locked(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode) {
+  const int rc = run_batch_inner(ctx, imgs, n, results, outs, resize_mode);
+  if (rc != IRP_OK) drain_streams(ctx);
+  return rc;
+}
+int run_batch_inner(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result* results, irp_out_desc* outs, int resize_mode) {
   if (n < 0 || (n > 0 && !imgs)) return fail(ctx, IRP_ERR_BAD_ARG, "bad batch arguments");
   if (n == 0) return IRP_OK;
   CK(cudaSetDevice(ctx->device));
@@ -1090,6 +1112,16 @@ int run_batch_locked(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result
   return IRP_OK;
 }
 
+#include "irp_icc.inc"
+
+// the profile an encode call attaches: id 0 = the context default (may be empty)
+std::shared_ptr<const std::vector<uint8_t>> resolve_icc(irp_ctx* ctx, int id) {
+  irp_ctx* root = ctx->parent ? ctx->parent : ctx;
+  std::lock_guard<std::mutex> lk(root->icc_mu);
+  if (id < 0 || id >= (int)root->icc_profiles.size()) return nullptr;
+  return root->icc_profiles[id];
+}
+
 #include "irp_jpeg_host.inc"
 #include "irp_jpeg_enc_host.inc"
 
@@ -1126,6 +1158,8 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
     return nullptr;
   }
   ctx = new irp_ctx();
+  ctx->icc_profiles.push_back(std::make_shared<const std::vector<uint8_t>>());                        // 0: default, none
+  ctx->icc_profiles.push_back(std::make_shared<const std::vector<uint8_t>>(make_srgb_profile()));     // IRP_ICC_SRGB
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (opts) memcpy(&ctx->opts, opts, std::min<size_t>(opts->struct_size, sizeof(irp_opts)));
@@ -1195,14 +1229,23 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
 
 void irp_destroy(irp_ctx* ctx) {
   if (!ctx) return;
-  for (irp_ctx* l : ctx->lanes) irp_destroy(l);
-  ctx->lanes.clear();
+  // the dispatcher drains its queue on stop and may still be inside a lane-split batch: stop and join it
+  // first, then take the lanes away (under their lock), then the context itself (under its lock)
   {
     std::lock_guard<std::mutex> lk(ctx->qmu);
     ctx->stop = true;
   }
   ctx->qcv.notify_all();
   if (ctx->dispatcher_started && ctx->dispatcher.joinable()) ctx->dispatcher.join();
+  {
+    std::vector<irp_ctx*> lanes;
+    {
+      std::lock_guard<std::mutex> lk(ctx->lanes_mu);
+      lanes.swap(ctx->lanes);
+    }
+    for (irp_ctx* l : lanes) irp_destroy(l);
+  }
+  { std::lock_guard<std::mutex> lk(ctx->mu); }   // a synchronous call still running on another thread finishes first
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   for (auto& ev : ctx->ev)
@@ -1220,6 +1263,7 @@ void irp_destroy(irp_ctx* ctx) {
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);
   if (ctx->h_error_flag) cudaFreeHost(ctx->h_error_flag);
+  for (void* p : ctx->pinned) cudaFreeHost(p);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1358,11 +1402,17 @@ int irp_decode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_o
   std::vector<JpegPlaced> pl;
   int rc = decode_jpegs_locked(ctx, jpegs, n, &pl);
   if (rc) return rc;
+  for (int i = 0; i < n; i++) {   // every output is checked before the first copy is queued
+    const irp_out_desc& od = outs[i];
+    const size_t tight = (size_t)pl[i].w * pl[i].c, pitch = od.pitch ? od.pitch : tight;
+    if (!od.pixels || pitch < tight || od.capacity < pitch * (size_t)(pl[i].h - 1) + tight) {
+      drain_streams(ctx);
+      return fail(ctx, IRP_ERR_CAPACITY, "output %d: capacity %zu too small for %dx%dx%d", i, od.capacity, pl[i].w, pl[i].h, pl[i].c);
+    }
+  }
   for (int i = 0; i < n; i++) {
     irp_out_desc& od = outs[i];
     const size_t tight = (size_t)pl[i].w * pl[i].c, pitch = od.pitch ? od.pitch : tight;
-    if (!od.pixels || pitch < tight || od.capacity < pitch * (size_t)(pl[i].h - 1) + tight)
-      return fail(ctx, IRP_ERR_CAPACITY, "output %d: capacity %zu too small for %dx%dx%d", i, od.capacity, pl[i].w, pl[i].h, pl[i].c);
     od.width = pl[i].w;
     od.height = pl[i].h;
     od.channels = pl[i].c;
@@ -1387,27 +1437,29 @@ static int run_in_lanes(irp_ctx* ctx, int n, const std::function<int(irp_ctx*, i
       irp_ctx* l = irp_create(ctx->device, &ctx->opts);
       if (!l) return f(ctx, 0, n);      // no memory for another lane: run unsplit
       l->is_lane = true;
+      l->parent = ctx;      // profiles (IRP_JPEG_ICC) resolve through the parent
       ctx->lanes.push_back(l);
     }
   }
-  for (int k = 1; k < want; k++) {   // the lanes encode with the parent's profile
-    std::lock_guard<std::mutex> lk(ctx->lanes[k - 1]->mu);
-    if (ctx->lanes[k - 1]->icc != ctx->icc) ctx->lanes[k - 1]->icc = ctx->icc;
+  std::vector<irp_ctx*> lanes;
+  {
+    std::lock_guard<std::mutex> lk(ctx->lanes_mu);
+    lanes = ctx->lanes;
   }
   std::vector<int> rc(want, IRP_OK);
   std::vector<std::thread> th;
   auto part = [&](int k) { return (int)((long long)n * k / want); };
-  for (int k = 1; k < want; k++) th.emplace_back([&, k] { rc[k] = f(ctx->lanes[k - 1], part(k), part(k + 1) - part(k)); });
+  for (int k = 1; k < want; k++) th.emplace_back([&, k] { rc[k] = f(lanes[k - 1], part(k), part(k + 1) - part(k)); });
   rc[0] = f(ctx, 0, part(1));
   for (auto& t : th) t.join();
   for (int k = 1; k < want; k++) {
     std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->timing.kernel_launches += ctx->lanes[k - 1]->timing.kernel_launches;
-    ctx->timing.classify_ms += ctx->lanes[k - 1]->timing.classify_ms;       // sums over lanes (they overlap in time)
-    ctx->timing.preprocess_ms += ctx->lanes[k - 1]->timing.preprocess_ms;
+    ctx->timing.kernel_launches += lanes[k - 1]->timing.kernel_launches;
+    ctx->timing.classify_ms += lanes[k - 1]->timing.classify_ms;       // sums over lanes (they overlap in time)
+    ctx->timing.preprocess_ms += lanes[k - 1]->timing.preprocess_ms;
     if (rc[k] != IRP_OK && rc[0] == IRP_OK) {
       rc[0] = rc[k];
-      ctx->err = ctx->lanes[k - 1]->err;
+      ctx->err = lanes[k - 1]->err;
     }
   }
   return rc[0];
@@ -1444,9 +1496,31 @@ static int analyze_jpeg_single(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, 
 // ---- compressed output: baseline JPEG encoded on the device ----
 int irp_set_output_icc(irp_ctx* ctx, const uint8_t* profile, size_t size) {
   if (!ctx || (size && !profile) || size > 255u * 65519u) return IRP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  ctx->icc.assign(profile, profile + size);
+  auto prof = std::make_shared<const std::vector<uint8_t>>(profile, profile + size);
+  std::lock_guard<std::mutex> lock(ctx->icc_mu);
+  ctx->icc_profiles[0] = prof;   // calls already running keep the profile they resolved
   return IRP_OK;
+}
+
+int irp_register_icc(irp_ctx* ctx, const uint8_t* profile, size_t size) {
+  if (!ctx || !profile || !size || size > 255u * 65519u) return IRP_ERR_BAD_ARG;
+  auto prof = std::make_shared<const std::vector<uint8_t>>(profile, profile + size);
+  std::lock_guard<std::mutex> lock(ctx->icc_mu);
+  for (size_t k = 1; k < ctx->icc_profiles.size(); k++)
+    if (*ctx->icc_profiles[k] == *prof) return (int)k;   // registering the same bytes again returns the same id
+  if (ctx->icc_profiles.size() >= 256) return IRP_ERR_CAPACITY;
+  ctx->icc_profiles.push_back(prof);
+  return (int)ctx->icc_profiles.size() - 1;
+}
+
+int irp_get_icc(irp_ctx* ctx, int id, uint8_t* out, size_t capacity, size_t* size) {
+  if (!size || (!ctx && id != IRP_ICC_SRGB)) return IRP_ERR_BAD_ARG;
+  // the generated sRGB profile needs no context (and no device): a host-only helper like irp_preprocess_dims
+  auto prof = ctx ? resolve_icc(ctx, id) : std::make_shared<const std::vector<uint8_t>>(make_srgb_profile());
+  if (!prof) return IRP_ERR_BAD_ARG;
+  *size = prof->size();
+  if (out && capacity >= prof->size() && !prof->empty()) memcpy(out, prof->data(), prof->size());
+  return (out && capacity < prof->size()) ? IRP_ERR_CAPACITY : IRP_OK;
 }
 
 int irp_encode_jpeg_batch(irp_ctx* ctx, const irp_image_desc* imgs, int n, int quality, irp_jpeg_out* outs) {
@@ -1783,11 +1857,21 @@ void* irp_host_alloc_pinned(irp_ctx* ctx, size_t bytes) {
     fail(ctx, IRP_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
     return nullptr;
   }
+  {
+    std::lock_guard<std::mutex> lk(ctx->pin_mu);
+    ctx->pinned.push_back(p);
+  }
   return p;
 }
 int irp_host_free_pinned(irp_ctx* ctx, void* p) {
   if (!ctx) return IRP_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
+  {
+    std::lock_guard<std::mutex> lk(ctx->pin_mu);
+    auto it = std::find(ctx->pinned.begin(), ctx->pinned.end(), p);
+    if (it == ctx->pinned.end()) return fail(ctx, IRP_ERR_BAD_ARG, "irp_host_free_pinned: not an allocation of this context");
+    ctx->pinned.erase(it);
+  }
   CK(cudaFreeHost(p));
   return IRP_OK;
 }

@@ -301,11 +301,11 @@ class Engine:
         return [a[:, :, 0] if a.shape[2] == 1 else a for a in arrays]
 
     # -- compressed output: baseline JPEG encoded on the device ---------------
-    def _encode_call(self, fn, n, caps):
-        """Run fn(outs) with host buffers of caps[i] bytes; one retry with the sizes the library asks for."""
+    def _encode_call(self, fn, n, caps, icc: int = 0):
+        """Run fn(outs) with host buffers of caps[i] bytes (+ the call's profile); one retry with the sizes the library asks for."""
+        extra = self._icc_overhead(icc)
         for attempt in range(2):
-            icc = getattr(self, "_icc_len", 0)
-            bufs = [np.empty(int(c) + icc + 18 * (icc // 65519 + 1), np.uint8) for c in caps]
+            bufs = [np.empty(int(c) + extra, np.uint8) for c in caps]
             outs = (_ffi.JpegOut * n)(*[_ffi.JpegOut(b.ctypes.data, b.size, 0, 0, 0, 0, 0) for b in bufs])
             rc = fn(outs)
             if rc == _ffi.IRP_ERR_CAPACITY and attempt == 0:
@@ -314,23 +314,49 @@ class Engine:
             self._check(rc)
             return [bytes(memoryview(b)[:o.size]) for b, o in zip(bufs, outs)]
 
+    # -- ICC profiles: chosen per call (IRP_JPEG_ICC), never toggled on the context ---------------
+    SRGB = _ffi.ICC_SRGB   # the library's generated sRGB profile, always registered
+
+    def register_icc(self, profile: bytes) -> int:
+        """Publish an immutable profile in the context's registry; the returned id goes into `icc=` of the encode calls."""
+        b = np.frombuffer(profile, np.uint8)
+        rc = self._lib.irp_register_icc(self._ctx, b.ctypes.data, b.size)
+        if rc < 0:
+            raise IrpError(rc, "irp_register_icc rejected the profile")
+        return rc
+
+    def icc_bytes(self, icc: int) -> bytes:
+        """The bytes of a registered profile (icc=Engine.SRGB: the generated sRGB one)."""
+        size = C.c_size_t()
+        self._check(self._lib.irp_get_icc(self._ctx, icc, None, 0, C.byref(size)))
+        buf = np.empty(max(size.value, 1), np.uint8)
+        self._check(self._lib.irp_get_icc(self._ctx, icc, buf.ctypes.data, buf.size, C.byref(size)))
+        return bytes(memoryview(buf)[: size.value])
+
+    def _icc_overhead(self, icc: int) -> int:
+        """Bytes the APP2 segments of profile `icc` add to a file (18 per 65519-byte segment)."""
+        size = C.c_size_t()
+        self._check(self._lib.irp_get_icc(self._ctx, icc, None, 0, C.byref(size)))
+        n = size.value
+        return n + 18 * ((n + 65518) // 65519) if n else 0
+
     def set_output_icc(self, profile: Optional[bytes]) -> None:
-        """Attach an ICC profile (`.withMetadata({icc})`, imagePreprocess.js:57-67) to every file encoded from now on; None clears it."""
+        """The context DEFAULT profile (used by calls that pass icc=0); None clears it.  Set it once, e.g. at start-up:
+        per-request profiles go through register_icc + `icc=`, which concurrent requests cannot disturb."""
         b = np.frombuffer(profile, np.uint8) if profile else None
         self._check(self._lib.irp_set_output_icc(self._ctx, b.ctypes.data if b is not None else None, b.size if b is not None else 0))
-        self._icc_len = 0 if b is None else int(b.size)
 
-    def encode_jpeg_batch(self, images: Sequence[ImageLike], quality: int = 85, optimize: bool = False) -> List[bytes]:
+    def encode_jpeg_batch(self, images: Sequence[ImageLike], quality: int = 85, optimize: bool = False, icc: int = 0) -> List[bytes]:
         """u8 RGB / grey images (host arrays or DeviceImages) -> baseline 4:4:4 JPEG files, byte-identical to
         libjpeg-turbo's (imagePreprocess.js:50-53 without mozjpeg's trellis / progressive passes)."""
         n = len(images)
         descs, keep = self._descs(images, True, None)
         caps = [d.width * d.height * d.channels + 4096 for d in descs]
-        q = quality | (0x100 if optimize else 0)   # IRP_JPEG_OPTIMIZE
-        return self._encode_call(lambda outs: self._lib.irp_encode_jpeg_batch(self._ctx, descs, n, q, outs), n, caps)
+        q = quality | (_ffi.JPEG_OPTIMIZE if optimize else 0) | _ffi.jpeg_icc(icc)
+        return self._encode_call(lambda outs: self._lib.irp_encode_jpeg_batch(self._ctx, descs, n, q, outs), n, caps, icc)
 
     def analyze_encode_batch(self, images: Sequence[ImageLike], is_jpeg=True, orientations=None, quality: int = 85, classify: bool = True,
-                             raw: bool = False):
+                             raw: bool = False, icc: int = 0):
         """analyze() + preprocessImage() of raw pixels: (score dicts, preprocessed JPEG FILES)."""
         n = len(images)
         descs, keep = self._descs(images, is_jpeg, orientations)
@@ -339,11 +365,13 @@ class Engine:
         for d in descs:
             ow, oh = self.preprocess_dims(d.width, d.height, d.exif_orientation)
             caps.append(ow * oh * (1 if d.channels == 1 else 3) // 2 + 4096)
-        files = self._encode_call(lambda outs: self._lib.irp_analyze_encode_batch(self._ctx, descs, n, res, quality, outs), n, caps)
+        q = quality | _ffi.jpeg_icc(icc)
+        files = self._encode_call(lambda outs: self._lib.irp_analyze_encode_batch(self._ctx, descs, n, res, q, outs), n, caps, icc)
         results = None if res is None else (list(res) if raw else [result_to_dict(r) for r in res])
         return results, files
 
-    def transcode_jpeg_batch(self, blobs: Sequence[bytes], orientations=None, quality: int = 85, classify: bool = True, raw: bool = False):
+    def transcode_jpeg_batch(self, blobs: Sequence[bytes], orientations=None, quality: int = 85, classify: bool = True, raw: bool = False,
+                             icc: int = 0):
         """JPEG files in -> (score dicts, preprocessed JPEG files): decode, classify, resize and re-encode on the
         device; only file bytes cross PCIe in either direction."""
         n = len(blobs)
@@ -359,7 +387,8 @@ class Engine:
             ow, oh = self.preprocess_dims(info[0], info[1], o)
             caps.append(ow * oh * (1 if info[2] == 1 else 3) // 2 + 4096)
         res = (_ffi.Result * n)() if classify else None
-        files = self._encode_call(lambda outs: self._lib.irp_transcode_jpeg_batch(self._ctx, descs, n, res, quality, outs), n, caps)
+        q = quality | _ffi.jpeg_icc(icc)
+        files = self._encode_call(lambda outs: self._lib.irp_transcode_jpeg_batch(self._ctx, descs, n, res, q, outs), n, caps, icc)
         results = None if res is None else (list(res) if raw else [result_to_dict(r) for r in res])
         return results, files
 
@@ -395,7 +424,7 @@ class Engine:
             raise IrpError(rc, "irp_submit_jpeg rejected the request")
         return {"ticket": ticket, "descs": desc, "keep": k, "outs": outs, "array": arr, "res": res}
 
-    def submit_transcode(self, blob: bytes, orientation: int = 1, quality: int = 85, classify: bool = True):
+    def submit_transcode(self, blob: bytes, orientation: int = 1, quality: int = 85, classify: bool = True, icc: int = 0):
         """Queue ONE baseline JPEG FILE for analyze() + preprocessImage(): wait() returns (scores, preprocessed FILE bytes)."""
         k = np.frombuffer(blob, np.uint8)
         info = self.jpeg_info(k)
@@ -403,7 +432,9 @@ class Engine:
             raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, "not a baseline JPEG the device decoder takes")
         desc = _ffi.JpegDesc(k.ctypes.data, k.size, orientation, 0)
         ow, oh = self.preprocess_dims(info[0], info[1], orientation)
-        buf = np.empty(ow * oh * (1 if info[2] == 1 else 3) + 4096, np.uint8)   # a file never exceeds its pixels by more than the header at q <= 95
+        # a file never exceeds its pixels by more than the header (and its profile) at q <= 95
+        buf = np.empty(ow * oh * (1 if info[2] == 1 else 3) + 4096 + self._icc_overhead(icc), np.uint8)
+        quality = quality | _ffi.jpeg_icc(icc)
         enc = _ffi.JpegOut(buf.ctypes.data, buf.size, 0, 0, 0, 0, 0)
         res = _ffi.Result() if classify else None
         ticket = C.c_void_p()

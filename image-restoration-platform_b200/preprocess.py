@@ -72,24 +72,11 @@ def _set(file, key, value):
         setattr(file, key, value)
 
 
-def _srgb_profile() -> Optional[bytes]:
-    """An sRGB profile for `.withMetadata({icc:'sRGB'})` (LittleCMS' built-in one through Pillow; libvips embeds its own)."""
-    try:
-        from PIL import ImageCms
-
-        return ImageCms.ImageCmsProfile(ImageCms.createProfile("sRGB")).tobytes()
-    except Exception:
-        return None
-
-
 def encode_jpeg(px: np.ndarray, engine: Optional[Engine] = None) -> bytes:
-    """.jpeg({quality:85, chromaSubsampling:'4:4:4'}).withMetadata({icc:'sRGB'}) — on the device."""
+    """.jpeg({quality:85, chromaSubsampling:'4:4:4'}).withMetadata({icc:'sRGB'}) — on the device.  The profile is named
+    per call (Engine.SRGB, the library's generated sRGB profile): nothing on the shared engine is toggled."""
     eng = engine if engine is not None else _get_engine(None)
-    eng.set_output_icc(_srgb_profile())      # the profile is a property of THIS middleware's files, not of the engine
-    try:
-        return eng.encode_jpeg_batch([px[:, :, 0] if px.shape[2] == 1 else px], quality=JPEG_QUALITY, optimize=True)[0]
-    finally:
-        eng.set_output_icc(None)
+    return eng.encode_jpeg_batch([px[:, :, 0] if px.shape[2] == 1 else px], quality=JPEG_QUALITY, optimize=True, icc=Engine.SRGB)[0]
 
 
 def _jpeg_orientation(buf) -> int:
@@ -124,18 +111,19 @@ def preprocess_image(req, _res, next):  # imagePreprocess.js:24-91
         if needs_resize(w, h):
             d = calculate_resize_dimensions(w, h)
             operations.append(f"resize_{d['width']}x{d['height']}")
-        if px is None:
-            out = eng.analyze_jpeg_batch([bytes(buf)], orientations=[orientation], classify=False)[1][0]
-        else:
-            out = eng.preprocess_batch([px], orientations=[orientation])[0]
         operations.append(f"compress_jpeg_q{JPEG_QUALITY}")
         operations.append("attach_sRGB_icc")
-        processed = encode_jpeg(out, eng)
+        q = JPEG_QUALITY | 0x100   # IRP_JPEG_OPTIMIZE: sharp's mozjpeg preset implies optimised Huffman tables
+        if px is None:   # a baseline JPEG upload: ONE call, file in -> file out, no pixel crosses PCIe
+            processed = eng.transcode_jpeg_batch([bytes(buf)], orientations=[orientation], quality=q, classify=False, icc=Engine.SRGB)[1][0]
+        else:            # other containers were decoded on the host: pixels in -> file out, still one call
+            processed = eng.analyze_encode_batch([px[:, :, 0] if c == 1 else px], is_jpeg=False, orientations=[orientation], quality=q,
+                                                 classify=False, icc=Engine.SRGB)[1][0]
+        ow, oh = eng.preprocess_dims(w, h, orientation)
         _set(file, "originalBuffer", buf)
         _set(file, "originalMetadata", source_metadata)
         _set(file, "buffer", processed)
-        _set(file, "processedMetadata", {"width": out.shape[1], "height": out.shape[0], "format": "jpeg", "channels": out.shape[2]})
-        _set(file, "processedPixels", out)  # decoded form, so the worker can classify without a re-decode
+        _set(file, "processedMetadata", {"width": ow, "height": oh, "format": "jpeg", "channels": 1 if c == 1 else 3})
         _set(file, "mimetype", "image/jpeg")
         _set(file, "detectedMime", "image/jpeg")
         _set(file, "detectedExt", "jpg")

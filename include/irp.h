@@ -197,11 +197,21 @@ typedef struct irp_jpeg_out {
   int32_t width, height, channels; /* out: dims of the encoded image             */
   int32_t reserved;
 } irp_jpeg_out;
-/* `.withMetadata({icc: 'srgb'})` (imagePreprocess.js:57-67): an ICC profile attached to every file this context
- * encodes from now on, as APP2 "ICC_PROFILE" segments right behind the JFIF header (jpeg_write_icc_profile's
- * layout, 65519 bytes per segment).  The bytes are the caller's (libvips' built-in sRGB profile is not
- * redistributed here); NULL / 0 clears it.  Output buffers must hold the profile as well. */
+/* `.withMetadata({icc: 'srgb'})` (imagePreprocess.js:57-67): an ICC profile attached to the files of an encode
+ * call as APP2 "ICC_PROFILE" segments right behind the JFIF header (jpeg_write_icc_profile's layout, 65519 bytes
+ * per segment).  The profile is chosen PER CALL: IRP_JPEG_ICC(id) OR-ed into `quality` names an immutable profile
+ * of the context's registry — IRP_ICC_SRGB (always there: an sRGB IEC 61966-2.1 v4 matrix/TRC profile generated
+ * by the library; libvips' own built-in file is not redistributed) or an id irp_register_icc returned.  Concurrent
+ * calls with different profiles do not interfere.  Output buffers must hold the profile as well.
+ * id 0 (no IRP_JPEG_ICC bits) = the context default set by irp_set_output_icc (none until then; NULL / 0 clears it):
+ * kept for callers that attach one profile to everything — do not toggle it around calls. */
+#define IRP_ICC_SRGB 1
+#define IRP_JPEG_ICC(id) (((id) & 0xFF) << 16)
 int irp_set_output_icc(irp_ctx *ctx, const uint8_t *profile, size_t size);
+/* returns the id (>= 2) of the profile, or a negative status; the same bytes always get the same id */
+int irp_register_icc(irp_ctx *ctx, const uint8_t *profile, size_t size);
+/* the bytes of profile `id` (out may be NULL to ask for the size); ctx may be NULL for IRP_ICC_SRGB */
+int irp_get_icc(irp_ctx *ctx, int id, uint8_t *out, size_t capacity, size_t *size);
 /* pixels (host or device, 1 or 3 channels) -> baseline JPEG files */
 int irp_encode_jpeg_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, int quality,
                           irp_jpeg_out *outs);

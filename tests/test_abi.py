@@ -171,3 +171,36 @@ def test_committed_jpeg_tables_are_what_libjpeg_turbo_writes(tmp_path):
     shutil.copy(os.path.join(root, "tools", "gen_jpeg_std_tables.py"), work / "tools" / "gen_jpeg_std_tables.py")
     subprocess.run([sys.executable, str(work / "tools" / "gen_jpeg_std_tables.py")], check=True, capture_output=True)
     assert open(work / "image-restoration-platform_b200" / "csrc" / "jpeg_std_tables.inc").read() == committed
+
+
+def test_generated_srgb_profile_is_a_valid_srgb_profile():
+    """`.withMetadata({icc:'sRGB'})` (imagePreprocess.js:63): the library generates its own sRGB profile (libvips' file
+    is not redistributed).  LittleCMS must parse it and it must be colorimetrically LittleCMS' own sRGB: converting
+    through either profile to Lab gives the same numbers; the bytes are reproducible (fixed date)."""
+    import ctypes as C
+    import io
+
+    import numpy as np
+    from PIL import Image, ImageCms
+
+    from irp_b200 import _ffi
+
+    lib = _ffi.load()
+    size = C.c_size_t()
+    assert lib.irp_get_icc(None, _ffi.ICC_SRGB, None, 0, C.byref(size)) == 0 and 400 < size.value < 1024
+    buf = (C.c_uint8 * size.value)()
+    assert lib.irp_get_icc(None, _ffi.ICC_SRGB, buf, size.value, C.byref(size)) == 0
+    prof = bytes(buf)
+    assert int.from_bytes(prof[:4], "big") == len(prof) and prof[36:40] == b"acsp" and prof[12:20] == b"mntrRGB "
+    assert lib.irp_get_icc(None, 0, None, 0, C.byref(size)) == _ffi.IRP_ERR_BAD_ARG   # other ids need a context
+    mine = ImageCms.ImageCmsProfile(io.BytesIO(prof))
+    assert ImageCms.getProfileDescription(mine).startswith("sRGB IEC61966-2.1")
+    theirs = ImageCms.createProfile("sRGB")
+    lab = ImageCms.createProfile("LAB")
+    rng = np.random.default_rng(3)
+    px = np.concatenate([rng.integers(0, 256, (64, 64, 3), dtype=np.uint8),
+                         np.repeat(np.arange(256, dtype=np.uint8)[None, :64, None], 3, axis=2).repeat(4, 0)], axis=0)
+    im = Image.fromarray(px)
+    a = np.asarray(ImageCms.profileToProfile(im, mine, lab, outputMode="LAB"), dtype=int)
+    b = np.asarray(ImageCms.profileToProfile(im, theirs, lab, outputMode="LAB"), dtype=int)
+    assert np.abs(a - b).max() <= 1

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 from PIL import Image
 
+import irp_b200
 from conftest import assert_result_parity, rand_image
 
 pytestmark = pytest.mark.gpu
@@ -172,6 +173,43 @@ def test_icc_profile_is_attached_like_libjpeg_turbo(engine):
     finally:
         engine.set_output_icc(None)
     assert engine.encode_jpeg_batch([img], quality=85)[0] == _pillow_encode(img, 85)
+
+
+def test_icc_profile_is_chosen_per_call_and_concurrent_calls_do_not_interfere(engine):
+    """the profile is an argument of the call (IRP_JPEG_ICC(id)), not mutable context state.
+    Threads encoding with different registered profiles, the generated sRGB one, and none at all, at the same
+    time, each get exactly their own profile in every file."""
+    import threading
+
+    img = rand_image(96, 128, 3, seed=8, kind="smooth")
+    rng = np.random.default_rng(11)
+    profs = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (600, 3144, 66000)]
+    ids = [engine.register_icc(p) for p in profs]
+    assert ids == [engine.register_icc(p) for p in profs] and len(set(ids)) == 3 and min(ids) >= 2
+    srgb = engine.icc_bytes(engine.SRGB)
+    assert srgb[36:40] == b"acsp" and engine.icc_bytes(ids[1]) == profs[1]
+    want = {0: None, engine.SRGB: srgb, **dict(zip(ids, profs))}
+    errors = []
+
+    def worker(icc):
+        try:
+            for _ in range(12):
+                f = engine.encode_jpeg_batch([img], quality=85, icc=icc)[0]
+                got = Image.open(io.BytesIO(f)).info.get("icc_profile")
+                if got != want[icc]:
+                    errors.append((icc, None if got is None else len(got)))
+        except Exception as ex:   # noqa: BLE001
+            errors.append((icc, repr(ex)))
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in want for _ in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", quality=85, subsampling=0, icc_profile=srgb)
+    assert engine.encode_jpeg_batch([img], quality=85, icc=engine.SRGB)[0] == b.getvalue()
+    with pytest.raises(irp_b200.IrpError):
+        engine.encode_jpeg_batch([img], quality=85, icc=200)   # never registered
 
 
 def test_decoded_pixels_equal_the_progressive_optimised_encoding(engine):

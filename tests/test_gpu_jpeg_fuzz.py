@@ -89,3 +89,24 @@ def test_header_over_the_pixel_limit_is_refused(engine):
         p += 2 + ((good[p + 2] << 8) | good[p + 3])
     good[p + 5:p + 9] = b"\xff\xff\xff\xff"      # 65535 x 65535
     assert engine.jpeg_info(bytes(good)) is None
+
+
+@pytest.mark.parametrize("restart", [0, 4])
+def test_restart_marker_flood_is_refused_without_overrunning_the_upload_slot(engine, restart):
+    """every RSTn pads the un-stuffed stream up to 4 bytes, so a scan made of 'X FF Dn' grows 3
+    input bytes into 4 output bytes.  With more markers than restart intervals the file is rejected (with DRI) or
+    any RSTn is (without DRI) — and the files sharing its batch and the context stay intact."""
+    img = rand_image(64, 64, 3, seed=5, kind="smooth")
+    good = _encode(img, quality=85, subsampling=0, restart_marker_blocks=restart) if restart else _encode(img, quality=85, subsampling=0)
+    ref = np.asarray(Image.open(io.BytesIO(good)))
+    s0 = _scan_start(good)
+    flood = b"".join(bytes([0x55, 0xFF, 0xD0 + (k & 7)]) for k in range(100000))
+    bad = good[:s0] + flood + b"\xff\xd9"
+    with pytest.raises(irp_b200.IrpError) as e:
+        engine.decode_jpeg_batch([bad])
+    assert "restart" in str(e.value)
+    neighbour = _encode(rand_image(200, 312, 3, seed=6, kind="smooth"), quality=90, subsampling=2)
+    with pytest.raises(irp_b200.IrpError):
+        engine.decode_jpeg_batch([neighbour, bad, good])
+    outs = engine.decode_jpeg_batch([neighbour, good])
+    assert np.array_equal(outs[0], np.asarray(Image.open(io.BytesIO(neighbour)))) and np.array_equal(outs[1], ref)
