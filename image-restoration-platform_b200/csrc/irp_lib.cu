@@ -33,6 +33,7 @@
 #include "irp_classify.cuh"
 #include "irp_classify_bulk.cuh"
 #include "irp_resize_tma.cuh"
+#include "irp_resize_mma.cuh"
 #include "irp_jpeg.cuh"
 #include "irp_jpeg_enc.cuh"
 #include "irp_resize.cuh"
@@ -93,6 +94,15 @@ struct PlanDev {
   uint32_t* hcols;   // [out][16]  ... and per-output-column horizontal table
   int n;
   std::vector<int32_t> h_start;   // host copy: tile footprints are sized on the host
+  // tensor-core resize (irp_resize_mma.cuh): edge-folded taps split hi / lo, first source index, pattern keys
+  int8_t* mm_tab = nullptr;       // [out][64]
+  int32_t* mm_first = nullptr;    // [out]
+  int32_t* mm_vkey = nullptr;     // [ceil(out / 128)]
+  int32_t* mm_hkey = nullptr;     // [ceil(out / 32)]
+  int mm_nt = 0;                  // taps per output after folding
+  int mm_rows = 0, mm_ksv = 0;    // as the vertical axis: source rows a 128-row tile touches, 32-row K steps per quarter
+  bool mm_v_ok = false, mm_h_ok = false;
+  std::vector<int32_t> h_mm_first;
 };
 
 }  // namespace
@@ -146,6 +156,10 @@ struct irp_ctx {
   std::deque<struct irp_request*> queue;
   bool stop = false, dispatcher_started = false;
   bool rtma_ok = true;    // IRP_NO_RTMA=1 keeps the generic resize kernel (A/B runs)
+  bool rmma_ok = false;   // the tensor-core resize kernel (IRP_NO_RMMA=1 turns it off)
+  std::map<std::string, int> mm_keys;   // coefficient-matrix pattern -> id (irp_resize_mma.cuh)
+  DevBuf d_mmjobs, d_mmmaps;
+  PinBuf h_mmjobs, h_mmmaps;
   bool bulk_ok = false;   // the streaming classify kernel's shared-memory map fits this device
   int* h_error_flag = nullptr;
   // compressed-input batches are cut into lanes: child contexts (own streams and scratch) driven by their own host
@@ -317,6 +331,92 @@ int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
   return IRP_OK;
 }
 
+// Tables of the tensor-core resize (irp_resize_mma.cuh) for one axis: per output its taps with the replicate edge
+// folded in (a tap that falls outside the image is added to the edge tap), split c = 128 * hi + lo; the first
+// source index they apply to; whether the axis fits the kernel's tile as the vertical / horizontal one; and one
+// pattern id per 128-row block / 32-column strip (equal ids = identical coefficient matrices).
+int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
+  const int no = (int)hp.start.size(), n = hp.n;
+  if (n > kMmMaxTaps) return IRP_OK;
+  std::vector<int8_t> tab((size_t)no * 64, 0);
+  std::vector<int32_t> first(no);
+  int nt_max = 1;
+  for (int o = 0; o < no; o++) {
+    const int s0 = hp.start[o];
+    const int16_t* ci = hp.coef.data() + (size_t)hp.phase[o] * kCoefStride;
+    const int lo_idx = std::min(std::max(s0, 0), in_size - 1), hi_idx = std::min(std::max(s0 + n - 1, 0), in_size - 1);
+    int acc[kMmMaxTaps] = {0};
+    for (int t = 0; t < n; t++) acc[std::min(std::max(s0 + t, 0), in_size - 1) - lo_idx] += ci[t];
+    const int nt = hi_idx - lo_idx + 1;
+    for (int j = 0; j < nt; j++) {
+      const int hi = (acc[j] + 64) >> 7, lo = acc[j] - 128 * hi;
+      if (hi < -128 || hi > 127) return IRP_OK;   // cannot happen for lanczos masks; the ALU kernels serve it
+      tab[(size_t)o * 64 + j] = (int8_t)hi;
+      tab[(size_t)o * 64 + 32 + j] = (int8_t)lo;
+    }
+    first[o] = lo_idx;
+    nt_max = std::max(nt_max, nt);
+  }
+  pd->mm_nt = nt_max;
+  pd->h_mm_first = first;
+  auto key_of = [&](const std::vector<int>& content) {
+    std::string k((const char*)content.data(), content.size() * sizeof(int));
+    auto it = ctx->mm_keys.find(k);
+    if (it == ctx->mm_keys.end()) it = ctx->mm_keys.emplace(k, (int)ctx->mm_keys.size() + 1).first;
+    return it->second;
+  };
+  // as the vertical axis: 128-row blocks cut into quarters of 32 rows, each with its own 8-aligned window start
+  std::vector<int32_t> vkey((no + kMmTR - 1) / kMmTR), hkey((no + kMmTC - 1) / kMmTC);
+  int rows = 0, ksv = 1;
+  for (int b = 0; b < (int)vkey.size(); b++) {
+    const int o0 = b * kMmTR, o1 = std::min(no, o0 + kMmTR) - 1;
+    rows = std::max(rows, first[o1] + nt_max - (first[o0] & ~7));
+    std::vector<int> content;
+    for (int o = o0; o <= o1; o++) {
+      const int q0 = o0 + ((o - o0) & ~31);
+      const int koff = first[o] - (first[q0] & ~7);
+      ksv = std::max(ksv, (koff + nt_max + 31) / 32);
+      content.push_back(koff);
+      for (int j = 0; j < 64; j += 4) content.push_back(*reinterpret_cast<const int*>(&tab[(size_t)o * 64 + j]));
+    }
+    content.push_back(-1 - (o1 - o0));
+    vkey[b] = key_of(content);
+  }
+  pd->mm_rows = (int)round_up((size_t)rows, 16);
+  pd->mm_ksv = ksv;
+  pd->mm_v_ok = ksv <= kMmMaxKsv;
+  // as the horizontal axis: 32-column strips over 256 source bytes starting at a 16-byte boundary
+  bool h_ok = true;
+  for (int b = 0; b < (int)hkey.size(); b++) {
+    const int o0 = b * kMmTC, o1 = std::min(no, o0 + kMmTC) - 1;
+    const int bx0 = (3 * first[o0]) & ~15, p0 = bx0 / 3, plast = first[o1] + nt_max - 1;
+    if (3 * plast + 2 > bx0 + kMmXB - 1 || plast - p0 >= kMmKH) h_ok = false;
+    std::vector<int> content;
+    for (int o = o0; o <= o1; o++) {
+      content.push_back(first[o] - p0);
+      for (int j = 0; j < 64; j += 4) content.push_back(*reinterpret_cast<const int*>(&tab[(size_t)o * 64 + j]));
+    }
+    content.push_back(-1000 - (o1 - o0));
+    hkey[b] = key_of(content);
+  }
+  pd->mm_h_ok = h_ok;
+  void* p;
+  int rc;
+  if ((rc = plan_alloc(ctx, tab.size(), &p))) return rc;
+  pd->mm_tab = (int8_t*)p;
+  if ((rc = plan_alloc(ctx, first.size() * 4, &p))) return rc;
+  pd->mm_first = (int32_t*)p;
+  if ((rc = plan_alloc(ctx, vkey.size() * 4, &p))) return rc;
+  pd->mm_vkey = (int32_t*)p;
+  if ((rc = plan_alloc(ctx, hkey.size() * 4, &p))) return rc;
+  pd->mm_hkey = (int32_t*)p;
+  CK(cudaMemcpy(pd->mm_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pd->mm_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pd->mm_vkey, vkey.data(), vkey.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pd->mm_hkey, hkey.data(), hkey.size() * 4, cudaMemcpyHostToDevice));
+  return IRP_OK;
+}
+
 int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* ap, const PlanDev** pdev = nullptr) {
   const bool identity = in_size == out_size;
   auto key = std::make_tuple(in_size, out_size, identity ? 1.0 : shrink);
@@ -376,6 +476,7 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
       CK(cudaMemcpy(pd.hcols, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
       pd.h_start = hp.start;
     }
+    if (!identity && (rc = build_mm_plan(ctx, hp, in_size, &pd))) return rc;
     CK(cudaMemcpy(pd.vpairs, vp.data(), vp.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pd.hpairs, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice));
     // synchronous copies: plans are built once per geometry and cached
@@ -689,9 +790,9 @@ int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* 
       g.orient_off = orient_total;
       orient_total += round_up(round_up((size_t)g.wo * d.channels, 16) * g.ho, 256);
     }
-    if (!od.on_device) {
+    if (!od.on_device) {   // staged rows get a 16-byte pitch: the tensor-core resize stores whole 8-byte pieces
       g.out_off = out_total;
-      out_total += round_up(tight * out_h, 256);
+      out_total += round_up(round_up(tight, 16) * out_h, 256);
     }
   }
   if (orient_total) CK(ctx->d_orient.reserve(orient_total));
@@ -704,7 +805,7 @@ int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* 
     if (od.on_device) {
       op = OutPlan{od.pixels, od.pitch ? od.pitch : (size_t)od.width * g.dc, false};
     } else {
-      op = OutPlan{(uint8_t*)ctx->d_stage_out.p + g.out_off, (size_t)od.width * g.dc, true};
+      op = OutPlan{(uint8_t*)ctx->d_stage_out.p + g.out_off, round_up((size_t)od.width * g.dc, 16), true};
     }
   }
   return IRP_OK;
@@ -774,6 +875,44 @@ int encode_source_tmap(irp_ctx* ctx, const uint8_t* px, size_t pitch, int w, int
   return IRP_OK;
 }
 
+// shared-memory map of the tensor-core resize kernel.  The source buffers come first: the last K step of a quarter may
+// read rows past its buffer (times zero coefficients), and what lies behind has to be mapped memory.
+MmLayout mm_layout(int rows, int ksv) {
+  MmLayout L;
+  L.R = rows;
+  L.ksv_max = ksv;
+  size_t p = 0;
+  L.off_src = (int)p;
+  p += (size_t)2 * 2 * rows * 128;
+  L.off_cv = (int)p;
+  p += (size_t)4 * ksv * 2048;
+  L.off_mid = (int)p;
+  p += (size_t)3 * kMmMidPlane;
+  L.off_ch = (int)p;
+  p += (size_t)2 * kMmChBytes;
+  L.off_info = (int)p;
+  p += 2 * sizeof(MmInfo) + 32;
+  p = round_up(p, 16);
+  L.off_bar = (int)p;
+  p += 64;
+  L.total = (int)p;
+  return L;
+}
+
+int encode_mm_tmap(irp_ctx* ctx, const uint8_t* px, size_t pitch, int w, int h, int box_rows, TmaDesc* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+  const cuuint64_t dims[2] = {(cuuint64_t)w * 3, (cuuint64_t)h};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {128, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  CUresult r = ((EncodeFn)ctx->encode_tiled)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)px, dims, strides,
+                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, IRP_ERR_CUDA, "cuTensorMapEncodeTiled (swizzled) failed (%d) for a %dx%d source, pitch %zu", (int)r, w, h, pitch);
+  return IRP_OK;
+}
+
 // orient + resize images [b, e); job slots [b, e) of the batch-wide arrays.  Jobs are grouped by
 // kernel: 1 / 3 / 4 channels on the generic kernel, and the streaming kernel for 3-channel sources
 // with aligned rows and a real shrink.
@@ -837,6 +976,10 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       }
       // no geometry change and nothing to normalise: the oriented pixels ARE the result, a row copy
       if (pv[i - b].n == 1 && ph[i - b].n == 1 && g.dc == d.channels && g.dw == g.wo && g.dh == g.ho) k = 4;
+      // the tensor-core kernel: 3-channel aligned sources whose geometry fits its tile, 8-byte aligned destination pieces
+      if ((k == 1 || k == 3) && ctx->rmma_ok && ((((uintptr_t)s.px | s.pitch) & 15) == 0) && dv[i - b]->mm_v_ok && dh[i - b]->mm_h_ok &&
+          ((((uintptr_t)oplans[i].dev | oplans[i].dev_pitch) & 15) == 0) && ((3 * g.ox) & 7) == 0 && mm_layout(dv[i - b]->mm_rows, dv[i - b]->mm_ksv).total <= (int)ctx->smem_optin_full - 2048)
+        k = 5;
       kern[i - b] = k;
     }
     if (!degraded || attempt == 1) break;
@@ -846,8 +989,9 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
   const RtLayout L = rt_layout(std::max(box_cols_px, 4), std::max(box_rows, 2), rt_groups, rt_toh);
   if (getenv("IRP_TRACE")) fprintf(stderr, "resize_tma: groups %d toh %d box %d x %d group_bytes %d\n", L.groups, rt_toh, L.box_cols, L.box_rows, L.group_bytes);
   // pass 2: job descriptors, grouped by kernel
-  int pos = b, group_begin[6], group_tiles[5];
-  for (int gi = 0; gi < 5; gi++) {
+  int pos = b, group_begin[7], group_tiles[6];
+  int mm_rows = 16, mm_ksv = 1;
+  for (int gi = 0; gi < 6; gi++) {
     group_begin[gi] = pos;
     int tiles = 0;
     for (int i = b; i < e; i++) {
@@ -870,6 +1014,26 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         K.row_base = tiles;
         K.pad = 0;
         tiles += g.dh;
+        pos++;
+        continue;
+      }
+      if (gi == 5) {
+        MmJob& M = ((MmJob*)ctx->h_mmjobs.p)[pos];
+        memset(&M, 0, sizeof M);
+        M.dst = op.dev;
+        M.dst_pitch = op.dev_pitch;
+        M.vtab = dv[i - b]->mm_tab; M.vfirst = dv[i - b]->mm_first; M.vkey = dv[i - b]->mm_vkey;
+        M.htab = dh[i - b]->mm_tab; M.hfirst = dh[i - b]->mm_first; M.hkey = dh[i - b]->mm_hkey;
+        M.sw = g.wo; M.sh = g.ho; M.dw = g.dw; M.dh = g.dh;
+        M.dst_x0 = g.ox; M.dst_y0 = g.oy;
+        M.tiles_x = (g.dw + kMmTC - 1) / kMmTC;
+        M.tiles_y = (g.dh + kMmTR - 1) / kMmTR;
+        M.tile_base = tiles;
+        M.vnt = dv[i - b]->mm_nt; M.hnt = dh[i - b]->mm_nt;
+        M.ksv = dv[i - b]->mm_ksv;
+        tiles += M.tiles_x * M.tiles_y;
+        mm_rows = std::max(mm_rows, dv[i - b]->mm_rows);
+        mm_ksv = std::max(mm_ksv, dv[i - b]->mm_ksv);
         pos++;
         continue;
       }
@@ -921,8 +1085,9 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       tiles += J.tiles_x * J.tiles_y;
     }
     group_tiles[gi] = tiles;
+    if (gi == 4) group_begin[5] = pos;
   }
-  group_begin[5] = pos;
+  group_begin[6] = pos;
   if (pos == b) return IRP_OK;
   ResizeJob* d_jobs = (ResizeJob*)ctx->d_jobs.p;
   if (group_begin[3] > b)
@@ -953,6 +1118,43 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     resize_tma_kernel<<<grid, L.groups * 128, smem, ctx->stream>>>(d_rt + g3, d_tm + g3, nrt, group_tiles[3], L);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches++;
+  }
+  if (const int nmm = group_begin[6] - group_begin[5]) {
+    // the tensor-core kernel: every job's source as a tensor map of 128-byte x (rows / 2) boxes with the 128-byte swizzle
+    const int g5 = group_begin[5];
+    const MmLayout ML = mm_layout(mm_rows, mm_ksv);
+    MmJob* h_mm = (MmJob*)ctx->h_mmjobs.p;
+    MmJob* d_mm = (MmJob*)ctx->d_mmjobs.p;
+    TmaDesc* h_mt = (TmaDesc*)(((uintptr_t)ctx->h_mmmaps.p + 63) & ~(uintptr_t)63);
+    TmaDesc* d_mt = (TmaDesc*)(((uintptr_t)ctx->d_mmmaps.p + 63) & ~(uintptr_t)63);
+    int slot = g5;
+    for (int i = b; i < e; i++) {
+      if (!imgs[i].pixels || kern[i - b] != 5) continue;
+      if ((rc = encode_mm_tmap(ctx, src[i - b].px, src[i - b].pitch, geo[i].wo, geo[i].ho, ML.R / 2, h_mt + slot))) return rc;
+      slot++;
+    }
+    CK(cudaMemcpyAsync(d_mm + g5, h_mm + g5, sizeof(MmJob) * nmm, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_mt + g5, h_mt + g5, sizeof(TmaDesc) * nmm, cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = std::min(group_tiles[5], ctx->sm_count);
+    const int per = (group_tiles[5] + grid - 1) / grid;
+    if (getenv("IRP_TRACE")) fprintf(stderr, "resize_mma: %d jobs, %d tiles, %d per CTA, rows %d, ksv %d, smem %d\n", nmm, group_tiles[5], per, ML.R, ML.ksv_max, ML.total);
+    long long* dbg = nullptr;
+    if (getenv("IRP_MMA_DEBUG")) {
+      CK(cudaMalloc(&dbg, 32 * 8));
+      CK(cudaMemsetAsync(dbg, 0, 32 * 8, ctx->stream));
+    }
+    resize_mma_kernel<<<grid, kMmThreads, ML.total + 1024, ctx->stream>>>(d_mm + g5, d_mt + g5, nmm, group_tiles[5], per, ML, dbg);
+    CK(cudaGetLastError());
+    ctx->timing.kernel_launches++;
+    if (dbg) {   // cycle stamps of the issuing thread through one steady-state tile (kernel experiments only)
+      long long h[32];
+      CK(cudaStreamSynchronize(ctx->stream));
+      CK(cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost));
+      cudaFree(dbg);
+      fprintf(stderr, "resize_mma stamps (cycles since tile start):");
+      for (int k = 1; k < 32 && h[k]; k++) fprintf(stderr, " %lld", h[k] - h[0]);
+      fprintf(stderr, "\n");
+    }
   }
   return IRP_OK;
 }
@@ -1024,6 +1226,10 @@ int run_batch_inner(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_result*
     CK(ctx->h_rtjobs.reserve(sizeof(RtJob) * n));
     CK(ctx->d_rtmaps.reserve(sizeof(TmaDesc) * n + 64));
     CK(ctx->h_rtmaps.reserve(sizeof(TmaDesc) * n + 64));
+    CK(ctx->d_mmjobs.reserve(sizeof(MmJob) * n));
+    CK(ctx->h_mmjobs.reserve(sizeof(MmJob) * n));
+    CK(ctx->d_mmmaps.reserve(sizeof(TmaDesc) * n + 64));
+    CK(ctx->h_mmmaps.reserve(sizeof(TmaDesc) * n + 64));
   }
   // chunk boundaries
   std::vector<int> cuts{0};
@@ -1219,6 +1425,11 @@ irp_ctx* irp_create(int device, const irp_opts* opts) {
     if (ctx->bulk_ok && (e = cudaFuncSetAttribute((const void*)resize_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
       return bail("cudaFuncSetAttribute(resize_tma_kernel)", e);
+    const char* off3 = getenv("IRP_NO_RMMA");
+    ctx->rmma_ok = ctx->bulk_ok && !(off3 && off3[0] == '1');
+    if (ctx->rmma_ok && (e = cudaFuncSetAttribute((const void*)resize_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)prop.sharedMemPerBlockOptin - 1024)) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(resize_mma_kernel)", e);
     if (ctx->bulk_ok &&
         (e = cudaFuncSetAttribute((const void*)classify_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)prop.sharedMemPerBlockOptin)) != cudaSuccess)
@@ -1256,9 +1467,9 @@ void irp_destroy(irp_ctx* ctx) {
   if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
   for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps, &ctx->d_rtjobs, &ctx->d_rtmaps,
                     &ctx->d_jdata, &ctx->d_jmeta, &ctx->d_jstate, &ctx->d_jcoef, &ctx->d_jplane, &ctx->d_jpix, &ctx->d_emeta,
-                    &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix, &ctx->d_ehuff})
+                    &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix, &ctx->d_ehuff, &ctx->d_mmjobs, &ctx->d_mmmaps})
     b->release();
-  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta, &ctx->h_emeta, &ctx->h_ehuff}) b->release();
+  for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta, &ctx->h_emeta, &ctx->h_ehuff, &ctx->h_mmjobs, &ctx->h_mmmaps}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_error_flag) cudaFree(ctx->d_error_flag);
