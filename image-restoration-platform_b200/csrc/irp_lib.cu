@@ -94,15 +94,16 @@ struct PlanDev {
   uint32_t* hcols;   // [out][16]  ... and per-output-column horizontal table
   int n;
   std::vector<int32_t> h_start;   // host copy: tile footprints are sized on the host
-  // tensor-core resize (irp_resize_mma.cuh): edge-folded taps split hi / lo, first source index, pattern keys
-  int8_t* mm_tab = nullptr;       // [out][64]
+  // tensor-core resize (irp_resize_mma.cuh): first source index per output, and the banded coefficient matrices
+  // (edge-folded taps split hi / lo, already in the MMA operand layout, de-duplicated) with their index tables
   int32_t* mm_first = nullptr;    // [out]
-  int32_t* mm_vkey = nullptr;     // [ceil(out / 128)]
-  int32_t* mm_hkey = nullptr;     // [ceil(out / 32)]
+  int32_t* mm_vmat = nullptr;     // [ceil(out / 128) * 4] as the vertical axis: matrix of each (row block, quarter)
+  uint8_t* mm_vmats = nullptr;    // mm_ksv * 2048 bytes each
+  int32_t* mm_hmat = nullptr;     // [ceil(out / 32)] as the horizontal axis: matrix of each 32-column strip
+  uint8_t* mm_hmats = nullptr;    // kMmChBytes each
   int mm_nt = 0;                  // taps per output after folding
   int mm_rows = 0, mm_ksv = 0;    // as the vertical axis: source rows a 128-row tile touches, 32-row K steps per quarter
   bool mm_v_ok = false, mm_h_ok = false;
-  std::vector<int32_t> h_mm_first;
 };
 
 }  // namespace
@@ -157,8 +158,7 @@ struct irp_ctx {
   bool stop = false, dispatcher_started = false;
   bool rtma_ok = true;    // IRP_NO_RTMA=1 keeps the generic resize kernel (A/B runs)
   bool rmma_ok = false;   // the tensor-core resize kernel (IRP_NO_RMMA=1 turns it off)
-  std::map<std::string, int> mm_keys;   // coefficient-matrix pattern -> id (irp_resize_mma.cuh)
-  DevBuf d_mmjobs, d_mmmaps;
+  DevBuf d_mmjobs, d_mmmaps, d_mmctr;
   PinBuf h_mmjobs, h_mmmaps;
   bool bulk_ok = false;   // the streaming classify kernel's shared-memory map fits this device
   int* h_error_flag = nullptr;
@@ -332,9 +332,12 @@ int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
 }
 
 // Tables of the tensor-core resize (irp_resize_mma.cuh) for one axis: per output its taps with the replicate edge
-// folded in (a tap that falls outside the image is added to the edge tap), split c = 128 * hi + lo; the first
-// source index they apply to; whether the axis fits the kernel's tile as the vertical / horizontal one; and one
-// pattern id per 128-row block / 32-column strip (equal ids = identical coefficient matrices).
+// folded in (a tap that falls outside the image is added to the edge tap), split c = 128 * hi + lo, and the first
+// source index they apply to.  From those, the banded coefficient matrices the kernel multiplies with, laid out as
+// the MMA's K-major N x K operand (16-byte rows of eight-row groups: byte (n, k) at (n >> 3) * 128 + (n & 7) * 16 +
+// (k >> 4) * 1024 + (k & 15); n = hi | lo half * 32 + output within the group of 32): one per (128-row block,
+// quarter) for the axis as the vertical one, one per 32-column strip as the horizontal one; identical matrices are
+// stored once (a periodic geometry such as 4000 -> 2048 needs a handful).
 int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
   const int no = (int)hp.start.size(), n = hp.n;
   if (n > kMmMaxTaps) return IRP_OK;
@@ -357,63 +360,100 @@ int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
     first[o] = lo_idx;
     nt_max = std::max(nt_max, nt);
   }
+  for (int o = 1; o < no; o++)
+    if (first[o] < first[o - 1]) return IRP_OK;   // windows must not move backwards
   pd->mm_nt = nt_max;
-  pd->h_mm_first = first;
-  auto key_of = [&](const std::vector<int>& content) {
-    std::string k((const char*)content.data(), content.size() * sizeof(int));
-    auto it = ctx->mm_keys.find(k);
-    if (it == ctx->mm_keys.end()) it = ctx->mm_keys.emplace(k, (int)ctx->mm_keys.size() + 1).first;
-    return it->second;
-  };
-  // as the vertical axis: 128-row blocks cut into quarters of 32 rows, each with its own 8-aligned window start
-  std::vector<int32_t> vkey((no + kMmTR - 1) / kMmTR), hkey((no + kMmTC - 1) / kMmTC);
-  int rows = 0, ksv = 1;
-  for (int b = 0; b < (int)vkey.size(); b++) {
-    const int o0 = b * kMmTR, o1 = std::min(no, o0 + kMmTR) - 1;
-    rows = std::max(rows, first[o1] + nt_max - (first[o0] & ~7));
-    std::vector<int> content;
-    for (int o = o0; o <= o1; o++) {
-      const int q0 = o0 + ((o - o0) & ~31);
-      const int koff = first[o] - (first[q0] & ~7);
-      ksv = std::max(ksv, (koff + nt_max + 31) / 32);
-      content.push_back(koff);
-      for (int j = 0; j < 64; j += 4) content.push_back(*reinterpret_cast<const int*>(&tab[(size_t)o * 64 + j]));
+  auto put = [&](std::vector<uint8_t>& m, int nrow, int o, int koff) {   // output o's taps into row nrow (and 32 + nrow) from K index koff
+    for (int hl = 0; hl < 2; hl++) {
+      const int nn = hl * 32 + nrow;
+      for (int j = 0; j < nt_max; j++) {
+        const int k = koff + j;
+        m[(size_t)(nn >> 3) * 128 + (nn & 7) * 16 + (size_t)(k >> 4) * 1024 + (k & 15)] = (uint8_t)tab[(size_t)o * 64 + hl * 32 + j];
+      }
     }
-    content.push_back(-1 - (o1 - o0));
-    vkey[b] = key_of(content);
+  };
+  // ---- as the vertical axis: the tile's box starts at first[o0]; each quarter's window at an 8-row boundary of the box
+  const int tiles_y = (no + kMmTR - 1) / kMmTR;
+  auto ws_of = [&](int o0, int q) { return (first[std::min(o0 + 32 * q, no - 1)] - first[o0]) & ~7; };
+  int rows = 16, ksv = 1;
+  for (int rb = 0; rb < tiles_y; rb++) {
+    const int o0 = rb * kMmTR;
+    for (int q = 0; q < 4; q++)
+      for (int o = o0 + 32 * q; o < std::min(no, o0 + 32 * q + 32); o++) {
+        const int koff = first[o] - first[o0] - ws_of(o0, q);
+        ksv = std::max(ksv, (koff + nt_max + 31) / 32);
+        rows = std::max(rows, first[o] + nt_max - first[o0]);
+      }
   }
   pd->mm_rows = (int)round_up((size_t)rows, 16);
   pd->mm_ksv = ksv;
   pd->mm_v_ok = ksv <= kMmMaxKsv;
-  // as the horizontal axis: 32-column strips over 256 source bytes starting at a 16-byte boundary
+  std::vector<int32_t> vmat((size_t)tiles_y * 4, 0);
+  std::vector<uint8_t> vmats;
+  if (pd->mm_v_ok) {
+    std::map<std::string, int> seen;
+    std::vector<uint8_t> m((size_t)ksv * 2048);
+    for (int rb = 0; rb < tiles_y; rb++) {
+      const int o0 = rb * kMmTR;
+      for (int q = 0; q < 4; q++) {
+        std::fill(m.begin(), m.end(), 0);
+        for (int o = o0 + 32 * q; o < std::min(no, o0 + 32 * q + 32); o++) put(m, o - o0 - 32 * q, o, first[o] - first[o0] - ws_of(o0, q));
+        auto it = seen.find(std::string((const char*)m.data(), m.size()));
+        if (it == seen.end()) {
+          it = seen.emplace(std::string((const char*)m.data(), m.size()), (int)seen.size()).first;
+          vmats.insert(vmats.end(), m.begin(), m.end());
+        }
+        vmat[(size_t)rb * 4 + q] = it->second;
+      }
+    }
+  }
+  // ---- as the horizontal axis: 32-column strips over 256 source bytes starting at a 16-byte boundary
+  const int tiles_x = (no + kMmTC - 1) / kMmTC;
   bool h_ok = true;
-  for (int b = 0; b < (int)hkey.size(); b++) {
+  for (int b = 0; b < tiles_x && h_ok; b++) {
     const int o0 = b * kMmTC, o1 = std::min(no, o0 + kMmTC) - 1;
     const int bx0 = (3 * first[o0]) & ~15, p0 = bx0 / 3, plast = first[o1] + nt_max - 1;
     if (3 * plast + 2 > bx0 + kMmXB - 1 || plast - p0 >= kMmKH) h_ok = false;
-    std::vector<int> content;
-    for (int o = o0; o <= o1; o++) {
-      content.push_back(first[o] - p0);
-      for (int j = 0; j < 64; j += 4) content.push_back(*reinterpret_cast<const int*>(&tab[(size_t)o * 64 + j]));
-    }
-    content.push_back(-1000 - (o1 - o0));
-    hkey[b] = key_of(content);
   }
   pd->mm_h_ok = h_ok;
+  std::vector<int32_t> hmat(tiles_x, 0);
+  std::vector<uint8_t> hmats;
+  if (h_ok) {
+    std::map<std::string, int> seen;
+    std::vector<uint8_t> m(kMmChBytes);
+    for (int b = 0; b < tiles_x; b++) {
+      const int o0 = b * kMmTC, p0 = ((3 * first[o0]) & ~15) / 3;
+      std::fill(m.begin(), m.end(), 0);
+      for (int o = o0; o < std::min(no, o0 + kMmTC); o++) put(m, o - o0, o, first[o] - p0);
+      auto it = seen.find(std::string((const char*)m.data(), m.size()));
+      if (it == seen.end()) {
+        it = seen.emplace(std::string((const char*)m.data(), m.size()), (int)seen.size()).first;
+        hmats.insert(hmats.end(), m.begin(), m.end());
+      }
+      hmat[b] = it->second;
+    }
+  }
   void* p;
   int rc;
-  if ((rc = plan_alloc(ctx, tab.size(), &p))) return rc;
-  pd->mm_tab = (int8_t*)p;
   if ((rc = plan_alloc(ctx, first.size() * 4, &p))) return rc;
   pd->mm_first = (int32_t*)p;
-  if ((rc = plan_alloc(ctx, vkey.size() * 4, &p))) return rc;
-  pd->mm_vkey = (int32_t*)p;
-  if ((rc = plan_alloc(ctx, hkey.size() * 4, &p))) return rc;
-  pd->mm_hkey = (int32_t*)p;
-  CK(cudaMemcpy(pd->mm_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pd->mm_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(pd->mm_vkey, vkey.data(), vkey.size() * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(pd->mm_hkey, hkey.data(), hkey.size() * 4, cudaMemcpyHostToDevice));
+  if (pd->mm_v_ok) {
+    if ((rc = plan_alloc(ctx, vmat.size() * 4, &p))) return rc;
+    pd->mm_vmat = (int32_t*)p;
+    if ((rc = plan_alloc(ctx, vmats.size(), &p))) return rc;
+    pd->mm_vmats = (uint8_t*)p;
+    CK(cudaMemcpy(pd->mm_vmat, vmat.data(), vmat.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd->mm_vmats, vmats.data(), vmats.size(), cudaMemcpyHostToDevice));
+  }
+  if (h_ok) {
+    if ((rc = plan_alloc(ctx, hmat.size() * 4, &p))) return rc;
+    pd->mm_hmat = (int32_t*)p;
+    if ((rc = plan_alloc(ctx, hmats.size(), &p))) return rc;
+    pd->mm_hmats = (uint8_t*)p;
+    CK(cudaMemcpy(pd->mm_hmat, hmat.data(), hmat.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd->mm_hmats, hmats.data(), hmats.size(), cudaMemcpyHostToDevice));
+  }
   return IRP_OK;
 }
 
@@ -890,11 +930,13 @@ MmLayout mm_layout(int rows, int ksv) {
   p += (size_t)3 * kMmMidPlane;
   L.off_ch = (int)p;
   p += (size_t)2 * kMmChBytes;
+  L.off_out = (int)p;
+  p += (size_t)kMmTR * kMmOutPitch;
   L.off_info = (int)p;
   p += 2 * sizeof(MmInfo) + 32;
   p = round_up(p, 16);
   L.off_bar = (int)p;
-  p += 64;
+  p += 8 * kBarCount;
   L.total = (int)p;
   return L;
 }
@@ -1022,16 +1064,15 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         memset(&M, 0, sizeof M);
         M.dst = op.dev;
         M.dst_pitch = op.dev_pitch;
-        M.vtab = dv[i - b]->mm_tab; M.vfirst = dv[i - b]->mm_first; M.vkey = dv[i - b]->mm_vkey;
-        M.htab = dh[i - b]->mm_tab; M.hfirst = dh[i - b]->mm_first; M.hkey = dh[i - b]->mm_hkey;
+        M.vfirst = dv[i - b]->mm_first; M.vmat = dv[i - b]->mm_vmat; M.vmats = dv[i - b]->mm_vmats;
+        M.hfirst = dh[i - b]->mm_first; M.hmat = dh[i - b]->mm_hmat; M.hmats = dh[i - b]->mm_hmats;
         M.sw = g.wo; M.sh = g.ho; M.dw = g.dw; M.dh = g.dh;
         M.dst_x0 = g.ox; M.dst_y0 = g.oy;
         M.tiles_x = (g.dw + kMmTC - 1) / kMmTC;
         M.tiles_y = (g.dh + kMmTR - 1) / kMmTR;
-        M.tile_base = tiles;
-        M.vnt = dv[i - b]->mm_nt; M.hnt = dh[i - b]->mm_nt;
+        M.strip_base = tiles;   // this group counts strips
         M.ksv = dv[i - b]->mm_ksv;
-        tiles += M.tiles_x * M.tiles_y;
+        tiles += M.tiles_x;
         mm_rows = std::max(mm_rows, dv[i - b]->mm_rows);
         mm_ksv = std::max(mm_ksv, dv[i - b]->mm_ksv);
         pos++;
@@ -1136,24 +1177,29 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     CK(cudaMemcpyAsync(d_mm + g5, h_mm + g5, sizeof(MmJob) * nmm, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_mt + g5, h_mt + g5, sizeof(TmaDesc) * nmm, cudaMemcpyHostToDevice, ctx->stream));
     const int grid = std::min(group_tiles[5], ctx->sm_count);
-    const int per = (group_tiles[5] + grid - 1) / grid;
-    if (getenv("IRP_TRACE")) fprintf(stderr, "resize_mma: %d jobs, %d tiles, %d per CTA, rows %d, ksv %d, smem %d\n", nmm, group_tiles[5], per, ML.R, ML.ksv_max, ML.total);
+    if (getenv("IRP_TRACE")) fprintf(stderr, "resize_mma: %d jobs, %d strips, rows %d, ksv %d, smem %d\n", nmm, group_tiles[5], ML.R, ML.ksv_max, ML.total);
+    if (auto e2 = ctx->d_mmctr.reserve(256); e2 != cudaSuccess) return fail(ctx, IRP_ERR_NOMEM, "strip counter: %s", cudaGetErrorString(e2));
+    CK(cudaMemsetAsync(ctx->d_mmctr.p, 0, 4, ctx->stream));
     long long* dbg = nullptr;
     if (getenv("IRP_MMA_DEBUG")) {
-      CK(cudaMalloc(&dbg, 32 * 8));
-      CK(cudaMemsetAsync(dbg, 0, 32 * 8, ctx->stream));
+      CK(cudaMalloc(&dbg, 80 * 8));
+      CK(cudaMemsetAsync(dbg, 0, 80 * 8, ctx->stream));
     }
-    resize_mma_kernel<<<grid, kMmThreads, ML.total + 1024, ctx->stream>>>(d_mm + g5, d_mt + g5, nmm, group_tiles[5], per, ML, dbg);
+    resize_mma_kernel<<<grid, kMmThreads, ML.total + 1024, ctx->stream>>>(d_mm + g5, d_mt + g5, nmm, group_tiles[5], (int*)ctx->d_mmctr.p, ML, dbg);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches++;
-    if (dbg) {   // cycle stamps of the issuing thread through one steady-state tile (kernel experiments only)
-      long long h[32];
+    if (dbg) {   // cycles block 0 spent waiting, per role and barrier kind (kernel experiments only)
+      long long h[80];
       CK(cudaStreamSynchronize(ctx->stream));
       CK(cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost));
       cudaFree(dbg);
-      fprintf(stderr, "resize_mma stamps (cycles since tile start):");
-      for (int k = 1; k < 32 && h[k]; k++) fprintf(stderr, " %lld", h[k] - h[0]);
-      fprintf(stderr, "\n");
+      const char* role[5] = {"epilogue w0 [VFull MidFree HFull Full - - | EV: ld st+pack arrive sts | EH: tmem global]", "producer [SrcFree CvFree ChFree]",
+                             "issuer 0 [VFree CvFull MidFull HFree ChFull Full]", "issuer 1", "issuer 2"};
+      for (int r = 0; r < 5; r++) {
+        fprintf(stderr, "resize_mma waits, %s:", role[r]);
+        for (int k = 0; k < 12; k++) fprintf(stderr, " %lld", h[16 * r + k]);
+        fprintf(stderr, "  of %lld cycles\n", h[16 * r + 15]);
+      }
     }
   }
   return IRP_OK;
@@ -1467,7 +1513,7 @@ void irp_destroy(irp_ctx* ctx) {
   if (ctx->copy_out_stream) cudaStreamDestroy(ctx->copy_out_stream);
   for (DevBuf* b : {&ctx->d_desc, &ctx->d_acc, &ctx->d_stage_in, &ctx->d_stage_out, &ctx->d_orient, &ctx->d_jobs, &ctx->d_tmaps, &ctx->d_rtjobs, &ctx->d_rtmaps,
                     &ctx->d_jdata, &ctx->d_jmeta, &ctx->d_jstate, &ctx->d_jcoef, &ctx->d_jplane, &ctx->d_jpix, &ctx->d_emeta,
-                    &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix, &ctx->d_ehuff, &ctx->d_mmjobs, &ctx->d_mmmaps})
+                    &ctx->d_eblk, &ctx->d_ebits, &ctx->d_eout, &ctx->d_epix, &ctx->d_ehuff, &ctx->d_mmjobs, &ctx->d_mmmaps, &ctx->d_mmctr})
     b->release();
   for (PinBuf* b : {&ctx->h_desc, &ctx->h_acc, &ctx->h_jobs, &ctx->h_tmaps, &ctx->h_rtjobs, &ctx->h_rtmaps, &ctx->h_jdata, &ctx->h_jmeta, &ctx->h_emeta, &ctx->h_ehuff, &ctx->h_mmjobs, &ctx->h_mmmaps}) b->release();
   for (void* p : ctx->plan_chunks) cudaFree(p);

@@ -15,59 +15,90 @@
 // rows on the host (taps that fall outside the image are added to the edge tap), so tiles need no patching and
 // TMA's zero fill outside the image is multiplied by zero.
 //
-// Tile = 128 output rows x 32 output columns.
+// Tile = 128 output rows x 32 output columns; a CTA takes whole 32-column STRIPS from a queue and walks them down.
 //   * source footprint: rows x 256 bytes, loaded by TMA as two 128-byte column blocks with the 128-byte swizzle
-//     (that IS the canonical MN-major operand layout, see tools/probes/umma_probe.cu), double buffered;
+//     (that IS the canonical MN-major operand layout, see tools/probes/umma_probe.cu), double buffered; the box
+//     starts at the first source row the tile needs, so the quarter windows sit at the same offsets in every
+//     tile of a periodic geometry (4000 -> 2048 is 125 : 64);
 //   * reducev, per quarter of 32 output rows and per column block:  D[x byte (lane)][hi | lo of 32 rows] +=
 //     SRC^T[x byte][source row] * CV[hi | lo row][source row]   (M 128, N 64, K 32 per step).
 //     Epilogue: thread = one source byte column; 16 rows -> one 16-byte store into the PLANAR intermediate
 //     (channel = byte index mod 3 is just part of the address): de-interleaving costs nothing;
 //   * reduceh, per channel plane:  D[row (lane)][hi | lo of 32 output pixels] += MID_c[row][pixel] * CH[.][pixel];
 //     epilogue: thread = one output row, packs R, G, B of 8 pixels into 24 interleaved bytes, three 8-byte stores.
-//   * CV / CH (the banded coefficient matrices) are rebuilt only when the tile's pattern key changes: for the
-//     usual ratios (4000 -> 2048 is 125 : 64) every tile of an image shares one pattern.
-// One CTA per SM, 16 warps; one thread issues TMA and MMA; completion through mbarriers (tcgen05.commit).
+//   * CV / CH (the banded coefficient matrices, already in the operand layout) are built ON THE HOST per
+//     (row block, quarter) / per strip, de-duplicated, and fetched by bulk copies into their shared-memory slots
+//     only when the slot holds a different matrix.  (The first version rebuilt them in the kernel from the tap
+//     tables: 8000 cycles of dependent L2 loads per tile.)
+// Roles (one CTA per SM, 20 warps): warps 0-15 epilogues (tensor memory -> registers -> shared / global memory),
+// warp 16 the producer (strip queue, tile records, TMA and bulk copies), warps 17-19 issue the MMAs (one lane each):
+// the two column blocks of reducev and the three planes of reduceh come from different warps.
+// Everything is handed over through mbarriers (tcgen05.commit on the tensor side); the tensor pipe sees, per tile,
+//   H(t-1)  V1(t)  V2(t)  V3(t)  V0(t+1)
+// and the epilogue warps run  EV0(t)  EH(t-1)  EV1(t)  EV2(t)  EV3(t), so that the reduceh of a tile overlaps the
+// first reducev epilogue of the next one and the single intermediate buffer never idles the tensor pipe.
 #pragma once
 #include "irp_classify_bulk.cuh"
 #include "irp_resize.cuh"
 
 namespace irp {
 
-constexpr int kMmThreads = 512;
+constexpr int kMmEpiWarps = 16;
+constexpr int kMmThreads = 32 * (kMmEpiWarps + 4);
+constexpr int kMmVLanes = 2, kMmHLanes = 3;   // arrivals on the accumulator-complete barriers: one per column block of reducev / per plane of reduceh
 constexpr int kMmTR = 128, kMmTC = 32, kMmXB = 256;   // tile rows, tile columns, source bytes per tile row
 constexpr int kMmMaxTaps = 32;                        // taps per output after edge folding (25 + slack)
 constexpr int kMmKH = 96;                             // K of the horizontal pass, pixels (3 steps of 32)
 constexpr int kMmMidPlane = (kMmTR / 16) * kMmKH * 16;   // bytes per channel plane of the intermediate
 constexpr int kMmChBytes = 64 * kMmKH;
 constexpr int kMmMaxKsv = 5;
+constexpr int kMmOutPitch = 104;                      // bytes per row of the output staging tile (96 + pad: 8-byte stores without bank conflicts)
 
 struct MmJob {
   uint8_t* dst;
   unsigned long long dst_pitch;
-  const int8_t* vtab;      // [dh][64]: hi[32] | lo[32], edge-folded taps of the output row
-  const int32_t* vfirst;   // [dh] first source row the taps apply to (clamped into the image)
-  const int32_t* vkey;     // [tiles_y] pattern id of the row block's CV
-  const int8_t* htab;      // [dw][64]
+  const int32_t* vfirst;   // [dh] first source row the (edge-folded) taps of an output row apply to
+  const int32_t* vmat;     // [tiles_y * 4] matrix of the (row block, quarter)
+  const uint8_t* vmats;    // matrices in the operand layout, ksv * 2048 bytes each
   const int32_t* hfirst;   // [dw]
-  const int32_t* hkey;     // [tiles_x]
+  const int32_t* hmat;     // [tiles_x]
+  const uint8_t* hmats;    // kMmChBytes each
   int sw, sh, dw, dh;
   int dst_x0, dst_y0;
-  int tiles_x, tiles_y, tile_base;
-  int vnt, hnt;            // taps per output row / column
+  int tiles_x, tiles_y, strip_base;
   int ksv;                 // 32-row K steps per quarter
-  int pad;
+  int pad[2];
 };
 
 struct MmLayout {          // byte offsets in dynamic shared memory (after 1024-byte alignment)
   int R;                   // rows of a source buffer (multiple of 16)
   int ksv_max;
-  int off_cv, off_mid, off_ch, off_info, off_bar, off_src, total;
+  int off_cv, off_mid, off_ch, off_out, off_info, off_bar, off_src, total;
 };
 
-struct MmInfo {            // one tile, written by the issuing thread
-  int job, ox0, oy0, sy0;
-  int bx0, ws0, ws1, ws2;
-  int ws3, vkey, hkey, valid;
+struct MmInfo {            // one tile, written by the producer
+  int rows, cols, bx0, valid;   // output rows / columns of the tile inside the image; first source byte column
+  int ws0, ws1, ws2, ws3;       // first source row of each quarter's window, relative to the box (multiples of 8)
+  int flags, ksv;               // flags: bits 0-3 quarter matrix reloaded, bit 4 CH reloaded, bit 5 CH slot
+  unsigned dst_lo, dst_hi;      // where the tile's first output byte goes
+  unsigned long long pitch;
+  int pad[2];
+};
+
+// mbarrier indices
+enum {
+  kBarFull = 0,      // [2] source buffer + tile record (producer, transaction bytes)
+  kBarSrcFree = 2,   // [2] reducev of the tile is through with the source buffer (commits of the issuing lanes)
+  kBarCvFull = 4,    // [4] quarter matrix landed
+  kBarCvFree = 8,    // [4] quarter's MMAs done
+  kBarChFull = 12,   // [2]
+  kBarChFree = 14,   // [2]
+  kBarVFull = 16,    // [2] reducev accumulators complete
+  kBarVFree = 18,    // [2] ... read out and re-armed (16 epilogue warps)
+  kBarHFull = 20,
+  kBarHFree = 21,
+  kBarMidFull = 22,  // intermediate tile written (16 epilogue warps)
+  kBarCount = 23
 };
 
 __device__ __forceinline__ unsigned long long mm_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -107,6 +138,10 @@ __device__ __forceinline__ void mm_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void mm_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void mm_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 // (128 * hi + lo) >> 12, four of them saturated to bytes; the accumulators already hold the rounding constant
 __device__ __forceinline__ uint32_t mm_pack4(const uint32_t* hi, const uint32_t* lo) {
   int v[4];
@@ -119,54 +154,66 @@ constexpr uint32_t kMmIdesc = (2u << 4) /* s32 */ | (0u << 7) /* A u8 */ | (1u <
                               ((64u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kMmColV = 0, kMmColH = 256;   // accumulator columns: reducev 2 x 128, reduceh 3 x 64
 
-// the issuing thread: describe tile `tile` and start the loads of its source footprint into buffer `buf`
-__device__ __forceinline__ void mm_issue_tile(int tile, int tile_end, int& job, const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tmaps, int n_jobs,
-                                              const MmLayout& L, uint32_t sbase, int buf) {
-  const uint32_t info = sbase + L.off_info + buf * (uint32_t)sizeof(MmInfo), bar = sbase + L.off_bar + 8u * buf;
-  if (tile >= tile_end) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(info + 44), "r"(0) : "memory");
-    mbar_arrive(bar);
-    return;
-  }
-  while (job + 1 < n_jobs && tile >= __ldg(&jobs[job + 1].tile_base)) job++;
-  const MmJob* J = jobs + job;
-  const int tiles_y = __ldg(&J->tiles_y), dh = __ldg(&J->dh);
-  const int t = tile - __ldg(&J->tile_base);
-  const int strip = t / tiles_y, rb = t - strip * tiles_y;
-  const int ox0 = strip * kMmTC, oy0 = rb * kMmTR;
-  const int32_t* vfirst = reinterpret_cast<const int32_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&J->vfirst)));
-  const int32_t* hfirst = reinterpret_cast<const int32_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&J->hfirst)));
-  const int32_t* vkey = reinterpret_cast<const int32_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&J->vkey)));
-  const int32_t* hkey = reinterpret_cast<const int32_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&J->hkey)));
-  const int sy0 = __ldg(vfirst + oy0) & ~7;
-  int ws[4];
-#pragma unroll
-  for (int q = 0; q < 4; q++) ws[q] = (__ldg(vfirst + min(oy0 + 32 * q, dh - 1)) & ~7) - sy0;
-  const int bx0 = (3 * __ldg(hfirst + ox0)) & ~15;
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info), "r"(job), "r"(ox0), "r"(oy0), "r"(sy0) : "memory");
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info + 16), "r"(bx0), "r"(ws[0]), "r"(ws[1]), "r"(ws[2]) : "memory");
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info + 32), "r"(ws[3]), "r"(__ldg(vkey + rb)), "r"(__ldg(hkey + strip)), "r"(1) : "memory");
-  const uint32_t src = sbase + L.off_src + (uint32_t)buf * (2u * L.R * 128u);
-  mbar_arrive_expect_tx(bar, 2u * L.R * 128u);
-#pragma unroll
-  for (int b = 0; b < 2; b++)
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-      tma_load_2d(src + b * (L.R * 128) + h * (L.R / 2) * 128, tmaps + job, bx0 + 128 * b, sy0 + h * (L.R / 2), bar);
+__device__ __forceinline__ MmInfo mm_load_info(uint32_t ia) {
+  MmInfo inf;
+  unsigned plo, phi;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.rows), "=r"(inf.cols), "=r"(inf.bx0), "=r"(inf.valid) : "r"(ia));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.ws0), "=r"(inf.ws1), "=r"(inf.ws2), "=r"(inf.ws3) : "r"(ia + 16));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.flags), "=r"(inf.ksv), "=r"(inf.dst_lo), "=r"(inf.dst_hi) : "r"(ia + 32));
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(plo), "=r"(phi) : "r"(ia + 48));
+  inf.pitch = ((unsigned long long)phi << 32) | plo;
+  return inf;
+}
+template <typename T>
+__device__ __forceinline__ const T* mm_ldptr(const T* const* p) {
+  return reinterpret_cast<const T*>(__ldg(reinterpret_cast<const unsigned long long*>(p)));
+}
+__device__ __forceinline__ uint32_t mm_clock() {
+  uint32_t c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  return c;
 }
 
 __global__ void __launch_bounds__(kMmThreads, 1)
-resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tmaps, int n_jobs, int total_tiles, int tiles_per_cta, MmLayout L,
-                  long long* __restrict__ dbg) {
+resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tmaps, int n_jobs, int total_strips, int* __restrict__ strip_counter,
+                  MmLayout L, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t mm_smem[];
   __shared__ uint32_t s_tmem;
   const uint32_t sbase = ((uint32_t)__cvta_generic_to_shared(mm_smem) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_cv = sbase + L.off_cv, a_mid = sbase + L.off_mid, a_ch = sbase + L.off_ch, a_info = sbase + L.off_info,
+  const uint32_t a_cv = sbase + L.off_cv, a_mid = sbase + L.off_mid, a_ch = sbase + L.off_ch, a_out = sbase + L.off_out, a_info = sbase + L.off_info,
                  a_bar = sbase + L.off_bar, a_src = sbase + L.off_src;
-  // mbarriers: [0,1] source buffers, [2,3] reducev accumulators, [4] reduceh accumulator
-  if (tid == 0)
-    for (int k = 0; k < 5; k++) mbar_init(a_bar + 8 * k, 1);
+  auto bar = [&](int k) { return a_bar + 8u * (uint32_t)k; };
+  // kernel experiments (IRP_MMA_DEBUG): cycles block 0 spends in each kind of wait and in the epilogue steps
+  uint32_t wacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool prof = dbg != nullptr && blockIdx.x == 0;
+  uint32_t tk = 0;
+  auto tick = [&](int slot) {
+    if (prof) {
+      const uint32_t t = mm_clock();
+      wacc[slot] += t - tk;
+      tk = t;
+    }
+  };
+  auto twait = [&](int slot, uint32_t b, uint32_t parity) {
+    if (prof) {
+      const uint32_t t0 = mm_clock();
+      mbar_wait(b, parity);
+      wacc[slot] += mm_clock() - t0;
+    } else {
+      mbar_wait(b, parity);
+    }
+  };
+  const uint32_t t_start = mm_clock();
+  if (tid == 0) {
+    for (int k = 0; k < 2; k++) mbar_init(bar(kBarFull + k), 1), mbar_init(bar(kBarSrcFree + k), 1);
+    for (int k = 0; k < 4; k++) mbar_init(bar(kBarCvFull + k), 1), mbar_init(bar(kBarCvFree + k), 1);
+    for (int k = 0; k < 2; k++) mbar_init(bar(kBarChFull + k), 1), mbar_init(bar(kBarChFree + k), 1);
+    for (int k = 0; k < 2; k++) mbar_init(bar(kBarVFull + k), kMmVLanes), mbar_init(bar(kBarVFree + k), kMmEpiWarps);
+    mbar_init(bar(kBarHFull), kMmHLanes);
+    mbar_init(bar(kBarHFree), kMmEpiWarps);
+    mbar_init(bar(kBarMidFull), kMmEpiWarps);
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -178,195 +225,207 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
   const uint32_t tm = s_tmem;
   const int lq = warp & 3;
   const uint32_t tlane = tm + ((uint32_t)(32 * lq) << 16);
-  // V epilogue item of this warp: column block b, rows [16 rh, 16 rh + 16) of the quarter
+  // V epilogue item of an epilogue warp: column block vb, rows [16 vrh, 16 vrh + 16) of the quarter
   const int vb = (warp >> 2) & 1, vrh = warp >> 3;
   // H epilogue item: pixels [8 pg, 8 pg + 8) of the tile's 32 output columns
   const int pg = warp >> 2;
-  // arm every accumulator: hi columns 0, lo columns 2048 (the rounding constant)
+  if (warp < kMmEpiWarps) {
+    // arm every accumulator: hi columns 0, lo columns 2048 (the rounding constant)
 #pragma unroll
-  for (int dv = 0; dv < 2; dv++) {
-    mm_st16(tlane + kMmColV + dv * 128 + vb * 64 + 16 * vrh, 0u);
-    mm_st16(tlane + kMmColV + dv * 128 + vb * 64 + 32 + 16 * vrh, 1u << (IRP_INTERP_SHIFT - 1));
-  }
+    for (int dv = 0; dv < 2; dv++) {
+      mm_st16(tlane + kMmColV + dv * 128 + vb * 64 + 16 * vrh, 0u);
+      mm_st16(tlane + kMmColV + dv * 128 + vb * 64 + 32 + 16 * vrh, 1u << (IRP_INTERP_SHIFT - 1));
+    }
 #pragma unroll
-  for (int c = 0; c < 3; c++) {
-    mm_st8(tlane + kMmColH + 64 * c + 8 * pg, 0u);
-    mm_st8(tlane + kMmColH + 64 * c + 32 + 8 * pg, 1u << (IRP_INTERP_SHIFT - 1));
+    for (int c = 0; c < 3; c++) {
+      mm_st8(tlane + kMmColH + 64 * c + 8 * pg, 0u);
+      mm_st8(tlane + kMmColH + 64 * c + 32 + 8 * pg, 1u << (IRP_INTERP_SHIFT - 1));
+    }
+    mm_wait_st();
   }
-  mm_wait_st();
+  mm_fence_before();
+  __syncthreads();
+  mm_fence_after();
 
-  const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(total_tiles, tile_begin + tiles_per_cta);
-  if (tile_begin >= tile_end) {
-    mm_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
-    return;
-  }
-  int issue_job = 0;
-  if (tid == 0) {
-    mm_issue_tile(tile_begin, tile_end, issue_job, jobs, tmaps, n_jobs, L, sbase, 0);
-    mm_issue_tile(tile_begin + 1, tile_end, issue_job, jobs, tmaps, n_jobs, L, sbase, 1);
-  }
-  int cur_vkey = -1, cur_hkey = -1, ch_sel = 0;
-  const int cvq = L.ksv_max * 2048;   // bytes of one quarter's CV
+  const uint32_t src_buf_bytes = 2u * L.R * 128u;
+  const uint32_t cv_slot = (uint32_t)L.ksv_max * 2048u;
 
-  // all threads: (re)build the coefficient matrices of the tile in `inf` when its pattern differs from what is loaded
-  auto build = [&](const MmInfo& inf, const MmJob* J) {
-    const bool need_v = inf.vkey != cur_vkey, need_h = inf.hkey != cur_hkey;
-    if (!need_v && !need_h) return;
-    if (need_h) ch_sel ^= 1;
-    const uint32_t chb = a_ch + ch_sel * kMmChBytes;
-    if (need_v)
-      for (int i = tid; i < 4 * cvq / 16; i += kMmThreads) mm_sts128(a_cv + 16 * i, 0, 0, 0, 0);
-    if (need_h)
-      for (int i = tid; i < kMmChBytes / 16; i += kMmThreads) mm_sts128(chb + 16 * i, 0, 0, 0, 0);
-    __syncthreads();
-    if (need_v) {
-      const int r = tid >> 2, hl = (tid >> 1) & 1, th = tid & 1, oy = inf.oy0 + r;
-      if (oy < J->dh) {
-        const int q = r >> 5, n = hl * 32 + (r & 31);
-        const int wsq = q == 0 ? inf.ws0 : (q == 1 ? inf.ws1 : (q == 2 ? inf.ws2 : inf.ws3));
-        const int koff = __ldg(J->vfirst + oy) - (inf.sy0 + wsq);
-        const int8_t* src = J->vtab + (size_t)oy * 64 + hl * 32;
-        const uint32_t rowa = a_cv + q * cvq + (n >> 3) * 128 + (n & 7) * 16;
-        const int jend = min(J->vnt, th * 16 + 16);
-        for (int j = th * 16; j < jend; j++) {
-          const int k = koff + j;
-          sts_u8(rowa + (k >> 4) * 1024 + (k & 15), (uint32_t)(uint8_t)__ldg(src + j));
+  if (warp == kMmEpiWarps) {
+    // =============================== producer ===============================
+    if (lane == 0) {
+      int i = 0, job = 0, chslot = 0, ch_uses[2] = {0, 0};
+      const uint8_t* cv_in[4] = {nullptr, nullptr, nullptr, nullptr};
+      const uint8_t* ch_in[2] = {nullptr, nullptr};
+      for (;;) {
+        const int s = atomicAdd(strip_counter, 1);
+        if (s >= total_strips) break;
+        while (job + 1 < n_jobs && s >= __ldg(&jobs[job + 1].strip_base)) job++;
+        const MmJob* J = jobs + job;
+        const int tiles_y = __ldg(&J->tiles_y), dh = __ldg(&J->dh), dw = __ldg(&J->dw), ksv = __ldg(&J->ksv);
+        const unsigned long long pitch = __ldg(&J->dst_pitch);
+        const int32_t* vfirst = mm_ldptr(&J->vfirst);
+        const int32_t* hfirst = mm_ldptr(&J->hfirst);
+        const int32_t* vmat = mm_ldptr(&J->vmat);
+        const uint8_t* vmats = mm_ldptr(&J->vmats);
+        const int strip = s - __ldg(&J->strip_base);
+        const int ox0 = strip * kMmTC;
+        const int bx0 = (3 * __ldg(hfirst + ox0)) & ~15;
+        const uint8_t* hm = mm_ldptr(&J->hmats) + (size_t)__ldg(mm_ldptr(&J->hmat) + strip) * kMmChBytes;
+        uint8_t* dst0 = const_cast<uint8_t*>(mm_ldptr(reinterpret_cast<const uint8_t* const*>(&J->dst))) + (size_t)__ldg(&J->dst_y0) * pitch +
+                        (size_t)(__ldg(&J->dst_x0) + ox0) * 3;
+        for (int rb = 0; rb < tiles_y; rb++, i++) {
+          const int buf = i & 1;
+          const int oy0 = rb * kMmTR;
+          const int sy0 = __ldg(vfirst + oy0);
+          int ws[4];
+          const uint8_t* vm[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            ws[q] = (__ldg(vfirst + min(oy0 + 32 * q, dh - 1)) - sy0) & ~7;
+            vm[q] = vmats + (size_t)__ldg(vmat + 4 * rb + q) * ((size_t)ksv * 2048);
+          }
+          int flags = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (vm[q] != cv_in[q]) flags |= 1 << q;
+          if (hm != ch_in[chslot]) {
+            chslot ^= 1;
+            if (hm != ch_in[chslot]) flags |= 16;
+          }
+          flags |= chslot << 5;
+          const unsigned long long dptr = (unsigned long long)(dst0 + (size_t)oy0 * pitch);
+          twait(0, bar(kBarSrcFree + buf), (uint32_t)((i >> 1) & 1) ^ 1u);
+          const uint32_t info = a_info + buf * (uint32_t)sizeof(MmInfo);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info), "r"(dh - oy0), "r"(dw - ox0), "r"(bx0), "r"(1) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info + 16), "r"(ws[0]), "r"(ws[1]), "r"(ws[2]), "r"(ws[3]) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info + 32), "r"(flags), "r"(ksv), "r"((uint32_t)dptr), "r"((uint32_t)(dptr >> 32)) : "memory");
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(info + 48), "r"((uint32_t)pitch), "r"((uint32_t)(pitch >> 32)) : "memory");
+          const uint32_t src = a_src + (uint32_t)buf * src_buf_bytes;
+          mbar_arrive_expect_tx(bar(kBarFull + buf), src_buf_bytes);
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+              tma_load_2d(src + b * (L.R * 128) + h * (L.R / 2) * 128, tmaps + job, bx0 + 128 * b, sy0 + h * (L.R / 2), bar(kBarFull + buf));
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (flags & (1 << q)) {
+              twait(1, bar(kBarCvFree + q), (uint32_t)(i & 1) ^ 1u);   // the quarter's MMAs of the previous tile are done
+              mbar_arrive_expect_tx(bar(kBarCvFull + q), (uint32_t)ksv * 2048u);
+              mm_bulk_g2s(a_cv + q * cv_slot, vm[q], (uint32_t)ksv * 2048u, bar(kBarCvFull + q));
+              cv_in[q] = vm[q];
+            }
+          if (flags & 16) {
+            twait(2, bar(kBarChFree + chslot), (uint32_t)(ch_uses[chslot] & 1) ^ 1u);
+            mbar_arrive_expect_tx(bar(kBarChFull + chslot), kMmChBytes);
+            mm_bulk_g2s(a_ch + chslot * kMmChBytes, hm, kMmChBytes, bar(kBarChFull + chslot));
+            ch_in[chslot] = hm;
+          }
+          ch_uses[chslot]++;
         }
       }
-      cur_vkey = inf.vkey;
+      // the record that ends the sequence
+      const int buf = i & 1;
+      mbar_wait(bar(kBarSrcFree + buf), (uint32_t)((i >> 1) & 1) ^ 1u);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_info + buf * (uint32_t)sizeof(MmInfo) + 12), "r"(0) : "memory");
+      mbar_arrive(bar(kBarFull + buf));
     }
-    if (need_h) {
-      const int r = tid >> 4, hl = (tid >> 3) & 1, part = tid & 7, ox = inf.ox0 + r;
-      if (ox < J->dw) {
-        const int n = hl * 32 + r;
-        const int koff = __ldg(J->hfirst + ox) - inf.bx0 / 3;
-        const int8_t* src = J->htab + (size_t)ox * 64 + hl * 32;
-        const uint32_t rowa = chb + (n >> 3) * 128 + (n & 7) * 16;
-        const int jend = min(J->hnt, part * 4 + 4);
-        for (int j = part * 4; j < jend; j++) {
-          const int k = koff + j;
-          sts_u8(rowa + (k >> 4) * 1024 + (k & 15), (uint32_t)(uint8_t)__ldg(src + j));
+  } else if (warp > kMmEpiWarps) {
+    // =============================== MMA issue ===============================
+    // Three issuing warps (one lane each): w = column block of reducev (0, 1) and channel plane of reduceh (0, 1, 2).
+    // Measured (tools/probes/umma_rate.cu): two or more WARPS issuing MMAs with a commit every few of them keep the
+    // tensor pipe at its floor for this shape (51.5 cycles per M128 N64 K32); lanes of one warp do not (57-93), and a
+    // lone thread that never commits gets 125.  What the producer waits for (matrix slot, source buffer, CH slot free
+    // again) is relayed by warp 0 with plain arrives once the epilogue has handed the accumulator back — by then the
+    // MMAs that read those operands are long done — so there is ONE commit per warp and event.
+    const int w = warp - kMmEpiWarps - 1;
+    uint32_t vuse0 = 0, vuse1 = 0, hcount = 0;
+    uint32_t cvl0 = 0, cvl1 = 0, cvl2 = 0, cvl3 = 0, chl0 = 0, chl1 = 0;
+    int vprev_q0 = 0, vprev_q1 = 0, vprev_buf0 = 0, vprev_buf1 = 0, hprev_slot = 0;
+    auto issue_v = [&](const MmInfo& inf, int buf, int q) {   // q is a literal at every call site
+      const int a = q & 1;
+      uint32_t& vuse = a ? vuse1 : vuse0;
+      int& vprev_q = a ? vprev_q1 : vprev_q0;
+      int& vprev_buf = a ? vprev_buf1 : vprev_buf0;
+      uint32_t& cvl = q == 0 ? cvl0 : (q == 1 ? cvl1 : (q == 2 ? cvl2 : cvl3));
+      twait(0, bar(kBarVFree + a), (vuse & 1u) ^ 1u);
+      if (w == 0 && vuse > 0) {
+        mbar_arrive(bar(kBarCvFree + vprev_q));
+        if (vprev_q == 3) mbar_arrive(bar(kBarSrcFree + vprev_buf));
+      }
+      vuse++;
+      vprev_q = q;
+      vprev_buf = buf;
+      if (inf.flags & (1 << q)) {
+        twait(1, bar(kBarCvFull + q), cvl & 1u);
+        cvl++;
+      }
+      mm_fence_after();
+      const int wsq = q == 0 ? inf.ws0 : (q == 1 ? inf.ws1 : (q == 2 ? inf.ws2 : inf.ws3));
+      const uint32_t src = a_src + (uint32_t)buf * src_buf_bytes + w * (L.R * 128) + wsq * 128;
+      for (int ks = 0; ks < inf.ksv; ks++)
+        mm_mma_i8(tm + kMmColV + a * 128 + w * 64, mm_desc(src + ks * 4096, (uint32_t)L.R * 128u, 1024u, 2u),
+                  mm_desc(a_cv + q * cv_slot + ks * 2048, 1024u, 128u, 0u), kMmIdesc);
+      mm_commit(bar(kBarVFull + a));
+    };
+    auto issue_h = [&](const MmInfo& inf) {
+      twait(2, bar(kBarMidFull), hcount & 1u);
+      twait(3, bar(kBarHFree), (hcount & 1u) ^ 1u);
+      if (w == 0 && hcount > 0) mbar_arrive(bar(kBarChFree + hprev_slot));
+      hcount++;
+      const int slot = (inf.flags >> 5) & 1;
+      hprev_slot = slot;
+      if (inf.flags & 16) {
+        uint32_t& chl = slot ? chl1 : chl0;
+        twait(4, bar(kBarChFull + slot), chl & 1u);
+        chl++;
+      }
+      mm_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < kMmKH / 32; ks++)
+        mm_mma_i8(tm + kMmColH + 64 * w, mm_desc(a_mid + w * kMmMidPlane + ks * 512, 128u, (uint32_t)kMmKH * 16u, 0u),
+                  mm_desc(a_ch + slot * kMmChBytes + ks * 2048, 1024u, 128u, 0u), kMmIdesc);
+      mm_commit(bar(kBarHFull));
+    };
+    if (lane == 0) {
+    mbar_wait(bar(kBarFull), 0);
+    MmInfo cur = mm_load_info(a_info), prev = cur;
+    if (cur.valid) {
+      if (w < 2) issue_v(cur, 0, 0);
+      for (int i = 0;; i++) {
+        const int buf = i & 1;
+        if (i > 0) issue_h(prev);
+        if (w < 2) {
+          issue_v(cur, buf, 1);
+          issue_v(cur, buf, 2);
+          issue_v(cur, buf, 3);
+        }
+        twait(5, bar(kBarFull + (buf ^ 1)), (uint32_t)((i + 1) >> 1) & 1u);
+        const MmInfo nxt = mm_load_info(a_info + (buf ^ 1) * (uint32_t)sizeof(MmInfo));
+        if (nxt.valid && w < 2) issue_v(nxt, buf ^ 1, 0);
+        prev = cur;
+        cur = nxt;
+        if (!cur.valid) {
+          issue_h(prev);
+          break;
         }
       }
-      cur_hkey = inf.hkey;
     }
-  };
-  auto load_info = [&](int buf) {
-    MmInfo inf;
-    const uint32_t ia = a_info + buf * (uint32_t)sizeof(MmInfo);
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.job), "=r"(inf.ox0), "=r"(inf.oy0), "=r"(inf.sy0) : "r"(ia));
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.bx0), "=r"(inf.ws0), "=r"(inf.ws1), "=r"(inf.ws2) : "r"(ia + 16));
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.ws3), "=r"(inf.vkey), "=r"(inf.hkey), "=r"(inf.valid) : "r"(ia + 32));
-    return inf;
-  };
-  // the issuing thread: the reducev MMAs of quarter q of the tile in source buffer `buf`
-  auto issue_v = [&](const MmInfo& inf, int buf, int q, int ksv) {
-    const int wsq = q == 0 ? inf.ws0 : (q == 1 ? inf.ws1 : (q == 2 ? inf.ws2 : inf.ws3));
-    const uint32_t src = a_src + (uint32_t)buf * (2u * L.R * 128u);
-#pragma unroll
-    for (int b = 0; b < 2; b++)
-      for (int ks = 0; ks < ksv; ks++) {
-        const unsigned long long ad = mm_desc(src + b * (L.R * 128) + (wsq + 32 * ks) * 128, (uint32_t)L.R * 128u, 1024u, 2u);
-        const unsigned long long bd = mm_desc(a_cv + q * cvq + ks * 2048, 1024u, 128u, 0u);
-        mm_mma_i8(tm + kMmColV + (q & 1) * 128 + b * 64, ad, bd, kMmIdesc);
-      }
-    mm_commit(a_bar + 8 * (2 + (q & 1)));
-  };
-
-  // ---- prologue: first tile's matrices and its first two quarters ----
-  MmInfo cur;
-  {
-    mbar_wait(a_bar, 0);
-    cur = load_info(0);
-    build(cur, jobs + cur.job);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    uint32_t hcnt = 0;
+    mbar_wait(bar(kBarFull), 0);
+    MmInfo cur = mm_load_info(a_info), prev = cur;
+    // reduceh epilogue of tile `inf`: thread = output row, 8 pixels x RGB -> 24 interleaved bytes into the staging tile;
+    // then the 16 warps write the tile out row by row (a warp instruction covers 2.7 rows of 96 contiguous bytes
+    // instead of 32 rows of 8).  No barrier guards the staging tile against the NEXT tile's writes: between this
+    // read and that write every warp passes two accumulator hand-overs that wait for all 16 warps.
+    auto epi_h = [&](const MmInfo& inf) {
+      twait(2, bar(kBarHFull), hcnt & 1u);
+      hcnt++;
       mm_fence_after();
-      const int ksv = jobs[cur.job].ksv;
-      issue_v(cur, 0, 0, ksv);
-      issue_v(cur, 0, 1, ksv);
-    }
-  }
-  int dbg_n = 0;
-  auto stamp = [&](int it_) {
-    if (dbg && tid == 0 && blockIdx.x == 0 && it_ == 3 && dbg_n < 32) dbg[dbg_n++] = clock64();
-  };
-  for (int it = 0;; it++) {
-    const int buf = it & 1;
-    const MmJob* J = jobs + cur.job;
-    stamp(it);
-    const int ksv = __ldg(&J->ksv);
-    // planar address of this thread's source byte column (reducev epilogue)
-    uint32_t mid_col;
-    {
-      const int xb = 128 * vb + 32 * lq + lane, B = cur.bx0 + xb, p = B / 3, c = B - 3 * p, kpx = p - cur.bx0 / 3;
-      mid_col = a_mid + c * kMmMidPlane + (kpx >> 3) * 128 + (kpx & 7) * 16;
-    }
-    // ---- reducev: four quarters through two accumulator buffers ----
-#pragma unroll 1
-    for (int q = 0; q < 4; q++) {
-      mbar_wait(a_bar + 8 * (2 + (q & 1)), (uint32_t)(q >> 1) & 1u);
-      mm_fence_after();
-      stamp(it);
-      uint32_t hi[16], lo[16];
-      const uint32_t ta = tlane + kMmColV + (q & 1) * 128 + vb * 64 + 16 * vrh;
-      mm_ld16(ta, hi);
-      mm_ld16(ta + 32, lo);
-      mm_wait_ld();
-      mm_st16(ta, 0u);   // re-arm the accumulator for the quarter after next
-      mm_st16(ta + 32, 1u << (IRP_INTERP_SHIFT - 1));
-      mm_sts128(mid_col + (2 * q + vrh) * (kMmKH * 16), mm_pack4(hi, lo), mm_pack4(hi + 4, lo + 4), mm_pack4(hi + 8, lo + 8), mm_pack4(hi + 12, lo + 12));
-      mm_wait_st();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the intermediate is read by the tensor core next
-      mm_fence_before();
-      __syncthreads();
-      stamp(it);
-      if (tid == 0 && q + 2 < 4) {
-        mm_fence_after();
-        issue_v(cur, buf, q + 2, ksv);
-      }
-    }
-    // ---- reduceh of this tile ----
-    if (tid == 0) {
-      mm_fence_after();
-      const uint32_t chb = a_ch + ch_sel * kMmChBytes;
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int ks = 0; ks < kMmKH / 32; ks++) {
-          const unsigned long long ad = mm_desc(a_mid + c * kMmMidPlane + ks * 512, 128u, (uint32_t)kMmKH * 16u, 0u);
-          const unsigned long long bd = mm_desc(chb + ks * 2048, 1024u, 128u, 0u);
-          mm_mma_i8(tm + kMmColH + 64 * c, ad, bd, kMmIdesc);
-        }
-      mm_commit(a_bar + 8 * 4);
-    }
-    stamp(it);
-    // ---- while it runs: the next tile's matrices, its first two quarters, and the loads of the tile after it ----
-    mbar_wait(a_bar + 8 * (buf ^ 1), (uint32_t)((it + 1) >> 1) & 1u);
-    const MmInfo nxt = load_info(buf ^ 1);
-    const int my_ch = ch_sel;   // the matrix the reduceh in flight reads
-    if (nxt.valid) {
-      build(nxt, jobs + nxt.job);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        mm_fence_after();
-        const int ksv2 = jobs[nxt.job].ksv;
-        issue_v(nxt, buf ^ 1, 0, ksv2);
-        issue_v(nxt, buf ^ 1, 1, ksv2);
-        mm_issue_tile(tile_begin + it + 2, tile_end, issue_job, jobs, tmaps, n_jobs, L, sbase, buf);   // this tile's buffer is free
-      }
-    }
-    (void)my_ch;
-    stamp(it);
-    // ---- reduceh epilogue: thread = output row, 8 pixels x RGB -> 24 interleaved bytes ----
-    mbar_wait(a_bar + 8 * 4, (uint32_t)it & 1u);
-    mm_fence_after();
-    stamp(it);
-    {
+      if (prof) tk = mm_clock();
       uint32_t hi[3][8], lo[3][8];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -384,28 +443,101 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
       for (int j = 0; j < 8; j++)
 #pragma unroll
         for (int c = 0; c < 3; c++) v[3 * j + c] = ((int)hi[c][j] * 128 + (int)lo[c][j]) >> IRP_INTERP_SHIFT;
-      uint32_t w[6];
+      const uint32_t so = a_out + (32 * lq + lane) * kMmOutPitch + 24 * pg;
 #pragma unroll
-      for (int k = 0; k < 6; k++) w[k] = pack_sat_u8(v[4 * k + 1], v[4 * k], pack_sat_u8(v[4 * k + 3], v[4 * k + 2], 0u));
-      const int row = 32 * lq + lane, oy = cur.oy0 + row, px0 = cur.ox0 + 8 * pg;
-      if (oy < J->dh && px0 < J->dw) {
-        uint8_t* d = J->dst + (size_t)(J->dst_y0 + oy) * J->dst_pitch + (size_t)(J->dst_x0 + px0) * 3;
-        if (px0 + 8 <= J->dw) {
-#pragma unroll
-          for (int k = 0; k < 3; k++) *reinterpret_cast<uint2*>(d + 8 * k) = make_uint2(w[2 * k], w[2 * k + 1]);
-        } else {
-          const int nb = 3 * (J->dw - px0);
-          for (int k = 0; k < nb; k++) d[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
-        }
+      for (int k = 0; k < 3; k++) {
+        const uint32_t w0 = pack_sat_u8(v[8 * k + 1], v[8 * k], pack_sat_u8(v[8 * k + 3], v[8 * k + 2], 0u));
+        const uint32_t w1 = pack_sat_u8(v[8 * k + 5], v[8 * k + 4], pack_sat_u8(v[8 * k + 7], v[8 * k + 6], 0u));
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(so + 8 * k), "r"(w0), "r"(w1) : "memory");
       }
       mm_wait_st();
+      mm_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarHFree));
+      tick(10);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kMmEpiWarps) : "memory");
+      uint8_t* dst = reinterpret_cast<uint8_t*>(((unsigned long long)inf.dst_hi << 32) | inf.dst_lo);
+      const int nbytes = 3 * min(inf.cols, kMmTC);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int idx = tid + 32 * kMmEpiWarps * k, row = idx / 12, c8 = 8 * (idx - 12 * row);
+        if (row < inf.rows && c8 < nbytes) {
+          uint32_t w0, w1;
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(a_out + row * kMmOutPitch + c8));
+          uint8_t* d = dst + (size_t)row * inf.pitch + c8;
+          if (c8 + 8 <= nbytes) {
+            *reinterpret_cast<uint2*>(d) = make_uint2(w0, w1);
+          } else {   // the image's last columns
+            const unsigned long long ww = ((unsigned long long)w1 << 32) | w0;
+            for (int j = 0; j < nbytes - c8; j++) d[j] = (uint8_t)(ww >> (8 * j));
+          }
+        }
+      }
+      tick(11);
+    };
+    if (cur.valid) {
+      for (int i = 0;; i++) {
+        const int buf = i & 1;
+        // planar address of this thread's source byte column (reducev epilogue)
+        uint32_t mid_col;
+        {
+          const int xb = 128 * vb + 32 * lq + lane, B = cur.bx0 + xb, p = B / 3, c = B - 3 * p, kpx = p - cur.bx0 / 3;
+          mid_col = a_mid + c * kMmMidPlane + (kpx >> 3) * 128 + (kpx & 7) * 16;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int a = q & 1;
+          twait(0, bar(kBarVFull + a), (uint32_t)(q >> 1));   // each accumulator completes twice per tile: phases 2 i, 2 i + 1
+          mm_fence_after();
+          if (prof) tk = mm_clock();
+          uint32_t hi[16], lo[16];
+          const uint32_t ta = tlane + kMmColV + a * 128 + vb * 64 + 16 * vrh;
+          mm_ld16(ta, hi);
+          mm_ld16(ta + 32, lo);
+          mm_wait_ld();
+          tick(6);
+          mm_st16(ta, 0u);   // re-arm the accumulator for the quarter after next
+          mm_st16(ta + 32, 1u << (IRP_INTERP_SHIFT - 1));
+          const uint32_t p0 = mm_pack4(hi, lo), p1 = mm_pack4(hi + 4, lo + 4), p2 = mm_pack4(hi + 8, lo + 8), p3 = mm_pack4(hi + 12, lo + 12);
+          tick(7);
+          mm_wait_st();
+          mm_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kBarVFree + a));
+          tick(8);
+          if (q == 0 && i > 0) {
+            // the previous tile's reduceh: its epilogue first (that wait also means the intermediate has been read),
+            // then this quarter's bytes may go in
+            epi_h(prev);
+            if (prof) tk = mm_clock();
+          }
+          mm_sts128(mid_col + (2 * q + vrh) * (kMmKH * 16), p0, p1, p2, p3);
+          if (q == 3) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the intermediate is read by the tensor core next
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarMidFull));
+          }
+          tick(9);
+        }
+        twait(3, bar(kBarFull + (buf ^ 1)), (uint32_t)((i + 1) >> 1) & 1u);
+        const MmInfo nxt = mm_load_info(a_info + (buf ^ 1) * (uint32_t)sizeof(MmInfo));
+        prev = cur;
+        cur = nxt;
+        if (!cur.valid) {
+          epi_h(prev);
+          break;
+        }
+      }
     }
-    mm_fence_before();
-    __syncthreads();
-    stamp(it);
-    if (!nxt.valid) break;
-    cur = nxt;
   }
+  if (prof && lane == 0 && (warp == 0 || warp >= kMmEpiWarps)) {   // rows: epilogue warp 0, producer, issuing warps
+    const int r = warp == 0 ? 0 : warp - kMmEpiWarps + 1;
+    for (int k = 0; k < 12; k++) dbg[16 * r + k] = wacc[k];
+    dbg[16 * r + 15] = mm_clock() - t_start;
+  }
+  __syncwarp();
+  mm_fence_before();
+  __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
