@@ -206,8 +206,8 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
   };
   const uint32_t t_start = mm_clock();
   if (tid == 0) {
-    for (int k = 0; k < 2; k++) mbar_init(bar(kBarFull + k), 1), mbar_init(bar(kBarSrcFree + k), 1);
-    for (int k = 0; k < 4; k++) mbar_init(bar(kBarCvFull + k), 1), mbar_init(bar(kBarCvFree + k), 1);
+    for (int k = 0; k < 2; k++) mbar_init(bar(kBarFull + k), 1), mbar_init(bar(kBarSrcFree + k), kMmVLanes);
+    for (int k = 0; k < 4; k++) mbar_init(bar(kBarCvFull + k), 1), mbar_init(bar(kBarCvFree + k), kMmVLanes);
     for (int k = 0; k < 2; k++) mbar_init(bar(kBarChFull + k), 1), mbar_init(bar(kBarChFree + k), 1);
     for (int k = 0; k < 2; k++) mbar_init(bar(kBarVFull + k), kMmVLanes), mbar_init(bar(kBarVFree + k), kMmEpiWarps);
     mbar_init(bar(kBarHFull), kMmHLanes);
@@ -308,13 +308,16 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
             for (int h = 0; h < 2; h++)
               tma_load_2d(src + b * (L.R * 128) + h * (L.R / 2) * 128, tmaps + job, bx0 + 128 * b, sy0 + h * (L.R / 2), bar(kBarFull + buf));
 #pragma unroll
-          for (int q = 0; q < 4; q++)
+          for (int q = 0; q < 4; q++) {
+            // the quarter's MMAs of the previous tile are done.  Waited for EVERY tile, reload or not: a parity wait
+            // must never fall two phases behind its barrier
+            twait(1, bar(kBarCvFree + q), (uint32_t)(i & 1) ^ 1u);
             if (flags & (1 << q)) {
-              twait(1, bar(kBarCvFree + q), (uint32_t)(i & 1) ^ 1u);   // the quarter's MMAs of the previous tile are done
               mbar_arrive_expect_tx(bar(kBarCvFull + q), (uint32_t)ksv * 2048u);
               mm_bulk_g2s(a_cv + q * cv_slot, vm[q], (uint32_t)ksv * 2048u, bar(kBarCvFull + q));
               cv_in[q] = vm[q];
             }
+          }
           if (flags & 16) {
             twait(2, bar(kBarChFree + chslot), (uint32_t)(ch_uses[chslot] & 1) ^ 1u);
             mbar_arrive_expect_tx(bar(kBarChFull + chslot), kMmChBytes);
@@ -335,27 +338,19 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
     // Three issuing warps (one lane each): w = column block of reducev (0, 1) and channel plane of reduceh (0, 1, 2).
     // Measured (tools/probes/umma_rate.cu): two or more WARPS issuing MMAs with a commit every few of them keep the
     // tensor pipe at its floor for this shape (51.5 cycles per M128 N64 K32); lanes of one warp do not (57-93), and a
-    // lone thread that never commits gets 125.  What the producer waits for (matrix slot, source buffer, CH slot free
-    // again) is relayed by warp 0 with plain arrives once the epilogue has handed the accumulator back — by then the
-    // MMAs that read those operands are long done — so there is ONE commit per warp and event.
+    // lone thread that never commits gets 125; commits are nearly free there.  So each warp commits to everything that
+    // waits for its MMAs: accumulator complete, matrix slot free, source buffer free.  (Only the CH slot is relayed
+    // by warp 0 with a plain arrive when the next reduceh is issued: reduceh is serialised by its one accumulator.)
     const int w = warp - kMmEpiWarps - 1;
     uint32_t vuse0 = 0, vuse1 = 0, hcount = 0;
     uint32_t cvl0 = 0, cvl1 = 0, cvl2 = 0, cvl3 = 0, chl0 = 0, chl1 = 0;
-    int vprev_q0 = 0, vprev_q1 = 0, vprev_buf0 = 0, vprev_buf1 = 0, hprev_slot = 0;
+    int hprev_slot = 0;
     auto issue_v = [&](const MmInfo& inf, int buf, int q) {   // q is a literal at every call site
       const int a = q & 1;
       uint32_t& vuse = a ? vuse1 : vuse0;
-      int& vprev_q = a ? vprev_q1 : vprev_q0;
-      int& vprev_buf = a ? vprev_buf1 : vprev_buf0;
       uint32_t& cvl = q == 0 ? cvl0 : (q == 1 ? cvl1 : (q == 2 ? cvl2 : cvl3));
       twait(0, bar(kBarVFree + a), (vuse & 1u) ^ 1u);
-      if (w == 0 && vuse > 0) {
-        mbar_arrive(bar(kBarCvFree + vprev_q));
-        if (vprev_q == 3) mbar_arrive(bar(kBarSrcFree + vprev_buf));
-      }
       vuse++;
-      vprev_q = q;
-      vprev_buf = buf;
       if (inf.flags & (1 << q)) {
         twait(1, bar(kBarCvFull + q), cvl & 1u);
         cvl++;
@@ -367,6 +362,8 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
         mm_mma_i8(tm + kMmColV + a * 128 + w * 64, mm_desc(src + ks * 4096, (uint32_t)L.R * 128u, 1024u, 2u),
                   mm_desc(a_cv + q * cv_slot + ks * 2048, 1024u, 128u, 0u), kMmIdesc);
       mm_commit(bar(kBarVFull + a));
+      mm_commit(bar(kBarCvFree + q));                  // the quarter's matrix slot can be refilled
+      if (q == 3) mm_commit(bar(kBarSrcFree + buf));   // ... and the tile's source buffer
     };
     auto issue_h = [&](const MmInfo& inf) {
       twait(2, bar(kBarMidFull), hcount & 1u);
@@ -438,6 +435,10 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
         mm_st8(tlane + kMmColH + 64 * c + 8 * pg, 0u);
         mm_st8(tlane + kMmColH + 64 * c + 32 + 8 * pg, 1u << (IRP_INTERP_SHIFT - 1));
       }
+      mm_wait_st();
+      mm_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarHFree));
       int v[24];   // interleaved: v[3 j + c]
 #pragma unroll
       for (int j = 0; j < 8; j++)
@@ -450,10 +451,6 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
         const uint32_t w1 = pack_sat_u8(v[8 * k + 5], v[8 * k + 4], pack_sat_u8(v[8 * k + 7], v[8 * k + 6], 0u));
         asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(so + 8 * k), "r"(w0), "r"(w1) : "memory");
       }
-      mm_wait_st();
-      mm_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarHFree));
       tick(10);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kMmEpiWarps) : "memory");
       uint8_t* dst = reinterpret_cast<uint8_t*>(((unsigned long long)inf.dst_hi << 32) | inf.dst_lo);
@@ -496,14 +493,14 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           mm_ld16(ta + 32, lo);
           mm_wait_ld();
           tick(6);
-          mm_st16(ta, 0u);   // re-arm the accumulator for the quarter after next
+          mm_st16(ta, 0u);   // re-arm the accumulator for the quarter after next and hand it back before anything else
           mm_st16(ta + 32, 1u << (IRP_INTERP_SHIFT - 1));
-          const uint32_t p0 = mm_pack4(hi, lo), p1 = mm_pack4(hi + 4, lo + 4), p2 = mm_pack4(hi + 8, lo + 8), p3 = mm_pack4(hi + 12, lo + 12);
-          tick(7);
           mm_wait_st();
           mm_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(kBarVFree + a));
+          tick(7);
+          const uint32_t p0 = mm_pack4(hi, lo), p1 = mm_pack4(hi + 4, lo + 4), p2 = mm_pack4(hi + 8, lo + 8), p3 = mm_pack4(hi + 12, lo + 12);
           tick(8);
           if (q == 0 && i > 0) {
             // the previous tile's reduceh: its epilogue first (that wait also means the intermediate has been read),
