@@ -45,7 +45,16 @@ export class ClassifierService {
         scores = await native.analyzeRaw(ctx, data, info.width, info.height, info.channels, metadata.format === 'jpeg');
       }
       const analysis = Object.fromEntries(KEYS.map((k, i) => [k, scores[i]]));
-      const topIssues = Object.entries(analysis).filter(([, s]) => s > 0.3).sort((a, b) => b[1] - a[1]).slice(0, 3);
+      // scores[7..10] = irp_result.issues: the three highest scores above 0.3 with their severity, already sorted
+      // (promptEnhancer.js:121-145); kept on the instance for PromptEnhancerService, the returned object stays the 7 keys
+      const SEVERITY = [null, 'low', 'medium', 'high'];
+      const issues = [];
+      for (let k = 0; k < scores[10]; k++) {
+        const v = scores[7 + k];
+        issues.push({ type: KEYS[v & 15], confidence: scores[v & 15], severity: SEVERITY[v >> 4] });
+      }
+      this.lastTopIssues = issues;
+      const topIssues = issues.map((i) => [i.type, i.confidence]);
       span.setAttributes({
         'image.width': metadata.width, 'image.height': metadata.height, 'image.format': metadata.format,
         'image.channels': metadata.channels,

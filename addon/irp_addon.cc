@@ -135,11 +135,14 @@ void Complete(napi_env env, napi_status, void* data) {
     napi_set_named_property(env, obj, "channels", v);
     napi_resolve_deferred(env, j->deferred, obj);
   } else {
+    // Float64Array(11): the seven scores, then irp_result.issues (three IRP_ISSUE bytes or 255, and their count) —
+    // PromptEnhancerService._identifyTopIssues' answer, already worked out by the library
     napi_value ab, arr;
     void* dst = nullptr;
-    napi_create_arraybuffer(env, sizeof(double) * IRP_NUM_SCORES, &dst, &ab);
+    napi_create_arraybuffer(env, sizeof(double) * (IRP_NUM_SCORES + 4), &dst, &ab);
     std::memcpy(dst, j->result.score, sizeof(double) * IRP_NUM_SCORES);
-    napi_create_typedarray(env, napi_float64_array, IRP_NUM_SCORES, ab, 0, &arr);
+    for (int k = 0; k < 4; k++) static_cast<double*>(dst)[IRP_NUM_SCORES + k] = j->result.issues[k];
+    napi_create_typedarray(env, napi_float64_array, IRP_NUM_SCORES + 4, ab, 0, &arr);
     napi_resolve_deferred(env, j->deferred, arr);
   }
   napi_delete_reference(env, j->input_ref);

@@ -29,7 +29,7 @@ FUSION_MAX_IMAGES = 3
 # every symbol include/irp.h declares (tests/test_abi.py checks the .so exports each one)
 SYMBOLS = (
     "irp_abi_version", "irp_device_count", "irp_create", "irp_destroy", "irp_last_error", "irp_set_stream",
-    "irp_get_timing", "irp_preprocess_dims", "irp_fusion_dims", "irp_scores_from_moments", "irp_grey_tables",
+    "irp_get_timing", "irp_preprocess_dims", "irp_fusion_dims", "irp_scores_from_moments", "irp_top_issues", "irp_grey_tables",
     "irp_classify_batch", "irp_preprocess_batch", "irp_analyze_batch", "irp_fusion_prepare_batch",
     "irp_submit", "irp_submit_jpeg", "irp_submit_transcode", "irp_wait", "irp_jpeg_info", "irp_decode_jpeg_batch", "irp_analyze_jpeg_batch",
     "irp_set_output_icc", "irp_register_icc", "irp_get_icc", "irp_encode_jpeg_batch", "irp_analyze_encode_batch", "irp_transcode_jpeg_batch",
@@ -40,7 +40,7 @@ SYMBOLS = (
 
 class Opts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("luma_mode", C.c_int32), ("coef_mode", C.c_int32),
-                ("reserved0", C.c_int32), ("staging_bytes", C.c_uint64)]
+                ("reserved0", C.c_int32), ("staging_bytes", C.c_uint64), ("blur_mode", C.c_int32), ("reduce_mode", C.c_int32)]
 
 
 class ImageDesc(C.Structure):
@@ -54,7 +54,7 @@ class Result(C.Structure):
                 ("e_sum", C.c_uint64 * 2), ("e_sumsq", C.c_uint64 * 2), ("b_sum", C.c_uint64),
                 ("b_sumsq", C.c_uint64), ("scratch_v", C.c_uint32), ("scratch_h", C.c_uint32),
                 ("block_edges", C.c_uint32 * 2), ("luma_hist", C.c_uint32 * 256), ("status", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("issues", C.c_uint8 * 4)]
 
 
 class OutDesc(C.Structure):

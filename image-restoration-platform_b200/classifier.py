@@ -126,9 +126,10 @@ class ClassifierService:
         out = []
         for (w, h), r in zip(sizes, results):
             analysis = {k: r["scores"][k] for k in SCORE_KEYS}
-            top = sorted(((k, v) for k, v in analysis.items() if v > 0.3), key=lambda kv: -kv[1])[:3]  # classifier.js:73-76
+            # classifier.js:73-76 — the library returns the top three next to the scores (irp_result.issues)
             self._log("debug", "[classifier] Analysis complete",
-                      {"topIssues": [{"type": k, "score": f"{v:.2f}"} for k, v in top], "imageSize": f"{w}x{h}"})
+                      {"topIssues": [{"type": t["type"], "score": f"{t['confidence']:.2f}"} for t in r["issues"]], "imageSize": f"{w}x{h}"})
+            self.last_top_issues = r["issues"]   # what PromptEnhancerService._identifyTopIssues would compute again (promptEnhancer.js:121-137)
             out.append(analysis)
         return out
 

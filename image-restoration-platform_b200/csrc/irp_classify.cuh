@@ -390,21 +390,28 @@ __device__ __forceinline__ void stage2(const Tiles<C>& T, Acc<C>& a, int tid, in
 // next step picks it with PRMT.
 struct HRow { uint32_t z[4]; };   // per column: (3(l+r) + 5c + 5) * 5958, the blurred byte is byte 2
 
-__device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip) {
+// the blur's three constants: tap weights as dp4a bytes (edge, centre, edge, 0), rounding term, and the multiplier
+// that leaves the quotient in byte 2.  IRP_BLUR_EXACT: (3, 5, 3) + 5, x 5958 (= / 11); IRP_BLUR_VECTOR (libvips'
+// SIMD convi as recalled, 8-bit mantissas): (35, 58, 35) + 64, x 512 (= >> 7; 32704 * 512 < 2^24).
+struct BlurK { uint32_t w, bias, mul; };
+__host__ __device__ constexpr BlurK blur_exact() { return BlurK{0x00030503u, 5u, 5958u}; }
+__host__ __device__ constexpr BlurK blur_vector() { return BlurK{0x00233A23u, 64u, 512u}; }
+
+__device__ __forceinline__ HRow hpass_row(const uint8_t* plane_row, int strip, const BlurK bk = blur_exact()) {
   const uint32_t* rp = reinterpret_cast<const uint32_t*>(plane_row) + 3 + strip;
   const uint32_t l = rp[0], c = rp[1], r = rp[2];
   HRow o;
   const uint32_t w0 = __funnelshift_r(l, c, 24);  // (l3, c0, c1, c2)
   const uint32_t w3 = __funnelshift_r(c, r, 16);  // (c2, c3, r0, r1)
-  o.z[0] = __dp4a(w0, 0x00030503u, 5u) * 5958u;
-  o.z[1] = __dp4a(c, 0x00030503u, 5u) * 5958u;
-  o.z[2] = __dp4a(c, 0x03050300u, 5u) * 5958u;
-  o.z[3] = __dp4a(w3, 0x00030503u, 5u) * 5958u;
+  o.z[0] = __dp4a(w0, bk.w, bk.bias) * bk.mul;
+  o.z[1] = __dp4a(c, bk.w, bk.bias) * bk.mul;
+  o.z[2] = __dp4a(c, bk.w << 8, bk.bias) * bk.mul;
+  o.z[3] = __dp4a(w3, bk.w, bk.bias) * bk.mul;
   return o;
 }
 
 template <int C, bool FULL, int PITCH = kPlanePitch>
-__device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, int x0, int y0, int W, int H) {
+__device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, int x0, int y0, int W, int H, const BlurK bk = blur_exact()) {
   const int strip = tid & (kStrips - 1), rg = tid / kStrips;
   const int x = x0 + strip * 4;
   const int r0 = rg * 8;
@@ -421,19 +428,19 @@ __device__ __forceinline__ void stage3(const Tiles<C>& T, Acc<C>& a, int tid, in
     // per column a sliding window of horizontal results: bytes (up, cur, dn, 0)
     uint32_t win[4];
     {
-      const HRow up = hpass_row(pl + r0 * PITCH, strip), cur = hpass_row(pl + (r0 + 1) * PITCH, strip);
+      const HRow up = hpass_row(pl + r0 * PITCH, strip, bk), cur = hpass_row(pl + (r0 + 1) * PITCH, strip, bk);
 #pragma unroll
       for (int j = 0; j < 4; j++) win[j] = __byte_perm(up.z[j], cur.z[j], 0x7620);  // (-, up, cur, 0)
     }
 #pragma unroll 4
     for (int i = 0; i < 8; i++) {
       if (!FULL && i >= nrows) break;
-      const HRow dn = hpass_row(pl + (r0 + i + 2) * PITCH, strip);
+      const HRow dn = hpass_row(pl + (r0 + i + 2) * PITCH, strip, bk);
       uint32_t zz[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         win[j] = __byte_perm(win[j], dn.z[j], 0x7621);                 // (up, cur, dn, 0)
-        zz[j] = __dp4a(win[j], 0x00030503u, 5u) * 5958u;               // vertical result in byte 2
+        zz[j] = __dp4a(win[j], bk.w, bk.bias) * bk.mul;                // vertical result in byte 2
       }
       uint32_t b4 = __byte_perm(__byte_perm(zz[0], zz[1], 0x0062), __byte_perm(zz[2], zz[3], 0x0062), 0x5410);
       if (!FULL) b4 &= vmask;
@@ -450,7 +457,7 @@ template <int C>
 __global__ void __launch_bounds__(kClassifyThreads, 3)
 classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, const ClassifyTables* __restrict__ tab,
                 unsigned long long* __restrict__ gacc, uint32_t* __restrict__ ghist, uint32_t dyn_smem_bytes,
-                int* __restrict__ error_flag) {
+                int* __restrict__ error_flag, BlurK bk) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const SmemMap map = make_smem_map(sbase, C);
@@ -556,10 +563,10 @@ classify_kernel(const ImgDev* __restrict__ imgs, int n_imgs, int total_tiles, co
     // ---- stage 2 + 3 ----
     if (x0 + kTileW < im.w && y0 + kTileH < im.h) {
       stage2<C, true>(T, acc, tid, x0, y0, im.w, im.h);
-      stage3<C, true>(T, acc, tid, x0, y0, im.w, im.h);
+      stage3<C, true>(T, acc, tid, x0, y0, im.w, im.h, bk);
     } else {
       stage2<C, false>(T, acc, tid, x0, y0, im.w, im.h);
-      stage3<C, false>(T, acc, tid, x0, y0, im.w, im.h);
+      stage3<C, false>(T, acc, tid, x0, y0, im.w, im.h, bk);
     }
     group_barrier(group);
   }

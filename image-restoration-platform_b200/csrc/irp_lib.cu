@@ -289,7 +289,7 @@ struct HostPlan {
   std::vector<int32_t> start, phase;
   std::vector<int16_t> coef;  // [65][kCoefStride]
 };
-bool build_plan(int in_size, int out_size, double shrink, int coef_mode, HostPlan* hp) {
+bool build_plan(int in_size, int out_size, double shrink, int coef_mode, int reduce_mode, HostPlan* hp) {
   int n = reduce_points(shrink);
   if (n > IRP_MAX_TAPS) return false;
   hp->n = n;
@@ -298,7 +298,10 @@ bool build_plan(int in_size, int out_size, double shrink, int coef_mode, HostPla
   for (int t = 0; t <= IRP_PHASES; t++) {
     lanczos_mask(mask, n, shrink, (double)t / IRP_PHASES);
     int16_t* ci = hp->coef.data() + (size_t)t * kCoefStride;
-    if (coef_mode == IRP_COEF_TRUNCATE)
+    if (reduce_mode == IRP_REDUCE_VECTOR_2_6) {   // 6 fractional bits, kept as multiples of 64: (sum 64 c p + 2048) >> 12 == (sum c p + 32) >> 6
+      to_fixed_point(mask, ci, n, 64);
+      for (int i = 0; i < n; i++) ci[i] = (int16_t)(ci[i] * 64);
+    } else if (coef_mode == IRP_COEF_TRUNCATE)
       for (int i = 0; i < n; i++) ci[i] = (int16_t)(mask[i] * (1 << IRP_INTERP_SHIFT));
     else
       to_fixed_point(mask, ci, n, 1 << IRP_INTERP_SHIFT);
@@ -470,9 +473,8 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
       hp.start.resize(out_size);
       hp.phase.assign(out_size, 0);
       for (int o = 0; o < out_size; o++) hp.start[o] = o;
-    } else if (!build_plan(in_size, out_size, shrink, ctx->opts.coef_mode, &hp)) {
-      return fail(ctx, IRP_ERR_UNSUPPORTED, "shrink factor %.4f needs more than %d taps (box pre-shrink not implemented)",
-                  shrink, IRP_MAX_TAPS);
+    } else if (!build_plan(in_size, out_size, shrink, ctx->opts.coef_mode, ctx->opts.reduce_mode, &hp)) {
+      return fail(ctx, IRP_ERR_UNSUPPORTED, "shrink factor %.4f needs more than %d taps", shrink, IRP_MAX_TAPS);
     }
     PlanDev pd;
     pd.n = hp.n;
@@ -558,6 +560,10 @@ struct Geo {      // per-image preprocess geometry
   int wo, ho, dw, dh, dc, ox, oy, o;
   double f;
   size_t orient_off, out_off;
+  // vips_resize's integer pre-shrink (axes shrinking 4x or more): factors, what the lanczos passes then see
+  int kh = 1, kv = 1, rw = 0, rh = 0;
+  double fh = 1.0, fv = 1.0;
+  size_t box_off = 0;
 };
 
 struct OutPlan {  // per image: where the kernel writes, and how the result gets to the caller
@@ -627,7 +633,8 @@ int launch_classify(irp_ctx* ctx, const ImgDev* d_imgs, int n, int total_tiles, 
   }
   int grid = std::min((total_tiles + kGroups - 1) / kGroups, ctx->sm_count * occ);
   classify_kernel<C><<<grid, kClassifyThreads, smem, ctx->stream>>>(d_imgs, n, total_tiles, ctx->d_tables, d_acc, d_hist,
-                                                                    (uint32_t)smem, ctx->d_error_flag);
+                                                                    (uint32_t)smem, ctx->d_error_flag,
+                                                                    ctx->opts.blur_mode == IRP_BLUR_VECTOR ? blur_vector() : blur_exact());
   CK(cudaGetLastError());
   ctx->timing.kernel_launches++;
   return IRP_OK;
@@ -677,7 +684,7 @@ int classify_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<S
     const bool aligned = (((uintptr_t)st[i].px | st[i].pitch) & 15) == 0;
     if (imgs[i].channels == 1) return 0;
     if (imgs[i].channels == 4) return 2;
-    return (aligned && ctx->bulk_ok) ? 3 : 1;
+    return (aligned && ctx->bulk_ok && ctx->opts.blur_mode == IRP_BLUR_EXACT) ? 3 : 1;   // the streaming kernel bakes the exact blur in
   };
   for (int g = 0; g < 4; g++) {
     group_begin[g] = pos;
@@ -814,7 +821,12 @@ int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* 
       fusion_dims(d.width, d.height, g.o, &g.dw, &g.dh, &g.ox, &g.oy, &g.f);
       g.dc = 3;
     }
-    if (g.f >= 4.0) return fail(ctx, IRP_ERR_UNSUPPORTED, "image %d: shrink %.3f >= 4 needs libvips' box pre-shrink (not implemented)", i, g.f);
+    g.kh = std::max(1, (int)std::floor((double)g.wo / g.dw / 2.0));
+    g.kv = std::max(1, (int)std::floor((double)g.ho / g.dh / 2.0));
+    g.rw = (g.wo + g.kh - 1) / g.kh;
+    g.rh = (g.ho + g.kv - 1) / g.kv;
+    g.fh = g.f / g.kh;
+    g.fv = g.f / g.kv;
     int out_w = mode == 0 ? g.dw : IRP_FUSION_CANVAS, out_h = mode == 0 ? g.dh : IRP_FUSION_CANVAS;
     irp_out_desc& od = outs[i];
     if (!od.pixels) return fail(ctx, IRP_ERR_BAD_ARG, "output %d: null pixels", i);
@@ -829,6 +841,10 @@ int plan_outputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, irp_out_desc* 
     if (g.o != 1) {
       g.orient_off = orient_total;
       orient_total += round_up(round_up((size_t)g.wo * d.channels, 16) * g.ho, 256);
+    }
+    if (g.kh > 1 || g.kv > 1) {
+      g.box_off = orient_total;
+      orient_total += round_up(round_up((size_t)g.rw * d.channels, 16) * g.rh, 256);
     }
     if (!od.on_device) {   // staged rows get a 16-byte pitch: the tensor-core resize stores whole 8-byte pieces
       g.out_off = out_total;
@@ -990,8 +1006,21 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     } else {
       s = Src{st[i].px, st[i].pitch};
     }
-    if ((rc = get_plan(ctx, g.ho, g.dh, g.f, &pv[i - b], &dv[i - b]))) return rc;
-    if ((rc = get_plan(ctx, g.wo, g.dw, g.f, &ph[i - b], &dh[i - b]))) return rc;
+    if (g.kh > 1 || g.kv > 1) {   // integer box pre-shrink; the lanczos passes then do the remaining factor in [2, 4)
+      uint8_t* bp = (uint8_t*)ctx->d_orient.p + g.box_off;
+      const size_t bpitch = round_up((size_t)g.rw * d.channels, 16);
+      const dim3 grid((g.rw * d.channels + 255) / 256, g.rh);
+      switch (d.channels) {
+        case 1: box_shrink_kernel<1><<<grid, 256, 0, ctx->stream>>>(s.px, s.pitch, g.wo, g.ho, g.kh, g.kv, bp, bpitch, g.rw, g.rh); break;
+        case 3: box_shrink_kernel<3><<<grid, 256, 0, ctx->stream>>>(s.px, s.pitch, g.wo, g.ho, g.kh, g.kv, bp, bpitch, g.rw, g.rh); break;
+        default: box_shrink_kernel<4><<<grid, 256, 0, ctx->stream>>>(s.px, s.pitch, g.wo, g.ho, g.kh, g.kv, bp, bpitch, g.rw, g.rh); break;
+      }
+      CK(cudaGetLastError());
+      ctx->timing.kernel_launches++;
+      s = Src{bp, bpitch};
+    }
+    if ((rc = get_plan(ctx, g.rh, g.dh, g.fv, &pv[i - b], &dv[i - b]))) return rc;
+    if ((rc = get_plan(ctx, g.rw, g.dw, g.fh, &ph[i - b], &dh[i - b]))) return rc;
   }
   // kernel choice.  The streaming kernel runs 5 groups x 24-row tiles per CTA when every eligible job keeps
   // a full-size tile inside a fifth of the shared memory, else 4 groups x 32-row tiles.
@@ -1017,7 +1046,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         }
       }
       // no geometry change and nothing to normalise: the oriented pixels ARE the result, a row copy
-      if (pv[i - b].n == 1 && ph[i - b].n == 1 && g.dc == d.channels && g.dw == g.wo && g.dh == g.ho) k = 4;
+      if (pv[i - b].n == 1 && ph[i - b].n == 1 && g.dc == d.channels && g.dw == g.rw && g.dh == g.rh) k = 4;
       // the tensor-core kernel: 3-channel aligned sources whose geometry fits its tile, 8-byte aligned destination pieces
       if ((k == 1 || k == 3) && ctx->rmma_ok && ((((uintptr_t)s.px | s.pitch) & 15) == 0) && dv[i - b]->mm_v_ok && dh[i - b]->mm_h_ok &&
           ((((uintptr_t)oplans[i].dev | oplans[i].dev_pitch) & 15) == 0) && ((3 * g.ox) & 7) == 0 && mm_layout(dv[i - b]->mm_rows, dv[i - b]->mm_ksv).total <= (int)ctx->smem_optin_full - 2048)
@@ -1066,7 +1095,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         M.dst_pitch = op.dev_pitch;
         M.vfirst = dv[i - b]->mm_first; M.vmat = dv[i - b]->mm_vmat; M.vmats = dv[i - b]->mm_vmats;
         M.hfirst = dh[i - b]->mm_first; M.hmat = dh[i - b]->mm_hmat; M.hmats = dh[i - b]->mm_hmats;
-        M.sw = g.wo; M.sh = g.ho; M.dw = g.dw; M.dh = g.dh;
+        M.sw = g.rw; M.sh = g.rh; M.dw = g.dw; M.dh = g.dh;
         M.dst_x0 = g.ox; M.dst_y0 = g.oy;
         M.tiles_x = (g.dw + kMmTC - 1) / kMmTC;
         M.tiles_y = (g.dh + kMmTR - 1) / kMmTR;
@@ -1087,7 +1116,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         R.hcols = dh[i - b]->hcols;
         R.vstart = dv[i - b]->start;
         R.hstart = dh[i - b]->start;
-        R.sw = g.wo; R.sh = g.ho; R.dw = g.dw; R.dh = g.dh;
+        R.sw = g.rw; R.sh = g.rh; R.dw = g.dw; R.dh = g.dh;
         R.dst_x0 = g.ox; R.dst_y0 = g.oy;
         R.tow = foot[i - b].tow; R.toh = foot[i - b].toh;
         R.tiles_x = (g.dw + R.tow - 1) / R.tow;
@@ -1097,7 +1126,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         tiles += R.tiles_x * R.tiles_y;
         R.box_cols = (int)round_up((size_t)foot[i - b].ncols * 3 + 12, 16);
         R.box_rows = foot[i - b].nrows;
-        if ((rc = encode_source_tmap(ctx, src[i - b].px, src[i - b].pitch, g.wo, g.ho, R.box_cols, R.box_rows, h_tm + pos))) return rc;
+        if ((rc = encode_source_tmap(ctx, src[i - b].px, src[i - b].pitch, g.rw, g.rh, R.box_cols, R.box_rows, h_tm + pos))) return rc;
         pos++;
         continue;
       }
@@ -1107,8 +1136,8 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       J.src_pitch = src[i - b].pitch;
       J.dst = op.dev;
       J.dst_pitch = op.dev_pitch;
-      J.sw = g.wo;
-      J.sh = g.ho;
+      J.sw = g.rw;
+      J.sh = g.rh;
       J.c = d.channels;
       J.dc = g.dc;
       J.dw = g.dw;
@@ -1119,7 +1148,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       J.aligned16 = (((uintptr_t)J.src | J.src_pitch) & 15) == 0;
       J.v = pv[i - b];
       J.h = ph[i - b];
-      choose_tile(g.f, J.v.n, J.h.n, d.channels, &J.tow, &J.toh, &J.pairrows_max);
+      choose_tile(std::max(g.fh, g.fv), J.v.n, J.h.n, d.channels, &J.tow, &J.toh, &J.pairrows_max);
       J.tiles_x = (J.dw + J.tow - 1) / J.tow;
       J.tiles_y = (J.dh + J.toh - 1) / J.toh;
       J.tile_base = tiles;
@@ -1171,7 +1200,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     int slot = g5;
     for (int i = b; i < e; i++) {
       if (!imgs[i].pixels || kern[i - b] != 5) continue;
-      if ((rc = encode_mm_tmap(ctx, src[i - b].px, src[i - b].pitch, geo[i].wo, geo[i].ho, ML.R / 2, h_mt + slot))) return rc;
+      if ((rc = encode_mm_tmap(ctx, src[i - b].px, src[i - b].pitch, geo[i].rw, geo[i].rh, ML.R / 2, h_mt + slot))) return rc;
       slot++;
     }
     CK(cudaMemcpyAsync(d_mm + g5, h_mm + g5, sizeof(MmJob) * nmm, cudaMemcpyHostToDevice, ctx->stream));
@@ -1545,7 +1574,7 @@ int irp_preprocess_dims(int width, int height, int exif_orientation, int* out_w,
   int o = (exif_orientation >= 1 && exif_orientation <= 8) ? exif_orientation : 1;
   double f;
   preprocess_dims(width, height, o, out_w, out_h, &f);
-  return f >= 4.0 ? IRP_ERR_UNSUPPORTED : IRP_OK;
+  return IRP_OK;
 }
 
 int irp_fusion_dims(int width, int height, int exif_orientation, int* out_w, int* out_h, int* off_x, int* off_y) {
@@ -1553,7 +1582,7 @@ int irp_fusion_dims(int width, int height, int exif_orientation, int* out_w, int
   int o = (exif_orientation >= 1 && exif_orientation <= 8) ? exif_orientation : 1;
   double f;
   fusion_dims(width, height, o, out_w, out_h, off_x, off_y, &f);
-  return f >= 4.0 ? IRP_ERR_UNSUPPORTED : IRP_OK;
+  return IRP_OK;
 }
 
 int irp_scores_from_moments(irp_result* r, int width, int height, int channels, int is_jpeg) {
@@ -1607,6 +1636,26 @@ int irp_scores_from_moments(irp_result* r, int width, int height, int channels, 
            bd = avg > 0 ? std::fabs(mean[2] - avg) / avg : 0;
     r->score[IRP_SCORE_COLORSHIFT] = jsmin(jsmax(jsmax(rd, gd), bd) * 2, 1.0);
   }
+  return irp_top_issues(r);
+}
+
+// PromptEnhancerService._identifyTopIssues / _determineSeverity (promptEnhancer.js:121-145)
+int irp_top_issues(irp_result* r) {
+  if (!r) return IRP_ERR_BAD_ARG;
+  int idx[IRP_NUM_SCORES], n = 0;
+  for (int k = 0; k < IRP_NUM_SCORES; k++)
+    if (r->score[k] > IRP_ISSUE_THRESHOLD) idx[n++] = k;
+  std::stable_sort(idx, idx + n, [&](int a, int b) { return r->score[a] > r->score[b]; });
+  n = std::min(n, 3);
+  for (int k = 0; k < 3; k++) {
+    if (k >= n) {
+      r->issues[k] = IRP_NO_ISSUE;
+      continue;
+    }
+    const double c = r->score[idx[k]];
+    r->issues[k] = IRP_ISSUE(c >= 0.7 ? IRP_SEVERITY_HIGH : (c >= 0.5 ? IRP_SEVERITY_MEDIUM : IRP_SEVERITY_LOW), idx[k]);
+  }
+  r->issues[3] = (uint8_t)n;
   return IRP_OK;
 }
 

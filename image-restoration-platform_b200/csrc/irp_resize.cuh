@@ -265,6 +265,25 @@ struct CopyJob {
   int row_bytes, rows, row_base, pad;
 };
 
+// vips_resize's integer pre-shrink (libvips resample/resize.c: shrinkv then shrinkh with "ceil"):
+// kv rows then kh columns averaged, (sum + k / 2) / k each, u8 between the passes, edge replicated.  Only axes that
+// shrink 4x or more come here (sides beyond 8192 px), so one thread per output byte is enough.
+template <int C>
+__global__ void __launch_bounds__(256) box_shrink_kernel(const uint8_t* __restrict__ src, size_t spitch, int w, int h, int kh, int kv,
+                                                         uint8_t* __restrict__ dst, size_t dpitch, int ow, int oh) {
+  const int xb = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (xb >= ow * C || y >= oh) return;
+  const int x = xb / C, ch = xb - x * C;
+  int acc = 0;
+  for (int i = 0; i < kh; i++) {
+    const int sx = min(x * kh + i, w - 1);
+    int col = 0;
+    for (int j = 0; j < kv; j++) col += __ldg(src + (size_t)min(y * kv + j, h - 1) * spitch + (size_t)sx * C + ch);
+    acc += (col + kv / 2) / kv;
+  }
+  dst[(size_t)y * dpitch + xb] = (uint8_t)((acc + kh / 2) / kh);
+}
+
 __global__ void __launch_bounds__(256) copy_rows_kernel(const CopyJob* __restrict__ jobs, int n_jobs, int total_rows) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;

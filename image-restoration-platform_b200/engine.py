@@ -61,13 +61,27 @@ def result_to_dict(r: _ffi.Result) -> dict:
         "sum": list(r.sum), "sumsq": list(r.sumsq), "e_sum": list(r.e_sum), "e_sumsq": list(r.e_sumsq),
         "b_sum": int(r.b_sum), "b_sumsq": int(r.b_sumsq), "scratch_v": int(r.scratch_v), "scratch_h": int(r.scratch_h),
         "block_edges": list(r.block_edges), "luma_hist": list(r.luma_hist), "status": int(r.status),
+        "issues": issues_of(r),
     }
 
 
+SEVERITY = {1: "low", 2: "medium", 3: "high"}
+
+
+def issues_of(r) -> list:
+    """irp_result.issues -> what PromptEnhancerService._identifyTopIssues returns (promptEnhancer.js:121-137):
+    [{type, confidence, severity}], highest confidence first, at most three."""
+    out = []
+    for k in range(int(r.issues[3])):
+        v = int(r.issues[k])
+        out.append({"type": SCORE_KEYS[v & 15], "confidence": float(r.score[v & 15]), "severity": SEVERITY[v >> 4]})
+    return out
+
+
 class Engine:
-    def __init__(self, device: int = 0, luma_mode: int = 0, coef_mode: int = 0):
+    def __init__(self, device: int = 0, luma_mode: int = 0, coef_mode: int = 0, blur_mode: int = 0, reduce_mode: int = 0):
         self._lib = _ffi.load()
-        opts = _ffi.Opts(C.sizeof(_ffi.Opts), luma_mode, coef_mode, 0, 0)
+        opts = _ffi.Opts(C.sizeof(_ffi.Opts), luma_mode, coef_mode, 0, 0, blur_mode, reduce_mode)
         self._ctx = self._lib.irp_create(device, C.byref(opts))
         if not self._ctx:
             raise IrpError(_ffi.IRP_ERR_NO_DEVICE, (self._lib.irp_last_error(None) or b"irp_create failed").decode())

@@ -28,7 +28,7 @@ extern "C" {
 enum {
   IRP_OK = 0,
   IRP_ERR_BAD_ARG = -1,     /* null pointer, bad dims, bad channel count        */
-  IRP_ERR_UNSUPPORTED = -2, /* shrink factor >= 4 (needs box pre-shrink), C == 2 */
+  IRP_ERR_UNSUPPORTED = -2, /* C == 2, progressive JPEG, ...                          */
   IRP_ERR_CUDA = -3,        /* a CUDA runtime call failed                       */
   IRP_ERR_NOMEM = -4,       /* host or device allocation failed                 */
   IRP_ERR_NO_DEVICE = -5,   /* no CUDA device / wrong architecture              */
@@ -51,6 +51,12 @@ enum {
 /* Switches for the libvips details SURVEY.md §8a tags MED/LOW confidence. */
 enum { IRP_LUMA_VIPS_USUAL = 0 /* 0.2/0.7/0.1 */, IRP_LUMA_CIE = 1 /* 0.2126/0.7152/0.0722 */ };
 enum { IRP_COEF_FIXED_POINT_SUM = 0 /* vips_vector_to_fixed_point */, IRP_COEF_TRUNCATE = 1 };
+/* gaussblur(1) of _detectBlockiness (classifier.js:297): libvips' C path of vips_convi, (sum + 22) / 44 exactly,
+ * or its SIMD path as recalled: 8-bit mantissas {35, 58, 35}, (sum + 64) >> 7 */
+enum { IRP_BLUR_EXACT = 0, IRP_BLUR_VECTOR = 1 };
+/* reducev / reduceh: 12-bit integer coefficients (the C and highway kernels), or 6 fractional bits ((sum + 32) >> 6,
+ * the precision of libvips' older orc vector path) */
+enum { IRP_REDUCE_INT12 = 0, IRP_REDUCE_VECTOR_2_6 = 1 };
 
 #define IRP_MAX_DIMENSION 2048 /* imagePreprocess.js:4  MAX_DIMENSION */
 #define IRP_FUSION_CANVAS 2048 /* SURVEY.md §8a row P5                */
@@ -64,6 +70,8 @@ typedef struct irp_opts {
   int32_t coef_mode;    /* IRP_COEF_*                                   */
   int32_t reserved0;
   uint64_t staging_bytes; /* pixels per pipeline chunk of a host-resident batch; 0 = 96 MiB */
+  int32_t blur_mode;    /* IRP_BLUR_*   (read when struct_size covers it)       */
+  int32_t reduce_mode;  /* IRP_REDUCE_*                                         */
 } irp_opts;
 
 typedef struct irp_image_desc {
@@ -87,8 +95,17 @@ typedef struct irp_result {
   uint32_t block_edges[2];       /* additive diagnostic: strong grey steps across 8-px column / row boundaries */
   uint32_t luma_hist[256];       /* additive diagnostic: histogram of the libvips B_W grey    */
   int32_t status;                /* per-image status (IRP_OK or an error code)                */
-  int32_t reserved;
+  /* PromptEnhancerService._identifyTopIssues (promptEnhancer.js:121-145): the scores above 0.3, highest first (ties
+   * in key order, as a stable sort leaves them), at most three.  issues[k] = IRP_ISSUE(severity, score index) or
+   * IRP_NO_ISSUE; issues[3] = how many.  Severity: >= 0.7 high, >= 0.5 medium, else low. */
+  uint8_t issues[4];
 } irp_result;
+enum { IRP_SEVERITY_LOW = 1, IRP_SEVERITY_MEDIUM = 2, IRP_SEVERITY_HIGH = 3 };
+#define IRP_ISSUE(severity, index) ((uint8_t)(((severity) << 4) | (index)))
+#define IRP_ISSUE_INDEX(v) ((v) & 15)
+#define IRP_ISSUE_SEVERITY(v) ((v) >> 4)
+#define IRP_NO_ISSUE 0xFF
+#define IRP_ISSUE_THRESHOLD 0.3   /* promptEnhancer.js:122 (and the logging filter, classifier.js:74) */
 
 typedef struct irp_out_desc {
   uint8_t *pixels;  /* caller-owned destination (host or device)                        */
@@ -131,6 +148,8 @@ int irp_fusion_dims(int width, int height, int exif_orientation, int *out_w, int
 /* the 7 JS formulas (classifier.js:119-121,146,159-167,180-186,223-228,240-253)
  * applied to the integer moments already in `r`; fills r->score. */
 int irp_scores_from_moments(irp_result *r, int width, int height, int channels, int is_jpeg);
+/* r->issues from r->score (called by irp_scores_from_moments; promptEnhancer.js:121-145) */
+int irp_top_issues(irp_result *r);
 /* copies of the baked grey tables (for the exhaustive 2^24 verification test) */
 int irp_grey_tables(int luma_mode, uint32_t lut_r[256], uint32_t lut_g[256], uint32_t lut_b[256],
                     uint32_t inv[4096]);
@@ -140,10 +159,13 @@ int irp_grey_tables(int luma_mode, uint32_t lut_r[256], uint32_t lut_g[256], uin
  * grey, 3 stencils, blur delta, scratch grid — one pass over each image. */
 int irp_classify_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_result *results);
 /* preprocessImage pixel stages (imagePreprocess.js:42-53): auto-orient,
- * lanczos3 fit-inside <= 2048, normalise to u8 RGB (grey stays 1 channel). */
+ * lanczos3 fit-inside <= 2048 (with vips_resize's integer box pre-shrink when an
+ * axis shrinks 4x or more), normalise to u8 RGB (grey stays 1 channel). */
 int irp_preprocess_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_out_desc *outs);
-/* classify + preprocess of the same sources in one submission; the second
- * pass over each source is served from L2 (BASELINE.json configs[1]). */
+/* classify + preprocess of the same sources in one submission (BASELINE.json
+ * configs[1]).  Two kernels, each reading the sources from HBM once: a batch is
+ * far larger than the 126 MB L2, so the second pass is NOT served from cache
+ * (profiles/: DRAM traffic 1.76x the fused figure; the kernels are issue-bound). */
 int irp_analyze_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n, irp_result *results,
                       irp_out_desc *outs);
 /* up to 3 images -> aligned 2048x2048x3 canvases, centred, black pad

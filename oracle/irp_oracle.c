@@ -130,7 +130,18 @@ int orc_stencil(const uint8_t *grey, int w, int h, int which, uint8_t *out) {
 /* classifier.js:297; separable [12,20,12]/44, horizontal then         */
 /* vertical, u8 between passes, replicate edges                        */
 /* ------------------------------------------------------------------ */
-int orc_blur1(const uint8_t *px, int w, int h, int c, size_t pitch, uint8_t *out) {
+/* blur_mode 0: libvips' C path of vips_convi — exact (sum + scale / 2) / scale.
+ * blur_mode 1 (IRP_BLUR_VECTOR): the SIMD path of vips_convi as recalled (convi.c vips_convi_intize + the
+ * highway kernel): the mask is baked into 8-bit mantissas with a shared exponent, here
+ * shift = ceil(log2(20/44) + 1) = 0, exp = 7, mant = rint(128 * {12,20,12}/44) = {35, 58, 35} (sum 128), and a
+ * pixel is (sum mant*p + 64) >> 7.  Which of the two the sharp prebuilt takes is not checkable offline (SURVEY.md
+ * section 8a row A4 tags it LOW); tests/test_sharp_golden.py decides once a sharp dump exists. */
+static inline int blur_tap(int l, int c, int r, int blur_mode) {
+  if (blur_mode == 1) return (35 * (l + r) + 58 * c + 64) >> 7;
+  return (IRP_GAUSS_EDGE * (l + r) + IRP_GAUSS_CENTRE * c + IRP_GAUSS_SCALE / 2) / IRP_GAUSS_SCALE;
+}
+
+int orc_blur1_m(const uint8_t *px, int w, int h, int c, size_t pitch, int blur_mode, uint8_t *out) {
   size_t n = (size_t)w * h * c;
   uint8_t *tmp = (uint8_t *)malloc(n);
   if (!tmp) return -4;
@@ -138,23 +149,22 @@ int orc_blur1(const uint8_t *px, int w, int h, int c, size_t pitch, uint8_t *out
     const uint8_t *row = px + (size_t)y * pitch;
     for (int x = 0; x < w; x++) {
       int xl = x > 0 ? x - 1 : 0, xr = x < w - 1 ? x + 1 : w - 1;
-      for (int ch = 0; ch < c; ch++) {
-        int s = IRP_GAUSS_EDGE * row[xl * c + ch] + IRP_GAUSS_CENTRE * row[x * c + ch] +
-                IRP_GAUSS_EDGE * row[xr * c + ch];
-        tmp[((size_t)y * w + x) * c + ch] = (uint8_t)((s + IRP_GAUSS_SCALE / 2) / IRP_GAUSS_SCALE);
-      }
+      for (int ch = 0; ch < c; ch++)
+        tmp[((size_t)y * w + x) * c + ch] = (uint8_t)blur_tap(row[xl * c + ch], row[x * c + ch], row[xr * c + ch], blur_mode);
     }
   }
   for (int y = 0; y < h; y++) {
     int yu = y > 0 ? y - 1 : 0, yd = y < h - 1 ? y + 1 : h - 1;
-    for (size_t i = 0; i < (size_t)w * c; i++) {
-      int s = IRP_GAUSS_EDGE * tmp[(size_t)yu * w * c + i] + IRP_GAUSS_CENTRE * tmp[(size_t)y * w * c + i] +
-              IRP_GAUSS_EDGE * tmp[(size_t)yd * w * c + i];
-      out[(size_t)y * w * c + i] = (uint8_t)((s + IRP_GAUSS_SCALE / 2) / IRP_GAUSS_SCALE);
-    }
+    for (size_t i = 0; i < (size_t)w * c; i++)
+      out[(size_t)y * w * c + i] =
+          (uint8_t)blur_tap(tmp[(size_t)yu * w * c + i], tmp[(size_t)y * w * c + i], tmp[(size_t)yd * w * c + i], blur_mode);
   }
   free(tmp);
   return 0;
+}
+
+int orc_blur1(const uint8_t *px, int w, int h, int c, size_t pitch, uint8_t *out) {
+  return orc_blur1_m(px, w, h, c, pitch, 0, out);
 }
 
 /* ------------------------------------------------------------------ */
@@ -206,6 +216,11 @@ static double dmax(double a, double b) { return (a != a || b != b) ? NAN : (a > 
 /* ------------------------------------------------------------------ */
 int orc_classify(const uint8_t *px, int w, int h, int c, size_t pitch, int is_jpeg, int luma_mode,
                  irp_result *out) {
+  return orc_classify_m(px, w, h, c, pitch, is_jpeg, luma_mode, 0, out);
+}
+
+int orc_classify_m(const uint8_t *px, int w, int h, int c, size_t pitch, int is_jpeg, int luma_mode, int blur_mode,
+                   irp_result *out) {
   if (!px || !out || w <= 0 || h <= 0 || pitch < (size_t)w * c) return -1;
   if (c != 1 && c != 3 && c != 4) return -2;
   memset(out, 0, sizeof *out);
@@ -275,7 +290,7 @@ int orc_classify(const uint8_t *px, int w, int h, int c, size_t pitch, int is_jp
   }
   /* A4 _analyzeCompression + _detectBlockiness, classifier.js:177-191,288-308 */
   for (int y = 0; y < h; y++) memcpy(o + (size_t)y * w * c, px + (size_t)y * pitch, (size_t)w * c);
-  orc_blur1(px, w, h, c, pitch, b);
+  orc_blur1_m(px, w, h, c, pitch, blur_mode, b);
   moments(b, N * c, &out->b_sum, &out->b_sumsq);
   if (is_jpeg) {
     double originalVariance = js_variance(o, N * c);
@@ -318,7 +333,35 @@ int orc_classify(const uint8_t *px, int w, int h, int c, size_t pitch, int is_jp
   }
   free(grey); free(e); free(o); free(b);
   out->status = 0;
+  orc_top_issues(out->score, out->issues);
   return 0;
+}
+
+/* PromptEnhancerService._identifyTopIssues + _determineSeverity, promptEnhancer.js:121-145: entries above 0.3,
+ * Array.prototype.sort by descending confidence (stable: ties keep the key order of classifier.js:62-70), first 3 */
+void orc_top_issues(const double score[IRP_NUM_SCORES], uint8_t issues[4]) {
+  int idx[IRP_NUM_SCORES], n = 0;
+  for (int k = 0; k < IRP_NUM_SCORES; k++)
+    if (score[k] > 0.3) idx[n++] = k;
+  for (int i = 1; i < n; i++) { /* insertion sort: stable */
+    int v = idx[i], j = i - 1;
+    while (j >= 0 && score[idx[j]] < score[v]) {
+      idx[j + 1] = idx[j];
+      j--;
+    }
+    idx[j + 1] = v;
+  }
+  if (n > 3) n = 3;
+  for (int k = 0; k < 3; k++) {
+    if (k >= n) {
+      issues[k] = IRP_NO_ISSUE;
+      continue;
+    }
+    double c = score[idx[k]];
+    int sev = c >= 0.7 ? IRP_SEVERITY_HIGH : (c >= 0.5 ? IRP_SEVERITY_MEDIUM : IRP_SEVERITY_LOW);
+    issues[k] = IRP_ISSUE(sev, idx[k]);
+  }
+  issues[3] = (uint8_t)n;
 }
 
 /* ------------------------------------------------------------------ */
@@ -462,6 +505,15 @@ static void to_fixed_point(const double *in, int16_t *out, int n, int scale) {
 
 int orc_reduce_plan(int in_size, int out_size, double shrink, int coef_mode, int *n_taps, int32_t *start,
                     int32_t *phase, int16_t *coefs /* [65][IRP_MAX_TAPS] */) {
+  return orc_reduce_plan_m(in_size, out_size, shrink, coef_mode, 0, n_taps, start, phase, coefs);
+}
+
+/* reduce_mode 0: the 12-bit integer path of reducev / reduceh (C and highway kernels agree on it).
+ * reduce_mode 1 (IRP_REDUCE_VECTOR_2_6): coefficients with 6 fractional bits, (sum + 32) >> 6 — the precision of
+ * libvips' older orc vector path; stated here as 12-bit coefficients that are multiples of 64, which is the same
+ * arithmetic ((sum 64 c6 p + 2048) >> 12 == (sum c6 p + 32) >> 6) and leaves every kernel untouched. */
+int orc_reduce_plan_m(int in_size, int out_size, double shrink, int coef_mode, int reduce_mode, int *n_taps,
+                      int32_t *start, int32_t *phase, int16_t *coefs /* [65][IRP_MAX_TAPS] */) {
   int n = reduce_points(shrink);
   if (n > IRP_MAX_TAPS) return -2;
   *n_taps = n;
@@ -470,9 +522,12 @@ int orc_reduce_plan(int in_size, int out_size, double shrink, int coef_mode, int
     lanczos_mask(mask, n, shrink, (double)t / IRP_PHASES);
     int16_t *ci = coefs + (size_t)t * IRP_MAX_TAPS;
     memset(ci, 0, sizeof(int16_t) * IRP_MAX_TAPS);
-    if (coef_mode == 1)
+    if (coef_mode == 1 && reduce_mode != 1)
       for (int i = 0; i < n; i++) ci[i] = (int16_t)(mask[i] * (1 << IRP_INTERP_SHIFT)); /* C cast: truncate */
-    else
+    else if (reduce_mode == 1) {
+      to_fixed_point(mask, ci, n, 64);
+      for (int i = 0; i < n; i++) ci[i] = (int16_t)(ci[i] * 64);
+    } else
       to_fixed_point(mask, ci, n, 1 << IRP_INTERP_SHIFT);
   }
   /* keep the image centred when out*shrink != in (libvips "extra_pixels") */
@@ -510,14 +565,60 @@ static void reduce_axis(const uint8_t *in, int in_w, int in_h, int c, int out_si
     }
 }
 
-/* oriented u8 image (tight) -> resized u8 image (tight); reducev first, then reduceh */
+/* vips_resize's integer pre-shrink (resample/resize.c, gap = 2.0, the default sharp leaves alone): when an axis
+ * shrinks by 4 or more, int_shrink = floor(in / target / gap) rows / columns are box-averaged first — vips_shrinkv
+ * then vips_shrinkh with "ceil" (the image is edge-extended to a multiple of the factor), each
+ * (sum + factor / 2) / factor in integers, u8 between the passes — and lanczos3 only does the remaining factor in
+ * [2, 4).   */
+int orc_box_factor(int in_size, int out_size) {
+  int k = (int)floor((double)in_size / out_size / 2.0);
+  return k < 1 ? 1 : k;
+}
+
+int orc_box_shrink(const uint8_t *in, int w, int h, int c, int kh, int kv, uint8_t *out /* ceil(w/kh) x ceil(h/kv) */) {
+  const int ow = (w + kh - 1) / kh, oh = (h + kv - 1) / kv;
+  uint8_t *tmp = (uint8_t *)malloc((size_t)w * oh * c);
+  if (!tmp) return -4;
+  for (int y = 0; y < oh; y++)
+    for (size_t i = 0; i < (size_t)w * c; i++) {
+      int sum = 0;
+      for (int j = 0; j < kv; j++) sum += in[(size_t)clampi(y * kv + j, 0, h - 1) * w * c + i];
+      tmp[(size_t)y * w * c + i] = (uint8_t)((sum + kv / 2) / kv);
+    }
+  for (int y = 0; y < oh; y++)
+    for (int x = 0; x < ow; x++)
+      for (int ch = 0; ch < c; ch++) {
+        int sum = 0;
+        for (int j = 0; j < kh; j++) sum += tmp[((size_t)y * w + clampi(x * kh + j, 0, w - 1)) * c + ch];
+        out[((size_t)y * ow + x) * c + ch] = (uint8_t)((sum + kh / 2) / kh);
+      }
+  free(tmp);
+  return 0;
+}
+
+/* oriented u8 image (tight) -> resized u8 image (tight); box pre-shrink if due, reducev, then reduceh */
 static int resize_tight(const uint8_t *img, int wo, int ho, int c, int ow, int oh, double shrink, int coef_mode,
-                        uint8_t *out) {
+                        int reduce_mode, uint8_t *out) {
   if (ow == wo && oh == ho) {
     memcpy(out, img, (size_t)wo * ho * c);
     return 0;
   }
   int rc = 0;
+  uint8_t *boxed = NULL;
+  double vshrink = shrink, hshrink = shrink;
+  const int kh = orc_box_factor(wo, ow), kv = orc_box_factor(ho, oh);
+  if (kh > 1 || kv > 1) {
+    const int bw = (wo + kh - 1) / kh, bh = (ho + kv - 1) / kv;
+    boxed = (uint8_t *)malloc((size_t)bw * bh * c);
+    if (!boxed) return -4;
+    rc = orc_box_shrink(img, wo, ho, c, kh, kv, boxed);
+    if (rc) { free(boxed); return rc; }
+    img = boxed;
+    wo = bw;
+    ho = bh;
+    hshrink = shrink / kh;
+    vshrink = shrink / kv;
+  }
   int16_t *coefs = (int16_t *)malloc(sizeof(int16_t) * (IRP_PHASES + 1) * IRP_MAX_TAPS);
   int32_t *start = (int32_t *)malloc(sizeof(int32_t) * (ow > oh ? ow : oh));
   int32_t *phase = (int32_t *)malloc(sizeof(int32_t) * (ow > oh ? ow : oh));
@@ -525,20 +626,20 @@ static int resize_tight(const uint8_t *img, int wo, int ho, int c, int ow, int o
   int n;
   const uint8_t *hsrc = img;
   if (oh != ho) {
-    rc = orc_reduce_plan(ho, oh, shrink, coef_mode, &n, start, phase, coefs);
+    rc = orc_reduce_plan_m(ho, oh, vshrink, coef_mode, reduce_mode, &n, start, phase, coefs);
     if (rc) goto done;
     reduce_axis(img, wo, ho, c, oh, 1, start, phase, coefs, n, mid);
     hsrc = mid;
   }
   if (ow != wo) {
-    rc = orc_reduce_plan(wo, ow, shrink, coef_mode, &n, start, phase, coefs);
+    rc = orc_reduce_plan_m(wo, ow, hshrink, coef_mode, reduce_mode, &n, start, phase, coefs);
     if (rc) goto done;
     reduce_axis(hsrc, wo, oh, c, ow, 0, start, phase, coefs, n, out);
   } else {
     memcpy(out, hsrc, (size_t)wo * oh * c);
   }
 done:
-  free(coefs); free(start); free(phase); free(mid);
+  free(coefs); free(start); free(phase); free(mid); free(boxed);
   return rc;
 }
 
@@ -556,19 +657,23 @@ static void normalise(const uint8_t *in, int w, int h, int c, uint8_t *out) {
 
 int orc_preprocess(const uint8_t *px, int w, int h, int c, size_t pitch, int orientation, int coef_mode,
                    uint8_t *out, int *ow, int *oh, int *oc) {
+  return orc_preprocess_m(px, w, h, c, pitch, orientation, coef_mode, 0, out, ow, oh, oc);
+}
+
+int orc_preprocess_m(const uint8_t *px, int w, int h, int c, size_t pitch, int orientation, int coef_mode,
+                     int reduce_mode, uint8_t *out, int *ow, int *oh, int *oc) {
   if (!px || !out || w <= 0 || h <= 0 || pitch < (size_t)w * c) return -1;
   if (c != 1 && c != 3 && c != 4) return -2;
   double shrink;
   int wo, ho;
   orc_orient_dims(w, h, orientation, &wo, &ho);
   orc_preprocess_dims(w, h, orientation, ow, oh, &shrink);
-  if (shrink >= 4.0) return -2;
   *oc = c == 4 ? 3 : c;
   uint8_t *oriented = (uint8_t *)malloc((size_t)wo * ho * c);
   uint8_t *resized = (uint8_t *)malloc((size_t)*ow * *oh * c);
   if (!oriented || !resized) { free(oriented); free(resized); return -4; }
   orc_orient(px, w, h, c, pitch, orientation, oriented);
-  int rc = resize_tight(oriented, wo, ho, c, *ow, *oh, shrink, coef_mode, resized);
+  int rc = resize_tight(oriented, wo, ho, c, *ow, *oh, shrink, coef_mode, reduce_mode, resized);
   if (!rc) normalise(resized, *ow, *oh, c, out);
   free(oriented); free(resized);
   return rc;
@@ -578,19 +683,23 @@ int orc_preprocess(const uint8_t *px, int w, int h, int c, size_t pitch, int ori
  * 2048x2048 (no enlargement) -> centred on a black 2048x2048x3 canvas. */
 int orc_fusion_canvas(const uint8_t *px, int w, int h, int c, size_t pitch, int orientation, int coef_mode,
                       uint8_t *canvas) {
+  return orc_fusion_canvas_m(px, w, h, c, pitch, orientation, coef_mode, 0, canvas);
+}
+
+int orc_fusion_canvas_m(const uint8_t *px, int w, int h, int c, size_t pitch, int orientation, int coef_mode,
+                        int reduce_mode, uint8_t *canvas) {
   if (!px || !canvas || w <= 0 || h <= 0 || pitch < (size_t)w * c) return -1;
   if (c != 1 && c != 3 && c != 4) return -2;
   int ow, oh, ox, oy, wo, ho;
   double shrink;
   orc_orient_dims(w, h, orientation, &wo, &ho);
   orc_fusion_dims(w, h, orientation, &ow, &oh, &ox, &oy, &shrink);
-  if (shrink >= 4.0) return -2;
   uint8_t *oriented = (uint8_t *)malloc((size_t)wo * ho * c);
   uint8_t *resized = (uint8_t *)malloc((size_t)ow * oh * c);
   uint8_t *norm = (uint8_t *)malloc((size_t)ow * oh * 3);
   if (!oriented || !resized || !norm) { free(oriented); free(resized); free(norm); return -4; }
   orc_orient(px, w, h, c, pitch, orientation, oriented);
-  int rc = resize_tight(oriented, wo, ho, c, ow, oh, shrink, coef_mode, resized);
+  int rc = resize_tight(oriented, wo, ho, c, ow, oh, shrink, coef_mode, reduce_mode, resized);
   if (!rc) {
     normalise(resized, ow, oh, c, norm);
     const int S = IRP_FUSION_CANVAS;

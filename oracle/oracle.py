@@ -34,7 +34,7 @@ class Result(C.Structure):
         ("block_edges", C.c_uint32 * 2),
         ("luma_hist", C.c_uint32 * 256),
         ("status", C.c_int32),
-        ("reserved", C.c_int32),
+        ("issues", C.c_uint8 * 4),
     ]
 
 
@@ -95,13 +95,15 @@ def result_to_dict(r: Result) -> dict:
         "block_edges": list(r.block_edges),
         "luma_hist": list(r.luma_hist),
         "status": int(r.status),
+        "issues": [{"type": SCORE_KEYS[int(r.issues[k]) & 15], "confidence": float(r.score[int(r.issues[k]) & 15]),
+                    "severity": {1: "low", 2: "medium", 3: "high"}[int(r.issues[k]) >> 4]} for k in range(int(r.issues[3]))],
     }
 
 
-def classify(a: np.ndarray, is_jpeg: bool = True, luma_mode: int = 0) -> dict:
+def classify(a: np.ndarray, is_jpeg: bool = True, luma_mode: int = 0, blur_mode: int = 0) -> dict:
     a, w, h, c = _img(a)
     r = Result()
-    rc = lib().orc_classify(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), int(is_jpeg), luma_mode, C.byref(r))
+    rc = lib().orc_classify_m(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), int(is_jpeg), luma_mode, blur_mode, C.byref(r))
     if rc:
         raise ValueError(f"orc_classify rc={rc}")
     return result_to_dict(r)
@@ -131,10 +133,23 @@ def stencil(g: np.ndarray, which: int) -> np.ndarray:
     return out
 
 
-def blur1(a: np.ndarray) -> np.ndarray:
+def blur1(a: np.ndarray, blur_mode: int = 0) -> np.ndarray:
     a, w, h, c = _img(a)
     out = np.empty((h, w, c), np.uint8)
-    lib().orc_blur1(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), out.ctypes.data_as(C.c_void_p))
+    lib().orc_blur1_m(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), blur_mode, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def box_factor(in_size: int, out_size: int) -> int:
+    return lib().orc_box_factor(in_size, out_size)
+
+
+def box_shrink(a: np.ndarray, kh: int, kv: int) -> np.ndarray:
+    a, w, h, c = _img(a)
+    out = np.empty(((h + kv - 1) // kv, (w + kh - 1) // kh, c), np.uint8)
+    rc = lib().orc_box_shrink(a.ctypes.data_as(C.c_void_p), w, h, c, kh, kv, out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise ValueError(f"orc_box_shrink rc={rc}")
     return out
 
 
@@ -159,37 +174,37 @@ def fusion_dims(w: int, h: int, orientation: int = 1):
     return ow.value, oh.value, ox.value, oy.value, sh.value
 
 
-def reduce_plan(in_size: int, out_size: int, shrink: float, coef_mode: int = 0):
+def reduce_plan(in_size: int, out_size: int, shrink: float, coef_mode: int = 0, reduce_mode: int = 0):
     n = C.c_int()
     start = np.empty(out_size, np.int32)
     phase = np.empty(out_size, np.int32)
     coefs = np.zeros((65, 25), np.int16)
-    rc = lib().orc_reduce_plan(in_size, out_size, C.c_double(shrink), coef_mode, C.byref(n), start.ctypes.data_as(C.c_void_p),
-                               phase.ctypes.data_as(C.c_void_p), coefs.ctypes.data_as(C.c_void_p))
+    rc = lib().orc_reduce_plan_m(in_size, out_size, C.c_double(shrink), coef_mode, reduce_mode, C.byref(n), start.ctypes.data_as(C.c_void_p),
+                                 phase.ctypes.data_as(C.c_void_p), coefs.ctypes.data_as(C.c_void_p))
     if rc:
         raise ValueError(f"orc_reduce_plan rc={rc}")
     return n.value, start, phase, coefs
 
 
-def preprocess(a: np.ndarray, orientation: int = 1, coef_mode: int = 0) -> np.ndarray:
+def preprocess(a: np.ndarray, orientation: int = 1, coef_mode: int = 0, reduce_mode: int = 0) -> np.ndarray:
     a, w, h, c = _img(a)
     ow, oh, _ = preprocess_dims(w, h, orientation)
     oc = 3 if c == 4 else c
     out = np.empty((oh, ow, oc), np.uint8)
     rw, rh, rc_ = C.c_int(), C.c_int(), C.c_int()
-    rc = lib().orc_preprocess(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), orientation, coef_mode,
-                              out.ctypes.data_as(C.c_void_p), C.byref(rw), C.byref(rh), C.byref(rc_))
+    rc = lib().orc_preprocess_m(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), orientation, coef_mode, reduce_mode,
+                                out.ctypes.data_as(C.c_void_p), C.byref(rw), C.byref(rh), C.byref(rc_))
     if rc:
         raise ValueError(f"orc_preprocess rc={rc}")
     assert (rw.value, rh.value, rc_.value) == (ow, oh, oc)
     return out
 
 
-def fusion_canvas(a: np.ndarray, orientation: int = 1, coef_mode: int = 0) -> np.ndarray:
+def fusion_canvas(a: np.ndarray, orientation: int = 1, coef_mode: int = 0, reduce_mode: int = 0) -> np.ndarray:
     a, w, h, c = _img(a)
     out = np.empty((2048, 2048, 3), np.uint8)
-    rc = lib().orc_fusion_canvas(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), orientation, coef_mode,
-                                 out.ctypes.data_as(C.c_void_p))
+    rc = lib().orc_fusion_canvas_m(a.ctypes.data_as(C.c_void_p), w, h, c, C.c_size_t(w * c), orientation, coef_mode, reduce_mode,
+                                   out.ctypes.data_as(C.c_void_p))
     if rc:
         raise ValueError(f"orc_fusion_canvas rc={rc}")
     return out

@@ -60,6 +60,8 @@ def assert_result_parity(got: dict, ref: dict, channels: int, tag: str = ""):
         assert g == r, f"{tag} {k}: {g if not isinstance(g, list) or len(g) < 9 else '...'} != {r if not isinstance(r, list) or len(r) < 9 else '...'}"
     for k, v in ref["scores"].items():
         assert rel_close(got["scores"][k], v), f"{tag} score {k}: {got['scores'][k]} vs {v}"
+    if "issues" in got and "issues" in ref:   # top three above 0.3 with their severity (promptEnhancer.js:121-145)
+        assert [(i["type"], i["severity"]) for i in got["issues"]] == [(i["type"], i["severity"]) for i in ref["issues"]], f"{tag} issues"
 
 
 def rand_image(h, w, c, seed, kind="noise"):

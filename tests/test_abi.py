@@ -51,14 +51,16 @@ def test_preprocess_and_fusion_dims_match_oracle(oracle, w, h, o):
     assert (ow.value, oh.value, ox.value, oy.value) == oracle.fusion_dims(w, h, o)[:4]
 
 
-def test_unsupported_shrink_is_reported_by_the_host_helper():
+def test_large_shrinks_are_sized_by_the_host_helper(oracle):
+    """Shrink factors of 4 and more (sides beyond 8192 px) used to be refused; they now take libvips' integer box
+    pre-shrink in front of the lanczos passes, and the host helper sizes them like the oracle."""
     from irp_b200 import _ffi
 
     ow, oh = C.c_int(), C.c_int()
-    assert _ffi.load().irp_preprocess_dims(9000, 16, 1, C.byref(ow), C.byref(oh)) == _ffi.IRP_ERR_UNSUPPORTED
+    for w, h, o in [(9000, 16, 1), (12000, 9000, 1), (24000, 300, 6), (100, 2049, 8)]:   # the last: the pre-rotation-dims quirk of SURVEY.md section 8a P3
+        assert _ffi.load().irp_preprocess_dims(w, h, o, C.byref(ow), C.byref(oh)) == 0
+        assert (ow.value, oh.value) == oracle.preprocess_dims(w, h, o)[:2]
     assert _ffi.load().irp_preprocess_dims(0, 16, 1, C.byref(ow), C.byref(oh)) == _ffi.IRP_ERR_BAD_ARG
-    # the pre-rotation-dims quirk can push a thin rotated image past shrink 4
-    assert _ffi.load().irp_preprocess_dims(100, 2049, 8, C.byref(ow), C.byref(oh)) == _ffi.IRP_ERR_UNSUPPORTED
 
 
 @pytest.mark.parametrize("c,jpeg", [(3, True), (3, False), (1, True), (4, True)])

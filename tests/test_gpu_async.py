@@ -67,13 +67,14 @@ def test_a_failing_request_fails_alone(engine, oracle):
     import irp_b200
 
     good = [rand_image(120, 180, 3, seed=i) for i in range(6)]
-    bad = rand_image(9000, 40, 3, seed=9)   # shrink >= 4: unsupported (libvips would box-shrink first)
+    bad = rand_image(90, 40, 3, seed=9)   # submitted below as a 2-channel image: unsupported
     hs = [engine.submit(g) for g in good[:3]]
     # the Python wrapper sizes the output before submitting; go through the C ABI directly for the bad one
     from irp_b200 import _ffi
     import ctypes as C
     descs, keep = engine._descs([bad], True, [1])
-    outbuf = np.empty((2048, 16, 3), np.uint8)
+    descs[0].channels = 2
+    outbuf = np.empty((90, 40, 3), np.uint8)
     outs = (_ffi.OutDesc * 1)(_ffi.OutDesc(outbuf.ctypes.data, 0, outbuf.nbytes, 0, 0, 0, 0))
     res = _ffi.Result()
     tk = C.c_void_p()
@@ -81,7 +82,7 @@ def test_a_failing_request_fails_alone(engine, oracle):
     hs += [engine.submit(g) for g in good[3:]]
     err = C.create_string_buffer(256)
     rc = engine._lib.irp_wait(engine._ctx, tk, err, len(err))
-    assert rc == _ffi.IRP_ERR_UNSUPPORTED and b"shrink" in err.value
+    assert rc == _ffi.IRP_ERR_UNSUPPORTED and b"channels" in err.value
     for g, hd in zip(good, hs):
         r, o = engine.wait(hd)
         assert_result_parity(r, oracle.classify(g), 3, "batch-mate of a failing request")

@@ -90,9 +90,30 @@ def test_fusion_canvases(engine, oracle):
         assert np.array_equal(got, oracle.fusion_canvas(img, ori))
 
 
-def test_too_large_shrink_is_reported(engine):
-    import irp_b200
+@pytest.mark.parametrize("h,w,c,o", [(9000, 12000, 3, 1), (300, 24000, 3, 1), (300, 24000, 3, 6), (9001, 9003, 1, 1), (40, 9000, 4, 3)])
+def test_shrinks_of_four_and_more_take_the_box_pre_shrink(engine, oracle, h, w, c, o):
+    """Sides beyond 8192 px: vips_resize box-averages by floor(shrink / 2) first (shrinkv, shrinkh with "ceil"), then
+    lanczos3 does the remaining factor in [2, 4) — imagePreprocess.js:46-53 resizes whatever the upload cap lets in."""
+    img = rand_image(h, w, c, seed=h + w + o, kind="smooth" if h * w > 50_000_000 else "noise")
+    got = engine.preprocess_batch([img], orientations=[o])[0]
+    ref = oracle.preprocess(img, o)
+    assert got.shape == ref.shape and max(got.shape[:2]) <= 2048
+    assert np.array_equal(got, ref)
 
-    with pytest.raises(irp_b200.IrpError) as e:
-        engine.preprocess_batch([np.zeros((16, 9000, 3), np.uint8)])
-    assert e.value.code == -2
+
+def test_switched_modes_follow_the_oracle(oracle):
+    """IRP_BLUR_VECTOR and IRP_REDUCE_VECTOR_2_6 (the libvips SIMD-path candidates) change the same bytes on the device
+    as in the oracle."""
+    import irp_b200
+    from conftest import assert_result_parity
+
+    a = rand_image(301, 517, 3, seed=77, kind="noise")
+    b = rand_image(2300, 2600, 3, seed=78, kind="smooth")
+    with irp_b200.Engine(0, blur_mode=1, reduce_mode=1) as eng:
+        res = eng.classify_batch([a])[0]
+        out = eng.preprocess_batch([b])[0]
+    ref = oracle.classify(a, blur_mode=1)
+    assert ref["b_sumsq"] != oracle.classify(a)["b_sumsq"]
+    assert_result_parity(res, ref, 3, "blur_mode 1")
+    assert np.array_equal(out, oracle.preprocess(b, 1, reduce_mode=1))
+    assert not np.array_equal(out, oracle.preprocess(b, 1))

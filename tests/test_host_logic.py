@@ -151,3 +151,29 @@ def test_world_size_2_gloo_shard_and_gather(tmp_path):
                         "--master-port", "29517", str(script), ROOT], capture_output=True, text=True, env=env, timeout=240)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("ok") == 2
+
+
+def test_top_issues_follow_the_prompt_enhancer():
+    """irp_result.issues: PromptEnhancerService._identifyTopIssues /
+    _determineSeverity, promptEnhancer.js:121-145 — above 0.3, highest first, stable for ties, at most 3."""
+    import ctypes as C
+
+    from irp_b200 import _ffi
+    from irp_b200.engine import SCORE_KEYS, issues_of
+
+    lib = _ffi.load()
+
+    def js(scores):   # the reference, literally
+        issues = [{"type": t, "confidence": c, "severity": "high" if c >= 0.7 else ("medium" if c >= 0.5 else "low")}
+                  for t, c in zip(SCORE_KEYS, scores) if c > 0.3]
+        return sorted(issues, key=lambda i: -i["confidence"])[:3]   # sorted() is stable, like Array.prototype.sort
+
+    rng = np.random.default_rng(7)
+    cases = [[0.0] * 7, [0.3] * 7, [0.31] * 7, [0.7, 0.5, 0.49999, 0.3000001, 1.0, 0.69999, 0.2], [0.9, 0.1, 0.9, 0.1, 0.9, 0.9, 0.1]]
+    cases += [list(np.round(rng.random(7), 2)) for _ in range(200)]
+    for sc in cases:
+        r = _ffi.Result()
+        for k, v in enumerate(sc):
+            r.score[k] = v
+        assert lib.irp_top_issues(C.byref(r)) == 0
+        assert issues_of(r) == js(sc), sc

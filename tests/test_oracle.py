@@ -200,3 +200,50 @@ def test_batch_threads_agree_with_single(oracle):
     r4, o4 = oracle.analyze_batch(imgs, threads=4)
     assert r1 == r4 and all(np.array_equal(a, b) for a, b in zip(o1, o4))
     assert r1[2] == oracle.classify(imgs[2])
+
+
+# ---- round 2: the switches for libvips' SIMD-path candidates, and vips_resize's integer box pre-shrink ----
+def test_blur_vector_mode_is_the_8_bit_mantissa_mask(oracle):
+    """IRP_BLUR_VECTOR: vips_convi_intize bakes {12, 20, 12} / 44 into rint(128 * c) = {35, 58, 35} (sum 128, shared
+    exponent 7): (sum + 64) >> 7 per pass, u8 between the passes, replicate edges."""
+    assert [round(128 * c / 44) for c in (12, 20, 12)] == [35, 58, 35]
+    img = rand_image(37, 53, 3, seed=5, kind="noise").astype(np.int64)
+    p = np.pad(img, ((0, 0), (1, 1), (0, 0)), mode="edge")
+    hp = (35 * (p[:, :-2] + p[:, 2:]) + 58 * p[:, 1:-1] + 64) >> 7
+    q = np.pad(hp, ((1, 1), (0, 0), (0, 0)), mode="edge")
+    vp = (35 * (q[:-2] + q[2:]) + 58 * q[1:-1] + 64) >> 7
+    assert np.array_equal(oracle.blur1(img.astype(np.uint8), blur_mode=1), vp.astype(np.uint8))
+    # the two modes differ by at most one level, and not everywhere
+    d = np.abs(oracle.blur1(img.astype(np.uint8), 0).astype(int) - vp)
+    assert 0 < d.max() <= 1
+
+
+def test_reduce_vector_mode_keeps_six_fractional_bits(oracle):
+    n, start, phase, coefs = oracle.reduce_plan(4000, 2048, 1.953125, reduce_mode=1)
+    assert np.all(coefs % 64 == 0) and np.all(coefs[:, :n].sum(axis=1) == 4096)
+    n0, start0, phase0, coefs0 = oracle.reduce_plan(4000, 2048, 1.953125)
+    assert n0 == n and np.array_equal(start, start0) and np.array_equal(phase, phase0)
+    assert np.abs(coefs.astype(int) - coefs0).max() <= 32 + 64   # quantisation plus the sum-preserving nudge
+
+
+@pytest.mark.parametrize("h,w,c,kh,kv", [(7, 9, 3, 2, 2), (10, 10, 1, 3, 2), (33, 64, 4, 2, 5)])
+def test_box_shrink_is_shrinkv_then_shrinkh_with_ceil(oracle, h, w, c, kh, kv):
+    img = rand_image(h, w, c, seed=h * w, kind="noise")
+    a = img.astype(np.int64)
+    oh, ow = -(-h // kv), -(-w // kh)
+    a = np.pad(a, ((0, oh * kv - h), (0, ow * kh - w), (0, 0)), mode="edge")
+    v = (a.reshape(oh, kv, ow * kh, c).sum(axis=1) + kv // 2) // kv
+    hh = (v.reshape(oh, ow, kh, c).sum(axis=2) + kh // 2) // kh
+    assert np.array_equal(oracle.box_shrink(img, kh, kv), hh.astype(np.uint8))
+
+
+def test_large_shrink_is_box_then_lanczos(oracle):
+    """12000 -> 2048: vips_resize pre-shrinks by floor(12000 / 2048 / 2) = 2 and lanczos3 does the remaining 2.93."""
+    assert [oracle.box_factor(i, o) for i, o in [(12000, 2048), (8191, 2048), (8192, 2048), (24000, 2048), (4000, 2048)]] == [2, 1, 2, 5, 1]
+    img = rand_image(40, 9000, 3, seed=3, kind="smooth")
+    ow, oh, f = oracle.preprocess_dims(9000, 40)
+    got = oracle.preprocess(img)
+    assert got.shape == (oh, ow, 3) and f > 4
+    # a flat image stays flat through both stages
+    flat = np.full((40, 9000, 3), 77, np.uint8)
+    assert np.all(oracle.preprocess(flat) == 77)
