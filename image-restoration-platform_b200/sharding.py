@@ -43,3 +43,30 @@ def gather_results(local: list, indices: Sequence[int], total: int, group=None) 
         for i, r in zip(idx, res):
             out[i] = r
     return out
+
+
+class PullQueue:
+    """The mixed-resolution job queue of BASELINE.json configs[4] ("dynamic pull from a shared
+    host queue"): every rank draws the next chunk index from ONE counter, so a rank that drew small images simply comes
+    back sooner.  The counter is an atomic add in the rendezvous store torch.distributed already runs (host side, a TCP
+    round trip per draw — no collective, nothing on the GPUs' data path); without a process group it is a local counter.
+    One key per pass over the queue."""
+
+    def __init__(self, n_items: int, key: str, store=None):
+        self.n, self.key, self.store, self._local = n_items, key, store, 0
+
+    @staticmethod
+    def default_store():
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.distributed_c10d._get_default_store()
+        return None
+
+    def pull(self):
+        """Next item index, or None when the queue is drained."""
+        if self.store is None:
+            i, self._local = self._local, self._local + 1
+        else:
+            i = self.store.add(self.key, 1) - 1
+        return i if i < self.n else None

@@ -108,6 +108,13 @@ def test_lpt_sharding_is_a_balanced_partition():
     assert shard_groups(7, 2) == [[0, 2, 4, 6], [1, 3, 5]]
 
 
+def test_pull_queue_without_a_process_group_is_a_local_counter():
+    from irp_b200.sharding import PullQueue
+
+    q = PullQueue(5, "k", PullQueue.default_store())
+    assert [q.pull() for _ in range(7)] == [0, 1, 2, 3, 4, None, None]
+
+
 def test_synthetic_generator_is_seeded_and_nontrivial():
     from irp_b200.synth import synth_batch, synth_image
 
@@ -123,7 +130,8 @@ import os, sys
 sys.path.insert(0, sys.argv[1])
 import torch.distributed as dist
 import irp_b200  # noqa: F401  (loads the package; no GPU work in this test)
-from irp_b200.sharding import lpt_assign, gather_results
+import time
+from irp_b200.sharding import lpt_assign, gather_results, shard_groups, PullQueue
 from irp_b200.synth import mixed_resolution_sizes
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -135,6 +143,26 @@ allres = gather_results(local, mine, len(sizes))
 assert [r["idx"] for r in allres] == list(range(len(sizes)))
 assert {r["rank"] for r in allres} == set(range(world))
 assert all(r["pixels"] == sizes[i][0] * sizes[i][1] for i, r in enumerate(allres))
+# fusion triplets stay whole (configs[2]) ...
+groups = shard_groups(7, world)
+assert sorted(g for s in groups for g in s) == list(range(7))
+# ... and the mixed-resolution queue (configs[4]) is pulled dynamically from ONE shared counter: every chunk goes to
+# exactly one rank, a slow rank draws fewer
+for step in range(2):
+    q = PullQueue(37, f"test_queue_{step}", PullQueue.default_store())
+    assert q.store is not None
+    got = []
+    while True:
+        i = q.pull()
+        if i is None:
+            break
+        got.append(i)
+        if rank == 0:
+            time.sleep(0.01)   # the slow rank
+    parts = [None] * world
+    dist.all_gather_object(parts, got)
+    assert sorted(i for p in parts for i in p) == list(range(37)), parts
+    assert len(parts[1]) > len(parts[0]), [len(p) for p in parts]
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
