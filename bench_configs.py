@@ -255,7 +255,7 @@ def run_c5(a, rank, local_rank, world):
 
     sizes = mixed_resolution_sizes(512)
     order = sorted(range(len(sizes)), key=lambda i: (-sizes[i][0] * sizes[i][1], i))   # largest first: the tail of the queue is small change
-    chunk = 8
+    chunk = 16
     chunks = [order[k:k + chunk] for k in range(0, len(order), chunk)]
     big = synth_image(6600, 6100, 11)   # covers 24 MP at every aspect of the set; every image is a window of it
     store = PullQueue.default_store()
