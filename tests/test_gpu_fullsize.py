@@ -25,13 +25,15 @@ def test_configs_against_oracle(engine, oracle, w, h, idx):
     assert np.array_equal(outs[0], ref)
 
 
-def test_24mp_geometry(engine, oracle):
+def test_24mp_against_oracle(engine, oracle):
+    """The top of the mixed-resolution range (BASELINE.json configs[4]): classify AND preprocess of a 6000x4000 image."""
     from irp_b200.synth import synth_image
 
     img = synth_image(6000, 4000, 3)
-    out = engine.preprocess_batch([img])[0]
-    assert out.shape == (1365, 2048, 3)
-    assert np.array_equal(out, oracle.preprocess(img))
+    res, outs = engine.analyze_batch([img])
+    assert_result_parity(res[0], oracle.classify(img), 3, "24 MP")
+    assert outs[0].shape == (1365, 2048, 3)
+    assert np.array_equal(outs[0], oracle.preprocess(img))
 
 
 def test_12mp_batch_properties(engine):
@@ -70,7 +72,8 @@ def test_fusion_triplet_of_12mp(engine, oracle):
 
     trip = [synth_image(4000, 3000, 10), synth_image(3000, 4000, 11), synth_image(3840, 2160, 12)]
     canv = engine.fusion_prepare_batch([trip])[0]
-    assert np.array_equal(canv[1], oracle.fusion_canvas(trip[1]))
+    for k in range(3):   # every aspect of the triplet
+        assert np.array_equal(canv[k], oracle.fusion_canvas(trip[k])), f"canvas {k}"
     for c, (ow, oh) in zip(canv, [(2048, 1536), (1536, 2048), (2048, 1152)]):
         ox, oy = (2048 - ow) // 2, (2048 - oh) // 2
         mask = np.ones((2048, 2048), bool)
@@ -83,7 +86,9 @@ def test_mixed_resolution_queue_slice(engine, oracle):
     """BASELINE.json configs[4], a slice: mixed sizes/aspects in one submission, checked per image."""
     from irp_b200.synth import mixed_resolution_sizes, synth_image
 
-    sizes = [s for s in mixed_resolution_sizes(64) if s[0] * s[1] < 3e6][:6]
+    every = mixed_resolution_sizes(64)
+    sizes = [s for s in every if s[0] * s[1] < 3e6][:5] + sorted(every, key=lambda s: -s[0] * s[1])[:2]   # ... and the two largest (>= 12 MP)
+    assert sizes[-1][0] * sizes[-1][1] >= 12e6
     imgs = [synth_image(w, h, 40 + i) for i, (w, h) in enumerate(sizes)]
     res, outs = engine.analyze_batch(imgs)
     for img, r, o in zip(imgs, res, outs):
