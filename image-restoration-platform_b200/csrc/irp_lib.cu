@@ -610,12 +610,20 @@ int plan_inputs(irp_ctx* ctx, const irp_image_desc* imgs, int n, std::vector<Sta
   return IRP_OK;
 }
 
+// rows -> rows; one linear copy when both sides are tight (a 2-D descriptor per image costs the copy engines more than
+// a linear one, which matters when eight ranks share one host)
+static cudaError_t copy_rows_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows, cudaMemcpyKind kind,
+                                   cudaStream_t stream) {
+  if (dpitch == row_bytes && spitch == row_bytes) return cudaMemcpyAsync(dst, src, row_bytes * rows, kind, stream);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, kind, stream);
+}
+
 int copy_inputs(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Staged>& st, int b, int e, cudaStream_t stream) {
   for (int i = b; i < e; i++) {
     const irp_image_desc& d = imgs[i];
     if (!d.pixels || d.on_device) continue;
-    CK(cudaMemcpy2DAsync((void*)st[i].px, st[i].pitch, d.pixels, d.pitch, (size_t)d.width * d.channels, d.height,
-                         cudaMemcpyHostToDevice, stream));
+    CK(copy_rows_async((void*)st[i].px, st[i].pitch, d.pixels, d.pitch, (size_t)d.width * d.channels, d.height,
+                       cudaMemcpyHostToDevice, stream));
   }
   return IRP_OK;
 }
@@ -1240,8 +1248,8 @@ int copy_outputs(irp_ctx* ctx, const irp_image_desc* imgs, irp_out_desc* outs, c
     if (!imgs[i].pixels || !oplans[i].via_stage) continue;
     irp_out_desc& od = outs[i];
     size_t tight = (size_t)od.width * od.channels;
-    CK(cudaMemcpy2DAsync(od.pixels, od.pitch ? od.pitch : tight, oplans[i].dev, oplans[i].dev_pitch, tight, od.height,
-                         cudaMemcpyDeviceToHost, stream));
+    CK(copy_rows_async(od.pixels, od.pitch ? od.pitch : tight, oplans[i].dev, oplans[i].dev_pitch, tight, od.height,
+                       cudaMemcpyDeviceToHost, stream));
   }
   return IRP_OK;
 }
