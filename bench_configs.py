@@ -250,7 +250,7 @@ def run_c5(a, rank, local_rank, world):
     torch, dist = _dist_setup(local_rank, world)
     import irp_b200
     from bench import ClockSampler
-    from irp_b200.sharding import PullQueue
+    from irp_b200.sharding import PullQueue, cleanup_queue_files
     from irp_b200.synth import mixed_resolution_sizes, synth_image
 
     sizes = mixed_resolution_sizes(512)
@@ -288,6 +288,7 @@ def run_c5(a, rank, local_rank, world):
                 mine.append(nxt)
                 th.join()
                 nxt = got[0]
+            q.close(unlink=False)
             done.append(mine)
 
         ms = _timed(torch, dist, world, stream, a.steps, a.warmup, step, sampler)
@@ -309,11 +310,15 @@ def run_c5(a, rank, local_rank, world):
                 w, h = sizes[i]
                 x0, y0 = (37 * i) % max(1, 6600 - w), (91 * i) % max(1, 6100 - h)
                 ok &= bool(np.array_equal(eng.download(d_out[i]), oracle.preprocess(np.ascontiguousarray(big[y0:y0 + h, x0:x0 + w]), 1)))
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            cleanup_queue_files()
     if rank == 0:
         n_l = launches[0] // (a.steps + max(a.warmup, 3)) * a.steps
         line = _line(a, world, px / 1e6 / (ms / 1e3), ms, "strong", CONFIG_NAMES["c5"],
                      {"images": len(sizes), "total_mpix": px / 1e6, "chunk_images": chunk, "chunks": len(chunks), "chunks_per_gpu_last_step": counts,
-                      "parallelism": f"{world} GPUs pulling chunks (largest images first) from one shared counter; no collective on the data path"},
+                      "parallelism": f"{world} GPUs pulling chunks (largest images first) from one shared counter (a flock-guarded file in /dev/shm); no collective on the data path"},
                      n_l, sampler.stop(), parity={"every_chunk_processed_exactly_once": covered, "sampled_outputs_equal_oracle": ok})
         print(json.dumps(line), flush=True)
     if world > 1:

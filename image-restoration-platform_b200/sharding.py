@@ -2,7 +2,9 @@
 and nothing is reduced across them — no NCCL on the data path.  One process per GPU."""
 from __future__ import annotations
 
+import fcntl
 import heapq
+import os
 from typing import List, Sequence
 
 
@@ -48,12 +50,17 @@ def gather_results(local: list, indices: Sequence[int], total: int, group=None) 
 class PullQueue:
     """The mixed-resolution job queue of BASELINE.json configs[4] ("dynamic pull from a shared
     host queue"): every rank draws the next chunk index from ONE counter, so a rank that drew small images simply comes
-    back sooner.  The counter is an atomic add in the rendezvous store torch.distributed already runs (host side, a TCP
-    round trip per draw — no collective, nothing on the GPUs' data path); without a process group it is a local counter.
-    One key per pass over the queue."""
+    back sooner.  On one box the counter is eight bytes of a file in /dev/shm, incremented under flock (a few
+    microseconds; host side, nothing on the GPUs' data path).  The rendezvous store's atomic add is the fallback for
+    ranks that do not share a /dev/shm — measured at 8 ranks it costs milliseconds per draw (small TCP writes), which
+    starved ranks outright.  Without a process group it is a local counter.  One key per pass over the queue."""
 
-    def __init__(self, n_items: int, key: str, store=None):
-        self.n, self.key, self.store, self._local = n_items, key, store, 0
+    def __init__(self, n_items: int, key: str, store=None, shm_dir: str = "/dev/shm"):
+        self.n, self.key, self.store, self._local, self._fd = n_items, key, store, 0, None
+        if store is not None and shm_dir and os.path.isdir(shm_dir) and int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0) == _world():
+            run = os.environ.get("TORCHELASTIC_RUN_ID", "run") + "_" + os.environ.get("MASTER_PORT", "0")
+            self._path = os.path.join(shm_dir, f"irp_queue_{run}_{key}")
+            self._fd = os.open(self._path, os.O_CREAT | os.O_RDWR, 0o600)
 
     @staticmethod
     def default_store():
@@ -67,6 +74,43 @@ class PullQueue:
         """Next item index, or None when the queue is drained."""
         if self.store is None:
             i, self._local = self._local, self._local + 1
+        elif self._fd is not None:
+            fcntl.flock(self._fd, fcntl.LOCK_EX)
+            try:
+                raw = os.pread(self._fd, 8, 0)
+                i = int.from_bytes(raw, "little") if len(raw) == 8 else 0
+                os.pwrite(self._fd, (i + 1).to_bytes(8, "little"), 0)
+            finally:
+                fcntl.flock(self._fd, fcntl.LOCK_UN)
         else:
             i = self.store.add(self.key, 1) - 1
         return i if i < self.n else None
+
+    def close(self, unlink: bool = False):
+        """Every rank closes; one of them (after a barrier) unlinks."""
+        if self._fd is not None:
+            os.close(self._fd)
+            self._fd = None
+            if unlink:
+                try:
+                    os.unlink(self._path)
+                except FileNotFoundError:
+                    pass
+
+
+def cleanup_queue_files(shm_dir: str = "/dev/shm") -> None:
+    """Remove this run's counter files (call on one rank, after a barrier)."""
+    import glob
+
+    run = os.environ.get("TORCHELASTIC_RUN_ID", "run") + "_" + os.environ.get("MASTER_PORT", "0")
+    for f in glob.glob(os.path.join(shm_dir, f"irp_queue_{run}_*")):
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
+
+
+def _world() -> int:
+    import torch.distributed as dist
+
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1

@@ -131,7 +131,7 @@ sys.path.insert(0, sys.argv[1])
 import torch.distributed as dist
 import irp_b200  # noqa: F401  (loads the package; no GPU work in this test)
 import time
-from irp_b200.sharding import lpt_assign, gather_results, shard_groups, PullQueue
+from irp_b200.sharding import lpt_assign, gather_results, shard_groups, PullQueue, cleanup_queue_files
 from irp_b200.synth import mixed_resolution_sizes
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -150,7 +150,7 @@ assert sorted(g for s in groups for g in s) == list(range(7))
 # exactly one rank, a slow rank draws fewer
 for step in range(2):
     q = PullQueue(37, f"test_queue_{step}", PullQueue.default_store())
-    assert q.store is not None
+    assert q.store is not None and q._fd is not None   # one box: the counter is a flock-guarded file in /dev/shm
     got = []
     while True:
         i = q.pull()
@@ -163,7 +163,19 @@ for step in range(2):
     dist.all_gather_object(parts, got)
     assert sorted(i for p in parts for i in p) == list(range(37)), parts
     assert len(parts[1]) > len(parts[0]), [len(p) for p in parts]
+    q.close()
+# the rendezvous store's atomic add is the fallback where ranks share no /dev/shm
+q = PullQueue(11, "test_queue_store", PullQueue.default_store(), shm_dir="")
+assert q._fd is None
+got = []
+while (i := q.pull()) is not None:
+    got.append(i)
+parts = [None] * world
+dist.all_gather_object(parts, got)
+assert sorted(i for p in parts for i in p) == list(range(11))
 dist.barrier()
+if rank == 0:
+    cleanup_queue_files()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
