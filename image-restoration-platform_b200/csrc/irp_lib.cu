@@ -139,6 +139,7 @@ struct irp_ctx {
   int jpeg_sweeps = 0;            // synchronisation sweeps of the last JPEG batch
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled
   std::vector<void*> plan_chunks;
+  size_t plan_total = 0;   // bytes of all plan chunks (the cache is flushed whole past IRP_PLAN_CACHE_MB, default 2048)
   size_t plan_used = 0, plan_cap = 0;
   std::map<std::tuple<int, int, double>, PlanDev> plans;
   cudaEvent_t ev[6]{};
@@ -326,6 +327,7 @@ int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
     void* p = nullptr;
     CK(cudaMalloc(&p, cap));
     ctx->plan_chunks.push_back(p);
+    ctx->plan_total += cap;
     ctx->plan_used = 0;
     ctx->plan_cap = cap;
   }
@@ -991,6 +993,19 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
   struct Src { const uint8_t* px; size_t pitch; };
   std::vector<Src> src(e - b);
   std::vector<int> kern(e - b, -1);
+  {
+    // Geometry plans (tap tables, the tensor-core kernel's operand matrices: up to ~1 MB per axis) are cached for the
+    // life of the context; uploads of ever-new sizes must not grow that without bound.  Past the cap the whole cache
+    // goes (nothing of it is in flight: plans are only referenced by this function's launches, drained here).
+    static const size_t cap = (size_t)(getenv("IRP_PLAN_CACHE_MB") ? std::max(1, atoi(getenv("IRP_PLAN_CACHE_MB"))) : 2048) << 20;
+    if (ctx->plan_total > cap) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (void* p : ctx->plan_chunks) cudaFree(p);
+      ctx->plan_chunks.clear();
+      ctx->plans.clear();
+      ctx->plan_total = ctx->plan_used = ctx->plan_cap = 0;
+    }
+  }
   std::vector<RtFoot> foot(e - b);
   std::vector<AxisPlan> pv(e - b), ph(e - b);
   std::vector<const PlanDev*> dv(e - b), dh(e - b);

@@ -39,6 +39,25 @@ def generic_engine():
     eng.close()
 
 
+@pytest.fixture(scope="module")
+def tma_engine():
+    """A third context without the tensor-core resize: 3-channel aligned images take resize_tma_kernel (the ALU
+    formulation, still the path for footprints the tensor-core kernel's shared memory cannot hold)."""
+    import irp_b200
+
+    old = os.environ.get("IRP_NO_RMMA")
+    os.environ["IRP_NO_RMMA"] = "1"
+    try:
+        eng = irp_b200.Engine(0)
+    finally:
+        if old is None:
+            os.environ.pop("IRP_NO_RMMA", None)
+        else:
+            os.environ["IRP_NO_RMMA"] = old
+    yield eng
+    eng.close()
+
+
 @pytest.mark.parametrize("h,w", EDGE_SIZES)
 def test_classify_streaming_and_generic_agree_with_oracle(engine, generic_engine, oracle, h, w):
     img = rand_image(h, w, 3, seed=7 * h + w, kind="smooth")
@@ -63,13 +82,35 @@ def test_classify_long_image_forces_mid_image_flushes(engine, oracle):
 
 @pytest.mark.parametrize("h,w", [(2049, 64), (64, 2049), (2050, 2050), (2500, 3100), (3100, 2500), (2200, 4099), (4099, 2200),
                                  (8000, 2100), (2100, 8000)])
-def test_resize_streaming_and_generic_agree_with_oracle(engine, generic_engine, oracle, h, w):
+def test_resize_streaming_and_generic_agree_with_oracle(engine, generic_engine, tma_engine, oracle, h, w):
     img = rand_image(h, w, 3, seed=h + 3 * w, kind="smooth")
     ref = oracle.preprocess(img, 1)
     a = engine.preprocess_batch([img])[0]
     b = generic_engine.preprocess_batch([img])[0]
-    assert a.shape == ref.shape and np.array_equal(a, ref), f"streaming {h}x{w}"
+    c = tma_engine.preprocess_batch([img])[0]
+    assert a.shape == ref.shape and np.array_equal(a, ref), f"tensor-core / streaming {h}x{w}"
     assert b.shape == ref.shape and np.array_equal(b, ref), f"generic {h}x{w}"
+    assert c.shape == ref.shape and np.array_equal(c, ref), f"streaming (ALU) {h}x{w}"
+
+
+def test_plan_cache_is_bounded(tmp_path):
+    """Geometry plans are cached per context; past IRP_PLAN_CACHE_MB the cache is flushed whole.  With a 1 MB cap every
+    call after the first few rebuilds its plans, and the pixels must not change."""
+    import subprocess
+    import sys
+
+    script = tmp_path / "cap.py"
+    script.write_text(
+        "import sys; sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + '/tests')\n"
+        "import numpy as np, irp_b200\nfrom conftest import rand_image\nfrom oracle import oracle\n"
+        "with irp_b200.Engine(0) as eng:\n"
+        "    for k in range(12):\n"
+        "        img = rand_image(2100 + 37 * k, 2300 + 53 * (k % 5), 3, seed=k, kind='smooth')\n"
+        "        assert np.array_equal(eng.preprocess_batch([img])[0], oracle.preprocess(img, 1)), k\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, env=dict(os.environ, IRP_PLAN_CACHE_MB="1"), timeout=600)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stdout + p.stderr
 
 
 def test_resize_mixed_geometries_in_one_launch(engine, oracle):
