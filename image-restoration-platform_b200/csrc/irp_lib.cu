@@ -418,7 +418,7 @@ int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
   for (int b = 0; b < tiles_x && h_ok; b++) {
     const int o0 = b * kMmTC, o1 = std::min(no, o0 + kMmTC) - 1;
     const int bx0 = (3 * first[o0]) & ~15, p0 = bx0 / 3, plast = first[o1] + nt_max - 1;
-    if (3 * plast + 2 > bx0 + kMmXB - 1 || plast - p0 >= kMmKH) h_ok = false;
+    if (3 * plast + 2 > bx0 + kMmXB - 1 || plast - p0 >= kMmKH - 1) h_ok = false;   // K index 95 is the rounding column
   }
   pd->mm_h_ok = h_ok;
   std::vector<int32_t> hmat(tiles_x, 0);
@@ -430,6 +430,8 @@ int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
       const int o0 = b * kMmTC, p0 = ((3 * first[o0]) & ~15) / 3;
       std::fill(m.begin(), m.end(), 0);
       for (int o = o0; o < std::min(no, o0 + kMmTC); o++) put(m, o - o0, o, first[o] - p0);
+      // reduceh's rounding constant: the intermediate's pixel 95 is a constant 1, every hi row holds 16 there (16 * 128 = 2048)
+      for (int nn = 0; nn < kMmTC; nn++) m[(size_t)(nn >> 3) * 128 + (nn & 7) * 16 + (size_t)((kMmKH - 1) >> 4) * 1024 + ((kMmKH - 1) & 15)] = 16;
       auto it = seen.find(std::string((const char*)m.data(), m.size()));
       if (it == seen.end()) {
         it = seen.emplace(std::string((const char*)m.data(), m.size()), (int)seen.size()).first;

@@ -10,8 +10,9 @@
 // host as c = 128 * hi + lo with lo in [-64, 63] (both halves s8); the hi and lo products are accumulated in
 // SEPARATE int32 columns of the same MMA (the coefficient operand is the N side: columns [0, 32) hold hi, columns
 // [32, 64) lo, of the same 32 outputs) and recombined as 128 * acc_hi + acc_lo — integer arithmetic end to end,
-// bit-identical to (sum c * p + 2048) >> 12.  The rounding constant 2048 is pre-loaded into the lo accumulator
-// columns (tcgen05.st) and the MMAs accumulate on top of it.  Replicate edges are folded into the coefficient
+// bit-identical to (sum c * p + 2048) >> 12.  The first K step of every accumulation overwrites its accumulator; the
+// rounding constant is added in the reducev epilogue and, for reduceh, comes out of the product itself (a constant-1
+// pixel column of the intermediate times a hi coefficient of 16).  Replicate edges are folded into the coefficient
 // rows on the host (taps that fall outside the image are added to the edge tap), so tiles need no patching and
 // TMA's zero fill outside the image is multiplied by zero.
 //
@@ -105,10 +106,10 @@ __device__ __forceinline__ unsigned long long mm_desc(uint32_t saddr, uint32_t l
   return (unsigned long long)((saddr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo >> 4) & 0x3FFFu) << 16) |
          ((unsigned long long)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((unsigned long long)layout << 61);
 }
-__device__ __forceinline__ void mm_mma_i8(uint32_t d, unsigned long long a, unsigned long long b, uint32_t idesc) {
+__device__ __forceinline__ void mm_mma_i8(uint32_t d, unsigned long long a, unsigned long long b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc)
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void mm_commit(uint32_t bar) {
@@ -142,11 +143,11 @@ __device__ __forceinline__ void mm_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// (128 * hi + lo) >> 12, four of them saturated to bytes; the accumulators already hold the rounding constant
+// (128 * hi + lo + 2048) >> 12, four of them saturated to bytes
 __device__ __forceinline__ uint32_t mm_pack4(const uint32_t* hi, const uint32_t* lo) {
   int v[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) v[j] = ((int)hi[j] * 128 + (int)lo[j]) >> IRP_INTERP_SHIFT;
+  for (int j = 0; j < 4; j++) v[j] = ((int)hi[j] * 128 + ((int)lo[j] + (1 << (IRP_INTERP_SHIFT - 1)))) >> IRP_INTERP_SHIFT;
   return pack_sat_u8(v[1], v[0], pack_sat_u8(v[3], v[2], 0u));
 }
 
@@ -230,18 +231,12 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
   // H epilogue item: pixels [8 pg, 8 pg + 8) of the tile's 32 output columns
   const int pg = warp >> 2;
   if (warp < kMmEpiWarps) {
-    // arm every accumulator: hi columns 0, lo columns 2048 (the rounding constant)
-#pragma unroll
-    for (int dv = 0; dv < 2; dv++) {
-      mm_st16(tlane + kMmColV + dv * 128 + vb * 64 + 16 * vrh, 0u);
-      mm_st16(tlane + kMmColV + dv * 128 + vb * 64 + 32 + 16 * vrh, 1u << (IRP_INTERP_SHIFT - 1));
-    }
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      mm_st8(tlane + kMmColH + 64 * c + 8 * pg, 0u);
-      mm_st8(tlane + kMmColH + 64 * c + 32 + 8 * pg, 1u << (IRP_INTERP_SHIFT - 1));
-    }
-    mm_wait_st();
+    // reduceh's rounding constant comes out of the product itself: pixel 95 of every intermediate row is a constant 1
+    // (the reducev epilogue never writes past pixel 85) and the hi half of every CH row holds 16 there: 16 * 128 = 2048
+    for (int k = tid; k < 3 * (kMmTR / 16); k += 32 * kMmEpiWarps)
+      mm_sts128(a_mid + (k / (kMmTR / 16)) * kMmMidPlane + (k % (kMmTR / 16)) * (kMmKH * 16) + ((kMmKH - 1) >> 3) * 128 + ((kMmKH - 1) & 7) * 16,
+                0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   mm_fence_before();
   __syncthreads();
@@ -358,9 +353,9 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
       mm_fence_after();
       const int wsq = q == 0 ? inf.ws0 : (q == 1 ? inf.ws1 : (q == 2 ? inf.ws2 : inf.ws3));
       const uint32_t src = a_src + (uint32_t)buf * src_buf_bytes + w * (L.R * 128) + wsq * 128;
-      for (int ks = 0; ks < inf.ksv; ks++)
+      for (int ks = 0; ks < inf.ksv; ks++)   // the first K step overwrites the accumulator: nothing to clear or re-arm
         mm_mma_i8(tm + kMmColV + a * 128 + w * 64, mm_desc(src + ks * 4096, (uint32_t)L.R * 128u, 1024u, 2u),
-                  mm_desc(a_cv + q * cv_slot + ks * 2048, 1024u, 128u, 0u), kMmIdesc);
+                  mm_desc(a_cv + q * cv_slot + ks * 2048, 1024u, 128u, 0u), kMmIdesc, ks > 0);
       mm_commit(bar(kBarVFull + a));
       mm_commit(bar(kBarCvFree + q));                  // the quarter's matrix slot can be refilled
       if (q == 3) mm_commit(bar(kBarSrcFree + buf));   // ... and the tile's source buffer
@@ -381,7 +376,7 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
 #pragma unroll
       for (int ks = 0; ks < kMmKH / 32; ks++)
         mm_mma_i8(tm + kMmColH + 64 * w, mm_desc(a_mid + w * kMmMidPlane + ks * 512, 128u, (uint32_t)kMmKH * 16u, 0u),
-                  mm_desc(a_ch + slot * kMmChBytes + ks * 2048, 1024u, 128u, 0u), kMmIdesc);
+                  mm_desc(a_ch + slot * kMmChBytes + ks * 2048, 1024u, 128u, 0u), kMmIdesc, ks > 0);
       mm_commit(bar(kBarHFull));
     };
     if (lane == 0) {
@@ -430,15 +425,9 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
         mm_ld8(tlane + kMmColH + 64 * c + 32 + 8 * pg, lo[c]);
       }
       mm_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        mm_st8(tlane + kMmColH + 64 * c + 8 * pg, 0u);
-        mm_st8(tlane + kMmColH + 64 * c + 32 + 8 * pg, 1u << (IRP_INTERP_SHIFT - 1));
-      }
-      mm_wait_st();
       mm_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarHFree));
+      if (lane == 0) mbar_arrive(bar(kBarHFree));   // the accumulators are in registers: the next reduceh may overwrite them
       int v[24];   // interleaved: v[3 j + c]
 #pragma unroll
       for (int j = 0; j < 8; j++)
@@ -493,10 +482,7 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           mm_ld16(ta + 32, lo);
           mm_wait_ld();
           tick(6);
-          mm_st16(ta, 0u);   // re-arm the accumulator for the quarter after next and hand it back before anything else
-          mm_st16(ta + 32, 1u << (IRP_INTERP_SHIFT - 1));
-          mm_wait_st();
-          mm_fence_before();
+          mm_fence_before();   // hand the accumulator back before anything else: the next quarter's first MMA overwrites it
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(kBarVFree + a));
           tick(7);
