@@ -11,7 +11,11 @@
  * reference's own tests pin only thresholds (server-node/tests/classifierService.test.js
  * :23,32,39,46,53-56).  What pins this file: those thresholds + the hand-derived
  * known answers of SURVEY.md §8c (tests/test_oracle.py), PIL exif_transpose for P2
- * and scipy.ndimage.correlate for K1.
+ * and scipy.ndimage.correlate for K1.  What WOULD pin it: tools/sharp_golden.mjs runs the
+ * reference's own ClassifierService / preprocessImage and their literal sharp calls on the
+ * seeded fixtures of tests/golden/sharp_cases.py wherever Node exists; tests/test_sharp_golden.py
+ * consumes that dump and votes on every switch below (luma_mode, coef_mode, blur_mode,
+ * reduce_mode — the _m entry points take them all).
  *
  * Every function cites the reference lines it follows.  JS-side formulas are
  * literal (two-pass, sequential double accumulation as Array.prototype.reduce
