@@ -1126,7 +1126,6 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         M.tiles_y = (g.dh + kMmTR - 1) / kMmTR;
         M.strip_base = tiles;   // this group counts strips
         M.ksv = dv[i - b]->mm_ksv;
-        M.hnt = dh[i - b]->mm_nt;
         tiles += M.tiles_x;
         mm_rows = std::max(mm_rows, dv[i - b]->mm_rows);
         mm_ksv = std::max(mm_ksv, dv[i - b]->mm_ksv);

@@ -68,8 +68,7 @@ struct MmJob {
   int dst_x0, dst_y0;
   int tiles_x, tiles_y, strip_base;
   int ksv;                 // 32-row K steps per quarter
-  int hnt;                 // taps per output column after edge folding
-  int pad;
+  int pad[2];
 };
 
 struct MmLayout {          // byte offsets in dynamic shared memory (after 1024-byte alignment)
@@ -84,8 +83,7 @@ struct MmInfo {            // one tile, written by the producer
   int flags, ksv;               // flags: bits 0-3 quarter matrix reloaded, bit 4 CH reloaded, bit 5 CH slot
   unsigned dst_lo, dst_hi;      // where the tile's first output byte goes
   unsigned long long pitch;
-  int kneed;                    // intermediate pixels reduceh reads (the strip's last window end): columns beyond are not produced
-  int pad;
+  int pad[2];
 };
 
 // mbarrier indices
@@ -164,7 +162,6 @@ __device__ __forceinline__ MmInfo mm_load_info(uint32_t ia) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.ws0), "=r"(inf.ws1), "=r"(inf.ws2), "=r"(inf.ws3) : "r"(ia + 16));
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inf.flags), "=r"(inf.ksv), "=r"(inf.dst_lo), "=r"(inf.dst_hi) : "r"(ia + 32));
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(plo), "=r"(phi) : "r"(ia + 48));
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(inf.kneed) : "r"(ia + 56));
   inf.pitch = ((unsigned long long)phi << 32) | plo;
   return inf;
 }
@@ -268,7 +265,6 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
         const int strip = s - __ldg(&J->strip_base);
         const int ox0 = strip * kMmTC;
         const int bx0 = (3 * __ldg(hfirst + ox0)) & ~15;
-        const int kneed = __ldg(hfirst + min(ox0 + kMmTC, dw) - 1) + __ldg(&J->hnt) - bx0 / 3;
         const uint8_t* hm = mm_ldptr(&J->hmats) + (size_t)__ldg(mm_ldptr(&J->hmat) + strip) * kMmChBytes;
         uint8_t* dst0 = const_cast<uint8_t*>(mm_ldptr(reinterpret_cast<const uint8_t* const*>(&J->dst))) + (size_t)__ldg(&J->dst_y0) * pitch +
                         (size_t)(__ldg(&J->dst_x0) + ox0) * 3;
@@ -299,7 +295,6 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info + 16), "r"(ws[0]), "r"(ws[1]), "r"(ws[2]), "r"(ws[3]) : "memory");
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info + 32), "r"(flags), "r"(ksv), "r"((uint32_t)dptr), "r"((uint32_t)(dptr >> 32)) : "memory");
           asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(info + 48), "r"((uint32_t)pitch), "r"((uint32_t)(pitch >> 32)) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(info + 56), "r"(kneed) : "memory");
           const uint32_t src = a_src + (uint32_t)buf * src_buf_bytes;
           mbar_arrive_expect_tx(bar(kBarFull + buf), src_buf_bytes);
 #pragma unroll
@@ -475,9 +470,6 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           const int xb = 128 * vb + 32 * lq + lane, B = cur.bx0 + xb, p = B / 3, c = B - 3 * p, kpx = p - cur.bx0 / 3;
           mid_col = a_mid + c * kMmMidPlane + (kpx >> 3) * 128 + (kpx & 7) * 16;
         }
-        // byte columns past the strip's last window (the slack of the 256-byte footprint: two warps at 125 : 64) are never
-        // read by reduceh: their warps only take part in the hand-overs
-        const bool v_skip = (cur.bx0 + 128 * vb + 32 * lq) / 3 - cur.bx0 / 3 >= cur.kneed;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const int a = q & 1;
@@ -486,18 +478,15 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           if (prof) tk = mm_clock();
           uint32_t hi[16], lo[16];
           const uint32_t ta = tlane + kMmColV + a * 128 + vb * 64 + 16 * vrh;
-          if (!v_skip) {
-            mm_ld16(ta, hi);
-            mm_ld16(ta + 32, lo);
-            mm_wait_ld();
-          }
+          mm_ld16(ta, hi);
+          mm_ld16(ta + 32, lo);
+          mm_wait_ld();
           tick(6);
           mm_fence_before();   // hand the accumulator back before anything else: the next quarter's first MMA overwrites it
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(kBarVFree + a));
           tick(7);
-          uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-          if (!v_skip) p0 = mm_pack4(hi, lo), p1 = mm_pack4(hi + 4, lo + 4), p2 = mm_pack4(hi + 8, lo + 8), p3 = mm_pack4(hi + 12, lo + 12);
+          const uint32_t p0 = mm_pack4(hi, lo), p1 = mm_pack4(hi + 4, lo + 4), p2 = mm_pack4(hi + 8, lo + 8), p3 = mm_pack4(hi + 12, lo + 12);
           tick(8);
           if (q == 0 && i > 0) {
             // the previous tile's reduceh: its epilogue first (that wait also means the intermediate has been read),
@@ -505,7 +494,7 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
             epi_h(prev);
             if (prof) tk = mm_clock();
           }
-          if (!v_skip) mm_sts128(mid_col + (2 * q + vrh) * (kMmKH * 16), p0, p1, p2, p3);
+          mm_sts128(mid_col + (2 * q + vrh) * (kMmKH * 16), p0, p1, p2, p3);
           if (q == 3) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the intermediate is read by the tensor core next
             __syncwarp();
