@@ -945,13 +945,14 @@ int encode_source_tmap(irp_ctx* ctx, const uint8_t* px, size_t pitch, int w, int
 
 // shared-memory map of the tensor-core resize kernel.  The source buffers come first: the last K step of a quarter may
 // read rows past its buffer (times zero coefficients), and what lies behind has to be mapped memory.
-MmLayout mm_layout(int rows, int ksv) {
+MmLayout mm_layout(int rows, int ksv, int nbuf) {
   MmLayout L;
   L.R = rows;
   L.ksv_max = ksv;
+  L.nbuf = nbuf;
   size_t p = 0;
   L.off_src = (int)p;
-  p += (size_t)2 * 2 * rows * 128;
+  p += (size_t)nbuf * 2 * rows * 128;
   L.off_cv = (int)p;
   p += (size_t)4 * ksv * 2048;
   L.off_mid = (int)p;
@@ -968,7 +969,6 @@ MmLayout mm_layout(int rows, int ksv) {
   L.total = (int)p;
   return L;
 }
-
 int encode_mm_tmap(irp_ctx* ctx, const uint8_t* px, size_t pitch, int w, int h, int box_rows, TmaDesc* out) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -1050,8 +1050,11 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
   // kernel choice.  The streaming kernel runs 5 groups x 24-row tiles per CTA when every eligible job keeps
   // a full-size tile inside a fifth of the shared memory, else 4 groups x 32-row tiles.
   int box_cols_px = 0, box_rows = 0, rt_groups = kRMaxGroups, rt_toh = 24;
+  int mm_fit_rows[2], mm_fit_ksv[2];
   for (int attempt = 0; attempt < 2; attempt++) {
     box_cols_px = box_rows = 0;
+    mm_fit_rows[0] = mm_fit_rows[1] = 16;
+    mm_fit_ksv[0] = mm_fit_ksv[1] = 1;
     const size_t budget = ((size_t)ctx->smem_optin_full - 4096) / rt_groups;
     bool degraded = false;
     for (int i = b; i < e; i++) {
@@ -1074,8 +1077,19 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       if (pv[i - b].n == 1 && ph[i - b].n == 1 && g.dc == d.channels && g.dw == g.rw && g.dh == g.rh) k = 4;
       // the tensor-core kernel: 3-channel aligned sources whose geometry fits its tile, 8-byte aligned destination pieces
       if ((k == 1 || k == 3) && ctx->rmma_ok && ((((uintptr_t)s.px | s.pitch) & 15) == 0) && dv[i - b]->mm_v_ok && dh[i - b]->mm_h_ok &&
-          ((((uintptr_t)oplans[i].dev | oplans[i].dev_pitch) & 15) == 0) && ((3 * g.ox) & 7) == 0 && mm_layout(dv[i - b]->mm_rows, dv[i - b]->mm_ksv).total <= (int)ctx->smem_optin_full - 2048)
-        k = 5;
+          ((((uintptr_t)oplans[i].dev | oplans[i].dev_pitch) & 15) == 0) && ((3 * g.ox) & 7) == 0) {
+        // a launch's layout is sized for the largest rows and K steps among its jobs: a job joins the double-buffered
+        // launch if the combined layout still fits, else the single-buffered one, else it stays with the ALU kernels
+        for (int mg = 0; mg < 2; mg++) {
+          const int r2 = std::max(mm_fit_rows[mg], dv[i - b]->mm_rows), k2 = std::max(mm_fit_ksv[mg], dv[i - b]->mm_ksv);
+          if (mm_layout(r2, k2, mg == 0 ? 2 : 1).total <= (int)ctx->smem_optin_full - 2048) {
+            mm_fit_rows[mg] = r2;
+            mm_fit_ksv[mg] = k2;
+            k = 5 + mg;
+            break;
+          }
+        }
+      }
       kern[i - b] = k;
     }
     if (!degraded || attempt == 1) break;
@@ -1085,9 +1099,9 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
   const RtLayout L = rt_layout(std::max(box_cols_px, 4), std::max(box_rows, 2), rt_groups, rt_toh);
   if (getenv("IRP_TRACE")) fprintf(stderr, "resize_tma: groups %d toh %d box %d x %d group_bytes %d\n", L.groups, rt_toh, L.box_cols, L.box_rows, L.group_bytes);
   // pass 2: job descriptors, grouped by kernel
-  int pos = b, group_begin[7], group_tiles[6];
-  int mm_rows = 16, mm_ksv = 1;
-  for (int gi = 0; gi < 6; gi++) {
+  int pos = b, group_begin[8], group_tiles[7];
+  int mm_rows[2] = {16, 16}, mm_ksv[2] = {1, 1};
+  for (int gi = 0; gi < 7; gi++) {
     group_begin[gi] = pos;
     int tiles = 0;
     for (int i = b; i < e; i++) {
@@ -1113,7 +1127,7 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         pos++;
         continue;
       }
-      if (gi == 5) {
+      if (gi >= 5) {
         MmJob& M = ((MmJob*)ctx->h_mmjobs.p)[pos];
         memset(&M, 0, sizeof M);
         M.dst = op.dev;
@@ -1127,8 +1141,8 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
         M.strip_base = tiles;   // this group counts strips
         M.ksv = dv[i - b]->mm_ksv;
         tiles += M.tiles_x;
-        mm_rows = std::max(mm_rows, dv[i - b]->mm_rows);
-        mm_ksv = std::max(mm_ksv, dv[i - b]->mm_ksv);
+        mm_rows[gi - 5] = std::max(mm_rows[gi - 5], dv[i - b]->mm_rows);
+        mm_ksv[gi - 5] = std::max(mm_ksv[gi - 5], dv[i - b]->mm_ksv);
         pos++;
         continue;
       }
@@ -1180,9 +1194,8 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
       tiles += J.tiles_x * J.tiles_y;
     }
     group_tiles[gi] = tiles;
-    if (gi == 4) group_begin[5] = pos;
   }
-  group_begin[6] = pos;
+  group_begin[7] = pos;
   if (pos == b) return IRP_OK;
   ResizeJob* d_jobs = (ResizeJob*)ctx->d_jobs.p;
   if (group_begin[3] > b)
@@ -1214,32 +1227,35 @@ int resize_range(irp_ctx* ctx, const irp_image_desc* imgs, const std::vector<Sta
     CK(cudaGetLastError());
     ctx->timing.kernel_launches++;
   }
-  if (const int nmm = group_begin[6] - group_begin[5]) {
-    // the tensor-core kernel: every job's source as a tensor map of 128-byte x (rows / 2) boxes with the 128-byte swizzle
-    const int g5 = group_begin[5];
-    const MmLayout ML = mm_layout(mm_rows, mm_ksv);
+  for (int mg = 0; mg < 2; mg++) {   // the tensor-core kernel: jobs whose footprint fits twice, then those that fit once
+    const int g5 = group_begin[5 + mg], nmm = group_begin[6 + mg] - g5, strips = group_tiles[5 + mg];
+    if (!nmm) continue;
+    // every job's source as a tensor map of 128-byte x (rows / 2) boxes with the 128-byte swizzle
+    const MmLayout ML = mm_layout(mm_rows[mg], mm_ksv[mg], mg == 0 ? 2 : 1);
     MmJob* h_mm = (MmJob*)ctx->h_mmjobs.p;
     MmJob* d_mm = (MmJob*)ctx->d_mmjobs.p;
     TmaDesc* h_mt = (TmaDesc*)(((uintptr_t)ctx->h_mmmaps.p + 63) & ~(uintptr_t)63);
     TmaDesc* d_mt = (TmaDesc*)(((uintptr_t)ctx->d_mmmaps.p + 63) & ~(uintptr_t)63);
     int slot = g5;
     for (int i = b; i < e; i++) {
-      if (!imgs[i].pixels || kern[i - b] != 5) continue;
+      if (!imgs[i].pixels || kern[i - b] != 5 + mg) continue;
       if ((rc = encode_mm_tmap(ctx, src[i - b].px, src[i - b].pitch, geo[i].rw, geo[i].rh, ML.R / 2, h_mt + slot))) return rc;
       slot++;
     }
     CK(cudaMemcpyAsync(d_mm + g5, h_mm + g5, sizeof(MmJob) * nmm, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_mt + g5, h_mt + g5, sizeof(TmaDesc) * nmm, cudaMemcpyHostToDevice, ctx->stream));
-    const int grid = std::min(group_tiles[5], ctx->sm_count);
-    if (getenv("IRP_TRACE")) fprintf(stderr, "resize_mma: %d jobs, %d strips, rows %d, ksv %d, smem %d\n", nmm, group_tiles[5], ML.R, ML.ksv_max, ML.total);
+    const int grid = std::min(strips, ctx->sm_count);
+    if (getenv("IRP_TRACE"))
+      fprintf(stderr, "resize_mma: %d jobs, %d strips, rows %d, ksv %d, %d source buffer(s), smem %d\n", nmm, strips, ML.R, ML.ksv_max, ML.nbuf, ML.total);
     if (auto e2 = ctx->d_mmctr.reserve(256); e2 != cudaSuccess) return fail(ctx, IRP_ERR_NOMEM, "strip counter: %s", cudaGetErrorString(e2));
-    CK(cudaMemsetAsync(ctx->d_mmctr.p, 0, 4, ctx->stream));
+    int* counter = (int*)ctx->d_mmctr.p + 16 * mg;
+    CK(cudaMemsetAsync(counter, 0, 4, ctx->stream));
     long long* dbg = nullptr;
     if (getenv("IRP_MMA_DEBUG")) {
       CK(cudaMalloc(&dbg, 80 * 8));
       CK(cudaMemsetAsync(dbg, 0, 80 * 8, ctx->stream));
     }
-    resize_mma_kernel<<<grid, kMmThreads, ML.total + 1024, ctx->stream>>>(d_mm + g5, d_mt + g5, nmm, group_tiles[5], (int*)ctx->d_mmctr.p, ML, dbg);
+    resize_mma_kernel<<<grid, kMmThreads, ML.total + 1024, ctx->stream>>>(d_mm + g5, d_mt + g5, nmm, strips, counter, ML, dbg);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches++;
     if (dbg) {   // cycles block 0 spent waiting, per role and barrier kind (kernel experiments only)

@@ -74,6 +74,7 @@ struct MmJob {
 struct MmLayout {          // byte offsets in dynamic shared memory (after 1024-byte alignment)
   int R;                   // rows of a source buffer (multiple of 16)
   int ksv_max;
+  int nbuf;                // source buffers: 2, or 1 for footprints that do not fit twice (shrinks above ~2)
   int off_cv, off_mid, off_ch, off_out, off_info, off_bar, off_src, total;
 };
 
@@ -244,6 +245,12 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
 
   const uint32_t src_buf_bytes = 2u * L.R * 128u;
   const uint32_t cv_slot = (uint32_t)L.ksv_max * 2048u;
+  // tile i lives in source buffer (and record slot) buf_of(i); it is that buffer's use number i / nbuf, whose parity the
+  // buffer's barriers go by.  With ONE buffer the next tile's load waits for this tile's last reducev MMA: the tensor
+  // pipe idles through a load, the epilogue warps (the bottleneck) mostly do not
+  const bool two_bufs = L.nbuf == 2;
+  auto buf_of = [&](int i) { return two_bufs ? (i & 1) : 0; };
+  auto par_of = [&](int i) { return (uint32_t)((two_bufs ? (i >> 1) : i) & 1); };
 
   if (warp == kMmEpiWarps) {
     // =============================== producer ===============================
@@ -269,7 +276,7 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
         uint8_t* dst0 = const_cast<uint8_t*>(mm_ldptr(reinterpret_cast<const uint8_t* const*>(&J->dst))) + (size_t)__ldg(&J->dst_y0) * pitch +
                         (size_t)(__ldg(&J->dst_x0) + ox0) * 3;
         for (int rb = 0; rb < tiles_y; rb++, i++) {
-          const int buf = i & 1;
+          const int buf = buf_of(i);
           const int oy0 = rb * kMmTR;
           const int sy0 = __ldg(vfirst + oy0);
           int ws[4];
@@ -289,7 +296,7 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           }
           flags |= chslot << 5;
           const unsigned long long dptr = (unsigned long long)(dst0 + (size_t)oy0 * pitch);
-          twait(0, bar(kBarSrcFree + buf), (uint32_t)((i >> 1) & 1) ^ 1u);
+          twait(0, bar(kBarSrcFree + buf), par_of(i) ^ 1u);
           const uint32_t info = a_info + buf * (uint32_t)sizeof(MmInfo);
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info), "r"(dh - oy0), "r"(dw - ox0), "r"(bx0), "r"(1) : "memory");
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(info + 16), "r"(ws[0]), "r"(ws[1]), "r"(ws[2]), "r"(ws[3]) : "memory");
@@ -323,8 +330,8 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
         }
       }
       // the record that ends the sequence
-      const int buf = i & 1;
-      mbar_wait(bar(kBarSrcFree + buf), (uint32_t)((i >> 1) & 1) ^ 1u);
+      const int buf = buf_of(i);
+      mbar_wait(bar(kBarSrcFree + buf), par_of(i) ^ 1u);
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_info + buf * (uint32_t)sizeof(MmInfo) + 12), "r"(0) : "memory");
       mbar_arrive(bar(kBarFull + buf));
     }
@@ -385,16 +392,16 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
     if (cur.valid) {
       if (w < 2) issue_v(cur, 0, 0);
       for (int i = 0;; i++) {
-        const int buf = i & 1;
+        const int buf = buf_of(i), nbuf = buf_of(i + 1);
         if (i > 0) issue_h(prev);
         if (w < 2) {
           issue_v(cur, buf, 1);
           issue_v(cur, buf, 2);
           issue_v(cur, buf, 3);
         }
-        twait(5, bar(kBarFull + (buf ^ 1)), (uint32_t)((i + 1) >> 1) & 1u);
-        const MmInfo nxt = mm_load_info(a_info + (buf ^ 1) * (uint32_t)sizeof(MmInfo));
-        if (nxt.valid && w < 2) issue_v(nxt, buf ^ 1, 0);
+        twait(5, bar(kBarFull + nbuf), par_of(i + 1));
+        const MmInfo nxt = mm_load_info(a_info + nbuf * (uint32_t)sizeof(MmInfo));
+        if (nxt.valid && w < 2) issue_v(nxt, nbuf, 0);
         prev = cur;
         cur = nxt;
         if (!cur.valid) {
@@ -463,7 +470,7 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
     };
     if (cur.valid) {
       for (int i = 0;; i++) {
-        const int buf = i & 1;
+        const int nbuf = buf_of(i + 1);
         // planar address of this thread's source byte column (reducev epilogue)
         uint32_t mid_col;
         {
@@ -502,8 +509,8 @@ resize_mma_kernel(const MmJob* __restrict__ jobs, const TmaDesc* __restrict__ tm
           }
           tick(9);
         }
-        twait(3, bar(kBarFull + (buf ^ 1)), (uint32_t)((i + 1) >> 1) & 1u);
-        const MmInfo nxt = mm_load_info(a_info + (buf ^ 1) * (uint32_t)sizeof(MmInfo));
+        twait(3, bar(kBarFull + nbuf), par_of(i + 1));
+        const MmInfo nxt = mm_load_info(a_info + nbuf * (uint32_t)sizeof(MmInfo));
         prev = cur;
         cur = nxt;
         if (!cur.valid) {

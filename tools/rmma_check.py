@@ -10,7 +10,7 @@ import irp_b200
 from irp_b200.synth import synth_image
 from oracle import oracle
 
-shapes = [(4000, 3000), (3840, 2160), (2304, 2200), (4000, 3000), (2100, 2050), (3000, 4000), (4096, 2048)]
+shapes = [(4000, 3000), (3840, 2160), (2304, 2200), (6000, 4000), (2100, 2050), (3000, 4000), (4096, 2048), (5986, 3991), (8000, 2100), (4597, 4597)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
 with irp_b200.Engine(0) as eng:
