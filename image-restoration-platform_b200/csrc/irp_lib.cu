@@ -27,6 +27,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <unordered_map>
 #include <deque>
 #include <thread>
 #include <cuda.h>   // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
@@ -336,6 +337,18 @@ int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
   return IRP_OK;
 }
 
+// A plan's tables are collected in one host blob and reach the device as ONE allocation and ONE copy: a dozen
+// synchronous small copies were a third of the 1-3 ms a new geometry cost.
+struct PlanBlob {
+  std::vector<uint8_t> bytes;
+  size_t add(const void* data, size_t n) {
+    const size_t off = round_up(bytes.size(), 256);
+    bytes.resize(off + n);
+    if (n) memcpy(bytes.data() + off, data, n);
+    return off;
+  }
+};
+
 // Tables of the tensor-core resize (irp_resize_mma.cuh) for one axis: per output its taps with the replicate edge
 // folded in (a tap that falls outside the image is added to the edge tap), split c = 128 * hi + lo, and the first
 // source index they apply to.  From those, the banded coefficient matrices the kernel multiplies with, laid out as
@@ -343,7 +356,8 @@ int plan_alloc(irp_ctx* ctx, size_t bytes, void** out) {
 // (k >> 4) * 1024 + (k & 15); n = hi | lo half * 32 + output within the group of 32): one per (128-row block,
 // quarter) for the axis as the vertical one, one per 32-column strip as the horizontal one; identical matrices are
 // stored once (a periodic geometry such as 4000 -> 2048 needs a handful).
-int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
+struct MmOffsets { size_t first = 0, vmat = 0, vmats = 0, hmat = 0, hmats = 0; };
+int build_mm_plan(const HostPlan& hp, int in_size, PlanDev* pd, PlanBlob* blob, MmOffsets* mo) {
   const int no = (int)hp.start.size(), n = hp.n;
   if (n > kMmMaxTaps) return IRP_OK;
   std::vector<int8_t> tab((size_t)no * 64, 0);
@@ -377,6 +391,18 @@ int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
       }
     }
   };
+  auto dedupe = [](std::unordered_multimap<uint64_t, int>& seen, std::vector<uint8_t>& store, const std::vector<uint8_t>& m) {
+    uint64_t h = 1469598103934665603ull;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(m.data());
+    for (size_t k = 0; k < m.size() / 8; k++) h = (h ^ w[k]) * 1099511628211ull;
+    auto range = seen.equal_range(h);
+    for (auto it = range.first; it != range.second; ++it)
+      if (!memcmp(store.data() + (size_t)it->second * m.size(), m.data(), m.size())) return it->second;
+    const int idx = (int)(store.size() / m.size());
+    store.insert(store.end(), m.begin(), m.end());
+    seen.emplace(h, idx);
+    return idx;
+  };
   // ---- as the vertical axis: the tile's box starts at first[o0]; each quarter's window at an 8-row boundary of the box
   const int tiles_y = (no + kMmTR - 1) / kMmTR;
   auto ws_of = [&](int o0, int q) { return (first[std::min(o0 + 32 * q, no - 1)] - first[o0]) & ~7; };
@@ -396,19 +422,14 @@ int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
   std::vector<int32_t> vmat((size_t)tiles_y * 4, 0);
   std::vector<uint8_t> vmats;
   if (pd->mm_v_ok) {
-    std::map<std::string, int> seen;
+    std::unordered_multimap<uint64_t, int> seen;   // content hash -> matrix index (compared byte for byte on a hit)
     std::vector<uint8_t> m((size_t)ksv * 2048);
     for (int rb = 0; rb < tiles_y; rb++) {
       const int o0 = rb * kMmTR;
       for (int q = 0; q < 4; q++) {
         std::fill(m.begin(), m.end(), 0);
         for (int o = o0 + 32 * q; o < std::min(no, o0 + 32 * q + 32); o++) put(m, o - o0 - 32 * q, o, first[o] - first[o0] - ws_of(o0, q));
-        auto it = seen.find(std::string((const char*)m.data(), m.size()));
-        if (it == seen.end()) {
-          it = seen.emplace(std::string((const char*)m.data(), m.size()), (int)seen.size()).first;
-          vmats.insert(vmats.end(), m.begin(), m.end());
-        }
-        vmat[(size_t)rb * 4 + q] = it->second;
+        vmat[(size_t)rb * 4 + q] = dedupe(seen, vmats, m);
       }
     }
   }
@@ -424,7 +445,7 @@ int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
   std::vector<int32_t> hmat(tiles_x, 0);
   std::vector<uint8_t> hmats;
   if (h_ok) {
-    std::map<std::string, int> seen;
+    std::unordered_multimap<uint64_t, int> seen;
     std::vector<uint8_t> m(kMmChBytes);
     for (int b = 0; b < tiles_x; b++) {
       const int o0 = b * kMmTC, p0 = ((3 * first[o0]) & ~15) / 3;
@@ -432,34 +453,17 @@ int build_mm_plan(irp_ctx* ctx, const HostPlan& hp, int in_size, PlanDev* pd) {
       for (int o = o0; o < std::min(no, o0 + kMmTC); o++) put(m, o - o0, o, first[o] - p0);
       // reduceh's rounding constant: the intermediate's pixel 95 is a constant 1, every hi row holds 16 there (16 * 128 = 2048)
       for (int nn = 0; nn < kMmTC; nn++) m[(size_t)(nn >> 3) * 128 + (nn & 7) * 16 + (size_t)((kMmKH - 1) >> 4) * 1024 + ((kMmKH - 1) & 15)] = 16;
-      auto it = seen.find(std::string((const char*)m.data(), m.size()));
-      if (it == seen.end()) {
-        it = seen.emplace(std::string((const char*)m.data(), m.size()), (int)seen.size()).first;
-        hmats.insert(hmats.end(), m.begin(), m.end());
-      }
-      hmat[b] = it->second;
+      hmat[b] = dedupe(seen, hmats, m);
     }
   }
-  void* p;
-  int rc;
-  if ((rc = plan_alloc(ctx, first.size() * 4, &p))) return rc;
-  pd->mm_first = (int32_t*)p;
-  CK(cudaMemcpy(pd->mm_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+  mo->first = blob->add(first.data(), first.size() * 4);
   if (pd->mm_v_ok) {
-    if ((rc = plan_alloc(ctx, vmat.size() * 4, &p))) return rc;
-    pd->mm_vmat = (int32_t*)p;
-    if ((rc = plan_alloc(ctx, vmats.size(), &p))) return rc;
-    pd->mm_vmats = (uint8_t*)p;
-    CK(cudaMemcpy(pd->mm_vmat, vmat.data(), vmat.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pd->mm_vmats, vmats.data(), vmats.size(), cudaMemcpyHostToDevice));
+    mo->vmat = blob->add(vmat.data(), vmat.size() * 4);
+    mo->vmats = blob->add(vmats.data(), vmats.size());
   }
   if (h_ok) {
-    if ((rc = plan_alloc(ctx, hmat.size() * 4, &p))) return rc;
-    pd->mm_hmat = (int32_t*)p;
-    if ((rc = plan_alloc(ctx, hmats.size(), &p))) return rc;
-    pd->mm_hmats = (uint8_t*)p;
-    CK(cudaMemcpy(pd->mm_hmat, hmat.data(), hmat.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pd->mm_hmats, hmats.data(), hmats.size(), cudaMemcpyHostToDevice));
+    mo->hmat = blob->add(hmat.data(), hmat.size() * 4);
+    mo->hmats = blob->add(hmats.data(), hmats.size());
   }
   return IRP_OK;
 }
@@ -482,14 +486,8 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
     }
     PlanDev pd;
     pd.n = hp.n;
-    void* p;
     int rc;
-    if ((rc = plan_alloc(ctx, hp.start.size() * 4, &p))) return rc;
-    pd.start = (int32_t*)p;
-    if ((rc = plan_alloc(ctx, hp.phase.size() * 4, &p))) return rc;
-    pd.phase = (int32_t*)p;
-    if ((rc = plan_alloc(ctx, hp.coef.size() * 2, &p))) return rc;
-    pd.coef = (int16_t*)p;
+    PlanBlob blob;
     // coefficient pairs pre-shifted for the kernels: pair p of shift s = (c[2p - s], c[2p + 1 - s])
     std::vector<uint32_t> vp((size_t)(IRP_PHASES + 1) * 2 * 16, 0), hq((size_t)(IRP_PHASES + 1) * 4 * 16, 0);
     for (int t = 0; t <= IRP_PHASES; t++) {
@@ -500,35 +498,44 @@ int get_plan(irp_ctx* ctx, int in_size, int out_size, double shrink, AxisPlan* a
       for (int sft = 0; sft < 4; sft++)
         for (int k = 0; k < kMaxHPairs; k++) hq[((size_t)t * 4 + sft) * 16 + k] = tap(2 * k - sft) | (tap(2 * k + 1 - sft) << 16);
     }
-    if ((rc = plan_alloc(ctx, vp.size() * 4, &p))) return rc;
-    pd.vpairs = (uint32_t*)p;
-    if ((rc = plan_alloc(ctx, hq.size() * 4, &p))) return rc;
-    pd.hpairs = (uint32_t*)p;
-    {  // one 16-word row per output row / column: its coefficient pairs and where its window starts
-      const size_t no = hp.start.size();
-      std::vector<uint32_t> vr(no * 16, 0), hc(no * kHTabWords, 0);
-      for (size_t o = 0; o < no; o++) {
-        const int s0 = hp.start[o], ph = hp.phase[o];
-        for (int k = 0; k < kMaxPairs; k++) vr[o * 16 + k] = vp[((size_t)ph * 2 + (s0 & 1)) * 16 + k];
-        vr[o * 16 + 15] = (uint32_t)(s0 >> 1);
-        for (int k = 0; k < kMaxHPairs; k++) hc[o * kHTabWords + k] = hq[((size_t)ph * 4 + (s0 & 3)) * 16 + k];
-        hc[o * kHTabWords + 15] = (uint32_t)(s0 >> 2);
-      }
-      if ((rc = plan_alloc(ctx, vr.size() * 4, &p))) return rc;
-      pd.vrows = (uint32_t*)p;
-      if ((rc = plan_alloc(ctx, hc.size() * 4, &p))) return rc;
-      pd.hcols = (uint32_t*)p;
-      CK(cudaMemcpy(pd.vrows, vr.data(), vr.size() * 4, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(pd.hcols, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
-      pd.h_start = hp.start;
+    // one 16-word row per output row / column: its coefficient pairs and where its window starts
+    const size_t no = hp.start.size();
+    std::vector<uint32_t> vr(no * 16, 0), hc(no * kHTabWords, 0);
+    for (size_t o = 0; o < no; o++) {
+      const int s0 = hp.start[o], ph = hp.phase[o];
+      for (int k = 0; k < kMaxPairs; k++) vr[o * 16 + k] = vp[((size_t)ph * 2 + (s0 & 1)) * 16 + k];
+      vr[o * 16 + 15] = (uint32_t)(s0 >> 1);
+      for (int k = 0; k < kMaxHPairs; k++) hc[o * kHTabWords + k] = hq[((size_t)ph * 4 + (s0 & 3)) * 16 + k];
+      hc[o * kHTabWords + 15] = (uint32_t)(s0 >> 2);
     }
-    if (!identity && (rc = build_mm_plan(ctx, hp, in_size, &pd))) return rc;
-    CK(cudaMemcpy(pd.vpairs, vp.data(), vp.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pd.hpairs, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice));
-    // synchronous copies: plans are built once per geometry and cached
-    CK(cudaMemcpy(pd.start, hp.start.data(), hp.start.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pd.phase, hp.phase.data(), hp.phase.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pd.coef, hp.coef.data(), hp.coef.size() * 2, cudaMemcpyHostToDevice));
+    const size_t o_start = blob.add(hp.start.data(), hp.start.size() * 4), o_phase = blob.add(hp.phase.data(), hp.phase.size() * 4),
+                 o_coef = blob.add(hp.coef.data(), hp.coef.size() * 2), o_vp = blob.add(vp.data(), vp.size() * 4),
+                 o_hq = blob.add(hq.data(), hq.size() * 4), o_vr = blob.add(vr.data(), vr.size() * 4), o_hc = blob.add(hc.data(), hc.size() * 4);
+    pd.h_start = hp.start;
+    MmOffsets mo;
+    if (!identity && (rc = build_mm_plan(hp, in_size, &pd, &blob, &mo))) return rc;
+    void* base;
+    if ((rc = plan_alloc(ctx, blob.bytes.size(), &base))) return rc;
+    CK(cudaMemcpy(base, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice));   // synchronous: built once per geometry and cached
+    uint8_t* d = (uint8_t*)base;
+    pd.start = (int32_t*)(d + o_start);
+    pd.phase = (int32_t*)(d + o_phase);
+    pd.coef = (int16_t*)(d + o_coef);
+    pd.vpairs = (uint32_t*)(d + o_vp);
+    pd.hpairs = (uint32_t*)(d + o_hq);
+    pd.vrows = (uint32_t*)(d + o_vr);
+    pd.hcols = (uint32_t*)(d + o_hc);
+    if (!identity) {
+      pd.mm_first = (int32_t*)(d + mo.first);
+      if (pd.mm_v_ok) {
+        pd.mm_vmat = (int32_t*)(d + mo.vmat);
+        pd.mm_vmats = d + mo.vmats;
+      }
+      if (pd.mm_h_ok) {
+        pd.mm_hmat = (int32_t*)(d + mo.hmat);
+        pd.mm_hmats = d + mo.hmats;
+      }
+    }
     it = ctx->plans.emplace(key, pd).first;
   }
   *ap = AxisPlan{it->second.start, it->second.phase, it->second.coef, it->second.vpairs, it->second.hpairs, it->second.n, 0};
