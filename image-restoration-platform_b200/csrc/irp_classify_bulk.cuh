@@ -122,16 +122,22 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
 // too: slower than SHF + LOP3, so the inverse-table and histogram addresses keep those.)
 struct MulConsts { uint32_t four; };
 
-template <int J>
-__device__ __forceinline__ uint32_t byte_idx(uint32_t w) {   // byte J of w, zero-extended (one ALU-pipe op)
-  return J == 3 ? (w >> 24) : (J == 0 ? (w & 0xFFu) : __byte_perm(w, 0u, 0x4440 + J));
+// Table addresses by IDP.4A: byte J of a packed word times 4 plus the table's base is ONE dot product with the
+// selector (4 << 8J) — extraction, scaling and base add in a single instruction (it was PRMT / SHF + IMAD, and for the
+// histogram SHF + LOP3), and it leaves the half-rate ALU pipe to the regroup and the stencils.
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
 }
-__device__ __forceinline__ uint32_t grey_top_fma(const Tiles<3>& T, const MulConsts& mc, uint32_t ri, uint32_t gi, uint32_t bi) {
-  const uint32_t I = lds_u32(ri * mc.four + T.a_lut_r) + lds_u32(gi * mc.four + T.a_lut_g) + lds_u32(bi * mc.four + T.a_lut_b);
+template <int J>
+__device__ __forceinline__ uint32_t grey_top_dp(const Tiles<3>& T, uint32_t R, uint32_t G, uint32_t B) {
+  constexpr uint32_t sel = 4u << (8 * J);
+  const uint32_t I = lds_u32(dp4a_uu(R, sel, T.a_lut_r)) + lds_u32(dp4a_uu(G, sel, T.a_lut_g)) + lds_u32(dp4a_uu(B, sel, T.a_lut_b));
   return lds_u32(((I >> 18) & 0x3FFCu) | T.a_inv) + I;
 }
-__device__ __forceinline__ void hist_add_fma(const Tiles<3>& T, const MulConsts& mc, uint32_t t) {
-  red_inc_shared(((t >> 22) & 0x3FCu) | T.a_hist);
+__device__ __forceinline__ void hist_add_dp(const Tiles<3>& T, uint32_t t) {
+  red_inc_shared(dp4a_uu(t, 0x04000000u, T.a_hist));
 }
 
 // 4 pixels (12 interleaved bytes in w0..w2) -> planar words + grey word.
@@ -157,14 +163,14 @@ __device__ __forceinline__ void s1_quad(const Tiles<3>& T, const MulConsts& mc, 
     a.q[2] = __dp4a(b, b, a.q[2]);
   }
   uint32_t t[4];
-  t[0] = grey_top_fma(T, mc, byte_idx<0>(R), byte_idx<0>(G), byte_idx<0>(B));
-  t[1] = grey_top_fma(T, mc, byte_idx<1>(R), byte_idx<1>(G), byte_idx<1>(B));
-  t[2] = grey_top_fma(T, mc, byte_idx<2>(R), byte_idx<2>(G), byte_idx<2>(B));
-  t[3] = grey_top_fma(T, mc, byte_idx<3>(R), byte_idx<3>(G), byte_idx<3>(B));
+  t[0] = grey_top_dp<0>(T, R, G, B);
+  t[1] = grey_top_dp<1>(T, R, G, B);
+  t[2] = grey_top_dp<2>(T, R, G, B);
+  t[3] = grey_top_dp<3>(T, R, G, B);
   if (COUNTED) {
 #pragma unroll
     for (int j = 0; j < 4; j++)
-      if (!MASKED || j < nvalid) hist_add_fma(T, mc, t[j]);
+      if (!MASKED || j < nvalid) hist_add_dp(T, t[j]);
   }
   Y = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x0073), 0x5410);
 }
