@@ -358,9 +358,12 @@ def main() -> int:
         ho = torch.empty(B * ow * oh * 3, dtype=torch.uint8).pin_memory()
         di, do = torch.empty_like(hi, device="cuda"), torch.empty_like(ho, device="cuda")
         sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        # all ranks copy AT THE SAME TIME (barrier before every repetition, slowest rank counts): on one box the ranks
+        # share the host's memory and PCIe root, and a floor measured while the others idle would flatter the link
         floor_ms = None
         for rep in range(3):
             torch.cuda.synchronize()
+            barrier()
             t1 = time.perf_counter()
             with torch.cuda.stream(sa):
                 di.copy_(hi, non_blocking=True)
@@ -368,6 +371,10 @@ def main() -> int:
                 ho.copy_(do, non_blocking=True)
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t1) * 1e3
+            if world > 1:
+                tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
             floor_ms = dt if floor_ms is None else min(floor_ms, dt)
         del hi, ho, di, do
         e2e = {"value": world * mpix_step / (ms / n_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": B * W * H * 3,

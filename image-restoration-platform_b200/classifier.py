@@ -4,8 +4,8 @@ Same constructor option (`logger`), same `analyze(imageBuffer)` coroutine return
 seven scores in the reference's key order (classifier.js:62-70), same static
 `getDegradationTypes()` and `createClassifierService(options)` factory (classifier.js:342-349).
 What changed is underneath: instead of six sharp pipelines and JS reductions, the decoded
-pixels make ONE trip through libirp_b200.so (hand-written sm_100a kernels).  Baseline JPEG files are
-decoded on the device too (bit-exact with libjpeg-turbo, sharp's decoder); PNG / WebP / progressive JPEG
+pixels make ONE trip through libirp_b200.so (hand-written sm_100a kernels).  JPEG files — baseline and
+progressive — are decoded on the device too (bit-exact with libjpeg-turbo, sharp's decoder); PNG / WebP
 containers are decoded on the host first.
 
 The reference's per-analysis fallback constants (classifier.js:123-126 ...) have no analogue:

@@ -18,6 +18,12 @@
 #pragma once
 #include "irp_classify.cuh"
 
+// Timing experiments only (tools/ablate.sh builds side libraries with -DIRP_ABLATE=mask; their RESULTS ARE WRONG):
+// 1 no histogram atomics, 2 no stage 2, 4 no stage 3, 8 grey without the tables, 16 no channel moments.
+#ifndef IRP_ABLATE
+#define IRP_ABLATE 0
+#endif
+
 namespace irp {
 
 constexpr int kBGroups = 6;                          // 4-warp groups per CTA
@@ -149,7 +155,7 @@ __device__ __forceinline__ void s1_quad(const Tiles<3>& T, const MulConsts& mc, 
   R = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
   G = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
   B = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
-  if (COUNTED) {
+  if (COUNTED && !(IRP_ABLATE & 16)) {
     uint32_t r = R, g = G, b = B;
     if (MASKED) {
       const uint32_t m = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * max(nvalid, 0))) - 1u);
@@ -163,11 +169,15 @@ __device__ __forceinline__ void s1_quad(const Tiles<3>& T, const MulConsts& mc, 
     a.q[2] = __dp4a(b, b, a.q[2]);
   }
   uint32_t t[4];
+  if (IRP_ABLATE & 8) {
+    Y = G;
+    return;
+  }
   t[0] = grey_top_dp<0>(T, R, G, B);
   t[1] = grey_top_dp<1>(T, R, G, B);
   t[2] = grey_top_dp<2>(T, R, G, B);
   t[3] = grey_top_dp<3>(T, R, G, B);
-  if (COUNTED) {
+  if (COUNTED && !(IRP_ABLATE & 1)) {
 #pragma unroll
     for (int j = 0; j < 4; j++)
       if (!MASKED || j < nvalid) hist_add_dp(T, t[j]);
@@ -363,11 +373,11 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
 
     // ---- stage 2 + 3 on the planes ----
     if (full) {
-      stage2<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
-      stage3<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
+      if (!(IRP_ABLATE & 2)) stage2<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
+      if (!(IRP_ABLATE & 4)) stage3<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
     } else {
-      stage2<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
-      stage3<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
+      if (!(IRP_ABLATE & 2)) stage2<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
+      if (!(IRP_ABLATE & 4)) stage3<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
     }
     group_barrier(group);
   }

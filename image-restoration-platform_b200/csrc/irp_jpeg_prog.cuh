@@ -1,0 +1,386 @@
+// irp_jpeg_prog.cuh — multi-scan JPEG on the device (sm_100a): progressive files (SOF2: spectral selection +
+// successive approximation — what `sharp(...).jpeg({progressive: true, mozjpeg: true})` writes,
+// server-node/src/middleware/imagePreprocess.js:57-61, and therefore what the classifier is handed in the planned
+// worker flow; accepted as uploads by uploadValidation.js:7) and sequential files with one scan per component.
+// The scans fill the SAME coefficient arena and compact DC array the baseline Huffman stage fills
+// (irp_jpeg.cuh: zigzag order, 64 int16 per block), so dequantisation, IDCT, upsampling and colour conversion are
+// shared and the pixels are libjpeg-turbo's (its jdphuff.c is the algorithm; the tests hold the result against Pillow).
+//
+// Parallelism.  A progressive scan is one Huffman stream whose state (band position, end-of-band run, and for the
+// refinements the history of every coefficient) does not re-synchronise the way a baseline stream does, so a scan is
+// decoded by ONE warp: lane 0 walks the symbols, the other lanes are its memory system —
+//   * the stream reaches lane 0 through a shared-memory ring the warp refills with coalesced loads (the bit reader
+//     never waits on global memory),
+//   * a refinement scan needs, per block, which coefficients are already nonzero and has to update them in place:
+//     the warp loads eight blocks at a time (lane = zigzag positions l and l + 32: two coalesced 64-byte rows per
+//     block), ballots give lane 0 a 64-bit history mask per block, lane 0 turns symbols and correction bits into
+//     three masks per block (correction, new coefficient, its sign) and the warp applies them and stores,
+//   * a DC refinement is one bit per block at a known position: every lane takes its own blocks.
+// The scans of a batch are independent across images and across the coefficient sets they touch; the host sorts
+// them into dependency levels (a scan waits for the earlier scans of the same component and band) and launches
+// one grid per level — three for libjpeg's standard script.
+#pragma once
+#include "irp_jpeg.cuh"
+
+namespace irp {
+
+constexpr int kProgRing = 2048;     // ring of stream words (8 KB); refilled in halves
+constexpr int kProgGroup = 8;       // blocks a refinement scan loads at a time
+// an MCU of a first pass consumes at most 10 blocks x 64 symbols x 31 bits < 640 words, a refinement group at most
+// 8 x 63 x 18 bits < 300 words: half a ring is always enough until the next refill point
+constexpr int kProgAhead = kProgRing / 2 - 64;   // after a refill: kProgAhead <= staged - next word < kProgRing - 64
+static_assert(kProgAhead >= 640, "ring too small for one MCU");
+
+struct ProgScan {                   // one scan of one image
+  int img, ns;                      // image, components in the scan
+  int comp[3];
+  int dc_tab[3], ac_tab[3];         // index into the batch's scan tables, -1: not needed by this scan
+  int ss, se, ah, al;
+  int restart;                      // MCUs per restart interval at this scan (0: one stream)
+  int stream_first, nstreams;
+  int pad;
+};
+struct ProgStream {                 // one restart interval of a scan (or the whole scan), un-stuffed, 4-byte aligned
+  unsigned long long word_off;      // into the batch data buffer, in 32-bit words
+  unsigned int nwords, pad;
+};
+
+struct ProgReader {
+  uint32_t* ring;
+  const uint32_t* src;
+  uint32_t nwords;        // words of the stream (zeros are fed past its end, as libjpeg does)
+  uint32_t staged;        // words staged so far (warp-uniform)
+  unsigned long long acc; // lane 0 only from here
+  int avail;
+  uint32_t nw;            // next word to merge into acc
+  uint32_t ahead;         // ring[nw], loaded when the previous word was merged: the shared-memory latency is off the symbol chain
+  __device__ __forceinline__ void open(uint32_t* r, const uint32_t* s, uint32_t n) {
+    ring = r; src = s; nwords = n; staged = 0; acc = 0; avail = 0; nw = 0; ahead = 0;
+  }
+  // warp-converged: keep at least kProgAhead unread words staged.  The ring always holds the 64 words BEFORE the
+  // next word to merge as well: up to two of them are still partly unread in lane 0's bit buffer, and the lanes
+  // fetch correction bits from there (bit_at) after lane 0 has moved past them.
+  __device__ __forceinline__ void refill(int lane) {
+    const uint32_t rd = __shfl_sync(0xffffffffu, nw, 0);
+    bool any = false;
+    while (staged - rd < (uint32_t)kProgAhead) {
+      for (int i = lane; i < kProgRing / 2; i += 32) {
+        const uint32_t w = staged + i;
+        ring[w & (kProgRing - 1)] = w < nwords ? bswap32(__ldg(src + w)) : 0u;
+      }
+      staged += kProgRing / 2;
+      any = true;
+    }
+    if (any) {
+      __syncwarp();
+      if (rd == 0 && lane == 0) ahead = ring[0];   // first refill of a stream
+    }
+  }
+  __device__ __forceinline__ void fill() {
+    if (avail < 32) {
+      acc |= (unsigned long long)ahead << (32 - avail);
+      avail += 32;
+      nw++;
+      ahead = ring[nw & (kProgRing - 1)];
+    }
+  }
+  __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(acc >> 32); }
+  __device__ __forceinline__ void skip(int n) {
+    acc <<= n;
+    avail -= n;
+  }
+  __device__ __forceinline__ uint32_t bits(int n) {   // 1 <= n <= 32
+    fill();
+    const uint32_t v = top32() >> (32 - n);
+    skip(n);
+    return v;
+  }
+  __device__ __forceinline__ uint32_t bit() {
+    fill();
+    const uint32_t v = (uint32_t)(acc >> 63);
+    skip(1);
+    return v;
+  }
+  __device__ __forceinline__ void skipn(int n) {      // any n >= 0
+    while (n > 0) {
+      fill();
+      const int t = min(n, 32);
+      skip(t);
+      n -= t;
+    }
+  }
+  __device__ __forceinline__ uint32_t pos() const { return nw * 32u - (uint32_t)avail; }   // bits consumed so far
+  // any lane: bit `b` of the stream, from the ring (valid for positions staged and not yet overwritten)
+  __device__ __forceinline__ uint32_t bit_at(uint32_t b) const { return (ring[(b >> 5) & (kProgRing - 1)] >> (31u - (b & 31u))) & 1u; }
+};
+
+struct ProgGeom {
+  int single;            // one component: the scan walks that component's own blocks
+  int mcus_x, mcus;      // MCUs per row / in the scan
+  int bpm;               // blocks per MCU of this scan
+};
+
+// the compact DC array is in MCU order of the FRAME (irp_jpeg.cuh): block (gy, gx) of component c
+__device__ __forceinline__ size_t prog_dc_index(const JpegImg& im, int c, int gy, int gx) {
+  const int ch = im.comp_h[c], cv = im.comp_v[c];
+  const int my = gy / cv, mx = gx / ch;
+  return (size_t)im.dc_off[c] + ((size_t)my * im.mcux + mx) * (ch * cv) + ((gy - my * cv) * ch + (gx - mx * ch));
+}
+
+__global__ void __launch_bounds__(32)
+prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ scans, const ProgStream* __restrict__ streams,
+                 const HuffDev* __restrict__ tabs, const uint32_t* __restrict__ data, int16_t* __restrict__ coef_arena,
+                 int16_t* __restrict__ dcv) {
+  __shared__ uint32_t ring[kProgRing];
+  __shared__ HuffDev ht[6];   // DC tables of the scan's components, then their AC tables
+  // refinement scans, per block of a group: history mask, new coefficients and their signs, and the correction-bit
+  // SEGMENTS: lane 0 only notes where in the band a run of correction bits starts (s_seg: one bit per start) and at
+  // which stream bit (s_segpos, in start order); the lane that owns a coefficient finds its own bit from those
+  __shared__ unsigned long long s_nz[kProgGroup], s_seg[kProgGroup], s_newp[kProgGroup], s_news[kProgGroup];
+  __shared__ uint32_t s_segpos[kProgGroup][64];
+  const int lane = threadIdx.x;
+  const ProgScan sc = scans[blockIdx.x];
+  const JpegImg& im = imgs[sc.img];
+  for (int t = 0; t < 6; t++) {
+    const int src = t < 3 ? sc.dc_tab[t] : sc.ac_tab[t - 3];
+    if ((t % 3) < sc.ns && src >= 0) {
+      const uint32_t* s = reinterpret_cast<const uint32_t*>(tabs + src);
+      uint32_t* d = reinterpret_cast<uint32_t*>(&ht[t]);
+      for (int i = lane; i < (int)(sizeof(HuffDev) / 4); i += 32) d[i] = __ldg(s + i);
+    }
+  }
+  __syncwarp();
+  ProgGeom g;
+  g.single = sc.ns == 1;
+  const int c0 = sc.comp[0];
+  if (g.single) {
+    g.mcus_x = (im.comp_dw[c0] + 7) >> 3;
+    g.mcus = g.mcus_x * ((im.comp_dh[c0] + 7) >> 3);
+    g.bpm = 1;
+  } else {
+    g.mcus_x = im.mcux;
+    g.mcus = im.mcux * im.mcuy;
+    g.bpm = 0;
+    for (int i = 0; i < sc.ns; i++) g.bpm += im.comp_h[sc.comp[i]] * im.comp_v[sc.comp[i]];
+  }
+  const int per = sc.restart > 0 ? sc.restart : g.mcus;
+  ProgReader rd;
+
+  for (int s = 0; s < sc.nstreams; s++) {
+    const int m0 = s * per, m1 = min(g.mcus, m0 + per);
+    if (m0 >= m1) break;
+    const ProgStream st = streams[sc.stream_first + s];
+    const uint32_t* src = data + st.word_off;
+
+    // ---------------- DC refinement: block b of the interval owns bit b ----------------
+    if (sc.ss == 0 && sc.ah > 0) {
+      const int nb = (m1 - m0) * g.bpm;
+      for (int b = lane; b < nb; b += 32) {
+        const uint32_t w = (uint32_t)(b >> 5) < st.nwords ? bswap32(__ldg(src + (b >> 5))) : 0u;
+        if (!((w >> (31 - (b & 31))) & 1u)) continue;
+        const int m = m0 + b / g.bpm;
+        int k = b - (b / g.bpm) * g.bpm;
+        const int my = m / g.mcus_x, mx = m - my * g.mcus_x;
+        for (int i = 0; i < sc.ns; i++) {
+          const int c = sc.comp[i];
+          const int nh = g.single ? 1 : im.comp_h[c], nv = g.single ? 1 : im.comp_v[c];
+          if (k < nh * nv) {
+            dcv[prog_dc_index(im, c, my * nv + k / nh, mx * nh + k % nh)] |= (int16_t)(1 << sc.al);
+            break;
+          }
+          k -= nh * nv;
+        }
+      }
+      continue;
+    }
+
+    rd.open(ring, src, st.nwords);
+    __syncwarp();
+    int eobrun = 0;
+
+    // ---------------- first passes (DC, AC, and the scans of a sequential file): lane 0 decodes and stores ----------------
+    if (sc.ah == 0) {
+      int pred[3] = {0, 0, 0};
+      int my = m0 / g.mcus_x, mx = m0 - my * g.mcus_x;
+      for (int m = m0; m < m1; m++) {
+        rd.refill(lane);
+        if (lane == 0) {
+#pragma unroll 1
+          for (int i = 0; i < sc.ns; i++) {
+            const int c = sc.comp[i];
+            const int nh = g.single ? 1 : im.comp_h[c], nv = g.single ? 1 : im.comp_v[c];
+            const HuffDev& dct = ht[i];
+            const HuffDev& act = ht[3 + i];
+            for (int by = 0; by < nv; by++)
+              for (int bx = 0; bx < nh; bx++) {
+                const int gy = my * nv + by, gx = mx * nh + bx;
+                if (sc.ss == 0) {
+                  rd.fill();
+                  const uint32_t b32 = rd.top32();
+                  int len;
+                  const int sz = huff_decode(dct, b32 >> 16, len) & 15;
+                  if (sz) pred[i] += huff_extend((int)((b32 << len) >> (32 - sz)), sz);
+                  rd.skip(len + sz);
+                  dcv[prog_dc_index(im, c, gy, gx)] = (int16_t)(pred[i] * (1 << sc.al));
+                }
+                if (sc.se > 0) {
+                  if (eobrun > 0) {
+                    eobrun--;
+                    continue;
+                  }
+                  int16_t* blk = coef_arena + im.coef_off[c] + ((size_t)gy * im.comp_bw[c] + gx) * 64;
+                  for (int k = max(sc.ss, 1); k <= sc.se; k++) {
+                    rd.fill();
+                    const uint32_t b32 = rd.top32();
+                    int len;
+                    const int rs = huff_decode(act, b32 >> 16, len);
+                    const int r = rs >> 4, sz = rs & 15;
+                    if (sz) {
+                      k += r;
+                      const int v = huff_extend((int)((b32 << len) >> (32 - sz)), sz);
+                      rd.skip(len + sz);
+                      if (k > 63) break;                       // corrupt data only
+                      blk[k] = (int16_t)(v * (1 << sc.al));    // the arena keeps zigzag order
+                    } else {
+                      rd.skip(len);
+                      if (r == 15) {
+                        k += 15;
+                      } else {                                 // end of band for 2^r + extra blocks, this one included
+                        eobrun = 1 << r;
+                        if (r) eobrun += (int)rd.bits(r);
+                        eobrun--;
+                        break;
+                      }
+                    }
+                  }
+                }
+              }
+          }
+        }
+        if (++mx == g.mcus_x) {
+          mx = 0;
+          my++;
+        }
+      }
+      continue;
+    }
+
+    // ---------------- AC refinement (one component): groups of eight blocks ----------------
+    {
+      const int c = c0;
+      const int p1 = 1 << sc.al;
+      const unsigned long long band = (sc.se >= 63 ? ~0ull : ((1ull << (sc.se + 1)) - 1ull)) & ~((1ull << sc.ss) - 1ull);
+      int16_t* base = coef_arena + im.coef_off[c];
+      const HuffDev& act = ht[3];
+      for (int n0 = m0; n0 < m1; n0 += kProgGroup) {
+        rd.refill(lane);
+        int16_t* ptr[kProgGroup];
+        int lo[kProgGroup], hi[kProgGroup];
+#pragma unroll
+        for (int q = 0; q < kProgGroup; q++) {
+          const int n = min(n0 + q, m1 - 1);
+          const int by = n / g.mcus_x, bx = n - by * g.mcus_x;
+          ptr[q] = base + ((size_t)by * im.comp_bw[c] + bx) * 64;
+          lo[q] = ptr[q][lane];
+          hi[q] = ptr[q][lane + 32];
+        }
+#pragma unroll
+        for (int q = 0; q < kProgGroup; q++) {
+          const uint32_t a = __ballot_sync(0xffffffffu, lo[q] != 0), b = __ballot_sync(0xffffffffu, hi[q] != 0);
+          if (lane == 0) s_nz[q] = (((unsigned long long)b << 32) | a) & band;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          const int cnt = min(kProgGroup, m1 - n0);
+#pragma unroll 1
+          for (int q = 0; q < cnt; q++) {
+            const unsigned long long nz = s_nz[q];
+            unsigned long long seg = 0, newp = 0, news = 0;
+            int nseg = 0;
+            int k = sc.ss;
+            if (eobrun == 0) {
+              while (k <= sc.se) {
+                rd.fill();
+                const uint32_t b32 = rd.top32();
+                int len;
+                const int rs = huff_decode(act, b32 >> 16, len);
+                int r = rs >> 4;
+                const int sz = rs & 15;
+                bool neg = false;
+                if (sz) {
+                  neg = !((b32 << len) >> 31);                 // a newly nonzero coefficient is +-1 at this bit position
+                  rd.skip(len + 1);
+                } else {
+                  rd.skip(len);
+                  if (r != 15) {
+                    eobrun = 1 << r;
+                    if (r) eobrun += (int)rd.bits(r);
+                    break;                                     // the rest of the band only takes correction bits
+                  }
+                }
+                // step over r still-zero coefficients: the target is the (r + 1)-th zero from k on; every nonzero
+                // coefficient passed on the way takes a correction bit
+                const unsigned long long from = ~0ull << k;
+                unsigned long long Z = ~nz & band & from;
+                for (; r > 0 && Z; r--) Z &= Z - 1;
+                const int target = Z ? __ffsll((long long)Z) - 1 : sc.se + 1;
+                const unsigned long long below = target >= 64 ? ~0ull : ((1ull << target) - 1ull);
+                const unsigned long long P = nz & from & below;
+                if (P) {
+                  seg |= 1ull << k;
+                  s_segpos[q][nseg++] = rd.pos();
+                  rd.skipn(__popcll(P));
+                }
+                if (sz && target <= sc.se) {
+                  newp |= 1ull << target;
+                  if (neg) news |= 1ull << target;
+                }
+                k = target + 1;
+              }
+            }
+            if (eobrun > 0) {
+              const unsigned long long P = k <= 63 ? nz & (~0ull << k) : 0ull;
+              if (P) {
+                seg |= 1ull << k;
+                s_segpos[q][nseg++] = rd.pos();
+                rd.skipn(__popcll(P));
+              }
+              eobrun--;
+            }
+            s_seg[q] = seg;
+            s_newp[q] = newp;
+            s_news[q] = news;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kProgGroup; q++) {
+          if (n0 + q >= m1) break;
+          const unsigned long long seg = s_seg[q], newp = s_newp[q], news = s_news[q], nz = s_nz[q];
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const int pos = lane + 32 * half;
+            int v = half ? hi[q] : lo[q];
+            const unsigned long long upto = (2ull << pos) - 1ull;        // positions <= pos
+            const unsigned long long started = seg & upto;               // segments that begin at or before this coefficient
+            bool cb = false;
+            if (((nz >> pos) & 1ull) && started) {
+              // the coefficient's segment is the last one started; its bit is the segment's first bit plus the number
+              // of nonzero coefficients between the segment's start and this one
+              const int ks = 63 - __clzll((long long)started);
+              const uint32_t rank = (uint32_t)__popcll(nz & (~0ull << ks) & (upto >> 1));
+              cb = rd.bit_at(s_segpos[q][__popcll(started) - 1] + rank) != 0u;
+            }
+            const bool nb = (newp >> pos) & 1ull;
+            if (cb && !(v & p1)) v += v >= 0 ? p1 : -p1;
+            if (nb) v = ((news >> pos) & 1ull) ? -p1 : p1;
+            if (cb || nb) ptr[q][pos] = (int16_t)v;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+}  // namespace irp

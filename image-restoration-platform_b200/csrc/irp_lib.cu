@@ -36,6 +36,7 @@
 #include "irp_resize_tma.cuh"
 #include "irp_resize_mma.cuh"
 #include "irp_jpeg.cuh"
+#include "irp_jpeg_prog.cuh"
 #include "irp_jpeg_enc.cuh"
 #include "irp_resize.cuh"
 

@@ -287,7 +287,7 @@ class Engine:
             if preprocess:
                 info = self.jpeg_info(k)
                 if info is None:
-                    raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a baseline JPEG the device decoder takes")
+                    raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a JPEG the device decoder takes")
                 ow, oh = self.preprocess_dims(info[0], info[1], o)
                 a = np.empty((oh, ow, 1 if info[2] == 1 else 3), np.uint8)
                 arrays.append(a)
@@ -307,7 +307,7 @@ class Engine:
         for i, k in enumerate(keep):
             info = self.jpeg_info(k)
             if info is None:
-                raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a baseline JPEG the device decoder takes")
+                raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a JPEG the device decoder takes")
             a = np.empty((info[1], info[0], info[2]), np.uint8)
             arrays.append(a)
             outs[i] = _ffi.OutDesc(a.ctypes.data, 0, a.nbytes, 0, 0, 0, 0)
@@ -397,7 +397,7 @@ class Engine:
             descs[i] = _ffi.JpegDesc(k.ctypes.data, k.size, o, 0)
             info = self.jpeg_info(k)
             if info is None:
-                raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a baseline JPEG the device decoder takes")
+                raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a JPEG the device decoder takes")
             ow, oh = self.preprocess_dims(info[0], info[1], o)
             caps.append(ow * oh * (1 if info[2] == 1 else 3) // 2 + 4096)
         res = (_ffi.Result * n)() if classify else None
@@ -424,7 +424,7 @@ class Engine:
         k = np.frombuffer(blob, np.uint8)
         info = self.jpeg_info(k)
         if info is None:
-            raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, "not a baseline JPEG the device decoder takes")
+            raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, "not a JPEG the device decoder takes")
         desc = _ffi.JpegDesc(k.ctypes.data, k.size, orientation, 0)
         outs, arr = None, None
         if preprocess:
@@ -443,7 +443,7 @@ class Engine:
         k = np.frombuffer(blob, np.uint8)
         info = self.jpeg_info(k)
         if info is None:
-            raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, "not a baseline JPEG the device decoder takes")
+            raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, "not a JPEG the device decoder takes")
         desc = _ffi.JpegDesc(k.ctypes.data, k.size, orientation, 0)
         ow, oh = self.preprocess_dims(info[0], info[1], orientation)
         # a file never exceeds its pixels by more than the header (and its profile) at q <= 95

@@ -3,8 +3,8 @@
 `preprocess_image(req, _res, next)` keeps the Express-middleware shape: it reads `req.file.buffer`,
 rewrites the same `req.file` fields (imagePreprocess.js:70-78), records the same operation strings
 (:43,54,64-65) and reports failures through `next(Problem)` with the same status codes (:25-34,81-90).
-Everything between the upload and the returned file runs in libirp_b200.so: baseline JPEG uploads are decoded on
-the device (other containers by Pillow on the host), then EXIF auto-orient, lanczos3 fit-inside <= 2048, normalise,
+Everything between the upload and the returned file runs in libirp_b200.so: JPEG uploads (baseline and progressive) are
+decoded on the device (other containers by Pillow on the host), then EXIF auto-orient, lanczos3 fit-inside <= 2048, normalise,
 and the q85 4:4:4 JPEG encode with optimised Huffman tables and the sRGB profile attached (SURVEY.md §8f rows 1-2;
 the file is libjpeg-turbo's optimised sequential file of those pixels, not mozjpeg's trellis / progressive one).
 """

@@ -28,7 +28,7 @@ extern "C" {
 enum {
   IRP_OK = 0,
   IRP_ERR_BAD_ARG = -1,     /* null pointer, bad dims, bad channel count        */
-  IRP_ERR_UNSUPPORTED = -2, /* C == 2, progressive JPEG, ...                          */
+  IRP_ERR_UNSUPPORTED = -2, /* C == 2, arithmetic-coded / lossless / CMYK JPEG, ...       */
   IRP_ERR_CUDA = -3,        /* a CUDA runtime call failed                       */
   IRP_ERR_NOMEM = -4,       /* host or device allocation failed                 */
   IRP_ERR_NO_DEVICE = -5,   /* no CUDA device / wrong architecture              */
@@ -182,10 +182,12 @@ int irp_fusion_prepare_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n_gro
  * baseline JPEG bytes, decode them ON THE DEVICE pixel-exact with that decoder
  * (parallel Huffman decode, integer IDCT, triangle chroma upsampling, YCbCr ->
  * RGB) and feed the pixels to the same kernels — ~4 MB instead of 36 MB per
- * 12 MP photo crosses PCIe and the host decodes nothing.  8-bit baseline
- * (SOF0/SOF1 Huffman), 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, with or
- * without restart markers; anything else returns IRP_ERR_UNSUPPORTED (no CPU
- * fallback). */
+ * 12 MP photo crosses PCIe and the host decodes nothing.  8-bit Huffman JPEG:
+ * baseline (SOF0/SOF1; one interleaved scan — the parallel self-synchronising
+ * decoder — or one scan per component) and progressive (SOF2, what
+ * imagePreprocess.js:57-61 writes: one warp per scan, scans in dependency
+ * levels), 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, with or without
+ * restart markers; anything else returns IRP_ERR_UNSUPPORTED (no CPU fallback). */
 typedef struct irp_jpeg_desc {
   const uint8_t *data;      /* host pointer to the JPEG file bytes          */
   size_t size;

@@ -15,7 +15,12 @@
  *   jidctint.c  jpeg_idct_islow (CONST_BITS 13, PASS1_BITS 2)
  *   jdsample.c  h2v1 / h2v2 / h1v2 fancy (triangle) upsampling, replicated edges
  *   jdcolor.c   YCbCr -> RGB with the 16-bit fixed-point tables
- * Scope: 8-bit baseline sequential (SOF0 / SOF1 Huffman), 1 or 3 components, sampling factors 1 or 2.
+ *   jdphuff.c   progressive scans: DC / AC first passes and refinements, EOB runs, correction bits
+ * Scope: 8-bit Huffman JPEG, baseline sequential (SOF0 / SOF1, one interleaved scan or one scan per component) and
+ * progressive (SOF2: spectral selection + successive approximation, what mozjpeg / `progressive: true` writes and
+ * imagePreprocess.js:57-61 therefore hands on), 1 or 3 components, sampling factors 1 or 2.  A complete progressive
+ * file needs no block smoothing (jdcoefct.c smooths only while AC precision is still missing), so its pixels are the
+ * IDCT of the final coefficients.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -50,6 +55,9 @@ typedef struct {
   const uint8_t* scan;
   size_t scan_len;
   int adobe_transform;  /* -1 none */
+  int progressive;      /* SOF2 */
+  int multi;            /* more than the one interleaved full-band scan: decode_multi() walks the scans */
+  size_t sos_pos;       /* index of the first SOS marker's 0xFF */
 } Jpeg;
 
 static int build_huff(HuffTab* t) {
@@ -65,6 +73,50 @@ static int build_huff(HuffTab* t) {
   t->maxcode[17] = 0xFFFFF;
   t->present = 1;
   return k <= 256 ? JO_OK : JO_ERR_FORMAT;
+}
+
+static int parse_dqt(Jpeg* J, const uint8_t* s, size_t sl) {
+  size_t o = 0;
+  while (o < sl) {
+    const int pq = s[o] >> 4, tq = s[o] & 15;
+    o++;
+    if (tq > 3) return JO_ERR_FORMAT;
+    for (int i = 0; i < 64; i++) {
+      int v;
+      if (pq) {
+        if (o + 2 > sl) return JO_ERR_FORMAT;
+        v = (s[o] << 8) | s[o + 1];
+        o += 2;
+      } else {
+        if (o + 1 > sl) return JO_ERR_FORMAT;
+        v = s[o++];
+      }
+      J->q[tq][kZigzag[i]] = (uint16_t)v;
+    }
+    J->qpresent[tq] = 1;
+  }
+  return JO_OK;
+}
+static int parse_dht(Jpeg* J, const uint8_t* s, size_t sl) {
+  size_t o = 0;
+  while (o < sl) {
+    if (o + 17 > sl) return JO_ERR_FORMAT;
+    const int tc = s[o] >> 4, th = s[o] & 15;
+    if (tc > 1 || th > 3) return JO_ERR_FORMAT;
+    HuffTab* t = tc ? &J->ac[th] : &J->dc[th];
+    int cnt = 0;
+    t->bits[0] = 0;
+    for (int l = 1; l <= 16; l++) {
+      t->bits[l] = s[o + l];
+      cnt += t->bits[l];
+    }
+    o += 17;
+    if (cnt > 256 || o + cnt > sl) return JO_ERR_FORMAT;
+    memcpy(t->vals, s + o, cnt);
+    o += cnt;
+    if (build_huff(t)) return JO_ERR_FORMAT;
+  }
+  return JO_OK;
 }
 
 static int parse(const uint8_t* d, size_t n, Jpeg* J) {
@@ -85,26 +137,10 @@ static int parse(const uint8_t* d, size_t n, Jpeg* J) {
     const uint8_t* s = d + p + 2;
     const size_t sl = len - 2;
     if (m == 0xDB) { /* DQT */
-      size_t o = 0;
-      while (o < sl) {
-        const int pq = s[o] >> 4, tq = s[o] & 15;
-        o++;
-        if (tq > 3) return JO_ERR_FORMAT;
-        for (int i = 0; i < 64; i++) {
-          int v;
-          if (pq) {
-            if (o + 2 > sl) return JO_ERR_FORMAT;
-            v = (s[o] << 8) | s[o + 1];
-            o += 2;
-          } else {
-            if (o + 1 > sl) return JO_ERR_FORMAT;
-            v = s[o++];
-          }
-          J->q[tq][kZigzag[i]] = (uint16_t)v;
-        }
-        J->qpresent[tq] = 1;
-      }
-    } else if (m == 0xC0 || m == 0xC1) { /* SOF0 / SOF1 */
+      const int rc = parse_dqt(J, s, sl);
+      if (rc) return rc;
+    } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) { /* SOF0 / SOF1 / SOF2 */
+      J->progressive = m == 0xC2;
       if (sl < 6 || s[0] != 8) return JO_ERR_UNSUPPORTED;
       J->h = (s[1] << 8) | s[2];
       J->w = (s[3] << 8) | s[4];
@@ -117,27 +153,11 @@ static int parse(const uint8_t* d, size_t n, Jpeg* J) {
         J->comp[i].tq = s[8 + 3 * i];
         if (J->comp[i].h < 1 || J->comp[i].h > 2 || J->comp[i].v < 1 || J->comp[i].v > 2 || J->comp[i].tq > 3) return JO_ERR_UNSUPPORTED;
       }
-    } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
-      return JO_ERR_UNSUPPORTED; /* progressive, lossless, arithmetic */
+    } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      return JO_ERR_UNSUPPORTED; /* lossless, arithmetic, hierarchical */
     } else if (m == 0xC4) { /* DHT */
-      size_t o = 0;
-      while (o < sl) {
-        if (o + 17 > sl) return JO_ERR_FORMAT;
-        const int tc = s[o] >> 4, th = s[o] & 15;
-        if (tc > 1 || th > 3) return JO_ERR_FORMAT;
-        HuffTab* t = tc ? &J->ac[th] : &J->dc[th];
-        int cnt = 0;
-        t->bits[0] = 0;
-        for (int l = 1; l <= 16; l++) {
-          t->bits[l] = s[o + l];
-          cnt += t->bits[l];
-        }
-        o += 17;
-        if (cnt > 256 || o + cnt > sl) return JO_ERR_FORMAT;
-        memcpy(t->vals, s + o, cnt);
-        o += cnt;
-        if (build_huff(t)) return JO_ERR_FORMAT;
-      }
+      const int rc = parse_dht(J, s, sl);
+      if (rc) return rc;
     } else if (m == 0xDD) { /* DRI */
       if (sl < 2) return JO_ERR_FORMAT;
       J->restart = (s[0] << 8) | s[1];
@@ -146,18 +166,21 @@ static int parse(const uint8_t* d, size_t n, Jpeg* J) {
     } else if (m == 0xDA) { /* SOS */
       if (!J->w || sl < 1) return JO_ERR_FORMAT;
       const int ns = s[0];
-      if (ns != J->ncomp || sl < (size_t)(1 + 2 * ns + 3)) return JO_ERR_UNSUPPORTED; /* non-interleaved scans not handled */
-      for (int i = 0; i < ns; i++) {
-        int ci = -1;
-        for (int k = 0; k < J->ncomp; k++)
-          if (J->comp[k].id == s[1 + 2 * i]) ci = k;
-        if (ci != i) return JO_ERR_UNSUPPORTED;
-        J->comp[ci].td = s[2 + 2 * i] >> 4;
-        J->comp[ci].ta = s[2 + 2 * i] & 15;
+      if (ns < 1 || ns > J->ncomp || sl < (size_t)(1 + 2 * ns + 3)) return JO_ERR_FORMAT;
+      J->sos_pos = p - 2;
+      J->multi = J->progressive || ns != J->ncomp || s[1 + 2 * ns] != 0 || s[2 + 2 * ns] != 63 || s[3 + 2 * ns] != 0;
+      if (!J->multi) {
+        for (int i = 0; i < ns; i++) {
+          int ci = -1;
+          for (int k = 0; k < J->ncomp; k++)
+            if (J->comp[k].id == s[1 + 2 * i]) ci = k;
+          if (ci != i) return JO_ERR_UNSUPPORTED;
+          J->comp[ci].td = s[2 + 2 * i] >> 4;
+          J->comp[ci].ta = s[2 + 2 * i] & 15;
+        }
+        J->scan = d + p + len;
+        J->scan_len = n - (p + len);
       }
-      if (s[1 + 2 * ns] != 0 || s[2 + 2 * ns] != 63 || s[3 + 2 * ns] != 0) return JO_ERR_UNSUPPORTED;
-      J->scan = d + p + len;
-      J->scan_len = n - (p + len);
       break;
     }
     p += len;
@@ -176,7 +199,8 @@ static int parse(const uint8_t* d, size_t n, Jpeg* J) {
     c->bh = J->mcuy * c->v;
     c->dw = (J->w * c->h + J->hmax - 1) / J->hmax;
     c->dh = (J->h * c->v + J->vmax - 1) / J->vmax;
-    if (!J->qpresent[c->tq] || !J->dc[c->td].present || !J->ac[c->ta].present) return JO_ERR_FORMAT;
+    if (!J->qpresent[c->tq]) return JO_ERR_FORMAT;
+    if (!J->multi && (!J->dc[c->td].present || !J->ac[c->ta].present)) return JO_ERR_FORMAT;
   }
   return JO_OK;
 }
@@ -278,6 +302,195 @@ static int decode_scan(Jpeg* J) {
       togo--;
     }
   return JO_OK;
+}
+
+/* ---- every scan of a multi-scan file (jdphuff.c; sequential scans of single components go the same way) ---- */
+typedef struct {
+  int ns, ci[3], td[3], ta[3], ss, se, ah, al;
+} ScanHdr;
+
+static int restart_sync(Bits* b) { /* byte-align, step over the RSTn marker */
+  b->acc = 0;
+  b->cnt = 0;
+  if (!b->marker) {
+    while (b->p + 1 < b->n && !(b->d[b->p] == 0xFF && b->d[b->p + 1] >= 0xD0 && b->d[b->p + 1] <= 0xD7)) b->p++;
+    if (b->p + 1 >= b->n) return JO_ERR_FORMAT;
+    b->p += 2;
+  }
+  b->marker = 0;
+  return JO_OK;
+}
+
+/* one block of an AC refinement scan (decode_mcu_AC_refine) */
+static void ac_refine_block(Bits* b, const HuffTab* t, int16_t* blk, const ScanHdr* h, int* eobrun) {
+  const int p1 = 1 << h->al, m1 = -(1 << h->al);
+  int k = h->ss;
+  if (*eobrun == 0) {
+    for (; k <= h->se; k++) {
+      const int rs = decode_sym(b, t);
+      int r = rs >> 4, s = rs & 15;
+      if (s) {
+        s = getbits(b, 1) ? p1 : m1; /* a newly nonzero coefficient is +-1 at this bit position */
+      } else if (r != 15) {
+        *eobrun = 1 << r;
+        if (r) *eobrun += getbits(b, r);
+        break; /* the rest of the band only takes correction bits */
+      }
+      /* step over r still-zero coefficients; every nonzero one met on the way takes a correction bit */
+      do {
+        int16_t* c = blk + kZigzag[k];
+        if (*c) {
+          if (getbits(b, 1) && !(*c & p1)) *c = (int16_t)(*c >= 0 ? *c + p1 : *c + m1);
+        } else if (--r < 0) {
+          break;
+        }
+        k++;
+      } while (k <= h->se);
+      if (s && k <= h->se) blk[kZigzag[k]] = (int16_t)s;
+    }
+  }
+  if (*eobrun > 0) {
+    for (; k <= h->se; k++) {
+      int16_t* c = blk + kZigzag[k];
+      if (*c && getbits(b, 1) && !(*c & p1)) *c = (int16_t)(*c >= 0 ? *c + p1 : *c + m1);
+    }
+    (*eobrun)--;
+  }
+}
+
+static int decode_one_scan(Jpeg* J, const ScanHdr* h, const uint8_t* data, size_t len) {
+  Bits b = {data, len, 0, 0, 0, 0};
+  int pred[3] = {0, 0, 0}, eobrun = 0, togo = J->restart;
+  /* a scan of one component walks that component's own blocks (ceil(samples / 8)), not the MCU-padded grid */
+  const int single = h->ns == 1;
+  const Comp* c0 = &J->comp[h->ci[0]];
+  const int mx_n = single ? (c0->dw + 7) / 8 : J->mcux, my_n = single ? (c0->dh + 7) / 8 : J->mcuy;
+  for (int my = 0; my < my_n; my++)
+    for (int mx = 0; mx < mx_n; mx++) {
+      if (J->restart && togo == 0) {
+        if (restart_sync(&b)) return JO_ERR_FORMAT;
+        pred[0] = pred[1] = pred[2] = 0;
+        eobrun = 0;
+        togo = J->restart;
+      }
+      for (int i = 0; i < h->ns; i++) {
+        Comp* c = &J->comp[h->ci[i]];
+        const int nh = single ? 1 : c->h, nv = single ? 1 : c->v;
+        for (int by = 0; by < nv; by++)
+          for (int bx = 0; bx < nh; bx++) {
+            int16_t* blk = c->coef + ((size_t)(my * nv + by) * c->bw + (mx * nh + bx)) * 64;
+            if (h->ss == 0) {
+              if (h->ah == 0) { /* DC first pass (also the DC of a sequential scan) */
+                const int s = decode_sym(&b, &J->dc[h->td[i]]);
+                if (s) pred[i] += extend(getbits(&b, s), s);
+                blk[0] = (int16_t)(pred[i] * (1 << h->al));
+              } else if (getbits(&b, 1)) { /* DC refinement: one more bit */
+                blk[0] |= (int16_t)(1 << h->al);
+              }
+              if (!J->progressive) { /* sequential: the AC coefficients follow in the same scan */
+                for (int k = 1; k < 64; k++) {
+                  const int rs = decode_sym(&b, &J->ac[h->ta[i]]);
+                  const int r = rs >> 4, s = rs & 15;
+                  if (s) {
+                    k += r;
+                    if (k > 63) break;
+                    blk[kZigzag[k]] = (int16_t)extend(getbits(&b, s), s);
+                  } else {
+                    if (r != 15) break;
+                    k += 15;
+                  }
+                }
+              }
+            } else if (h->ah == 0) { /* AC first pass */
+              if (eobrun > 0) {
+                eobrun--;
+              } else {
+                for (int k = h->ss; k <= h->se; k++) {
+                  const int rs = decode_sym(&b, &J->ac[h->ta[i]]);
+                  const int r = rs >> 4, s = rs & 15;
+                  if (s) {
+                    k += r;
+                    if (k > 63) break;
+                    blk[kZigzag[k]] = (int16_t)(extend(getbits(&b, s), s) * (1 << h->al));
+                  } else if (r == 15) {
+                    k += 15;
+                  } else {
+                    eobrun = 1 << r;
+                    if (r) eobrun += getbits(&b, r);
+                    eobrun--; /* this block is the first of the run */
+                    break;
+                  }
+                }
+              }
+            } else {
+              ac_refine_block(&b, &J->ac[h->ta[i]], blk, h, &eobrun);
+            }
+          }
+      }
+      togo--;
+    }
+  return JO_OK;
+}
+
+static int decode_multi(Jpeg* J, const uint8_t* d, size_t n) {
+  size_t p = J->sos_pos;
+  for (;;) {
+    if (p + 2 > n) return JO_OK; /* no EOI: what was decoded stands */
+    if (d[p] != 0xFF) return JO_ERR_FORMAT;
+    while (p < n && d[p] == 0xFF) p++;
+    if (p >= n) return JO_OK;
+    const int m = d[p++];
+    if (m == 0xD9) return JO_OK;
+    if (p + 2 > n) return JO_ERR_FORMAT;
+    const size_t len = ((size_t)d[p] << 8) | d[p + 1];
+    if (len < 2 || p + len > n) return JO_ERR_FORMAT;
+    const uint8_t* s = d + p + 2;
+    const size_t sl = len - 2;
+    int rc = JO_OK;
+    if (m == 0xC4) rc = parse_dht(J, s, sl);
+    else if (m == 0xDB) rc = parse_dqt(J, s, sl);
+    else if (m == 0xDD) {
+      if (sl < 2) return JO_ERR_FORMAT;
+      J->restart = (s[0] << 8) | s[1];
+    } else if (m == 0xDA) {
+      ScanHdr h;
+      if (sl < 1) return JO_ERR_FORMAT;
+      h.ns = s[0];
+      if (h.ns < 1 || h.ns > J->ncomp || sl < (size_t)(1 + 2 * h.ns + 3)) return JO_ERR_FORMAT;
+      for (int i = 0; i < h.ns; i++) {
+        h.ci[i] = -1;
+        for (int k = 0; k < J->ncomp; k++)
+          if (J->comp[k].id == s[1 + 2 * i]) h.ci[i] = k;
+        if (h.ci[i] < 0) return JO_ERR_FORMAT;
+        h.td[i] = s[2 + 2 * i] >> 4;
+        h.ta[i] = s[2 + 2 * i] & 15;
+        if (h.td[i] > 3 || h.ta[i] > 3) return JO_ERR_FORMAT;
+      }
+      h.ss = s[1 + 2 * h.ns];
+      h.se = s[2 + 2 * h.ns];
+      h.ah = s[3 + 2 * h.ns] >> 4;
+      h.al = s[3 + 2 * h.ns] & 15;
+      if (J->progressive) {
+        if (h.ss > h.se || h.se > 63 || (h.ss == 0 && h.se != 0) || (h.ss > 0 && h.ns != 1) || h.al > 13) return JO_ERR_FORMAT;
+      } else if (h.ss != 0 || h.se != 63 || h.ah || h.al) {
+        return JO_ERR_FORMAT;
+      }
+      for (int i = 0; i < h.ns; i++) {
+        if (h.ss == 0 && h.ah == 0 && !J->dc[h.td[i]].present) return JO_ERR_FORMAT;
+        if ((h.ss > 0 || !J->progressive) && !J->ac[h.ta[i]].present) return JO_ERR_FORMAT;
+      }
+      /* the entropy-coded segment runs to the next marker that is neither a stuffed zero nor RSTn */
+      size_t e = p + len;
+      const size_t d0 = e;
+      while (e + 1 < n && !(d[e] == 0xFF && d[e + 1] != 0x00 && d[e + 1] != 0xFF && !(d[e + 1] >= 0xD0 && d[e + 1] <= 0xD7))) e++;
+      if (e + 1 >= n) e = n;
+      if ((rc = decode_one_scan(J, &h, d + d0, e - d0))) return rc;
+      p = e;
+      continue;
+    }
+    if (rc) return rc;
+    p += len;
+  }
 }
 
 /* ---- jidctint.c ---- */
@@ -485,7 +698,7 @@ int irp_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out, int16_t* coef
       return JO_ERR_NOMEM;
     }
   }
-  if ((rc = decode_scan(&J))) {
+  if ((rc = J.multi ? decode_multi(&J, data, len) : decode_scan(&J))) {
     free_all(&J);
     return rc;
   }

@@ -151,7 +151,10 @@ def test_jpeg_header_parse_runs_without_a_gpu():
         assert info(enc(rgb, quality=80, subsampling=ss)) == (0, (53, 37, 3))
     assert info(enc(rgb[:, :, 0], quality=80)) == (0, (53, 37, 1))
     assert info(enc(rgb, quality=80, restart_marker_rows=1)) == (0, (53, 37, 3))
-    assert info(enc(rgb, quality=80, progressive=True))[0] == _ffi.IRP_ERR_UNSUPPORTED
+    assert info(enc(rgb, quality=80, progressive=True)) == (0, (53, 37, 3))
+    b4 = io.BytesIO()
+    Image.fromarray(rgb).convert("CMYK").save(b4, "JPEG", quality=80)
+    assert info(b4.getvalue())[0] == _ffi.IRP_ERR_UNSUPPORTED   # four components
     assert info(b"\x89PNG\r\n\x1a\n" + b"\0" * 64)[0] == _ffi.IRP_ERR_UNSUPPORTED
     assert info(enc(rgb, quality=80)[:40])[0] == _ffi.IRP_ERR_UNSUPPORTED   # truncated inside the header
 

@@ -91,7 +91,7 @@ def test_a_failing_request_fails_alone(engine, oracle):
 
 def test_concurrent_jpeg_file_requests(engine, oracle):
     """JPEG files submitted one by one from several threads: decoded on the device in whatever batch the
-    dispatcher formed, each answer equal to the oracle's on libjpeg-turbo's pixels; a progressive file is refused
+    dispatcher formed, each answer equal to the oracle's on libjpeg-turbo's pixels; a file that is not a JPEG is refused
     at submission by the wrapper and a mixed queue (raw + file requests) works."""
     import io
 
@@ -135,7 +135,7 @@ def test_concurrent_jpeg_file_requests(engine, oracle):
     import irp_b200
 
     with pytest.raises(irp_b200.IrpError):
-        engine.submit_jpeg(enc(rand_image(64, 64, 3, seed=1), quality=80, progressive=True))
+        engine.submit_jpeg(b"\x89PNG\r\n\x1a\n" + b"\0" * 64)
 
 
 def test_concurrent_transcode_requests(engine, oracle):

@@ -7,11 +7,14 @@ import io
 
 import numpy as np
 import pytest
-from PIL import Image
+from PIL import Image, ImageFile
 
 from conftest import assert_result_parity, rand_image
 
 pytestmark = pytest.mark.gpu
+
+
+ImageFile.MAXBLOCK = 1 << 24   # progressive files of noisy images outgrow Pillow's default encoder buffer
 
 
 def _encode(img, **kw):
@@ -105,12 +108,65 @@ def test_analyze_from_compressed_bytes_equals_analyze_from_pixels(engine, oracle
         assert np.array_equal(arrays[i], oracle.preprocess(px, orients[i]))
 
 
-def test_progressive_is_refused_loudly(engine):
+PROG_SHAPES = [(8, 8), (1, 1), (3, 5), (17, 33), (37, 53), (100, 161), (241, 319), (600, 900)]
+
+
+@pytest.mark.parametrize("subsampling", [0, 1, 2])
+def test_progressive_matches_libjpeg_turbo(engine, subsampling):
+    """SOF2 files (spectral selection + successive approximation: libjpeg's standard script, what `progressive: true`
+    writes — imagePreprocess.js:57-61) decoded on the device scan by scan (prog_scan_kernel): pixels equal to
+    libjpeg-turbo's and to the pinned restatement, for fixed and optimised tables, with restart intervals, in one batch
+    together with baseline files."""
+    from oracle import jpeg_oracle
+
+    blobs = []
+    for i, (h, w) in enumerate(PROG_SHAPES):
+        img = rand_image(h, w, 3, seed=200 + i, kind="smooth" if i % 2 else "noise")
+        kw = [{}, {"optimize": True}, {"restart_marker_blocks": 5}][i % 3]
+        blobs.append(_encode(img, quality=(35, 80, 95)[i % 3], subsampling=subsampling, progressive=True, **kw))
+        if i % 4 == 0:
+            blobs.append(_encode(img, quality=85, subsampling=subsampling))          # a baseline neighbour in the same launch
+    blobs.append(_encode(rand_image(77, 130, 1, seed=9)[:, :, 0], quality=70, progressive=True))   # greyscale
+    got = _decode_batch(engine, blobs)
+    for b, g in zip(blobs, got):
+        ref = _pillow(b)
+        assert np.array_equal(g, ref), f"{ref.shape}: max diff {np.abs(g.astype(int) - ref).max()}"
+        assert np.array_equal(g, jpeg_oracle.decode(b))
+
+
+def test_progressive_photo_sized_and_analyzed(engine, oracle):
+    """A 3 MP progressive file — the size preprocessImage hands on — through irp_analyze_jpeg_batch: scores and
+    preprocessed pixels equal those computed from libjpeg-turbo's pixels."""
+    from irp_b200 import _ffi
+    from irp_b200.engine import result_to_dict
+
+    img = rand_image(1536, 2048, 3, seed=77, kind="smooth")
+    blob = _encode(img, quality=85, subsampling=2, progressive=True, optimize=True)
+    px = np.ascontiguousarray(_pillow(blob))
+    assert np.array_equal(_decode_batch(engine, [blob])[0], px)
+    keep = np.frombuffer(blob, np.uint8)
+    descs = (_ffi.JpegDesc * 1)(_ffi.JpegDesc(keep.ctypes.data, keep.size, 1, 0))
+    res = (_ffi.Result * 1)()
+    ow, oh = engine.preprocess_dims(px.shape[1], px.shape[0], 1)
+    a = np.empty((oh, ow, 3), np.uint8)
+    outs = (_ffi.OutDesc * 1)(_ffi.OutDesc(a.ctypes.data, 0, a.nbytes, 0, 0, 0, 0))
+    engine._check(engine._lib.irp_analyze_jpeg_batch(engine._ctx, descs, 1, res, outs))
+    assert_result_parity(result_to_dict(res[0]), oracle.classify(px), 3, "progressive")
+    assert np.array_equal(a, oracle.preprocess(px, 1))
+
+
+def test_unsupported_kinds_are_refused_loudly(engine):
     from irp_b200 import _ffi
 
-    blob = np.frombuffer(_encode(rand_image(64, 64, 3, seed=1), quality=80, progressive=True), np.uint8)
+    cmyk = np.frombuffer(_encode_cmyk(), np.uint8)
     w, h, c = C.c_int(), C.c_int(), C.c_int()
-    assert engine._lib.irp_jpeg_info(blob.ctypes.data, blob.size, C.byref(w), C.byref(h), C.byref(c)) == _ffi.IRP_ERR_UNSUPPORTED
+    assert engine._lib.irp_jpeg_info(cmyk.ctypes.data, cmyk.size, C.byref(w), C.byref(h), C.byref(c)) == _ffi.IRP_ERR_UNSUPPORTED
+
+
+def _encode_cmyk():
+    b = io.BytesIO()
+    Image.fromarray(rand_image(64, 64, 3, seed=1)).convert("CMYK").save(b, "JPEG", quality=80)
+    return b.getvalue()
 
 
 def test_truncated_and_corrupted_streams_do_not_poison_the_context(engine):
