@@ -146,6 +146,20 @@ __device__ __forceinline__ void hist_add_dp(const Tiles<3>& T, uint32_t t) {
   red_inc_shared(dp4a_uu(t, 0x04000000u, T.a_hist));
 }
 
+// Horizontal [12,20,12]/44 pass (== floor((3(l+r) + 5c + 5) / 11), irp_classify.cuh stage 3) of the four pixels of planar
+// word c; l ends with the pixel left of them (its byte 3), r starts with the pixel right of them (its byte 0).  Stage 1
+// runs it while the pixels are in registers and stores the BLURRED rows: stage 3 then only has the vertical pass to do,
+// reads one word instead of three per strip and row, and the rows a thread's window shares with its neighbour's are
+// blurred once instead of twice.
+__device__ __forceinline__ uint32_t hblur_word(uint32_t l, uint32_t c, uint32_t r) {
+  constexpr BlurK bk = blur_exact();
+  const uint32_t w0 = __funnelshift_r(l, c, 24);  // (l3, c0, c1, c2)
+  const uint32_t w3 = __funnelshift_r(c, r, 16);  // (c2, c3, r0, r1)
+  const uint32_t z0 = __dp4a(w0, bk.w, bk.bias) * bk.mul, z1 = __dp4a(c, bk.w, bk.bias) * bk.mul;
+  const uint32_t z2 = __dp4a(c, bk.w << 8, bk.bias) * bk.mul, z3 = __dp4a(w3, bk.w, bk.bias) * bk.mul;
+  return __byte_perm(__byte_perm(z0, z1, 0x0062), __byte_perm(z2, z3, 0x0062), 0x5410);   // the quotients are the products' byte 2
+}
+
 // 4 pixels (12 interleaved bytes in w0..w2) -> planar words + grey word.
 // nvalid < 4 masks the moments / histogram (image edge); COUNTED = false for halo rows.
 template <bool COUNTED, bool MASKED>
@@ -185,19 +199,70 @@ __device__ __forceinline__ void s1_quad(const Tiles<3>& T, const MulConsts& mc, 
   Y = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x0073), 0x5410);
 }
 
-// one 16-pixel segment of a core row: 3 x LDS.128 from the raw tile -> 4 x STS.128 to the planes
+// one 16-pixel segment of a core row: 3 x LDS.128 (+ the two neighbour pixels) from the raw tile -> 4 x STS.128 to the
+// planes: grey, and the horizontally blurred R, G, B
 template <bool COUNTED, bool MASKED>
 __device__ __forceinline__ void s1_segment(const Tiles<3>& T, const MulConsts& mc, Acc<3>& a, uint32_t raw_addr, uint32_t plane_addr, int nvalid) {
   const uint4 v0 = lds_v4(raw_addr), v1 = lds_v4(raw_addr + 16), v2 = lds_v4(raw_addr + 32);
+  const uint32_t lw = lds_b32(raw_addr - 4), rw = lds_b32(raw_addr + 48);   // (x, R, G, B) of pixel -1 | (R, G, B, x) of pixel 16
   const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
   uint32_t R[4], G[4], B[4], Y[4];
 #pragma unroll
   for (int k = 0; k < 4; k++)
     s1_quad<COUNTED, MASKED>(T, mc, a, w[3 * k], w[3 * k + 1], w[3 * k + 2], nvalid - 4 * k, R[k], G[k], B[k], Y[k]);
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr), "r"(Y[0]), "r"(Y[1]), "r"(Y[2]), "r"(Y[3]) : "memory");
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + kBPlane), "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]) : "memory");
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + 2 * kBPlane), "r"(G[0]), "r"(G[1]), "r"(G[2]), "r"(G[3]) : "memory");
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + 3 * kBPlane), "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]) : "memory");
+  if (IRP_ABLATE & 4) return;
+  // left neighbours as words that END with the pixel (byte 3), right neighbours as words that START with it (byte 0)
+  const uint32_t lR = lw << 16, lG = lw << 8, lB = lw, rR = rw, rG = rw >> 8, rB = rw >> 16;
+  uint32_t H[4];
+  H[0] = hblur_word(lR, R[0], R[1]); H[1] = hblur_word(R[0], R[1], R[2]); H[2] = hblur_word(R[1], R[2], R[3]); H[3] = hblur_word(R[2], R[3], rR);
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + kBPlane), "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]) : "memory");
+  H[0] = hblur_word(lG, G[0], G[1]); H[1] = hblur_word(G[0], G[1], G[2]); H[2] = hblur_word(G[1], G[2], G[3]); H[3] = hblur_word(G[2], G[3], rG);
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + 2 * kBPlane), "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]) : "memory");
+  H[0] = hblur_word(lB, B[0], B[1]); H[1] = hblur_word(B[0], B[1], B[2]); H[2] = hblur_word(B[1], B[2], B[3]); H[3] = hblur_word(B[2], B[3], rB);
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(plane_addr + 3 * kBPlane), "r"(H[0]), "r"(H[1]), "r"(H[2]), "r"(H[3]) : "memory");
+}
+
+// Stage 3 of the streaming kernel: the VERTICAL [12,20,12]/44 pass over rows stage 1 already blurred horizontally
+// (same arithmetic and the same sums as stage3<> of irp_classify.cuh, which tests/test_gpu_paths.py holds it equal to).
+template <bool FULL>
+__device__ __forceinline__ void stage3v(const Tiles<3>& T, Acc<3>& a, int tid, int x0, int y0, int W, int H) {
+  constexpr BlurK bk = blur_exact();
+  const int strip = tid & (kStrips - 1), rg = tid / kStrips;
+  const int x = x0 + strip * 4;
+  const int r0 = rg * 8;
+  int nvalid = 4, nrows = 8;
+  if (!FULL) {
+    if (x >= W || y0 + r0 >= H) return;
+    nvalid = min(4, W - x);
+    nrows = min(8, H - (y0 + r0));
+  }
+  const uint32_t vmask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+#pragma unroll 1   // one copy of the row loop: the hot code has to stay inside the instruction cache
+  for (int ch = 0; ch < 3; ch++) {
+    const uint32_t* hp = reinterpret_cast<const uint32_t*>(T.plane[0] + ch * kBPlane + r0 * kBPitch) + 4 + strip;
+    // per column a sliding window of horizontal results: bytes (up, cur, dn, 0)
+    uint32_t win[4];
+    {
+      const uint32_t up = hp[0], cur = hp[kBPitch / 4];
+      win[0] = __byte_perm(up, cur, 0x7400); win[1] = __byte_perm(up, cur, 0x7510);
+      win[2] = __byte_perm(up, cur, 0x7620); win[3] = __byte_perm(up, cur, 0x7730);      // (-, up, cur, 0)
+    }
+#pragma unroll 4
+    for (int i = 0; i < 8; i++) {
+      if (!FULL && i >= nrows) break;
+      const uint32_t dn = hp[(i + 2) * (kBPitch / 4)];
+      uint32_t zz[4];
+      win[0] = __byte_perm(win[0], dn, 0x7421); win[1] = __byte_perm(win[1], dn, 0x7521);
+      win[2] = __byte_perm(win[2], dn, 0x7621); win[3] = __byte_perm(win[3], dn, 0x7721);  // (up, cur, dn, 0)
+#pragma unroll
+      for (int j = 0; j < 4; j++) zz[j] = __dp4a(win[j], bk.w, bk.bias) * bk.mul;         // vertical result in byte 2
+      uint32_t b4 = __byte_perm(__byte_perm(zz[0], zz[1], 0x0062), __byte_perm(zz[2], zz[3], 0x0062), 0x5410);
+      if (!FULL) b4 &= vmask;
+      a.bs = __dp4a(b4, 0x01010101u, a.bs);
+      a.bq = __dp4a(b4, b4, a.bq);
+    }
+  }
 }
 
 // the issuing warp: describe this group's next tile and start its row copies
@@ -340,7 +405,8 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
           s1_segment<false, false>(T, mc, acc, ra, pa, 0);
       }
     }
-    // halo rows (0 and 33) as 4-pixel pieces, halo columns as single pixels: spread over the group
+    // halo rows (0 and 33) as 4-pixel pieces, halo columns (grey only: the vertical blur pass has no horizontal
+    // neighbours) as single pixels: spread over the group
     if (tid >= 64) {
       const int q = tid - 64;
       const int row = (q >> 5) ? kRows - 1 : 0, c4 = q & 31;
@@ -349,9 +415,12 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
         uint32_t R, G, B, Y;
         s1_quad<false, false>(T, mc, acc, lds_b32(ra), lds_b32(ra + 4), lds_b32(ra + 8), 0, R, G, B, Y);
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(Y) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + kBPlane), "r"(R) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + 2 * kBPlane), "r"(G) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + 3 * kBPlane), "r"(B) : "memory");
+        if (!(IRP_ABLATE & 4)) {
+          const uint32_t lw = lds_b32(ra - 4), rw = lds_b32(ra + 12);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + kBPlane), "r"(hblur_word(lw << 16, R, rw)) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + 2 * kBPlane), "r"(hblur_word(lw << 8, G, rw >> 8)) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa + 3 * kBPlane), "r"(hblur_word(lw, B, rw >> 16)) : "memory");
+        }
       }
     }
     if (tid < 2 * kRows) {
@@ -360,11 +429,7 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
       const uint32_t ra = a_raw + row * kRawPitch + (right ? 16 + 3 * vw : 13);
       const uint32_t pa = a_planes + (right ? row * kBPitch + 16 + vw : row * kBPitch + 15);
       const uint32_t r = lds_u8(ra), g = lds_u8(ra + 1), b = lds_u8(ra + 2);
-      const uint32_t y = grey_top_off(T, r << 2, g << 2, b << 2) >> 24;
-      sts_u8(pa, y);
-      sts_u8(pa + kBPlane, r);
-      sts_u8(pa + 2 * kBPlane, g);
-      sts_u8(pa + 3 * kBPlane, b);
+      sts_u8(pa, grey_top_off(T, r << 2, g << 2, b << 2) >> 24);
     }
     group_barrier(group);
 
@@ -374,10 +439,10 @@ classify_bulk_kernel(const ImgDev* __restrict__ imgs, const TmaDesc* __restrict_
     // ---- stage 2 + 3 on the planes ----
     if (full) {
       if (!(IRP_ABLATE & 2)) stage2<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
-      if (!(IRP_ABLATE & 4)) stage3<3, true, kBPitch>(T, acc, tid, x0, y0, W, H);
+      if (!(IRP_ABLATE & 4)) stage3v<true>(T, acc, tid, x0, y0, W, H);
     } else {
       if (!(IRP_ABLATE & 2)) stage2<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
-      if (!(IRP_ABLATE & 4)) stage3<3, false, kBPitch>(T, acc, tid, x0, y0, W, H);
+      if (!(IRP_ABLATE & 4)) stage3v<false>(T, acc, tid, x0, y0, W, H);
     }
     group_barrier(group);
   }
