@@ -155,6 +155,19 @@ def test_progressive_photo_sized_and_analyzed(engine, oracle):
     assert np.array_equal(a, oracle.preprocess(px, 1))
 
 
+def test_progressive_upload_through_the_whole_upload_route(engine, oracle):
+    """analyze(buf) + preprocessImage(buf) of ONE progressive upload with files on both sides (irp_transcode_jpeg_batch):
+    the returned file is libjpeg-turbo's encoding of the oracle's preprocessed pixels of libjpeg-turbo's decode."""
+    img = rand_image(900, 1300, 3, seed=31, kind="smooth")
+    blob = _encode(img, quality=88, subsampling=2, progressive=True)
+    px = np.ascontiguousarray(_pillow(blob))
+    res, files = engine.transcode_jpeg_batch([blob], quality=85)
+    assert_result_parity(res[0], oracle.classify(px), 3, "progressive upload")
+    b = io.BytesIO()
+    Image.fromarray(oracle.preprocess(px, 1)).save(b, "JPEG", quality=85, subsampling=0)
+    assert files[0] == b.getvalue()
+
+
 def test_unsupported_kinds_are_refused_loudly(engine):
     from irp_b200 import _ffi
 

@@ -110,3 +110,65 @@ def test_restart_marker_flood_is_refused_without_overrunning_the_upload_slot(eng
         engine.decode_jpeg_batch([neighbour, bad, good])
     outs = engine.decode_jpeg_batch([neighbour, good])
     assert np.array_equal(outs[0], np.asarray(Image.open(io.BytesIO(neighbour)))) and np.array_equal(outs[1], ref)
+
+
+def _markers(data):
+    """(offset, marker, segment length) of every marker segment up to EOI, entropy-coded data skipped."""
+    out, p = [], 2
+    while p + 4 <= len(data):
+        if data[p] != 0xFF:
+            p += 1
+            continue
+        m = data[p + 1]
+        if m in (0x00, 0xFF) or 0xD0 <= m <= 0xD7:
+            p += 2 if m != 0xFF else 1
+            continue
+        if m == 0xD9:
+            break
+        ln = (data[p + 2] << 8) | data[p + 3]
+        out.append((p, m, ln))
+        p += 2 + ln
+    return out
+
+
+@pytest.mark.parametrize("subsampling", [0, 2])
+def test_damaged_progressive_files_neither_fault_nor_poison_the_context(engine, subsampling):
+    """The same for multi-scan files: cuts inside any scan, flipped bytes in the entropy-coded data of every scan,
+    scan headers with out-of-range parameters, a missing scan.  prog_scan_kernel's loops are bounded by the frame
+    geometry, so damaged data can only produce wrong coefficients, never a hang or an out-of-range store."""
+    rng = np.random.default_rng(300 + subsampling)
+    img = rand_image(320, 480, 3, seed=23, kind="smooth")
+    good = _encode(img, quality=85, subsampling=subsampling, progressive=True)
+    ref = np.asarray(Image.open(io.BytesIO(good)))
+    segs = _markers(good)
+    sos = [(p, ln) for p, m, ln in segs if m == 0xDA]
+    assert len(sos) >= 6
+    variants = []
+    for cut in sorted(rng.integers(sos[0][0] + 20, len(good) - 2, 16)):   # truncated inside some scan
+        variants.append(good[:int(cut)])
+    for k in (1, 5, 50, 400):                                            # flipped bytes anywhere after the first SOS
+        b = bytearray(good)
+        for pos in rng.integers(sos[0][0] + sos[0][1] + 2, len(good) - 2, k):
+            b[int(pos)] ^= int(rng.integers(1, 256))
+        variants.append(bytes(b))
+    for (p, ln), (off, val) in zip(sos, [(-3, 70), (-2, 99), (-1, 0xFE), (-3, 0), (2, 9), (-2, 0)]):   # scan parameters
+        b = bytearray(good)
+        b[p + 2 + ln + off if off < 0 else p + 4 + off] = val
+        variants.append(bytes(b))
+    p, ln = sos[3]
+    nxt = [q for q, m, _ in segs if q > p][0]
+    variants.append(good[:p] + good[nxt:])                               # one scan missing altogether
+    for v in variants:
+        _try_decode(engine, v, ref.shape)
+    # the complete scans of a file cut inside its LAST scan were all applied: the picture is close to the full one
+    last = sos[-1][0]
+    out = _try_decode(engine, good[: last + (len(good) - last) // 2], ref.shape)
+    if out is not None:
+        assert np.abs(out.astype(int) - ref).mean() < 12.0
+        assert np.all(out[:32] == ref[:32]), "rows whose last refinement precedes the cut must be exact"
+    assert np.array_equal(engine.decode_jpeg_batch([good])[0], ref)
+    try:
+        outs = engine.decode_jpeg_batch([variants[0], good])
+        assert np.array_equal(outs[1], ref)
+    except irp_b200.IrpError:
+        pass
