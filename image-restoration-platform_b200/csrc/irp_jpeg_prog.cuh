@@ -133,11 +133,16 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
                  int16_t* __restrict__ dcv) {
   __shared__ uint32_t ring[kProgRing];
   __shared__ HuffDev ht[6];   // DC tables of the scan's components, then their AC tables
-  // refinement scans, per block of a group: history mask, new coefficients and their signs, and the correction-bit
-  // SEGMENTS: lane 0 only notes where in the band a run of correction bits starts (s_seg: one bit per start) and at
-  // which stream bit (s_segpos, in start order); the lane that owns a coefficient finds its own bit from those
-  __shared__ unsigned long long s_nz[kProgGroup], s_seg[kProgGroup], s_newp[kProgGroup], s_news[kProgGroup];
+  // refinement scans, per block of a group: the history mask and the list of zero positions (built by the warp), and
+  // what lane 0 leaves behind — the new coefficients, and the correction-bit SEGMENTS: only where in the band a run of
+  // correction bits starts (s_mark) and at which stream bit (s_segpos); the lane that owns a coefficient finds its own
+  // bit from those
+  __shared__ unsigned long long s_nz[kProgGroup];
   __shared__ uint32_t s_segpos[kProgGroup][64];
+  __shared__ __align__(16) uint8_t s_zl[kProgGroup][64];     // band positions of the block's still-zero coefficients, ascending
+  __shared__ __align__(16) uint8_t s_mark[kProgGroup][64];   // at the band position where a run of correction bits starts: its index + 1
+  __shared__ __align__(16) uint8_t s_new[kProgGroup][64];    // coefficient that becomes nonzero in this scan: 1 positive, 2 negative
+  __shared__ int s_nzr[kProgGroup];
   const int lane = threadIdx.x;
   const ProgScan sc = scans[blockIdx.x];
   const JpegImg& im = imgs[sc.img];
@@ -268,8 +273,9 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
     // ---------------- AC refinement (one component): groups of eight blocks ----------------
     {
       const int c = c0;
+      const int ss = sc.ss, se = sc.se;
       const int p1 = 1 << sc.al;
-      const unsigned long long band = (sc.se >= 63 ? ~0ull : ((1ull << (sc.se + 1)) - 1ull)) & ~((1ull << sc.ss) - 1ull);
+      const unsigned long long band = (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
       int16_t* base = coef_arena + im.coef_off[c];
       const HuffDev& act = ht[3];
       for (int n0 = m0; n0 < m1; n0 += kProgGroup) {
@@ -284,28 +290,38 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
           lo[q] = ptr[q][lane];
           hi[q] = ptr[q][lane + 32];
         }
+        for (int i = lane; i < kProgGroup * 16; i += 32) {       // last group's marks and new coefficients
+          reinterpret_cast<uint32_t*>(&s_mark[0][0])[i] = 0u;
+          reinterpret_cast<uint32_t*>(&s_new[0][0])[i] = 0u;
+        }
 #pragma unroll
         for (int q = 0; q < kProgGroup; q++) {
           const uint32_t a = __ballot_sync(0xffffffffu, lo[q] != 0), b = __ballot_sync(0xffffffffu, hi[q] != 0);
-          if (lane == 0) s_nz[q] = (((unsigned long long)b << 32) | a) & band;
+          const unsigned long long nz = (((unsigned long long)b << 32) | a) & band;
+          // zero positions of the band in order: a symbol's run of r zeros is then one table look-up for lane 0
+          const unsigned long long Z = ~nz & band;
+          if ((Z >> lane) & 1ull) s_zl[q][__popcll(Z & ((1ull << lane) - 1ull))] = (uint8_t)lane;
+          if ((Z >> (lane + 32)) & 1ull) s_zl[q][__popcll(Z & ((1ull << (lane + 32)) - 1ull))] = (uint8_t)(lane + 32);
+          if (lane == 0) {
+            s_nz[q] = nz;
+            s_nzr[q] = __popcll(Z);
+          }
         }
         __syncwarp();
         if (lane == 0) {
           const int cnt = min(kProgGroup, m1 - n0);
 #pragma unroll 1
           for (int q = 0; q < cnt; q++) {
-            const unsigned long long nz = s_nz[q];
-            unsigned long long seg = 0, newp = 0, news = 0;
-            int nseg = 0;
-            int k = sc.ss;
+            const int nzr = s_nzr[q];
+            int nseg = 0, j = 0;   // j: zeros of the band below position k
+            int k = ss;
             if (eobrun == 0) {
-              while (k <= sc.se) {
+              while (k <= se) {
                 rd.fill();
                 const uint32_t b32 = rd.top32();
                 int len;
                 const int rs = huff_decode(act, b32 >> 16, len);
-                int r = rs >> 4;
-                const int sz = rs & 15;
+                const int r = rs >> 4, sz = rs & 15;
                 bool neg = false;
                 if (sz) {
                   neg = !((b32 << len) >> 31);                 // a newly nonzero coefficient is +-1 at this bit position
@@ -320,43 +336,43 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
                 }
                 // step over r still-zero coefficients: the target is the (r + 1)-th zero from k on; every nonzero
                 // coefficient passed on the way takes a correction bit
-                const unsigned long long from = ~0ull << k;
-                unsigned long long Z = ~nz & band & from;
-                for (; r > 0 && Z; r--) Z &= Z - 1;
-                const int target = Z ? __ffsll((long long)Z) - 1 : sc.se + 1;
-                const unsigned long long below = target >= 64 ? ~0ull : ((1ull << target) - 1ull);
-                const unsigned long long P = nz & from & below;
-                if (P) {
-                  seg |= 1ull << k;
-                  s_segpos[q][nseg++] = rd.pos();
-                  rd.skipn(__popcll(P));
+                int target, zeros;
+                if (j + r < nzr) {
+                  target = s_zl[q][j + r];
+                  zeros = r;
+                } else {                                       // band exhausted (corrupt data only)
+                  target = se + 1;
+                  zeros = nzr - j;
                 }
-                if (sz && target <= sc.se) {
-                  newp |= 1ull << target;
-                  if (neg) news |= 1ull << target;
+                const int ncorr = target - k - zeros;
+                if (ncorr > 0) {
+                  s_segpos[q][nseg] = rd.pos();
+                  s_mark[q][k] = (uint8_t)(++nseg);
+                  rd.skipn(ncorr);
                 }
+                if (sz && target <= se) s_new[q][target] = neg ? 2 : 1;
                 k = target + 1;
+                j += zeros + 1;
               }
             }
             if (eobrun > 0) {
-              const unsigned long long P = k <= 63 ? nz & (~0ull << k) : 0ull;
-              if (P) {
-                seg |= 1ull << k;
-                s_segpos[q][nseg++] = rd.pos();
-                rd.skipn(__popcll(P));
+              const int ncorr = k <= se ? se + 1 - k - (nzr - min(j, nzr)) : 0;
+              if (ncorr > 0) {
+                s_segpos[q][nseg] = rd.pos();
+                s_mark[q][k] = (uint8_t)(++nseg);
+                rd.skipn(ncorr);
               }
               eobrun--;
             }
-            s_seg[q] = seg;
-            s_newp[q] = newp;
-            s_news[q] = news;
           }
         }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < kProgGroup; q++) {
           if (n0 + q >= m1) break;
-          const unsigned long long seg = s_seg[q], newp = s_newp[q], news = s_news[q], nz = s_nz[q];
+          const unsigned long long nz = s_nz[q];
+          const unsigned long long seg = ((unsigned long long)__ballot_sync(0xffffffffu, s_mark[q][lane + 32] != 0) << 32) |
+                                         __ballot_sync(0xffffffffu, s_mark[q][lane] != 0);
 #pragma unroll
           for (int half = 0; half < 2; half++) {
             const int pos = lane + 32 * half;
@@ -369,12 +385,12 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
               // of nonzero coefficients between the segment's start and this one
               const int ks = 63 - __clzll((long long)started);
               const uint32_t rank = (uint32_t)__popcll(nz & (~0ull << ks) & (upto >> 1));
-              cb = rd.bit_at(s_segpos[q][__popcll(started) - 1] + rank) != 0u;
+              cb = rd.bit_at(s_segpos[q][s_mark[q][ks] - 1] + rank) != 0u;
             }
-            const bool nb = (newp >> pos) & 1ull;
+            const int nv = s_new[q][pos];
             if (cb && !(v & p1)) v += v >= 0 ? p1 : -p1;
-            if (nb) v = ((news >> pos) & 1ull) ? -p1 : p1;
-            if (cb || nb) ptr[q][pos] = (int16_t)v;
+            if (nv) v = nv == 2 ? -p1 : p1;
+            if (cb || nv) ptr[q][pos] = (int16_t)v;
           }
         }
         __syncwarp();
