@@ -28,6 +28,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <unordered_map>
+#include <immintrin.h>   // the host un-stuffing loop (irp_jpeg_host.inc) copies 32 bytes at a time
 #include <deque>
 #include <thread>
 #include <cuda.h>   // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
