@@ -454,6 +454,36 @@ def main() -> int:
                 "d2h_bytes_per_step": int(sum(o.size for o in fouts)) + B * C.sizeof(_ffi.Result),
                 "first_file_equals_libjpeg_turbo": h_out[0].reshape(-1)[:fouts[0].size].tobytes() == ref_file.getvalue(),
                 "output": "baseline JPEG q85 4:4:4 files with per-image optimised Huffman tables, encoded on the device (irp_transcode_jpeg_batch, IRP_JPEG_OPTIMIZE), byte-identical to libjpeg-turbo's optimize_coding files"}
+            # the same call on PROGRESSIVE files (what preprocessImage itself writes, imagePreprocess.js:57-61): one warp per
+            # scan, scans in dependency levels (csrc/irp_jpeg_prog.cuh) — latency-bound per image, so it is reported apart
+            if world == 1:
+                from PIL import ImageFile
+
+                ImageFile.MAXBLOCK = 1 << 26
+                pblobs = []
+                for im in imgs[:2]:
+                    bio = io.BytesIO()
+                    Image.fromarray(im).save(bio, "JPEG", quality=90, subsampling=2, progressive=True, optimize=True)
+                    pblobs.append(np.frombuffer(bio.getvalue(), np.uint8))
+                pj = [pblobs[i % len(pblobs)] for i in range(B)]
+                pdescs = (_ffi.JpegDesc * B)(*[_ffi.JpegDesc(k.ctypes.data, k.size, 1, 0) for k in pj])
+
+                def step_prog():
+                    rc = eng._lib.irp_analyze_jpeg_batch(eng._ctx, pdescs, B, jres, jouts)
+                    if rc:
+                        eng._check(rc)
+                    return jres[0].score[0]
+
+                step_prog()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    step_prog()
+                dtp = (time.perf_counter() - t0) / 2
+                same = bool(np.array_equal(eng.decode_jpeg_batch([pj[0].tobytes()])[0], np.asarray(Image.open(io.BytesIO(pj[0].tobytes())))))
+                e2e_jpeg["progressive"] = {
+                    "value": mpix_step / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "files_per_s": B / dtp,
+                    "h2d_bytes_per_step": int(sum(k.size for k in pj)), "first_image_equals_libjpeg_turbo": same,
+                    "input": "progressive JPEG q90 4:2:0 with optimised tables (libjpeg's 10-scan script), decoded on the device scan by scan"}
         except Exception as ex:  # the raw-pixel numbers above stand on their own
             e2e_jpeg = dict(e2e_jpeg or {}, unavailable=repr(ex))
 
