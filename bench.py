@@ -422,7 +422,7 @@ def main() -> int:
             e2e_jpeg = {"value": world * mpix_step / dtj, "unit": UNIT, "ms_per_step": dtj * 1e3,
                         "h2d_bytes_per_step": int(sum(k.size for k in jb)), "d2h_bytes_per_step": B * ow * oh * 3 + B * C.sizeof(_ffi.Result),
                         "upload_and_device_decode_ms": tj["h2d_ms"], "classify_ms": tj["classify_ms"], "preprocess_ms": tj["preprocess_ms"],
-                        "lanes": int(os.environ.get("IRP_LANES", "8")),
+                        "lanes": int(os.environ.get("IRP_LANES") or max(2, min(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))),
                         "input": "baseline JPEG q90 4:2:0 bytes in host memory, decoded on the device bit-exact with libjpeg-turbo "
                                  "(irp_analyze_jpeg_batch); the host decodes nothing"}
             # files in, files out: the preprocessed image re-encoded on the device (imagePreprocess.js:50-53), so that
