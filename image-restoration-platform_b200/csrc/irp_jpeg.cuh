@@ -565,6 +565,9 @@ idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, cons
 // fancy upsampling of one chroma sample position + colour conversion, one thread per output pixel
 __device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ pl, int pw, int dw, int dh, int hx, int vx, int x, int y) {
   if (hx == 1 && vx == 1) return pl[(size_t)y * pw + x];
+  // jdsample.c picks the fancy h2v1 / h2v2 upsamplers only for components more than two samples wide; narrower ones
+  // (images of 4 pixels or less across) get plain replication, vertically too
+  if (hx == 2 && dw <= 2) return pl[(size_t)(vx == 2 ? y >> 1 : y) * pw + (x >> 1)];
   if (hx == 2 && vx == 1) {
     const uint8_t* in = pl + (size_t)y * pw;
     const int i = x >> 1;

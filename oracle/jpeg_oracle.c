@@ -41,7 +41,9 @@ typedef struct {
 typedef struct {
   int id, h, v, tq, td, ta;
   int bw, bh;        /* blocks per row / block rows, MCU padded */
-  int dw, dh;        /* downsampled (real) width / height in samples */
+  int dw, dh;        /* downsampled (real) width / height in samples (at the decode scale) */
+  int S, hx, vx;     /* DCT_scaled_size (8 = full size) and the upsampler's expansion factors */
+  int fw, fh;        /* downsampled size at FULL scale: what a scan of this component alone walks */
   int16_t* coef;     /* [bh][bw][64] natural order, DC already integrated */
   uint8_t* plane;    /* [bh*8][bw*8] */
 } Comp;
@@ -56,6 +58,7 @@ typedef struct {
   size_t scan_len;
   int adobe_transform;  /* -1 none */
   int progressive;      /* SOF2 */
+  int out_w, out_h, fancy; /* output size and upsampler kind at the decode scale (w, h, 1 at full size) */
   int multi;            /* more than the one interleaved full-band scan: decode_multi() walks the scans */
   size_t sos_pos;       /* index of the first SOS marker's 0xFF */
 } Jpeg;
@@ -199,10 +202,39 @@ static int parse(const uint8_t* d, size_t n, Jpeg* J) {
     c->bh = J->mcuy * c->v;
     c->dw = (J->w * c->h + J->hmax - 1) / J->hmax;
     c->dh = (J->h * c->v + J->vmax - 1) / J->vmax;
+    c->fw = c->dw;
+    c->fh = c->dh;
+    c->S = 8;
+    c->hx = J->hmax / c->h;
+    c->vx = J->vmax / c->v;
     if (!J->qpresent[c->tq]) return JO_ERR_FORMAT;
     if (!J->multi && (!J->dc[c->td].present || !J->ac[c->ta].present)) return JO_ERR_FORMAT;
   }
+  J->out_w = J->w;
+  J->out_h = J->h;
+  J->fancy = 1;
   return JO_OK;
+}
+
+/* jdmaster.c, jpeg_core_output_dimensions + jdsample.c jinit_upsampler for scale 1/denom (denom 2, 4, 8 — libvips'
+ * shrink-on-load): the output is ceil(size / denom); every component gets the LARGEST IDCT size that still needs no
+ * more than the frame's upsampling (a 2x subsampled chroma component is scaled up by its IDCT instead of the
+ * upsampler), and fancy upsampling is only used while the smallest IDCT is larger than 1x1. */
+static void set_scale(Jpeg* J, int denom) {
+  const int minS = 8 / denom;
+  J->out_w = (J->w + denom - 1) / denom;
+  J->out_h = (J->h + denom - 1) / denom;
+  J->fancy = minS > 1;
+  for (int i = 0; i < J->ncomp; i++) {
+    Comp* c = &J->comp[i];
+    int ssize = minS;
+    while (ssize < 8 && (J->hmax * minS) % (c->h * ssize * 2) == 0 && (J->vmax * minS) % (c->v * ssize * 2) == 0) ssize *= 2;
+    c->S = ssize;
+    c->dw = (J->w * c->h * ssize + J->hmax * 8 - 1) / (J->hmax * 8);
+    c->dh = (J->h * c->v * ssize + J->vmax * 8 - 1) / (J->vmax * 8);
+    c->hx = J->hmax / ((c->h * ssize) / minS);
+    c->vx = J->vmax / ((c->v * ssize) / minS);
+  }
 }
 
 /* ---- entropy decoding (jdhuff.c) ---- */
@@ -364,7 +396,7 @@ static int decode_one_scan(Jpeg* J, const ScanHdr* h, const uint8_t* data, size_
   /* a scan of one component walks that component's own blocks (ceil(samples / 8)), not the MCU-padded grid */
   const int single = h->ns == 1;
   const Comp* c0 = &J->comp[h->ci[0]];
-  const int mx_n = single ? (c0->dw + 7) / 8 : J->mcux, my_n = single ? (c0->dh + 7) / 8 : J->mcuy;
+  const int mx_n = single ? (c0->fw + 7) / 8 : J->mcux, my_n = single ? (c0->fh + 7) / 8 : J->mcuy;
   for (int my = 0; my < my_n; my++)
     for (int mx = 0; mx < mx_n; mx++) {
       if (J->restart && togo == 0) {
@@ -591,10 +623,68 @@ static void idct_islow(const int16_t* in, const uint16_t* q, uint8_t* out, int s
   }
 }
 
+/* ---- jidctred.c: reduced-size inverse DCTs (4x4, 2x2, 1x1 output from one 8x8 coefficient block) ---- */
+static void idct_4x4(const int16_t* in, const uint16_t* q, uint8_t* out, int stride) {
+  int32_t ws[8 * 4];
+  for (int c = 0; c < 8; c++) {
+    if (c == 4) continue; /* the second pass never reads column 4 */
+    const int16_t* ip = in + c;
+    const uint16_t* qp = q + c;
+    int32_t tmp0 = (int32_t)(ip[0] * qp[0]) * (1 << (CONST_BITS + 1));
+    int32_t z2 = ip[16] * qp[16], z3 = ip[48] * qp[48];
+    int32_t tmp2 = z2 * 15137 + z3 * (-6270);
+    const int32_t tmp10 = tmp0 + tmp2, tmp12 = tmp0 - tmp2;
+    const int32_t z1 = ip[56] * qp[56];
+    z2 = ip[40] * qp[40];
+    z3 = ip[24] * qp[24];
+    const int32_t z4 = ip[8] * qp[8];
+    tmp0 = z1 * (-1730) + z2 * 11893 + z3 * (-17799) + z4 * 8697;
+    tmp2 = z1 * (-4176) + z2 * (-4926) + z3 * 7373 + z4 * 20995;
+    ws[c + 0] = DESCALE(tmp10 + tmp2, CONST_BITS - PASS1_BITS + 1);
+    ws[c + 24] = DESCALE(tmp10 - tmp2, CONST_BITS - PASS1_BITS + 1);
+    ws[c + 8] = DESCALE(tmp12 + tmp0, CONST_BITS - PASS1_BITS + 1);
+    ws[c + 16] = DESCALE(tmp12 - tmp0, CONST_BITS - PASS1_BITS + 1);
+  }
+  for (int r = 0; r < 4; r++) {
+    const int32_t* w = ws + 8 * r;
+    int32_t tmp0 = w[0] * (1 << (CONST_BITS + 1));
+    int32_t tmp2 = w[2] * 15137 + w[6] * (-6270);
+    const int32_t tmp10 = tmp0 + tmp2, tmp12 = tmp0 - tmp2;
+    const int32_t z1 = w[7], z2 = w[5], z3 = w[3], z4 = w[1];
+    tmp0 = z1 * (-1730) + z2 * 11893 + z3 * (-17799) + z4 * 8697;
+    tmp2 = z1 * (-4176) + z2 * (-4926) + z3 * 7373 + z4 * 20995;
+    uint8_t* o = out + (size_t)r * stride;
+    o[0] = range_limit(DESCALE(tmp10 + tmp2, CONST_BITS + PASS1_BITS + 3 + 1));
+    o[3] = range_limit(DESCALE(tmp10 - tmp2, CONST_BITS + PASS1_BITS + 3 + 1));
+    o[1] = range_limit(DESCALE(tmp12 + tmp0, CONST_BITS + PASS1_BITS + 3 + 1));
+    o[2] = range_limit(DESCALE(tmp12 - tmp0, CONST_BITS + PASS1_BITS + 3 + 1));
+  }
+}
+static void idct_2x2(const int16_t* in, const uint16_t* q, uint8_t* out, int stride) {
+  int32_t ws[8 * 2];
+  for (int c = 0; c < 8; c++) {
+    if (c == 2 || c == 4 || c == 6) continue; /* never read by the second pass */
+    const int16_t* ip = in + c;
+    const uint16_t* qp = q + c;
+    const int32_t tmp10 = (int32_t)(ip[0] * qp[0]) * (1 << (CONST_BITS + 2));
+    const int32_t tmp0 = (ip[56] * qp[56]) * (-5906) + (ip[40] * qp[40]) * 6967 + (ip[24] * qp[24]) * (-10426) + (ip[8] * qp[8]) * 29692;
+    ws[c] = DESCALE(tmp10 + tmp0, CONST_BITS - PASS1_BITS + 2);
+    ws[c + 8] = DESCALE(tmp10 - tmp0, CONST_BITS - PASS1_BITS + 2);
+  }
+  for (int r = 0; r < 2; r++) {
+    const int32_t* w = ws + 8 * r;
+    const int32_t tmp10 = w[0] * (1 << (CONST_BITS + 2));
+    const int32_t tmp0 = w[7] * (-5906) + w[5] * 6967 + w[3] * (-10426) + w[1] * 29692;
+    out[(size_t)r * stride] = range_limit(DESCALE(tmp10 + tmp0, CONST_BITS + PASS1_BITS + 3 + 2));
+    out[(size_t)r * stride + 1] = range_limit(DESCALE(tmp10 - tmp0, CONST_BITS + PASS1_BITS + 3 + 2));
+  }
+}
+static void idct_1x1(const int16_t* in, const uint16_t* q, uint8_t* out) { out[0] = range_limit(DESCALE((int32_t)(in[0] * q[0]), 3)); }
+
 /* ---- jdsample.c: fancy upsampling of one component to full resolution (at least w x h) ---- */
 static uint8_t* upsample(const Jpeg* J, const Comp* c, int* out_stride) {
-  const int hx = J->hmax / c->h, vx = J->vmax / c->v;
-  const int pw = c->bw * 8; /* padded plane width */
+  const int hx = c->hx, vx = c->vx;
+  const int pw = c->bw * c->S; /* padded plane width */
   const int ow = c->dw * hx, oh = c->dh * vx;
   uint8_t* o = (uint8_t*)malloc((size_t)(ow + 2) * (oh + 2));
   if (!o) return NULL;
@@ -602,6 +692,13 @@ static uint8_t* upsample(const Jpeg* J, const Comp* c, int* out_stride) {
 #define ROW(r) (c->plane + (size_t)((r) < 0 ? 0 : ((r) >= c->dh ? c->dh - 1 : (r))) * pw)
   if (hx == 1 && vx == 1) {
     for (int y = 0; y < oh; y++) memcpy(o + (size_t)y * ow, ROW(y), ow);
+  } else if ((hx == 2 && (c->dw <= 2 || !J->fancy)) || (hx == 1 && vx == 2 && !J->fancy)) {
+    /* jinit_upsampler: the fancy h2v1 / h2v2 routines only when downsampled_width > 2; else h2v1_upsample /
+     * h2v2_upsample, plain replication (vertically too) */
+    for (int y = 0; y < oh; y++) {
+      const uint8_t* in = ROW(vx == 2 ? y >> 1 : y);
+      for (int x = 0; x < ow; x++) o[(size_t)y * ow + x] = in[hx == 2 ? x >> 1 : x];
+    }
   } else if (hx == 2 && vx == 1) {
     for (int y = 0; y < oh; y++) {
       const uint8_t* in = ROW(y);
@@ -685,10 +782,20 @@ int irp_jpeg_info(const uint8_t* data, size_t len, int* w, int* h, int* ncomp, i
 
 /* out: w*h*3 (RGB) for 3 components, w*h for 1.  coef_out (optional): the quantised coefficients of
  * component `coef_comp`, [block rows][blocks per row][64] natural order (for the device stages' tests). */
+static int decode_at_scale(const uint8_t* data, size_t len, int denom, uint8_t* out, int16_t* coef_out, int coef_comp);
 int irp_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out, int16_t* coef_out, int coef_comp) {
+  return decode_at_scale(data, len, 1, out, coef_out, coef_comp);
+}
+/* libjpeg's scale_num / scale_denom = 1 / denom (2, 4 or 8): out holds ceil(h / denom) x ceil(w / denom) pixels */
+int irp_jpeg_decode_scaled(const uint8_t* data, size_t len, int denom, uint8_t* out) {
+  if (denom != 1 && denom != 2 && denom != 4 && denom != 8) return JO_ERR_UNSUPPORTED;
+  return decode_at_scale(data, len, denom, out, NULL, -1);
+}
+static int decode_at_scale(const uint8_t* data, size_t len, int denom, uint8_t* out, int16_t* coef_out, int coef_comp) {
   Jpeg J;
   int rc = parse(data, len, &J);
   if (rc) return rc;
+  if (denom > 1) set_scale(&J, denom);
   for (int i = 0; i < J.ncomp; i++) {
     Comp* c = &J.comp[i];
     c->coef = (int16_t*)calloc((size_t)c->bw * c->bh * 64, sizeof(int16_t));
@@ -706,16 +813,23 @@ int irp_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out, int16_t* coef
     memcpy(coef_out, J.comp[coef_comp].coef, (size_t)J.comp[coef_comp].bw * J.comp[coef_comp].bh * 64 * sizeof(int16_t));
   for (int i = 0; i < J.ncomp; i++) {
     Comp* c = &J.comp[i];
+    const int S = c->S, pw = c->bw * S;
     for (int by = 0; by < c->bh; by++)
-      for (int bx = 0; bx < c->bw; bx++)
-        idct_islow(c->coef + ((size_t)by * c->bw + bx) * 64, J.q[c->tq], c->plane + ((size_t)by * 8 * c->bw + bx) * 8, c->bw * 8);
+      for (int bx = 0; bx < c->bw; bx++) {
+        const int16_t* blk = c->coef + ((size_t)by * c->bw + bx) * 64;
+        uint8_t* o = c->plane + ((size_t)by * S * c->bw + bx) * S;
+        if (S == 8) idct_islow(blk, J.q[c->tq], o, pw);
+        else if (S == 4) idct_4x4(blk, J.q[c->tq], o, pw);
+        else if (S == 2) idct_2x2(blk, J.q[c->tq], o, pw);
+        else idct_1x1(blk, J.q[c->tq], o);
+      }
   }
   if (!out) {
     free_all(&J);
     return JO_OK;
   }
   if (J.ncomp == 1) {
-    for (int y = 0; y < J.h; y++) memcpy(out + (size_t)y * J.w, J.comp[0].plane + (size_t)y * J.comp[0].bw * 8, J.w);
+    for (int y = 0; y < J.out_h; y++) memcpy(out + (size_t)y * J.out_w, J.comp[0].plane + (size_t)y * J.comp[0].bw * J.comp[0].S, J.out_w);
     free_all(&J);
     return JO_OK;
   }
@@ -730,10 +844,10 @@ int irp_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out, int16_t* coef
     }
   }
   const int rgb_passthrough = J.adobe_transform == 0;
-  for (int y = 0; y < J.h; y++)
-    for (int x = 0; x < J.w; x++) {
+  for (int y = 0; y < J.out_h; y++)
+    for (int x = 0; x < J.out_w; x++) {
       const int Y = up[0][(size_t)y * st[0] + x], cb = up[1][(size_t)y * st[1] + x], cr = up[2][(size_t)y * st[2] + x];
-      uint8_t* o = out + ((size_t)y * J.w + x) * 3;
+      uint8_t* o = out + ((size_t)y * J.out_w + x) * 3;
       if (rgb_passthrough) {
         o[0] = (uint8_t)Y;
         o[1] = (uint8_t)cb;

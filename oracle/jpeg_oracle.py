@@ -26,6 +26,7 @@ def _load():
         lib = C.CDLL(_SO)
         lib.irp_jpeg_info.argtypes = [C.c_char_p, C.c_size_t] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_int * 6)]
         lib.irp_jpeg_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        lib.irp_jpeg_decode_scaled.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -47,6 +48,18 @@ def decode(data: bytes) -> np.ndarray:
     shape = (i["height"], i["width"], 3) if i["components"] == 3 else (i["height"], i["width"])
     out = np.empty(shape, np.uint8)
     rc = _load().irp_jpeg_decode(data, len(data), out.ctypes.data, None, -1)
+    if rc:
+        raise ValueError(f"jpeg oracle: error {rc}")
+    return out
+
+
+def decode_scaled(data: bytes, denom: int) -> np.ndarray:
+    """The picture at libjpeg's scale 1 / denom (2, 4, 8): ceil(H / denom) x ceil(W / denom), reduced-size IDCTs
+    (jidctred.c) — what libvips' shrink-on-load asks libjpeg-turbo for."""
+    i = info(data)
+    h, w = -(-i["height"] // denom), -(-i["width"] // denom)
+    out = np.empty((h, w, 3) if i["components"] == 3 else (h, w), np.uint8)
+    rc = _load().irp_jpeg_decode_scaled(data, len(data), denom, out.ctypes.data)
     if rc:
         raise ValueError(f"jpeg oracle: error {rc}")
     return out

@@ -46,7 +46,7 @@ def _decode_batch(engine, blobs):
     return [a[:, :, 0] if a.shape[2] == 1 else a for a in arrays]
 
 
-SHAPES = [(8, 8), (1, 1), (3, 5), (17, 33), (37, 53), (64, 48), (100, 161), (241, 319), (600, 900)]
+SHAPES = [(8, 8), (1, 1), (3, 5), (5, 3), (9, 4), (16, 2), (17, 33), (37, 53), (64, 48), (100, 161), (241, 319), (600, 900)]   # widths 2-4: chroma two samples wide or less takes libjpeg's plain upsampler
 
 
 @pytest.mark.parametrize("subsampling", [0, 1, 2])

@@ -84,6 +84,17 @@ def test_progressive_matches_libjpeg_turbo(subsampling):
     assert np.array_equal(jpeg_oracle.decode(grey), _pillow(grey))
 
 
+@pytest.mark.parametrize("subsampling", [1, 2])
+def test_narrow_images_take_the_plain_upsampler(subsampling):
+    """jinit_upsampler selects the fancy h2v1 / h2v2 routines only for components more than two samples wide: images of
+    four pixels or less across are upsampled by replication."""
+    for i, (h, w) in enumerate([(5, 3), (5, 4), (3, 3), (2, 2), (16, 4), (40, 3), (1, 2), (9, 1)]):
+        img = rand_image(h, w, 3, seed=80 + i)
+        for prog in (False, True):
+            data = _encode(img, quality=90, subsampling=subsampling, progressive=prog)
+            assert np.array_equal(jpeg_oracle.decode(data), _pillow(data)), f"{h}x{w} progressive={prog}"
+
+
 def test_four_components_are_reported_unsupported():
     import io
 
@@ -99,3 +110,37 @@ def test_coefficients_hook_shape():
     data = _encode(rand_image(37, 53, 3, seed=2, kind="smooth"), quality=85, subsampling=2)
     y, cb = jpeg_oracle.coefficients(data, 0), jpeg_oracle.coefficients(data, 1)
     assert y.shape == (6, 8, 64) and cb.shape == (3, 4, 64) and y.any()
+
+
+def _pillow_scaled(data, denom, mode="RGB"):
+    """libjpeg-turbo's own decode at scale 1 / denom (Pillow's draft mode sets scale_denom and keeps JDCT_ISLOW and
+    fancy upsampling); None when Pillow settles for another scale."""
+    im = Image.open(io.BytesIO(data))
+    w, h = im.size
+    im.draft(mode, (max(1, w // denom), max(1, h // denom)))
+    a = np.asarray(im)
+    return a if a.shape[:2] == (-(-h // denom), -(-w // denom)) else None
+
+
+@pytest.mark.parametrize("denom", [2, 4, 8])
+def test_reduced_size_decode_matches_libjpeg_turbo(denom):
+    """Shrink-on-load (libvips asks libjpeg-turbo for scale 1/2, 1/4, 1/8): jidctred.c's 4x4 / 2x2 / 1x1 inverse DCTs,
+    per-component IDCT sizes (a 2x subsampled chroma component is scaled up by a larger IDCT instead of the upsampler),
+    fancy upsampling only while the smallest IDCT is larger than 1x1 — baseline and progressive files, every sampling."""
+    n = 0
+    for i, (h, w) in enumerate([(64, 64), (333, 517), (17, 9), (100, 161), (255, 257), (8, 8), (5, 3), (31, 33), (16, 4), (9, 20)]):
+        img = rand_image(h, w, 3, seed=90 + i, kind="smooth" if i % 2 else "noise")
+        for sub in (0, 1, 2):
+            for prog in (False, True):
+                data = _encode(img, quality=85, subsampling=sub, progressive=prog)
+                ref = _pillow_scaled(data, denom)
+                if ref is None:
+                    continue
+                assert np.array_equal(jpeg_oracle.decode_scaled(data, denom), ref), f"{h}x{w} sub {sub} progressive {prog}"
+                n += 1
+        grey = _encode(img[:, :, 0], quality=85)
+        ref = _pillow_scaled(grey, denom, "L")
+        if ref is not None:
+            assert np.array_equal(jpeg_oracle.decode_scaled(grey, denom), ref)
+            n += 1
+    assert n >= 40
