@@ -63,7 +63,7 @@ class OutDesc(C.Structure):
 
 
 class JpegDesc(C.Structure):
-    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t), ("exif_orientation", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t), ("exif_orientation", C.c_int32), ("scale_denom", C.c_int32)]
 
 
 class JpegOut(C.Structure):

@@ -56,6 +56,12 @@ struct JpegImg {                       // one image of a decode launch (device c
   unsigned long long out_off;              // byte offset of the RGB / grey output in the pixel arena
   unsigned long long out_pitch;
   int huff_base;                           // first of this image's kHuffSlots tables
+  int fancy;                               // fancy (triangle) upsampling; libjpeg drops it when the smallest IDCT is 1x1
+  // the decode scale (libjpeg scale 1 / 1, 2, 4, 8 — shrink-on-load): output size, and per component the IDCT size
+  // (8 = full), the size of its plane in samples and the expansion the upsampler still has to do.  The entropy-coded
+  // data does not know about the scale: the Huffman / scan kernels keep using comp_dw / comp_dh / comp_bw / comp_bh.
+  int ow, oh;
+  int comp_S[3], comp_sdw[3], comp_sdh[3], comp_hx[3], comp_vx[3];
   int pad;
 };
 
@@ -492,13 +498,60 @@ __device__ __forceinline__ void idct_1d(const int in[8], int out[8], int shift) 
   out[3] = descale(tmp13 + tmp0, shift); out[4] = descale(tmp13 - tmp0, shift);
 }
 
+// jidctred.c: reduced-size inverse DCTs on the dequantised coefficients d[64] (natural order) of one block
+__device__ __forceinline__ void idct_4x4_store(const int d[64], uint8_t* out, size_t pitch) {
+  int ws[4][8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    if (c == 4) continue;   // the second pass never reads column 4
+    int tmp0 = d[c] * (1 << 14);
+    int tmp2 = d[16 + c] * 15137 + d[48 + c] * (-6270);
+    const int tmp10 = tmp0 + tmp2, tmp12 = tmp0 - tmp2;
+    const int z1 = d[56 + c], z2 = d[40 + c], z3 = d[24 + c], z4 = d[8 + c];
+    tmp0 = z1 * (-1730) + z2 * 11893 + z3 * (-17799) + z4 * 8697;
+    tmp2 = z1 * (-4176) + z2 * (-4926) + z3 * 7373 + z4 * 20995;
+    ws[0][c] = descale(tmp10 + tmp2, 12); ws[3][c] = descale(tmp10 - tmp2, 12);
+    ws[1][c] = descale(tmp12 + tmp0, 12); ws[2][c] = descale(tmp12 - tmp0, 12);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    int tmp0 = ws[r][0] * (1 << 14);
+    int tmp2 = ws[r][2] * 15137 + ws[r][6] * (-6270);
+    const int tmp10 = tmp0 + tmp2, tmp12 = tmp0 - tmp2;
+    const int z1 = ws[r][7], z2 = ws[r][5], z3 = ws[r][3], z4 = ws[r][1];
+    tmp0 = z1 * (-1730) + z2 * 11893 + z3 * (-17799) + z4 * 8697;
+    tmp2 = z1 * (-4176) + z2 * (-4926) + z3 * 7373 + z4 * 20995;
+    uint8_t* o = out + (size_t)r * pitch;
+    o[0] = (uint8_t)range_limit(descale(tmp10 + tmp2, 19)); o[3] = (uint8_t)range_limit(descale(tmp10 - tmp2, 19));
+    o[1] = (uint8_t)range_limit(descale(tmp12 + tmp0, 19)); o[2] = (uint8_t)range_limit(descale(tmp12 - tmp0, 19));
+  }
+}
+__device__ __forceinline__ void idct_2x2_store(const int d[64], uint8_t* out, size_t pitch) {
+  int ws[2][8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    if (c == 2 || c == 4 || c == 6) continue;
+    const int tmp10 = d[c] * (1 << 15);
+    const int tmp0 = d[56 + c] * (-5906) + d[40 + c] * 6967 + d[24 + c] * (-10426) + d[8 + c] * 29692;
+    ws[0][c] = descale(tmp10 + tmp0, 13);
+    ws[1][c] = descale(tmp10 - tmp0, 13);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int tmp10 = ws[r][0] * (1 << 15);
+    const int tmp0 = ws[r][7] * (-5906) + ws[r][5] * 6967 + ws[r][3] * (-10426) + ws[r][1] * 29692;
+    out[(size_t)r * pitch] = (uint8_t)range_limit(descale(tmp10 + tmp0, 20));
+    out[(size_t)r * pitch + 1] = (uint8_t)range_limit(descale(tmp10 - tmp0, 20));
+  }
+}
+
 struct IdctJob {                // one component of one image
   unsigned long long coef_off, plane_off;
   int nblocks, bw;              // blocks, blocks per row
   int block_base;               // first global block index of this job
   int qidx;                     // index into the quantisation-table array (64 x u16 each)
   unsigned long long dc_off;    // the component's first entry in the compact DC array
-  int ch, cv, mcux, pad;        // sampling factors and MCUs per row: block (by, bx) -> MCU-order DC index
+  int ch, cv, mcux, S;          // sampling factors and MCUs per row: block (by, bx) -> MCU-order DC index; IDCT size (8, 4, 2, 1)
 };
 
 // One thread per 8x8 block: the block's 128 bytes are read as 8 x 16 bytes (the lanes of a warp read neighbouring
@@ -543,6 +596,14 @@ idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, cons
     const size_t di = (size_t)J.dc_off + ((size_t)my * J.mcux + mx) * (J.ch * J.cv) + ((by - my * J.cv) * J.ch + (bx - mx * J.ch));
     d[0] = (int)__ldg(dcv + di) * (int)(__ldg(qtabs + J.qidx * 64));
   }
+  if (J.S != 8) {   // reduced-size decode (shrink-on-load): S x S samples per block, plane pitch bw * S
+    const size_t pitch = (size_t)J.bw * J.S;
+    uint8_t* o = plane_arena + J.plane_off + (size_t)(by * J.S) * pitch + (size_t)bx * J.S;
+    if (J.S == 4) idct_4x4_store(d, o, pitch);
+    else if (J.S == 2) idct_2x2_store(d, o, pitch);
+    else o[0] = (uint8_t)range_limit(descale(d[0], 3));
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 8; c++) {
     int v[8], o[8];
@@ -563,11 +624,11 @@ idct_kernel(const IdctJob* __restrict__ jobs, int n_jobs, int total_blocks, cons
 }
 
 // fancy upsampling of one chroma sample position + colour conversion, one thread per output pixel
-__device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ pl, int pw, int dw, int dh, int hx, int vx, int x, int y) {
+__device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ pl, int pw, int dw, int dh, int hx, int vx, int fancy, int x, int y) {
   if (hx == 1 && vx == 1) return pl[(size_t)y * pw + x];
   // jdsample.c picks the fancy h2v1 / h2v2 upsamplers only for components more than two samples wide; narrower ones
-  // (images of 4 pixels or less across) get plain replication, vertically too
-  if (hx == 2 && dw <= 2) return pl[(size_t)(vx == 2 ? y >> 1 : y) * pw + (x >> 1)];
+  // (images of 4 pixels or less across) get plain replication, vertically too — and so does everything at scale 1/8
+  if (!fancy || (hx == 2 && dw <= 2)) return pl[(size_t)(vx == 2 ? y >> 1 : y) * pw + (hx == 2 ? x >> 1 : x)];
   if (hx == 2 && vx == 1) {
     const uint8_t* in = pl + (size_t)y * pw;
     const int i = x >> 1;
@@ -596,7 +657,7 @@ __device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ pl, int pw,
 // is this image the common camera layout (3 components, 4:2:0, not tiny)?  Those take colour420_kernel.
 __device__ __forceinline__ bool is_plain_420(const JpegImg& im) {
   return im.ncomp == 3 && im.hmax == 2 && im.vmax == 2 && im.comp_h[1] == 1 && im.comp_v[1] == 1 && im.comp_h[2] == 1 &&
-         im.comp_v[2] == 1 && im.w >= 16;
+         im.comp_v[2] == 1 && im.w >= 16 && im.comp_S[0] == 8;   // full scale only: a reduced decode takes colour_kernel
 }
 
 // 4:2:0: a 8 x 2 patch of output pixels per thread — the two rows share their near chroma row, so each chroma
@@ -690,12 +751,18 @@ colour_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __res
   const JpegImg& im = imgs[img];
   if (is_plain_420(im)) return;   // colour420_kernel's
   const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x0 >= im.w || y >= im.h) return;
+  if (x0 >= im.ow || y >= im.oh) return;
   uint8_t* out = pix_arena + im.out_off + (size_t)y * im.out_pitch;
   const uint8_t* p0 = plane_arena + im.plane_off[0];
-  const int pw0 = im.comp_bw[0] * 8;
-  const uint32_t yw = *reinterpret_cast<const uint32_t*>(p0 + (size_t)y * pw0 + x0);   // plane rows are multiples of 8 wide
-  const int nvalid = min(4, im.w - x0);
+  const int pw0 = im.comp_bw[0] * im.comp_S[0];
+  const int nvalid = min(4, im.ow - x0);
+  uint32_t yw;
+  if (im.comp_S[0] == 8) {
+    yw = *reinterpret_cast<const uint32_t*>(p0 + (size_t)y * pw0 + x0);   // plane rows are multiples of 8 wide
+  } else {   // reduced decode: rows of bw * S samples, any alignment
+    yw = 0;
+    for (int k = 0; k < nvalid; k++) yw |= (uint32_t)p0[(size_t)y * pw0 + x0 + k] << (8 * k);
+  }
   if (im.ncomp == 1) {
     if (nvalid == 4 && (im.out_pitch & 3) == 0)
       *reinterpret_cast<uint32_t*>(out + x0) = yw;
@@ -705,15 +772,15 @@ colour_kernel(const JpegImg* __restrict__ imgs, int n_imgs, const uint8_t* __res
   }
   const uint8_t* p1 = plane_arena + im.plane_off[1];
   const uint8_t* p2 = plane_arena + im.plane_off[2];
-  const int pw1 = im.comp_bw[1] * 8, pw2 = im.comp_bw[2] * 8;
-  const int hx1 = im.hmax / im.comp_h[1], vx1 = im.vmax / im.comp_v[1], hx2 = im.hmax / im.comp_h[2], vx2 = im.vmax / im.comp_v[2];
+  const int pw1 = im.comp_bw[1] * im.comp_S[1], pw2 = im.comp_bw[2] * im.comp_S[2];
+  const int hx1 = im.comp_hx[1], vx1 = im.comp_vx[1], hx2 = im.comp_hx[2], vx2 = im.comp_vx[2];
   uint32_t px[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int x = min(x0 + k, im.w - 1);
+    const int x = min(x0 + k, im.ow - 1);
     const int Y = (yw >> (8 * k)) & 0xFF;
-    const int cb = chroma_at(p1, pw1, im.comp_dw[1], im.comp_dh[1], hx1, vx1, x, y);
-    const int cr = chroma_at(p2, pw2, im.comp_dw[2], im.comp_dh[2], hx2, vx2, x, y);
+    const int cb = chroma_at(p1, pw1, im.comp_sdw[1], im.comp_sdh[1], hx1, vx1, im.fancy, x, y);
+    const int cr = chroma_at(p2, pw2, im.comp_sdw[2], im.comp_sdh[2], hx2, vx2, im.fancy, x, y);
     const int xb = cb - 128, xr = cr - 128;
     const int r = Y + ((91881 * xr + 32768) >> 16);
     const int g = Y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);

@@ -146,6 +146,7 @@ struct irp_ctx {
   size_t plan_used = 0, plan_cap = 0;
   std::map<std::tuple<int, int, double>, PlanDev> plans;
   cudaEvent_t ev[6]{};
+  bool jpeg_allow_scale = false;    // set by irp_decode_jpeg_batch around its decode: the other entry points classify, and that needs the full picture
   cudaEvent_t ev_block = nullptr;   // cudaEventBlockingSync: wait_stream() sleeps on it under IRP_BLOCKING_SYNC=1
   irp_timing timing{};
   int occ_classify[5]{};  // CTAs per SM for C = 1, 3, 4
@@ -1789,7 +1790,9 @@ int irp_decode_jpeg_batch(irp_ctx* ctx, const irp_jpeg_desc* jpegs, int n, irp_o
   if (!n) return IRP_OK;
   ctx->timing = irp_timing{};
   std::vector<JpegPlaced> pl;
+  ctx->jpeg_allow_scale = true;
   int rc = decode_jpegs_locked(ctx, jpegs, n, &pl);
+  ctx->jpeg_allow_scale = false;
   if (rc) return rc;
   for (int i = 0; i < n; i++) {   // every output is checked before the first copy is queued
     const irp_out_desc& od = outs[i];

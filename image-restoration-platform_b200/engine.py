@@ -297,18 +297,20 @@ class Engine:
         results = None if res is None else (list(res) if raw else [result_to_dict(r) for r in res])
         return results, (arrays if preprocess else None)
 
-    def decode_jpeg_batch(self, blobs: Sequence[bytes]):
-        """JPEG file bytes -> decoded u8 images (HxWx3 or HxW), bit-exact with libjpeg-turbo's default decode."""
+    def decode_jpeg_batch(self, blobs: Sequence[bytes], scale_denom: int = 1):
+        """JPEG file bytes -> decoded u8 images (HxWx3 or HxW), bit-exact with libjpeg-turbo's default decode; with
+        scale_denom 2, 4 or 8 at libjpeg's reduced scale (ceil(H / denom) x ceil(W / denom): shrink-on-load)."""
         n = len(blobs)
         keep = [np.frombuffer(b, np.uint8) for b in blobs]
-        descs = (_ffi.JpegDesc * n)(*[_ffi.JpegDesc(k.ctypes.data, k.size, 1, 0) for k in keep])
+        descs = (_ffi.JpegDesc * n)(*[_ffi.JpegDesc(k.ctypes.data, k.size, 1, scale_denom) for k in keep])
         outs = (_ffi.OutDesc * n)()
         arrays = []
         for i, k in enumerate(keep):
             info = self.jpeg_info(k)
             if info is None:
                 raise IrpError(_ffi.IRP_ERR_UNSUPPORTED, f"blob {i} is not a JPEG the device decoder takes")
-            a = np.empty((info[1], info[0], info[2]), np.uint8)
+            d = max(1, scale_denom)
+            a = np.empty((-(-info[1] // d), -(-info[0] // d), info[2]), np.uint8)
             arrays.append(a)
             outs[i] = _ffi.OutDesc(a.ctypes.data, 0, a.nbytes, 0, 0, 0, 0)
         self._check(self._lib.irp_decode_jpeg_batch(self._ctx, descs, n, outs))

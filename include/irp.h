@@ -192,7 +192,7 @@ typedef struct irp_jpeg_desc {
   const uint8_t *data;      /* host pointer to the JPEG file bytes          */
   size_t size;
   int32_t exif_orientation; /* 1..8 (from the caller's header parse), else 1 */
-  int32_t reserved;
+  int32_t scale_denom;      /* irp_decode_jpeg_batch only: decode at libjpeg scale 1 / 2, 4 or 8 (0, 1 = full size) */
 } irp_jpeg_desc;
 /* header only: stored dims and channels (1 grey, 3 colour) — sharp(buf).metadata(), classifier.js:51 */
 int irp_jpeg_info(const uint8_t *data, size_t size, int *width, int *height, int *channels);

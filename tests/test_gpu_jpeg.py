@@ -168,6 +168,40 @@ def test_progressive_upload_through_the_whole_upload_route(engine, oracle):
     assert files[0] == b.getvalue()
 
 
+@pytest.mark.parametrize("denom", [2, 4, 8])
+def test_reduced_size_decode_matches_libjpeg_turbo(engine, denom):
+    """irp_jpeg_desc.scale_denom: libjpeg's scale 1/2, 1/4, 1/8 (libvips' shrink-on-load) on the device — reduced IDCTs
+    (jidctred.c), per-component IDCT sizes, plain upsampling at 1/8 — against Pillow's draft mode (libjpeg-turbo itself)
+    and the pinned restatement; baseline and progressive files of every sampling in one batch."""
+    from oracle import jpeg_oracle
+
+    blobs = []
+    for i, (h, w) in enumerate([(64, 64), (333, 517), (17, 9), (100, 161), (255, 257), (8, 8), (5, 3), (31, 33), (600, 900)]):
+        img = rand_image(h, w, 3, seed=300 + i, kind="smooth" if i % 2 else "noise")
+        for sub in (0, 1, 2):
+            blobs.append(_encode(img, quality=85, subsampling=sub, progressive=bool((i + sub) % 2)))
+    blobs.append(_encode(rand_image(77, 130, 1, seed=9)[:, :, 0], quality=70))
+    got = engine.decode_jpeg_batch(blobs, scale_denom=denom)
+    pinned = 0
+    for b, g in zip(blobs, got):
+        assert np.array_equal(g, jpeg_oracle.decode_scaled(b, denom)), f"{g.shape}"
+        im = Image.open(io.BytesIO(b))
+        w, h = im.size
+        im.draft(im.mode, (max(1, w // denom), max(1, h // denom)))
+        ref = np.asarray(im)
+        if ref.shape[:2] == g.shape[:2]:     # Pillow settled for this scale
+            assert np.array_equal(g, ref)
+            pinned += 1
+    assert pinned >= 10
+    with pytest.raises(Exception):           # the analysing entry points need the full picture
+        from irp_b200 import _ffi
+
+        k = np.frombuffer(blobs[0], np.uint8)
+        descs = (_ffi.JpegDesc * 1)(_ffi.JpegDesc(k.ctypes.data, k.size, 1, denom))
+        res = (_ffi.Result * 1)()
+        engine._check(engine._lib.irp_analyze_jpeg_batch(engine._ctx, descs, 1, res, None))
+
+
 def test_unsupported_kinds_are_refused_loudly(engine):
     from irp_b200 import _ffi
 
