@@ -1,0 +1,122 @@
+"""Test helper: rewrite a baseline interleaved JPEG as a SEQUENTIAL file with one scan per component (SOF0, three
+non-interleaved SOS segments) carrying the same quantised coefficients and the same Huffman tables.  Pillow cannot
+write such files, libjpeg-turbo reads them, and the decoded pixels must equal those of the original file — a pin for
+the multi-scan path of the decoders that does not involve progressive coding."""
+import numpy as np
+
+from oracle import jpeg_oracle
+
+_ZZ = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49,
+       56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+
+
+def _segments(data):
+    p, out = 2, []
+    while True:
+        assert data[p] == 0xFF
+        m = data[p + 1]
+        ln = (data[p + 2] << 8) | data[p + 3]
+        out.append((m, data[p + 4:p + 2 + ln]))
+        p += 2 + ln
+        if m == 0xDA:
+            return out
+
+
+def _huff_codes(payload):
+    """DHT payload -> {(class, id): {symbol: (code, length)}}"""
+    tabs, o = {}, 0
+    while o < len(payload):
+        tc, th = payload[o] >> 4, payload[o] & 15
+        bits = payload[o + 1:o + 17]
+        n = sum(bits)
+        vals = payload[o + 17:o + 17 + n]
+        code, k, t = 0, 0, {}
+        for ln in range(1, 17):
+            for _ in range(bits[ln - 1]):
+                t[vals[k]] = (code, ln)
+                code += 1
+                k += 1
+            code <<= 1
+        tabs[(tc, th)] = t
+        o += 17 + n
+    return tabs
+
+
+class _Bits:
+    def __init__(self):
+        self.out, self.acc, self.n = bytearray(), 0, 0
+
+    def put(self, v, ln):
+        if not ln:
+            return
+        self.acc = (self.acc << ln) | (v & ((1 << ln) - 1))
+        self.n += ln
+        while self.n >= 8:
+            b = (self.acc >> (self.n - 8)) & 0xFF
+            self.out.append(b)
+            if b == 0xFF:
+                self.out.append(0)
+            self.n -= 8
+
+    def flush(self):
+        if self.n:
+            self.put((1 << (8 - self.n)) - 1, 8 - self.n)
+        return bytes(self.out)
+
+
+def _mag(v):
+    a = abs(int(v))
+    s = a.bit_length()
+    return s, (int(v) if v >= 0 else int(v) + (1 << s) - 1)
+
+
+def one_scan_per_component(data: bytes) -> bytes:
+    info = jpeg_oracle.info(data)
+    assert info["components"] == 3 and info["restart_interval"] == 0
+    segs = _segments(data)
+    tabs = {}
+    for m, pl in segs:
+        if m == 0xC4:
+            tabs.update(_huff_codes(pl))
+    sos = [pl for m, pl in segs if m == 0xDA][0]
+    sel = {sos[1 + 2 * i]: (sos[2 + 2 * i] >> 4, sos[2 + 2 * i] & 15) for i in range(3)}
+    sof = [pl for m, pl in segs if m in (0xC0, 0xC1)][0]
+    ids = [sof[6 + 3 * i] for i in range(3)]
+    hmax = max(h for h, _ in info["sampling"])
+    vmax = max(v for _, v in info["sampling"])
+    out = bytearray(b"\xff\xd8")
+    for m, pl in segs:
+        if m != 0xDA:
+            out += bytes([0xFF, m]) + (len(pl) + 2).to_bytes(2, "big") + bytes(pl)
+    for ci in range(3):
+        h, v = info["sampling"][ci]
+        coef = jpeg_oracle.coefficients(data, ci)                      # [block rows][blocks per row][64], natural order
+        bw = -(-(-(-info["width"] * h // hmax)) // 8)                   # the component's OWN block grid, not the MCU-padded one
+        bh = -(-(-(-info["height"] * v // vmax)) // 8)
+        td, ta = sel[ids[ci]]
+        dc, ac = tabs[(0, td)], tabs[(1, ta)]
+        bits, pred = _Bits(), 0
+        for by in range(bh):
+            for bx in range(bw):
+                blk = coef[by, bx]
+                s, val = _mag(int(blk[0]) - pred)
+                pred = int(blk[0])
+                bits.put(*dc[s])
+                bits.put(val, s)
+                run = 0
+                for k in range(1, 64):
+                    c = int(blk[_ZZ[k]])
+                    if c == 0:
+                        run += 1
+                        continue
+                    while run > 15:
+                        bits.put(*ac[0xF0])
+                        run -= 16
+                    s, val = _mag(c)
+                    bits.put(*ac[(run << 4) | s])
+                    bits.put(val, s)
+                    run = 0
+                if run:
+                    bits.put(*ac[0x00])
+        out += b"\xff\xda" + (8).to_bytes(2, "big") + bytes([1, ids[ci], (td << 4) | ta, 0, 63, 0]) + bits.flush()
+    return bytes(out + b"\xff\xd9")

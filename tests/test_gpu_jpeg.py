@@ -202,6 +202,21 @@ def test_reduced_size_decode_matches_libjpeg_turbo(engine, denom):
         engine._check(engine._lib.irp_analyze_jpeg_batch(engine._ctx, descs, 1, res, None))
 
 
+@pytest.mark.parametrize("subsampling", [0, 1, 2])
+def test_sequential_file_with_one_scan_per_component(engine, subsampling):
+    """A baseline file whose components come in separate scans takes the multi-scan route (prog_scan_kernel's first-pass
+    handler with DC and AC in one scan); same pixels as the interleaved original."""
+    from jpeg_rescan import one_scan_per_component
+
+    blobs, refs = [], []
+    for i, (h, w) in enumerate([(37, 53), (64, 64), (100, 161), (9, 17), (241, 319)]):
+        data = _encode(rand_image(h, w, 3, seed=70 + i, kind="smooth"), quality=85, subsampling=subsampling)
+        blobs.append(one_scan_per_component(data))
+        refs.append(_pillow(data))
+    for g, r in zip(_decode_batch(engine, blobs), refs):
+        assert np.array_equal(g, r)
+
+
 def test_unsupported_kinds_are_refused_loudly(engine):
     from irp_b200 import _ffi
 

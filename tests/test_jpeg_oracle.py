@@ -95,6 +95,19 @@ def test_narrow_images_take_the_plain_upsampler(subsampling):
             assert np.array_equal(jpeg_oracle.decode(data), _pillow(data)), f"{h}x{w} progressive={prog}"
 
 
+@pytest.mark.parametrize("subsampling", [0, 1, 2])
+def test_sequential_file_with_one_scan_per_component(subsampling):
+    """SOF0 with three non-interleaved scans (tests/jpeg_rescan.py re-codes a Pillow file's own coefficients that way):
+    a scan of one component walks that component's own block grid, not the MCU-padded one."""
+    from jpeg_rescan import one_scan_per_component
+
+    for i, (h, w) in enumerate([(37, 53), (64, 64), (100, 161), (9, 17), (8, 8)]):
+        data = _encode(rand_image(h, w, 3, seed=70 + i, kind="smooth"), quality=85, subsampling=subsampling)
+        multi = one_scan_per_component(data)
+        assert np.array_equal(_pillow(multi), _pillow(data))            # libjpeg-turbo reads the rewritten file as the same picture
+        assert np.array_equal(jpeg_oracle.decode(multi), _pillow(data))
+
+
 def test_four_components_are_reported_unsupported():
     import io
 
