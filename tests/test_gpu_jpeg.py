@@ -193,6 +193,8 @@ def test_reduced_size_decode_matches_libjpeg_turbo(engine, denom):
             assert np.array_equal(g, ref)
             pinned += 1
     assert pinned >= 10
+    for b in (blobs[2], blobs[14]):          # a 4:2:0 file ALONE in its call (no other image brings the generic colour kernel along)
+        assert np.array_equal(engine.decode_jpeg_batch([b], scale_denom=denom)[0], jpeg_oracle.decode_scaled(b, denom))
     with pytest.raises(Exception):           # the analysing entry points need the full picture
         from irp_b200 import _ffi
 
