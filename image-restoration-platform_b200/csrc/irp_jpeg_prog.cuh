@@ -16,9 +16,14 @@
 //     block), ballots give lane 0 a 64-bit history mask per block, lane 0 turns symbols and correction bits into
 //     three masks per block (correction, new coefficient, its sign) and the warp applies them and stores,
 //   * a DC refinement is one bit per block at a known position: every lane takes its own blocks.
-// The scans of a batch are independent across images and across the coefficient sets they touch; the host sorts
-// them into dependency levels (a scan waits for the earlier scans of the same component and band) and launches
-// one grid per level — three for libjpeg's standard script.
+// The scans of a batch are independent across images and across the coefficient sets they touch.  A scan that touches
+// coefficients an earlier scan of the same image wrote (a refinement after its first pass) does NOT wait for that
+// scan to end: both walk the component's blocks in the same order, so it trails its predecessor BLOCK-WISE — every
+// scan publishes how many blocks it has completed, a dependent scan reads that before it loads its next group.  All
+// scans of a batch are ONE launch; a warp takes its scan from a ticket counter, and the host lists predecessors
+// before their dependents, so a warp only ever waits for warps that started before it (no deadlock, whatever the
+// number of resident warps).  The luma chain of libjpeg's standard script (first passes | refinement | last
+// refinement) thereby costs its longest scan instead of the sum of the three.
 #pragma once
 #include "irp_jpeg.cuh"
 
@@ -26,6 +31,8 @@ namespace irp {
 
 constexpr int kProgRing = 2048;     // ring of stream words (8 KB); refilled in halves
 constexpr int kProgGroup = 8;       // blocks a refinement scan loads at a time
+constexpr int kProgMaxPred = 6;     // predecessors a scan can name (the host falls back to "after everything before it" past that)
+constexpr int kProgDone = 0x7FFFFFFF;
 // an MCU of a first pass consumes at most 10 blocks x 64 symbols x 31 bits < 640 words, a refinement group at most
 // 8 x 63 x 18 bits < 300 words: half a ring is always enough until the next refill point
 constexpr int kProgAhead = kProgRing / 2 - 64;   // after a refill: kProgAhead <= staged - next word < kProgRing - 64
@@ -38,7 +45,9 @@ struct ProgScan {                   // one scan of one image
   int ss, se, ah, al;
   int restart;                      // MCUs per restart interval at this scan (0: one stream)
   int stream_first, nstreams;
-  int pad;
+  int npred;                        // earlier scans of the same image whose coefficients this scan reads or overwrites
+  int pred[kProgMaxPred];           // their indices in the batch's scan list (always lower than this scan's)
+  int pred_blockwise[kProgMaxPred]; // 1: same block order (trail it block by block); 0: wait for its end
 };
 struct ProgStream {                 // one restart interval of a scan (or the whole scan), un-stuffed, 4-byte aligned
   unsigned long long word_off;      // into the batch data buffer, in 32-bit words
@@ -130,7 +139,7 @@ __device__ __forceinline__ size_t prog_dc_index(const JpegImg& im, int c, int gy
 __global__ void __launch_bounds__(32)
 prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ scans, const ProgStream* __restrict__ streams,
                  const HuffDev* __restrict__ tabs, const uint32_t* __restrict__ data, int16_t* __restrict__ coef_arena,
-                 int16_t* __restrict__ dcv) {
+                 int16_t* __restrict__ dcv, int* __restrict__ progress /* [0]: ticket counter, [1 + scan]: blocks completed */) {
   __shared__ uint32_t ring[kProgRing];
   __shared__ HuffDev ht[6];   // DC tables of the scan's components, then their AC tables
   // refinement scans, per block of a group: the history mask and the list of zero positions (built by the warp), and
@@ -144,8 +153,31 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
   __shared__ __align__(16) uint8_t s_new[kProgGroup][64];    // coefficient that becomes nonzero in this scan: 1 positive, 2 negative
   __shared__ int s_nzr[kProgGroup];
   const int lane = threadIdx.x;
-  const ProgScan sc = scans[blockIdx.x];
+  // scans are taken in ticket order: whoever this scan waits for holds a lower ticket, i.e. is running or done
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(progress, 1);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  const ProgScan sc = scans[ticket];
   const JpegImg& im = imgs[sc.img];
+  volatile int* my_progress = progress + 1 + ticket;
+  // wait until every predecessor has completed `need` blocks (or has ended, for one with another block order)
+  auto wait_for = [&](int need) {
+    if (sc.npred == 0) return;
+    if (lane == 0) {
+      for (int k = 0; k < sc.npred; k++) {
+        const volatile int* pp = progress + 1 + sc.pred[k];
+        const int target = sc.pred_blockwise[k] ? need : kProgDone;
+        while (*pp < target) __nanosleep(200);
+      }
+      __threadfence();
+    }
+    __syncwarp();
+  };
+  auto publish = [&](int done) {   // all lanes: their stores first
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *my_progress = done;
+  };
   for (int t = 0; t < 6; t++) {
     const int src = t < 3 ? sc.dc_tab[t] : sc.ac_tab[t - 3];
     if ((t % 3) < sc.ns && src >= 0) {
@@ -179,6 +211,7 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
 
     // ---------------- DC refinement: block b of the interval owns bit b ----------------
     if (sc.ss == 0 && sc.ah > 0) {
+      wait_for(m1);
       const int nb = (m1 - m0) * g.bpm;
       for (int b = lane; b < nb; b += 32) {
         const uint32_t w = (uint32_t)(b >> 5) < st.nwords ? bswap32(__ldg(src + (b >> 5))) : 0u;
@@ -190,12 +223,14 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
           const int c = sc.comp[i];
           const int nh = g.single ? 1 : im.comp_h[c], nv = g.single ? 1 : im.comp_v[c];
           if (k < nh * nv) {
-            dcv[prog_dc_index(im, c, my * nv + k / nh, mx * nh + k % nh)] |= (int16_t)(1 << sc.al);
+            int16_t* dp = dcv + prog_dc_index(im, c, my * nv + k / nh, mx * nh + k % nh);
+            *dp = (int16_t)(__ldcg(dp) | (1 << sc.al));   // written by another warp moments ago: read past L1
             break;
           }
           k -= nh * nv;
         }
       }
+      publish(m1);
       continue;
     }
 
@@ -209,6 +244,10 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
       int my = m0 / g.mcus_x, mx = m0 - my * g.mcus_x;
       for (int m = m0; m < m1; m++) {
         rd.refill(lane);
+        if ((m & 15) == 0 || m == m0) {
+          wait_for(min((m | 15) + 1, m1));
+          if (m > m0) publish(m);   // lane 0's stores of the last sixteen MCUs
+        }
         if (lane == 0) {
 #pragma unroll 1
           for (int i = 0; i < sc.ns; i++) {
@@ -267,6 +306,7 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
           my++;
         }
       }
+      publish(m1);
       continue;
     }
 
@@ -280,6 +320,7 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
       const HuffDev& act = ht[3];
       for (int n0 = m0; n0 < m1; n0 += kProgGroup) {
         rd.refill(lane);
+        wait_for(min(n0 + kProgGroup, m1));
         int16_t* ptr[kProgGroup];
         int lo[kProgGroup], hi[kProgGroup];
 #pragma unroll
@@ -287,8 +328,8 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
           const int n = min(n0 + q, m1 - 1);
           const int by = n / g.mcus_x, bx = n - by * g.mcus_x;
           ptr[q] = base + ((size_t)by * im.comp_bw[c] + bx) * 64;
-          lo[q] = ptr[q][lane];
-          hi[q] = ptr[q][lane + 32];
+          lo[q] = __ldcg(ptr[q] + lane);        // the predecessor scan wrote these moments ago, from another SM: read past L1
+          hi[q] = __ldcg(ptr[q] + lane + 32);
         }
         for (int i = lane; i < kProgGroup * 16; i += 32) {       // last group's marks and new coefficients
           reinterpret_cast<uint32_t*>(&s_mark[0][0])[i] = 0u;
@@ -393,10 +434,11 @@ prog_scan_kernel(const JpegImg* __restrict__ imgs, const ProgScan* __restrict__ 
             if (cb || nv) ptr[q][pos] = (int16_t)v;
           }
         }
-        __syncwarp();
+        publish(min(n0 + kProgGroup, m1));   // (also the warp barrier between this group's reads of the marks and the next one's clearing)
       }
     }
   }
+  publish(kProgDone);
 }
 
 }  // namespace irp
