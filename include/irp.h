@@ -185,8 +185,8 @@ int irp_fusion_prepare_batch(irp_ctx *ctx, const irp_image_desc *imgs, int n_gro
  * 12 MP photo crosses PCIe and the host decodes nothing.  8-bit Huffman JPEG:
  * baseline (SOF0/SOF1; one interleaved scan — the parallel self-synchronising
  * decoder — or one scan per component) and progressive (SOF2, what
- * imagePreprocess.js:57-61 writes: one warp per scan, scans in dependency
- * levels), 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, with or without
+ * imagePreprocess.js:57-61 writes: one warp per scan, dependent scans
+ * overlapped block by block), 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0, with or without
  * restart markers; anything else returns IRP_ERR_UNSUPPORTED (no CPU fallback). */
 typedef struct irp_jpeg_desc {
   const uint8_t *data;      /* host pointer to the JPEG file bytes          */
