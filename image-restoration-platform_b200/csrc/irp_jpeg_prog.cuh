@@ -111,6 +111,10 @@ struct ProgReader {
     return v;
   }
   __device__ __forceinline__ void skipn(int n) {      // any n >= 0
+    if (n <= avail - 32) {                              // the common case: a handful of correction bits
+      skip(n);
+      return;
+    }
     while (n > 0) {
       fill();
       const int t = min(n, 32);
