@@ -500,7 +500,7 @@ def main() -> int:
         t0 = time.perf_counter()
         oracle.analyze_batch(imgs[:sample], threads=T, with_preprocess=True)
         dt = time.perf_counter() - t0
-        jpeg_cpu = jpeg_enc_cpu = None
+        jpeg_cpu = jpeg_enc_cpu = jpeg_prog_cpu = None
         try:  # what the host would spend BEFORE any of this if it had to decode the files itself (libjpeg-turbo via Pillow)
             import io
             from concurrent.futures import ThreadPoolExecutor
@@ -513,6 +513,16 @@ def main() -> int:
                 tj0 = time.perf_counter()
                 list(ex.map(lambda _: np.asarray(Image.open(io.BytesIO(blob))).shape, range(2 * T)))
                 jpeg_cpu = 2 * T * W * H / 1e6 / (time.perf_counter() - tj0)
+                # the same for a PROGRESSIVE file of the same picture (beside e2e_from_jpeg.progressive)
+                from PIL import ImageFile
+
+                ImageFile.MAXBLOCK = 1 << 26
+                bio = io.BytesIO()
+                Image.fromarray(imgs[0]).save(bio, "JPEG", quality=90, subsampling=2, progressive=True, optimize=True)
+                pblob = bio.getvalue()
+                tp0 = time.perf_counter()
+                list(ex.map(lambda _: np.asarray(Image.open(io.BytesIO(pblob))).shape, range(T)))
+                jpeg_prog_cpu = T / (time.perf_counter() - tp0)
                 # ... and AFTER it, to turn the resized image into the file preprocessImage returns (per OUTPUT pixel)
                 small = np.ascontiguousarray(imgs[0][:oh, :ow])
 
@@ -526,7 +536,7 @@ def main() -> int:
                 jpeg_enc_cpu = 2 * T * ow * oh / 1e6 / (time.perf_counter() - te0)
         except Exception:
             pass
-        cpu = {"value": sample * W * H / 1e6 / dt, "unit": UNIT, "cores": T, "kind": "port", "host_jpeg_decode_mpix_s": jpeg_cpu,
+        cpu = {"value": sample * W * H / 1e6 / dt, "unit": UNIT, "cores": T, "kind": "port", "host_jpeg_decode_mpix_s": jpeg_cpu, "host_progressive_jpeg_files_per_s": jpeg_prog_cpu,
                "host_jpeg_encode_out_mpix_s": jpeg_enc_cpu,
                "sample": f"{sample} of the {B} images, {T} threads, one image per thread, {dt:.1f} s wall",
                "note": "oracle port of the reference arithmetic; the real sharp path adds 6 decodes and ~16 N JS closure visits per image"}
