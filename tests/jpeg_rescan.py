@@ -120,3 +120,134 @@ def one_scan_per_component(data: bytes) -> bytes:
                     bits.put(*ac[0x00])
         out += b"\xff\xda" + (8).to_bytes(2, "big") + bytes([1, ids[ci], (td << 4) | ta, 0, 63, 0]) + bits.flush()
     return bytes(out + b"\xff\xd9")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# progressive files with ARBITRARY scan scripts (jcphuff.c's coding, without end-of-band runs longer than one block so
+# that the Annex K tables of the source file suffice)
+# ---------------------------------------------------------------------------------------------------------------
+def _frame(data):
+    info = jpeg_oracle.info(data)
+    segs = _segments(data)
+    tabs = {}
+    for m, pl in segs:
+        if m == 0xC4:
+            tabs.update(_huff_codes(pl))
+    sof = [pl for m, pl in segs if m in (0xC0, 0xC1)][0]
+    ids = [sof[6 + 3 * i] for i in range(info["components"])]
+    return info, segs, tabs, ids
+
+
+def progressive_with_script(data: bytes, script) -> bytes:
+    """Re-code a baseline 3-component file as SOF2 with the given scans: (components, Ss, Se, Ah, Al) each, components a
+    tuple of indices (several only for DC scans).  The script has to send every bit of every coefficient eventually."""
+    info, segs, tabs, ids = _frame(data)
+    assert info["restart_interval"] == 0
+    hmax = max(h for h, _ in info["sampling"])
+    vmax = max(v for _, v in info["sampling"])
+    W, H = info["width"], info["height"]
+    mcux, mcuy = -(-W // (8 * hmax)), -(-H // (8 * vmax))
+    coefs = [jpeg_oracle.coefficients(data, c) for c in range(3)]
+    dc, ac = tabs[(0, 0)], tabs[(1, 0)]                      # the luma tables serve every scan
+    out = bytearray(b"\xff\xd8")
+    for m, pl in segs:
+        if m in (0xC0, 0xC1):
+            out += bytes([0xFF, 0xC2]) + (len(pl) + 2).to_bytes(2, "big") + bytes(pl)
+        elif m != 0xDA:
+            out += bytes([0xFF, m]) + (len(pl) + 2).to_bytes(2, "big") + bytes(pl)
+    for comps, ss, se, ah, al in script:
+        bits = _Bits()
+        if ss == 0:                                          # DC scan: interleaved MCUs, or one component's own grid
+            if len(comps) > 1:
+                order = [(c, my * info["sampling"][c][1] + by, mx * info["sampling"][c][0] + bx)
+                         for my in range(mcuy) for mx in range(mcux) for c in comps
+                         for by in range(info["sampling"][c][1]) for bx in range(info["sampling"][c][0])]
+            else:
+                c = comps[0]
+                h, v = info["sampling"][c]
+                bw, bh = -(-(-(-W * h // hmax)) // 8), -(-(-(-H * v // vmax)) // 8)
+                order = [(c, y, x) for y in range(bh) for x in range(bw)]
+            pred = {c: 0 for c in comps}
+            for c, y, x in order:
+                d = int(coefs[c][y, x][0])
+                if ah == 0:
+                    t = d >> al                              # arithmetic shift, as jcphuff.c does for DC
+                    s, val = _mag(t - pred[c])
+                    pred[c] = t
+                    bits.put(*dc[s])
+                    bits.put(val, s)
+                else:
+                    bits.put((d >> al) & 1, 1)
+        else:
+            c = comps[0]
+            h, v = info["sampling"][c]
+            bw, bh = -(-(-(-W * h // hmax)) // 8), -(-(-(-H * v // vmax)) // 8)
+            for y in range(bh):
+                for x in range(bw):
+                    blk = coefs[c][y, x]
+                    if ah == 0:                              # first pass: magnitudes shifted towards zero
+                        run = 0
+                        for k in range(ss, se + 1):
+                            cf = int(blk[_ZZ[k]])
+                            t = abs(cf) >> al
+                            if t == 0:
+                                run += 1
+                                continue
+                            while run > 15:
+                                bits.put(*ac[0xF0])
+                                run -= 16
+                            s = t.bit_length()
+                            bits.put(*ac[(run << 4) | s])
+                            bits.put(t if cf > 0 else (~t) & ((1 << s) - 1), s)
+                            run = 0
+                        if run:
+                            bits.put(*ac[0x00])
+                    else:                                    # refinement: correction bits ride behind the next symbol
+                        absv = [abs(int(blk[_ZZ[k]])) >> al for k in range(64)]
+                        eob = max([k for k in range(ss, se + 1) if absv[k] == 1], default=-1)
+                        run, br = 0, []
+                        for k in range(ss, se + 1):
+                            t = absv[k]
+                            if t == 0:
+                                run += 1
+                                continue
+                            while run > 15 and k <= eob:
+                                bits.put(*ac[0xF0])
+                                run -= 16
+                                for b in br:
+                                    bits.put(b, 1)
+                                br = []
+                            if t > 1:
+                                br.append(t & 1)
+                                continue
+                            bits.put(*ac[(run << 4) | 1])
+                            bits.put(0 if int(blk[_ZZ[k]]) < 0 else 1, 1)
+                            for b in br:
+                                bits.put(b, 1)
+                            br, run = [], 0
+                        if run or br:
+                            bits.put(*ac[0x00])
+                            for b in br:
+                                bits.put(b, 1)
+        hdr = bytes([len(comps)]) + b"".join(bytes([ids[c], 0x00]) for c in comps) + bytes([ss, se, (ah << 4) | al])
+        out += b"\xff\xda" + (len(hdr) + 2).to_bytes(2, "big") + hdr + bits.flush()
+    return bytes(out + b"\xff\xd9")
+
+
+# scan scripts that libjpeg's standard one does not cover
+SCRIPTS = {
+    "spectral selection only": [((0, 1, 2), 0, 0, 0, 0), ((0,), 1, 63, 0, 0), ((1,), 1, 63, 0, 0), ((2,), 1, 63, 0, 0)],
+    "dc per component, deep approximation": [
+        ((0,), 0, 0, 0, 2), ((1,), 0, 0, 0, 2), ((2,), 0, 0, 0, 2),
+        ((0,), 1, 2, 0, 1), ((0,), 3, 63, 0, 2), ((1,), 1, 63, 0, 1), ((2,), 1, 63, 0, 1),
+        ((0,), 3, 63, 2, 1), ((0,), 0, 0, 2, 1), ((1,), 0, 0, 2, 1), ((2,), 0, 0, 2, 1),
+        ((0,), 1, 63, 1, 0), ((1,), 1, 63, 1, 0), ((2,), 1, 63, 1, 0),
+        ((0,), 0, 0, 1, 0), ((1,), 0, 0, 1, 0), ((2,), 0, 0, 1, 0)],
+    "fine bands refined one by one": [
+        ((0, 1, 2), 0, 0, 0, 1),
+        ((0,), 1, 5, 0, 1), ((0,), 6, 20, 0, 1), ((0,), 21, 63, 0, 1),
+        ((1,), 1, 10, 0, 1), ((1,), 11, 63, 0, 1), ((2,), 1, 63, 0, 1),
+        ((0, 1, 2), 0, 0, 1, 0),
+        ((0,), 21, 63, 1, 0), ((0,), 1, 5, 1, 0), ((0,), 6, 20, 1, 0),
+        ((1,), 1, 63, 1, 0), ((2,), 1, 30, 1, 0), ((2,), 31, 63, 1, 0)],
+}

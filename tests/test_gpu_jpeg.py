@@ -219,6 +219,27 @@ def test_sequential_file_with_one_scan_per_component(engine, subsampling):
         assert np.array_equal(g, r)
 
 
+def test_progressive_scan_scripts_beyond_the_standard_one(engine):
+    """Scan scripts with several predecessors per scan, refinements of sub-bands in another order than their first
+    passes, DC scans per component and three approximation levels: the block-wise scan pipeline (a scan trails every
+    earlier scan that touched its coefficients) has to give the baseline file's pixels back for each of them — files of
+    all scripts and samplings in ONE batch, so that many dependency chains run side by side."""
+    from jpeg_rescan import SCRIPTS, progressive_with_script
+
+    blobs, refs = [], []
+    for i, (h, w) in enumerate([(37, 53), (64, 64), (100, 161), (241, 319), (9, 17)]):
+        for sub in (0, 1, 2):
+            data = _encode(rand_image(h, w, 3, seed=40 + i, kind="smooth" if (i + sub) % 2 else "noise"), quality=90, subsampling=sub)
+            for script in SCRIPTS.values():
+                blobs.append(progressive_with_script(data, script))
+                refs.append(_pillow(data))
+    for g, r in zip(_decode_batch(engine, blobs), refs):
+        assert np.array_equal(g, r)
+    big = _encode(rand_image(360, 540, 3, seed=55, kind="noise"), quality=92, subsampling=2)
+    for script in SCRIPTS.values():          # long scans: the dependents really do run while their predecessors are still at it
+        assert np.array_equal(_decode_batch(engine, [progressive_with_script(big, script)])[0], _pillow(big))
+
+
 def test_unsupported_kinds_are_refused_loudly(engine):
     from irp_b200 import _ffi
 

@@ -108,6 +108,22 @@ def test_sequential_file_with_one_scan_per_component(subsampling):
         assert np.array_equal(jpeg_oracle.decode(multi), _pillow(data))
 
 
+@pytest.mark.parametrize("name", ["spectral selection only", "dc per component, deep approximation", "fine bands refined one by one"])
+def test_progressive_scan_scripts_beyond_the_standard_one(name):
+    """Progressive files with scan scripts libjpeg's standard progression does not produce (what mozjpeg's scan search
+    may write): DC scans per component, three approximation levels, bands split finely and refined one by one.
+    tests/jpeg_rescan.py re-codes a baseline file's own coefficients under the script; libjpeg-turbo and the restatement
+    must both give the baseline file's pixels back."""
+    from jpeg_rescan import SCRIPTS, progressive_with_script
+
+    for i, (h, w) in enumerate([(37, 53), (64, 64), (100, 161), (9, 17)]):
+        for sub in (0, 1, 2):
+            data = _encode(rand_image(h, w, 3, seed=40 + i, kind="smooth" if (i + sub) % 2 else "noise"), quality=90, subsampling=sub)
+            f = progressive_with_script(data, SCRIPTS[name])
+            assert np.array_equal(_pillow(f), _pillow(data))
+            assert np.array_equal(jpeg_oracle.decode(f), _pillow(data))
+
+
 def test_four_components_are_reported_unsupported():
     import io
 
