@@ -251,3 +251,34 @@ SCRIPTS = {
         ((0,), 21, 63, 1, 0), ((0,), 1, 5, 1, 0), ((0,), 6, 20, 1, 0),
         ((1,), 1, 63, 1, 0), ((2,), 1, 30, 1, 0), ((2,), 31, 63, 1, 0)],
 }
+
+
+def random_script(rng, max_al=2):
+    """A random VALID progression for 3 components: every band of every component gets a first pass at some Al and is
+    then refined one bit at a time; bands, depths and the interleaving of the scans are drawn at random (per coefficient
+    the order first pass -> refinements is kept, as jdphuff.c demands)."""
+    chains = []                                             # each: list of scans that must stay in order
+    al = int(rng.integers(0, max_al + 1))
+    if rng.random() < 0.5:
+        dc = [((0, 1, 2), 0, 0, 0, al)] + [((0, 1, 2), 0, 0, a + 1, a) for a in range(al - 1, -1, -1)]
+        chains.append(dc)
+    else:
+        for c in range(3):
+            a0 = int(rng.integers(0, max_al + 1))
+            chains.append([((c,), 0, 0, 0, a0)] + [((c,), 0, 0, a + 1, a) for a in range(a0 - 1, -1, -1)])
+    for c in range(3):
+        cuts = sorted(set(int(x) for x in rng.integers(2, 63, int(rng.integers(0, 3)))))
+        edges = [1] + cuts + [64]
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            a0 = int(rng.integers(0, max_al + 1))
+            chains.append([((c,), lo, hi - 1, 0, a0)] + [((c,), lo, hi - 1, a + 1, a) for a in range(a0 - 1, -1, -1)])
+    script = []
+    while chains:                                           # a random interleaving that keeps every chain's order
+        k = int(rng.integers(0, len(chains)))
+        script.append(chains[k].pop(0))
+        if not chains[k]:
+            chains.pop(k)
+    # AC scans may not precede the first DC scan of their component (jdphuff.c checks coef_bits[0] >= 0): DC first passes lead
+    head = [s for s in script if s[1] == 0 and s[3] == 0]
+    rest = [s for s in script if not (s[1] == 0 and s[3] == 0)]
+    return head + rest

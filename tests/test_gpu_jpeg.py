@@ -240,6 +240,22 @@ def test_progressive_scan_scripts_beyond_the_standard_one(engine):
     assert np.array_equal(_decode_batch(engine, [progressive_with_script(big, SCRIPTS["fine bands refined one by one"])])[0], _pillow(big))
 
 
+def test_random_progressive_scan_scripts(engine):
+    """Random valid progressions in one batch: whatever order the scans of a file come in, every scan only trails the
+    scans that wrote its coefficients before it."""
+    from jpeg_rescan import progressive_with_script, random_script
+
+    rng = np.random.default_rng(12)
+    blobs, refs = [], []
+    for t in range(24):
+        h, w, sub = int(rng.integers(8, 140)), int(rng.integers(8, 200)), int(rng.integers(0, 3))
+        data = _encode(rand_image(h, w, 3, seed=t, kind="noise" if t % 2 else "smooth"), quality=int(rng.integers(60, 96)), subsampling=sub)
+        blobs.append(progressive_with_script(data, random_script(rng)))
+        refs.append(_pillow(data))
+    for t, (g, r) in enumerate(zip(_decode_batch(engine, blobs), refs)):
+        assert np.array_equal(g, r), f"case {t}"
+
+
 def test_unsupported_kinds_are_refused_loudly(engine):
     from irp_b200 import _ffi
 

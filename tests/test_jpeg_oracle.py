@@ -124,6 +124,19 @@ def test_progressive_scan_scripts_beyond_the_standard_one(name):
             assert np.array_equal(jpeg_oracle.decode(f), _pillow(data))
 
 
+def test_random_progressive_scan_scripts():
+    """Random valid progressions (bands, approximation depths and scan order drawn at random, jpeg_rescan.random_script)."""
+    from jpeg_rescan import progressive_with_script, random_script
+
+    rng = np.random.default_rng(11)
+    for t in range(16):
+        h, w, sub = int(rng.integers(8, 90)), int(rng.integers(8, 120)), int(rng.integers(0, 3))
+        data = _encode(rand_image(h, w, 3, seed=t, kind="noise" if t % 2 else "smooth"), quality=int(rng.integers(60, 96)), subsampling=sub)
+        f = progressive_with_script(data, random_script(rng))
+        assert np.array_equal(_pillow(f), _pillow(data))
+        assert np.array_equal(jpeg_oracle.decode(f), _pillow(data)), f"case {t}"
+
+
 def test_four_components_are_reported_unsupported():
     import io
 
