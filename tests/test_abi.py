@@ -159,6 +159,50 @@ def test_jpeg_header_parse_runs_without_a_gpu():
     assert info(enc(rgb, quality=80)[:40])[0] == _ffi.IRP_ERR_UNSUPPORTED   # truncated inside the header
 
 
+def test_progressive_scan_headers_are_validated_on_the_host():
+    """jdphuff.c's rules for scan parameters are enforced by the parser (irp_jpeg_info walks every scan of a multi-scan
+    file, no GPU involved): the device only ever sees scans it can walk."""
+    import ctypes as C
+    import io
+
+    import numpy as np
+    from PIL import Image
+
+    from irp_b200 import _ffi
+
+    lib = _ffi.load()
+
+    def info(blob):
+        k = np.frombuffer(bytes(blob), np.uint8)
+        w, h, c = C.c_int(), C.c_int(), C.c_int()
+        return lib.irp_jpeg_info(k.ctypes.data, k.size, C.byref(w), C.byref(h), C.byref(c))
+
+    b = io.BytesIO()
+    Image.fromarray(np.zeros((40, 56, 3), np.uint8)).save(b, "JPEG", quality=80, progressive=True)
+    good = b.getvalue()
+    assert info(good) == 0
+    sos = [i for i in range(len(good) - 1) if good[i] == 0xFF and good[i + 1] == 0xDA]
+    assert len(sos) >= 6
+
+    def patched(k, off, val):       # byte `off` of the k-th scan header's payload (negative: from its end)
+        p = sos[k]
+        ln = (good[p + 2] << 8) | good[p + 3]
+        out = bytearray(good)
+        out[p + 2 + ln + off if off < 0 else p + 4 + off] = val
+        return out
+
+    assert info(patched(1, -3, 70)) == _ffi.IRP_ERR_UNSUPPORTED      # Ss > 63
+    assert info(patched(1, -2, 0)) == _ffi.IRP_ERR_UNSUPPORTED       # Se < Ss
+    assert info(patched(1, -1, 0x0F)) == _ffi.IRP_ERR_UNSUPPORTED    # Al > 13
+    assert info(patched(0, -2, 5)) == _ffi.IRP_ERR_UNSUPPORTED       # a DC scan with Se != 0
+    assert info(patched(0, 3, good[sos[0] + 5])) == _ffi.IRP_ERR_UNSUPPORTED   # the same component twice in one scan
+    assert info(patched(1, 2, 0x09)) == _ffi.IRP_ERR_UNSUPPORTED     # table selector > 3
+    assert info(patched(1, 1, 0x7E)) == _ffi.IRP_ERR_UNSUPPORTED     # a component the frame does not have
+    eoi = good.rfind(b"\xff\xd9")
+    one = good[sos[-1]:eoi]
+    assert info(good[:eoi] + one * 70 + b"\xff\xd9") == _ffi.IRP_ERR_UNSUPPORTED   # more scans than any script holds
+
+
 def test_committed_jpeg_tables_are_what_libjpeg_turbo_writes(tmp_path):
     """csrc/jpeg_std_tables.inc (the encoder's Annex K quantisation / Huffman tables) is generated from files
     written by libjpeg-turbo; regenerating it must reproduce the committed file byte for byte."""
