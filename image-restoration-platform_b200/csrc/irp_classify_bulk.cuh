@@ -248,7 +248,7 @@ __device__ __forceinline__ void stage3v(const Tiles<3>& T, Acc<3>& a, int tid, i
       win[0] = __byte_perm(up, cur, 0x7400); win[1] = __byte_perm(up, cur, 0x7510);
       win[2] = __byte_perm(up, cur, 0x7620); win[3] = __byte_perm(up, cur, 0x7730);      // (-, up, cur, 0)
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < 8; i++) {
       if (!FULL && i >= nrows) break;
       const uint32_t dn = hp[(i + 2) * (kBPitch / 4)];
