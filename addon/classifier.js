@@ -1,6 +1,6 @@
 // Drop-in for server-node/src/services/classifier.js — SOURCE ONLY / UNVERIFIED (no Node here).
 // Same exports, same analyze() key order, same logging and span calls; the six sharp pipelines
-// and the JS reductions are replaced by ONE native call.  Baseline JPEG files are handed over as they
+// and the JS reductions are replaced by ONE native call.  JPEG files (baseline or progressive) are handed over as they
 // are (decoded on the device); other containers are decoded by sharp once instead of six times.
 import { trace, SpanStatusCode } from '@opentelemetry/api';
 import sharp from 'sharp';
@@ -36,11 +36,11 @@ export class ClassifierService {
       const metadata = await sharp(imageBuffer).metadata();
       let scores;
       try {
-        // a baseline JPEG goes to the GPU as it is: decoded there bit-exactly as libjpeg-turbo (sharp's decoder) would
+        // a JPEG (baseline or progressive) goes to the GPU as it is: decoded there bit-exactly as libjpeg-turbo (sharp's decoder) would
         scores = await native.analyzeFile(ctx, imageBuffer);
       } catch (e) {
         if (e.message !== 'unsupported') throw e;
-        // PNG / WebP / progressive JPEG: one sharp decode (instead of six), then the raw entry point
+        // PNG / WebP (and JPEG kinds the device refuses): one sharp decode (instead of six), then the raw entry point
         const { data, info } = await sharp(imageBuffer).raw().toBuffer({ resolveWithObject: true });
         scores = await native.analyzeRaw(ctx, data, info.width, info.height, info.channels, metadata.format === 'jpeg');
       }

@@ -7,7 +7,7 @@
 //
 // JS surface (used by addon/classifier.js and addon/imagePreprocess.js):
 //   createContext(device:number) -> external
-//   analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>   (baseline JPEG bytes, decoded on the device)
+//   analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>   (JPEG bytes, baseline or progressive, decoded on the device)
 //   transcodeFile(ctx, file:Buffer, orientation, quality) -> Promise<{scores:Float64Array(7), file:Buffer, width, height, channels}>
 //       analyze() + preprocessImage() of one upload with files on both sides (irp_transcode_jpeg_batch)
 //       `quality` carries the flags of include/irp.h: IRP_JPEG_OPTIMIZE, IRP_JPEG_ICC(id) (IRP_ICC_SRGB = the generated sRGB profile)
@@ -199,7 +199,7 @@ napi_value Submit(napi_env env, napi_callback_info info, bool preprocess) {
   return promise;
 }
 
-// analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>; rejects with "unsupported" for anything but a baseline
+// analyzeFile(ctx, file:Buffer) -> Promise<Float64Array(7)>; rejects with "unsupported" for anything but a Huffman-coded 8-bit
 // JPEG, in which case the shim decodes with sharp and calls analyzeRaw
 napi_value AnalyzeFile(napi_env env, napi_callback_info info) {
   size_t argc = 2;
@@ -235,7 +235,7 @@ napi_value AnalyzeFile(napi_env env, napi_callback_info info) {
   return promise;
 }
 
-// transcodeFile(ctx, file:Buffer, orientation, quality): rejects with "unsupported" for anything but a baseline JPEG
+// transcodeFile(ctx, file:Buffer, orientation, quality): rejects with "unsupported" for anything but a Huffman-coded 8-bit JPEG
 napi_value TranscodeFile(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value argv[4];
