@@ -1,7 +1,7 @@
 // Drop-in for server-node/src/middleware/imagePreprocess.js — SOURCE ONLY / UNVERIFIED (no Node here).
 // Same export, same req.file fields, same operation strings and the same problem documents; the sharp pipeline
-// (.rotate() -> resize fit inside 2048 -> .jpeg(q85 4:4:4) -> ICC) is ONE native call when the upload is a JPEG (baseline or progressive; the library says which it takes): a baseline
-// JPEG: decoded, oriented, resized and re-encoded on the device (optimised Huffman tables as `mozjpeg: true`
+// (.rotate() -> resize fit inside 2048 -> .jpeg(q85 4:4:4) -> ICC) is ONE native call when the upload is a JPEG the
+// library takes (baseline or progressive): decoded, oriented, resized and re-encoded on the device (optimised Huffman tables as `mozjpeg: true`
 // implies; no trellis quantisation, sequential instead of progressive scans).  Other containers are decoded by
 // sharp once, processed natively as raw pixels and encoded by sharp as before.
 import sharp from 'sharp';
