@@ -203,6 +203,36 @@ def test_progressive_scan_headers_are_validated_on_the_host():
     assert info(good[:eoi] + one * 70 + b"\xff\xd9") == _ffi.IRP_ERR_UNSUPPORTED   # more scans than any script holds
 
 
+def test_parser_survives_mutated_headers():
+    """irp_jpeg_info on thousands of randomly damaged baseline and progressive files: every call returns (accepted or
+    IRP_ERR_UNSUPPORTED), none reads outside the buffer it was given (the copy ends exactly at the file's last byte)."""
+    import ctypes as C
+    import io
+
+    import numpy as np
+    from PIL import Image
+
+    from irp_b200 import _ffi
+
+    lib = _ffi.load()
+    rng = np.random.default_rng(3)
+    seen = set()
+    for prog in (True, False):
+        b = io.BytesIO()
+        Image.fromarray(rng.integers(0, 255, (48, 64, 3), dtype=np.uint8)).save(b, "JPEG", quality=80, progressive=prog, subsampling=2)
+        good = b.getvalue()
+        for t in range(4000):
+            a = bytearray(good)
+            for _ in range(int(rng.integers(1, 4))):
+                a[int(rng.integers(2, len(a)))] = int(rng.integers(0, 256))
+            if t % 7 == 0:
+                a = a[: int(rng.integers(4, len(a)))]
+            k = np.frombuffer(bytes(a), np.uint8)
+            w, h, c = C.c_int(), C.c_int(), C.c_int()
+            seen.add(lib.irp_jpeg_info(k.ctypes.data, k.size, C.byref(w), C.byref(h), C.byref(c)))
+    assert seen <= {0, _ffi.IRP_ERR_UNSUPPORTED}
+
+
 def test_committed_jpeg_tables_are_what_libjpeg_turbo_writes(tmp_path):
     """csrc/jpeg_std_tables.inc (the encoder's Annex K quantisation / Huffman tables) is generated from files
     written by libjpeg-turbo; regenerating it must reproduce the committed file byte for byte."""
